@@ -1,0 +1,191 @@
+/* libdeepj_sm100.so -- C ABI of the B200-native DeepJ biaxial-LSTM hot path.
+ *
+ * Every entry point is what a binding for the reference's model.py /
+ * generate.py hot path would call (reference = calclavia/music-generator;
+ * file:line below are into that repository).  The reference has no native
+ * code or FFI of its own: its "interface" for this path is the Keras layer
+ * graph of model.py and the NumPy sampling loop of generate.py, so each
+ * function names the graph segment it replaces.
+ *
+ * Conventions
+ *   - plain C, no torch types; all pointers are DEVICE pointers on the current
+ *     device unless the name says host; the caller owns every buffer.
+ *   - every function returns 0 on success, <0 for an invalid argument /
+ *     unsupported shape, >0 = cudaError_t.  dj_last_error() gives the text.
+ *   - all launches are asynchronous on `stream` (a cudaStream_t passed as
+ *     void*); no hidden synchronisation.
+ *   - activations use one canonical row order: row = (b*T + t)*48 + n, so the
+ *     reference's Permute layers (model.py:72,81,88) cost nothing.
+ *   - there is NO CPU fallback.
+ */
+#ifndef DEEPJ_B200_H
+#define DEEPJ_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DJ_NUM_NOTES 48      /* constants.py:54-56 */
+#define DJ_NOTE_UNITS 3      /* constants.py:72 */
+#define DJ_BEAT 16           /* constants.py:63 */
+#define DJ_OCTAVE 12         /* constants.py:51 */
+#define DJ_CONV_K 24         /* model.py:56 (2*OCTAVE) */
+#define DJ_OCTAVE_UNITS 64   /* constants.py:70 */
+#define DJ_STYLE_UNITS 64    /* constants.py:71 */
+#define DJ_FEAT0 94          /* model.py:61-67: 1+12+1+64+16 */
+
+/* dtype tags for GEMM operands produced by the glue kernels */
+#define DJ_F32 0
+#define DJ_BF16 1
+
+/* One dropout site (model.py:58,80,85,116,123,136-138).  mode 0 = inactive
+ * (predict), 1 = one hash word per 4 elements (rate*256 integral), 2 = one
+ * word per element.  Built by dj_make_dropout. */
+typedef struct dj_dropout {
+  uint32_t key;
+  uint32_t thr;
+  float scale;
+  int32_t mode;
+} dj_dropout;
+
+int dj_version(void);
+const char* dj_last_error(void);
+/* host helper: fills *out for Dropout(rate) at `site` (1..12 = D1..D12 of SURVEY 8a). */
+int dj_make_dropout(uint64_t seed, int site, float rate, dj_dropout* out);
+/* debug: dump the 0/1 keep mask of a site with `rows` rows of F elements
+ * (element index = row*roundup4(F)+f) so a CPU checker can replay it. */
+int dj_dropout_mask_materialize(dj_dropout d, int64_t rows, int F, float* out, void* stream);
+
+/* ---- front end --------------------------------------------------------------
+ * dj_style_fwd replaces Dense(64,name='style') (model.py:141-142) and the four
+ * per-layer Dense(F)+tanh style projections (model.py:77-79,113-115).
+ *   style_in[b*style_bstride + t*style_tstride + s], s<num_styles
+ *   emb [B*T,64];  sp[l] [B*T,F[l]] = tanh(emb.Wsd[l]+bsd[l]) */
+int dj_style_fwd(const float* style_in, int64_t style_bstride, int64_t style_tstride, int num_styles,
+                 int B, int T, const float* Ws, const float* bs, int n_proj,
+                 const float* const* Wsd, const float* const* bsd, const int* F,
+                 float* emb, float* const* sp, void* stream);
+/* dj_frontend_fwd replaces input Dropout (model.py:136-137), the octave
+ * Conv1D+tanh+Dropout (model.py:56-58), pitch_pos/pitch_class/pitch_bins
+ * (model.py:22-49, including the reshape scramble over the LOCAL batch), the
+ * beat RepeatVector, Concatenate, Permute (model.py:61-72) and the layer-0
+ * style Add (model.py:78-82).  Writes the time-axis layer-0 GEMM A operand
+ * A0[M, ldA] (cols >= 94 zero). */
+int dj_frontend_fwd(const float* notes_in, int64_t notes_bstride, const float* beat_in,
+                    int64_t beat_bstride, int B, int T, const float* Wc, const float* bc,
+                    const float* sp0, dj_dropout d_notes, dj_dropout d_beat, dj_dropout d_conv,
+                    dj_dropout d_sp, void* A0, int ldA, int a_dtype, void* stream);
+/* dj_layer_input replaces, for every LSTM layer but the first, the Dropout of
+ * the previous layer output (model.py:85,123), the style Add (model.py:82,117)
+ * and -- for note-axis layer 0 -- shift_chosen + Concatenate (model.py:101-106,
+ * chosen post input-Dropout model.py:138).
+ *   h_prev row for (b,t,n) = h_row0 + b*h_b_rows + t*48 + n, Uprev columns
+ *   chosen_in (nullable) [B,T,48,3] with batch stride chosen_bstride
+ *   A[M, ldA]: cols [0,Uprev) = drop(h) + drop(sp); cols [Uprev,F) = shifted
+ *   chosen + drop(sp); cols >= F zero. */
+int dj_layer_input(const float* h_prev, int Uprev, int64_t h_row0, int64_t h_b_rows, dj_dropout d_h,
+                   const float* sp, int F, dj_dropout d_sp, const float* chosen_in,
+                   int64_t chosen_bstride, dj_dropout d_chosen, int B, int T, void* A, int ldA,
+                   int a_dtype, void* stream);
+
+/* ---- gate projections (the dense part of keras LSTM: x.W + b, model.py:84,120)
+ * Generic CUDA-core GEMM with fp32 accumulation; operands DJ_F32 or DJ_BF16
+ * (generation path at fp32, small style/conv gradients, cross-check of the
+ * tensor-core kernels):
+ *   C[m,n] (+)= sum_k A(m,k) B(k,n) (+ bias[n])
+ *   A(m,k) = A[m*a_sm + k*a_sk], B(k,n) = B[k*b_sk + n*b_sn], C[m*ldc + n]
+ *   a_shift/a_period: if a_period>0, A(m,k) reads row k-a_shift and is zero
+ *   where (k % a_period) < a_shift  (h_{t-1} operand of the U weight gradient). */
+int dj_gemm_simt(const void* A, int a_dtype, int64_t a_sm, int64_t a_sk, const void* B, int b_dtype,
+                 int64_t b_sk, int64_t b_sn, float* C, int64_t ldc, const float* bias, int M, int N,
+                 int K, int accumulate, int64_t a_shift, int64_t a_period, void* stream);
+/* tcgen05 + TMA bf16 GEMM, fp32 accumulate in TMEM:
+ *   C[M,N] = A[M,K] . Bt[N,K]^T + bias[N]      (both operands K-major, bf16)
+ *   lda/ldb in elements (multiples of 8), K padded with zeros up to lda. */
+int dj_gate_gemm_bf16(const void* A, int64_t lda, const void* Bt, int64_t ldb, float* C, int64_t ldc,
+                      const float* bias, int M, int N, int K, void* stream);
+/* tcgen05 weight-gradient GEMM (contraction over the M rows, split across CTAs,
+ * fp32 atomics):  C[Ka,Nb] += A[M,Ka]^T . B[M,Nb]   (bf16 operands, MN-major)
+ *   a_shift/a_period as in dj_gemm_simt (rows shifted by a_shift, zero-filled). */
+int dj_wgrad_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, float* C, int64_t ldc,
+                       int Ka, int Nb, int64_t M, int64_t a_shift, int64_t a_period, void* stream);
+/* fp32 -> bf16 operand copies: out[r, c] = in[r, c] (c<cols) else 0, out ld = ldo;
+ * transpose!=0 writes out[c, r] (ldo >= rows). */
+int dj_cast_bf16(const float* in, int rows, int cols, void* out, int ldo, int transpose, void* stream);
+
+/* ---- recurrence (the sequential part of keras LSTM, model.py:84,120) ---------
+ * Persistent thread-block-cluster kernel: the recurrent weights U [units,4*units]
+ * stay in shared memory, split by hidden unit over the CTAs of a cluster; h is
+ * exchanged through distributed shared memory; cell state lives in registers.
+ *   Z [M,4*units] fp32: in = x.W+b, out = activated gates i,f,g,o (saved for bwd)
+ *   row(seq, step) = (seq/seq_inner)*seq_outer_stride + (seq%seq_inner)*seq_inner_stride
+ *                    + step*step_stride
+ *   h_out [M,units] fp32; c_out nullable (training only); h_bf16 nullable.
+ *   hard != 0: hard_sigmoid gates (Keras < 2.3), else sigmoid. */
+int dj_lstm_scan_fwd(float* Z, float* h_out, float* c_out, void* h_bf16, const float* Uw, int S,
+                     int steps, int units, int seq_inner, int64_t seq_outer_stride,
+                     int64_t seq_inner_stride, int64_t step_stride, int hard, void* stream);
+/* reverse scan: consumes gates/c and dY (gradient w.r.t. the DROPPED-OUT layer
+ * output, row stride ldY; the kernel applies the mask d_y itself), produces
+ * dZ [M,4*units] (dz_dtype) and accumulates db[4*units] (fp32 atomics). */
+int dj_lstm_scan_bwd(const float* gates, const float* c, const float* dY, int64_t ldY, dj_dropout d_y,
+                     const float* Uw, void* dZ, int dz_dtype, float* db, int S, int steps, int units,
+                     int seq_inner, int64_t seq_outer_stride, int64_t seq_inner_stride,
+                     int64_t step_stride, int hard, void* stream);
+
+/* ---- heads + loss (model.py:94-95,125 and primary_loss model.py:14-20) -------
+ * probs[M,3] = [sigmoid(x.Wn+bn), x.Wv+bv], x = drop(h).  With y_true != NULL it
+ * also writes per-block loss / head-gradient partials and dX[M,units] (gradient
+ * w.r.t. x).  partials must hold dj_head_partials_size(units) floats. */
+int64_t dj_head_partials_size(int units);
+int dj_head_loss(const float* h, int units, dj_dropout d_h, const float* Wn, const float* bn,
+                 const float* Wv, const float* bv, const float* y_true, float* probs, float* dX,
+                 float* partials, int64_t M, void* stream);
+/* sums the partials: loss_out[0] = loss; dWn[units,2], dbn[2], dWv[units], dbv[1] (overwrite). */
+int dj_head_finalize(const float* partials, int units, float* loss_out, float* dWn, float* dbn,
+                     float* dWv, float* dbv, void* stream);
+
+/* ---- backward glue ----------------------------------------------------------
+ * ds[bt,f] = (1-sp^2) * sum_n drop_mask(d_sp)(row,f) * dA[row,f]   (model.py:78-82 backward) */
+int dj_style_bwd_reduce(const float* dA, int64_t ldA, int F, const float* sp, dj_dropout d_sp,
+                        int BT, float* ds, void* stream);
+/* out[c] (+)= sum_r X[r*ldx + c] */
+int dj_colsum(const float* X, int64_t ldx, int64_t R, int C, float* out, int accumulate, void* stream);
+/* conv weight/bias gradient (model.py:56-58 backward); recomputes tanh(conv);
+ * dA0 = gradient of the layer-0 A operand [M, ldA] fp32; accumulates (atomics). */
+int dj_conv_bwd(const float* notes_in, int64_t notes_bstride, int B, int T, const float* Wc,
+                const float* bc, dj_dropout d_notes, dj_dropout d_conv, const float* dA0, int64_t ldA,
+                float* dWc, float* dbc, void* stream);
+
+/* ---- optimizer: keras.optimizers.Nadam (model.py:152) on flat buffers --------
+ * g is scaled by gscale (1/world for the NCCL-summed gradient) first. */
+int dj_nadam_step(float* p, const float* g, float* m, float* v, int64_t n, float gscale, float lr,
+                  float beta1, float beta2, float eps, float mu_t, float mu_t1, float m_sched_new,
+                  float m_sched_next, float bias2, void* stream);
+
+/* ---- generation (generate.py:47-79,98-121) -----------------------------------
+ * Persistent note-by-note sampler: for each of `G` sequences walks the 48 notes
+ * carrying the note-axis LSTM state, applies the temperature transform, draws
+ * play/replay against the uniform stream and writes the event row.
+ *   zpre [G*48, 4*units]: note-layer-0 projection of [time_out + style, style]
+ *        (everything but the chosen_{n-1} term), from the gate GEMM
+ *   W0c [3,4*units]: rows Ut..Ut+2 of note0.lstm.W;  U0, W1, U1, b1 as in Keras
+ *   sp1 [G,units]: tanh style projection of note layer 1
+ *   stream_mode 0: reference stream -- one CTA walks all sequences, uniforms
+ *        consumed n-major/sequence-minor with the conditional second draw,
+ *        *ucursor (device int64) advanced;  1: indexed stream U[g][n][2].
+ *   state per sequence: temperature (double), silent_time (int32)
+ *   events [G,48,3] written (also appended by the caller to the window),
+ *   probs_out nullable [G,48,3], margin_out nullable [G] (min |u-p|). */
+int dj_gen_sample(const float* zpre, const float* W0c, const float* U0, const float* W1,
+                  const float* U1, const float* b1, const float* sp1, const float* Wn,
+                  const float* bn, const float* Wv, const float* bv, int units, int G,
+                  const double* uniforms, int64_t* ucursor, int stream_mode, double* temperature,
+                  int32_t* silent_time, double default_temp, int hard, float* events,
+                  float* probs_out, double* margin_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEEPJ_B200_H */

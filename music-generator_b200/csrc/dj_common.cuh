@@ -1,0 +1,103 @@
+// Shared device/host helpers for the DeepJ sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/deepj_b200.h"
+
+// ---- error plumbing (C-ABI: every export returns int, never throws) ---------
+void dj_set_error(const char* fmt, ...);
+#define DJ_CHECK_ARG(cond, ...)                                   \
+  do {                                                            \
+    if (!(cond)) { dj_set_error(__VA_ARGS__); return -1; }        \
+  } while (0)
+#define DJ_CUDA(call)                                                                   \
+  do {                                                                                  \
+    cudaError_t e__ = (call);                                                           \
+    if (e__ != cudaSuccess) {                                                           \
+      dj_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+      return (int)e__;                                                                  \
+    }                                                                                   \
+  } while (0)
+#define DJ_LAUNCH_CHECK() DJ_CUDA(cudaGetLastError())
+
+static inline int dj_num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+// ---- counter-based dropout masks --------------------------------------------
+// A mask bit is a pure function of (seed, site, element index), so the backward
+// kernels regenerate it instead of reading a stored mask.  Two lowbias32 rounds
+// per 32-bit word; for rates whose threshold is a whole number of 1/256ths one
+// word serves 4 consecutive elements (one byte each), otherwise one word per
+// element.  tests/ re-implement the same function in numpy.
+__host__ __device__ __forceinline__ uint32_t dj_mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  return x;
+}
+__host__ __device__ __forceinline__ uint32_t dj_site_key(uint64_t seed, int site) {
+  uint32_t k = dj_mix32((uint32_t)seed ^ 0x9E3779B9U * (uint32_t)(site + 1));
+  return dj_mix32(k + (uint32_t)(seed >> 32));
+}
+// word for element-group q of a site
+__host__ __device__ __forceinline__ uint32_t dj_mask_word(uint32_t key, uint32_t q) {
+  return dj_mix32(dj_mix32(q) + key);
+}
+// single element keep decision (element index e within the site's padded layout)
+__device__ __forceinline__ bool dj_keep(const dj_dropout& d, uint32_t e) {
+  if (d.mode == 1) {
+    uint32_t w = dj_mask_word(d.key, e >> 2);
+    return ((w >> (8 * (e & 3))) & 0xffU) >= (d.thr >> 24);
+  }
+  return dj_mask_word(d.key, e) >= d.thr;
+}
+// multiplier (0 or scale) for one element; identity when the site is off
+__device__ __forceinline__ float dj_dropmul(const dj_dropout& d, uint32_t e) {
+  if (d.mode == 0) return 1.0f;
+  return dj_keep(d, e) ? d.scale : 0.0f;
+}
+// 4 consecutive elements starting at e (e % 4 == 0)
+__device__ __forceinline__ void dj_dropmul4(const dj_dropout& d, uint32_t e, float m[4]) {
+  if (d.mode == 0) { m[0] = m[1] = m[2] = m[3] = 1.0f; return; }
+  if (d.mode == 1) {
+    uint32_t w = dj_mask_word(d.key, e >> 2), t = d.thr >> 24;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) m[j] = (((w >> (8 * j)) & 0xffU) >= t) ? d.scale : 0.0f;
+    return;
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) m[j] = (dj_mask_word(d.key, e + j) >= d.thr) ? d.scale : 0.0f;
+}
+
+// ---- activations (Keras-2 semantics) ------------------------------------------
+__device__ __forceinline__ float dj_hard_sigmoid(float x) {
+  return fminf(fmaxf(0.2f * x + 0.5f, 0.0f), 1.0f);
+}
+__device__ __forceinline__ float dj_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ float dj_gate_act(float x, int hard) {
+  return hard ? dj_hard_sigmoid(x) : dj_sigmoid(x);
+}
+// derivative of the gate activation expressed through the stored activation a
+__device__ __forceinline__ float dj_gate_dact(float a, int hard) {
+  return hard ? ((a > 0.0f && a < 1.0f) ? 0.2f : 0.0f) : a * (1.0f - a);
+}
+
+__device__ __forceinline__ float dj_warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <typename T> __device__ __forceinline__ T dj_from_float(float v);
+template <> __device__ __forceinline__ float dj_from_float<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 dj_from_float<__nv_bfloat16>(float v) {
+  return __float2bfloat16_rn(v);
+}

@@ -1,0 +1,354 @@
+// Note-feature front end and inter-layer glue (forward).
+// Replaces model.py:22-49,56-82,101-117,136-142 of the reference (Keras Lambda /
+// Conv1D / Dense / Dropout / Concatenate / Permute layers) with fused kernels
+// that write the LSTM gate-GEMM A operands directly in canonical row order.
+#include "dj_common.cuh"
+
+namespace {
+
+constexpr int N_ = DJ_NUM_NOTES;      // 48
+constexpr int NU_ = DJ_NOTE_UNITS;    // 3
+constexpr int CK_ = DJ_CONV_K;        // 24
+constexpr int OU_ = DJ_OCTAVE_UNITS;  // 64
+constexpr int F0_ = DJ_FEAT0;         // 94
+constexpr int F0P_ = 96;              // roundup4(94)
+constexpr int PADL_ = (CK_ - 1) / 2;  // TF 'SAME', even kernel: 11 left / 12 right
+
+__device__ __forceinline__ void store4(float* p, const float v[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void store4(__nv_bfloat16* p, const float v[4]) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]);
+  __nv_bfloat162 b = __floats2bfloat162_rn(v[2], v[3]);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&a);
+  u.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+
+// ---------------------------------------------------------------------------
+// style embedding + the four tanh style projections; 8 (b,t) rows per block
+// ---------------------------------------------------------------------------
+struct StyleProj {
+  const float* W[4];
+  const float* b[4];
+  float* out[4];
+  int F[4];
+};
+
+__global__ void __launch_bounds__(256) style_fwd_kernel(const float* __restrict__ style_in,
+                                                        int64_t bstride, int64_t tstride, int ns,
+                                                        int B, int T, const float* __restrict__ Ws,
+                                                        const float* __restrict__ bs, int n_proj,
+                                                        StyleProj pr, float* __restrict__ emb) {
+  constexpr int R = 8, SU = DJ_STYLE_UNITS;
+  __shared__ float sin_[R][32];
+  __shared__ float embs[R][SU];
+  const int BT = B * T, row0 = blockIdx.x * R, tid = threadIdx.x;
+  for (int i = tid; i < R * 32; i += 256) {
+    int r = i / 32, s = i % 32, row = row0 + r;
+    float v = 0.f;
+    if (row < BT && s < ns) v = style_in[(int64_t)(row / T) * bstride + (int64_t)(row % T) * tstride + s];
+    sin_[r][s] = v;
+  }
+  __syncthreads();
+  for (int i = tid; i < R * SU; i += 256) {
+    int r = i / SU, o = i % SU;
+    float acc = bs[o];
+    for (int s = 0; s < ns; ++s) acc = fmaf(sin_[r][s], Ws[s * SU + o], acc);
+    embs[r][o] = acc;
+    if (row0 + r < BT) emb[(int64_t)(row0 + r) * SU + o] = acc;
+  }
+  __syncthreads();
+  for (int l = 0; l < n_proj; ++l) {
+    const int F = pr.F[l];
+    const float* __restrict__ W = pr.W[l];
+    for (int j = tid; j < F; j += 256) {
+      float acc[R];
+      const float bj = pr.b[l][j];
+#pragma unroll
+      for (int r = 0; r < R; ++r) acc[r] = bj;
+      for (int k = 0; k < SU; ++k) {
+        const float w = W[k * F + j];
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] = fmaf(embs[r][k], w, acc[r]);
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        if (row0 + r < BT) pr.out[l][(int64_t)(row0 + r) * F + j] = tanhf(acc[r]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// front end: one (b,t) per loop iteration of a persistent block
+// ---------------------------------------------------------------------------
+template <typename TA>
+__global__ void __launch_bounds__(256) frontend_fwd_kernel(
+    const float* __restrict__ notes_in, int64_t notes_bstride, const float* __restrict__ beat_in,
+    int64_t beat_bstride, int B, int T, const float* __restrict__ Wc, const float* __restrict__ bc,
+    const float* __restrict__ sp0, dj_dropout d_notes, dj_dropout d_beat, dj_dropout d_conv,
+    dj_dropout d_sp, TA* __restrict__ A0, int ldA) {
+  __shared__ float Wc_s[CK_ * NU_ * OU_];
+  __shared__ float bc_s[OU_];
+  __shared__ float xs[(N_ + CK_ - 1) * NU_];
+  __shared__ __align__(16) float tile[N_][F0P_];
+  __shared__ float bins_s[N_];
+  __shared__ float beat_s[DJ_BEAT];
+  const int tid = threadIdx.x, BT = B * T;
+  for (int i = tid; i < CK_ * NU_ * OU_; i += 256) Wc_s[i] = Wc[i];
+  if (tid < OU_) bc_s[tid] = bc[tid];
+  for (int i = tid; i < (N_ + CK_ - 1) * NU_; i += 256) xs[i] = 0.f;   // halo stays zero
+  __syncthreads();
+
+  for (int bt = blockIdx.x; bt < BT; bt += gridDim.x) {
+    const int b = bt / T, t = bt % T;
+    const float* nrow = notes_in + (int64_t)b * notes_bstride + (int64_t)t * (N_ * NU_);
+    if (tid < N_ * NU_) {
+      const int n = tid / NU_, c = tid % NU_;
+      xs[(n + PADL_) * NU_ + c] = nrow[tid] * dj_dropmul(d_notes, (uint32_t)(bt * N_ + n) * 4u + c);
+    } else if (tid < N_ * NU_ + DJ_BEAT) {
+      const int j = tid - N_ * NU_;
+      beat_s[j] = beat_in[(int64_t)b * beat_bstride + (int64_t)t * DJ_BEAT + j] *
+                  dj_dropmul(d_beat, (uint32_t)bt * DJ_BEAT + j);
+    } else if (tid < N_ * NU_ + DJ_BEAT + N_) {
+      // pitch_bins_f (model.py:43-49): the raw reshape of the [48,B,T] tensor
+      const int n = tid - N_ * NU_ - DJ_BEAT;
+      const int64_t flat = (int64_t)bt * N_ + n;
+      const int p = (int)(flat / BT), r = (int)(flat % BT);
+      const int pc = p % DJ_OCTAVE;
+      const float* src = notes_in + (int64_t)(r / T) * notes_bstride + (int64_t)(r % T) * (N_ * NU_);
+      float s = 0.f;
+#pragma unroll
+      for (int o = 0; o < N_ / DJ_OCTAVE; ++o) {
+        const int nn = o * DJ_OCTAVE + pc;
+        s += src[nn * NU_] * dj_dropmul(d_notes, (uint32_t)(r * N_ + nn) * 4u);
+      }
+      bins_s[n] = s;
+    }
+    __syncthreads();
+    {  // octave convolution: thread = (out channel, group of 12 notes)
+      const int o = tid % OU_, ng = tid / OU_;
+      float acc[12];
+#pragma unroll
+      for (int j = 0; j < 12; ++j) acc[j] = bc_s[o];
+      for (int kc = 0; kc < CK_ * NU_; ++kc) {
+        const float w = Wc_s[kc * OU_ + o];
+        const int k = kc / NU_, c = kc % NU_;
+#pragma unroll
+        for (int j = 0; j < 12; ++j) acc[j] = fmaf(xs[(ng * 12 + j + k) * NU_ + c], w, acc[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 12; ++j) {
+        const int n = ng * 12 + j;
+        tile[n][14 + o] = tanhf(acc[j]) * dj_dropmul(d_conv, (uint32_t)(bt * N_ + n) * OU_ + o);
+      }
+    }
+    for (int i = tid; i < N_ * 32; i += 256) {   // the 30 non-conv features + 2 pad columns
+      const int n = i / 32, q = i % 32;
+      const int col = q < 14 ? q : 78 + (q - 14);
+      float v;
+      if (col == 0) v = (float)n / (float)N_;
+      else if (col <= DJ_OCTAVE) v = (n % DJ_OCTAVE == col - 1) ? 1.f : 0.f;
+      else if (col == 13) v = bins_s[n];
+      else if (col < F0_) v = beat_s[col - 78];
+      else v = 0.f;
+      tile[n][col] = v;
+    }
+    __syncthreads();
+    for (int i = tid; i < N_ * (F0P_ / 4); i += 256) {   // + style term, coalesced write-out
+      const int n = i / (F0P_ / 4), f4 = (i % (F0P_ / 4)) * 4;
+      const uint32_t row = (uint32_t)bt * N_ + n;
+      float m[4], v[4];
+      dj_dropmul4(d_sp, row * F0P_ + f4, m);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int f = f4 + j;
+        v[j] = tile[n][f];
+        if (f < F0_) v[j] = fmaf(sp0[(int64_t)bt * F0_ + f], m[j], v[j]);
+      }
+      store4(A0 + (int64_t)row * ldA + f4, v);
+    }
+    for (int i = tid; i < N_ * ((ldA - F0P_) / 4); i += 256) {   // zero any extra padding
+      const int w = (ldA - F0P_) / 4, n = i / w, f4 = F0P_ + (i % w) * 4;
+      const float z[4] = {0.f, 0.f, 0.f, 0.f};
+      store4(A0 + ((int64_t)bt * N_ + n) * ldA + f4, z);
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------
+// A operand of LSTM layers 1.. : drop(h_prev) (+ shifted chosen) + drop(style)
+// ---------------------------------------------------------------------------
+template <typename TA>
+__global__ void __launch_bounds__(256) layer_input_kernel(
+    const float* __restrict__ h_prev, int Uprev, int64_t h_row0, int64_t h_b_rows, dj_dropout d_h,
+    const float* __restrict__ sp, int F, dj_dropout d_sp, const float* __restrict__ chosen_in,
+    int64_t chosen_bstride, dj_dropout d_chosen, int B, int T, TA* __restrict__ A, int ldA) {
+  const int ld4 = (F + 3) & ~3;
+  const int g_per_row = ldA / 4;
+  const int64_t total = (int64_t)B * T * N_ * g_per_row;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / g_per_row;
+    const int f4 = (int)(i % g_per_row) * 4;
+    const int n = (int)(row % N_);
+    const int64_t bt = row / N_;
+    const int b = (int)(bt / T), t = (int)(bt % T);
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (f4 < Uprev) {
+      const int64_t hrow = h_row0 + (int64_t)b * h_b_rows + (int64_t)t * N_ + n;
+      const float4 hv = *reinterpret_cast<const float4*>(h_prev + hrow * Uprev + f4);
+      float m[4];
+      dj_dropmul4(d_h, (uint32_t)row * Uprev + f4, m);
+      v[0] = hv.x * m[0]; v[1] = hv.y * m[1]; v[2] = hv.z * m[2]; v[3] = hv.w * m[3];
+    } else if (f4 < F && chosen_in != nullptr && n > 0) {
+      // shift_chosen (model.py:101): previous NOTE of the same timestep, 3 channels
+      const float* cr = chosen_in + (int64_t)b * chosen_bstride + ((int64_t)t * N_ + (n - 1)) * NU_;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = f4 + j - Uprev;
+        if (c < NU_) v[j] = cr[c] * dj_dropmul(d_chosen, (uint32_t)(row - 1) * 4u + c);
+      }
+    }
+    if (f4 < F) {
+      float m[4];
+      dj_dropmul4(d_sp, (uint32_t)row * ld4 + f4, m);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (f4 + j < F) v[j] = fmaf(sp[bt * F + f4 + j], m[j], v[j]);
+    }
+    store4(A + row * ldA + f4, v);
+  }
+}
+
+__global__ void mask_materialize_kernel(dj_dropout d, int64_t rows, int F, float* __restrict__ out) {
+  const int ld4 = (F + 3) & ~3;
+  const int64_t total = rows * F;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / F;
+    const int f = (int)(i % F);
+    out[i] = (d.mode == 0 || dj_keep(d, (uint32_t)(row * ld4 + f))) ? 1.f : 0.f;
+  }
+}
+
+__global__ void cast_bf16_kernel(const float* __restrict__ in, int rows, int cols,
+                                 __nv_bfloat16* __restrict__ out, int ldo, int transpose, int orows) {
+  // out has `orows` rows of ldo; element (r_o, c_o) comes from in[r_o, c_o] or in[c_o, r_o]
+  const int64_t total = (int64_t)orows * ldo;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int ro = (int)(i / ldo), co = (int)(i % ldo);
+    float v = 0.f;
+    if (!transpose) { if (co < cols) v = in[(int64_t)ro * cols + co]; }
+    else { if (co < rows) v = in[(int64_t)co * cols + ro]; }
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+
+inline int grid_for(int64_t total, int threads, int max_blocks) {
+  int64_t b = (total + threads - 1) / threads;
+  if (b < 1) b = 1;
+  return (int)(b > max_blocks ? max_blocks : b);
+}
+
+}  // namespace
+
+extern "C" int dj_make_dropout(uint64_t seed, int site, float rate, dj_dropout* out) {
+  DJ_CHECK_ARG(out != nullptr, "dj_make_dropout: out is NULL");
+  DJ_CHECK_ARG(rate >= 0.f && rate < 1.f, "dj_make_dropout: rate %f outside [0,1)", rate);
+  if (rate == 0.f) { out->key = 0; out->thr = 0; out->scale = 1.f; out->mode = 0; return 0; }
+  const double thr = (double)rate * 4294967296.0;
+  out->key = dj_site_key(seed, site);
+  out->thr = (uint32_t)thr;
+  out->scale = 1.0f / (1.0f - rate);
+  const double t256 = (double)rate * 256.0;
+  out->mode = (t256 == (double)(int)t256) ? 1 : 2;
+  return 0;
+}
+
+extern "C" int dj_dropout_mask_materialize(dj_dropout d, int64_t rows, int F, float* out, void* stream) {
+  DJ_CHECK_ARG(out && rows > 0 && F > 0, "dj_dropout_mask_materialize: bad arguments");
+  DJ_CHECK_ARG(rows * ((F + 3) & ~3) < (int64_t)4294967296LL, "dj_dropout_mask_materialize: site too large");
+  mask_materialize_kernel<<<grid_for(rows * F, 256, dj_num_sms() * 8), 256, 0, (cudaStream_t)stream>>>(d, rows, F, out);
+  DJ_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int dj_style_fwd(const float* style_in, int64_t style_bstride, int64_t style_tstride,
+                            int num_styles, int B, int T, const float* Ws, const float* bs, int n_proj,
+                            const float* const* Wsd, const float* const* bsd, const int* F, float* emb,
+                            float* const* sp, void* stream) {
+  DJ_CHECK_ARG(style_in && Ws && bs && emb, "dj_style_fwd: NULL pointer");
+  DJ_CHECK_ARG(num_styles > 0 && num_styles <= 32, "dj_style_fwd: num_styles %d not in 1..32", num_styles);
+  DJ_CHECK_ARG(B > 0 && T > 0 && n_proj >= 0 && n_proj <= 4, "dj_style_fwd: bad sizes");
+  StyleProj pr{};
+  for (int l = 0; l < n_proj; ++l) {
+    DJ_CHECK_ARG(Wsd[l] && bsd[l] && sp[l] && F[l] > 0, "dj_style_fwd: projection %d incomplete", l);
+    pr.W[l] = Wsd[l]; pr.b[l] = bsd[l]; pr.out[l] = sp[l]; pr.F[l] = F[l];
+  }
+  const int BT = B * T;
+  style_fwd_kernel<<<(BT + 7) / 8, 256, 0, (cudaStream_t)stream>>>(style_in, style_bstride, style_tstride,
+                                                                  num_styles, B, T, Ws, bs, n_proj, pr, emb);
+  DJ_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int dj_frontend_fwd(const float* notes_in, int64_t notes_bstride, const float* beat_in,
+                               int64_t beat_bstride, int B, int T, const float* Wc, const float* bc,
+                               const float* sp0, dj_dropout d_notes, dj_dropout d_beat, dj_dropout d_conv,
+                               dj_dropout d_sp, void* A0, int ldA, int a_dtype, void* stream) {
+  DJ_CHECK_ARG(notes_in && beat_in && Wc && bc && sp0 && A0, "dj_frontend_fwd: NULL pointer");
+  DJ_CHECK_ARG(B > 0 && T > 0, "dj_frontend_fwd: bad B/T");
+  DJ_CHECK_ARG(ldA >= F0P_ && ldA % 8 == 0, "dj_frontend_fwd: ldA %d must be >=96 and a multiple of 8", ldA);
+  DJ_CHECK_ARG((int64_t)B * T * N_ * F0P_ < (int64_t)4294967296LL, "dj_frontend_fwd: batch too large");
+  const int grid = grid_for((int64_t)B * T, 1, dj_num_sms() * 4);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (a_dtype == DJ_F32)
+    frontend_fwd_kernel<float><<<grid, 256, 0, st>>>(notes_in, notes_bstride, beat_in, beat_bstride, B, T, Wc,
+                                                     bc, sp0, d_notes, d_beat, d_conv, d_sp, (float*)A0, ldA);
+  else if (a_dtype == DJ_BF16)
+    frontend_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(notes_in, notes_bstride, beat_in, beat_bstride, B,
+                                                             T, Wc, bc, sp0, d_notes, d_beat, d_conv, d_sp,
+                                                             (__nv_bfloat16*)A0, ldA);
+  else DJ_CHECK_ARG(false, "dj_frontend_fwd: unknown dtype %d", a_dtype);
+  DJ_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int dj_layer_input(const float* h_prev, int Uprev, int64_t h_row0, int64_t h_b_rows,
+                              dj_dropout d_h, const float* sp, int F, dj_dropout d_sp,
+                              const float* chosen_in, int64_t chosen_bstride, dj_dropout d_chosen, int B,
+                              int T, void* A, int ldA, int a_dtype, void* stream) {
+  DJ_CHECK_ARG(h_prev && sp && A, "dj_layer_input: NULL pointer");
+  DJ_CHECK_ARG(Uprev > 0 && Uprev % 4 == 0 && F >= Uprev, "dj_layer_input: bad Uprev %d / F %d", Uprev, F);
+  DJ_CHECK_ARG(F == Uprev || (chosen_in && F == Uprev + NU_), "dj_layer_input: F must be Uprev or Uprev+3 with chosen");
+  DJ_CHECK_ARG(ldA >= ((F + 3) & ~3) && ldA % 8 == 0, "dj_layer_input: ldA %d too small or not a multiple of 8", ldA);
+  DJ_CHECK_ARG((int64_t)B * T * N_ * ((F + 3) & ~3) < (int64_t)4294967296LL, "dj_layer_input: batch too large");
+  const int64_t total = (int64_t)B * T * N_ * (ldA / 4);
+  const int grid = grid_for(total, 256, dj_num_sms() * 16);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (a_dtype == DJ_F32)
+    layer_input_kernel<float><<<grid, 256, 0, st>>>(h_prev, Uprev, h_row0, h_b_rows, d_h, sp, F, d_sp,
+                                                    chosen_in, chosen_bstride, d_chosen, B, T, (float*)A, ldA);
+  else if (a_dtype == DJ_BF16)
+    layer_input_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(h_prev, Uprev, h_row0, h_b_rows, d_h, sp, F, d_sp,
+                                                            chosen_in, chosen_bstride, d_chosen, B, T,
+                                                            (__nv_bfloat16*)A, ldA);
+  else DJ_CHECK_ARG(false, "dj_layer_input: unknown dtype %d", a_dtype);
+  DJ_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int dj_cast_bf16(const float* in, int rows, int cols, void* out, int ldo, int transpose,
+                            void* stream) {
+  DJ_CHECK_ARG(in && out && rows > 0 && cols > 0, "dj_cast_bf16: bad arguments");
+  const int orows = transpose ? cols : rows;
+  DJ_CHECK_ARG(ldo >= (transpose ? rows : cols), "dj_cast_bf16: ldo %d too small", ldo);
+  cast_bf16_kernel<<<grid_for((int64_t)orows * ldo, 256, dj_num_sms() * 8), 256, 0, (cudaStream_t)stream>>>(
+      in, rows, cols, (__nv_bfloat16*)out, ldo, transpose, orows);
+  DJ_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,339 @@
+// tcgen05 / TMA / TMEM GEMMs for the LSTM gate projections (sm_100a only).
+//
+//   dj_gate_gemm_bf16 : C[M,N] = A[M,K] . Bt[N,K]^T + bias     (x.W+b of keras
+//       LSTM, model.py:84,120, and its data gradient dX = dZ.W^T)
+//   dj_wgrad_gemm_bf16: C[Ka,Nb] += A[M,Ka]^T . B[M,Nb]         (dW = X^T.dZ and
+//       dU = H_{t-1}^T.dZ: contraction over the M = B*T*48 rows)
+//
+// Structure of both: persistent CTAs, warp 0 = TMA producer (one lane), warp 1 =
+// MMA issuer (one lane, tcgen05.mma cta_group::1, 128xN tile, fp32 accumulators
+// in TMEM), warp 2 = TMEM allocator, warps 4-7 = epilogue (tcgen05.ld -> regs ->
+// swizzled smem -> TMA store / fp32 reduction).  smem stages are 128B-swizzled
+// tiles written by TMA and read by the tensor core through shared-memory matrix
+// descriptors; full/empty mbarriers pipeline TMA against MMA, tmem_full/empty
+// pipeline MMA against the epilogue (two accumulator stages).
+#include <cuda.h>
+
+#include "dj_common.cuh"
+
+namespace {
+
+// ---- PTX wrappers -----------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  const long long t0 = clock64();
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (clock64() - t0 > 4000000000LL) {   // ~2 s: a pipeline bug must not hang the GPU
+      printf("deepj gemm_tc: mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x,
+             threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];\n" ::"l"(map), "r"(src),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;\n" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
+  asm volatile("prefetch.tensormap [%0];\n" ::"l"(m) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t v[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+}
+
+// ---- descriptors ------------------------------------------------------------
+// shared-memory matrix descriptor (sm_100 format): start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout_type [61,64) (2 = SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// instruction descriptor for kind::f16: D=f32 (bits 4-5 = 1), A=B=bf16 (bits 7-9, 10-12 = 1),
+// a_major bit 15, b_major bit 16 (0 = K-major, 1 = MN-major), N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+constexpr int BM = 128, BN = 128, BK = 64;
+constexpr int STAGES = 4, ACC_STAGES = 2;
+constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
+constexpr int EPI_WARP_BYTES = 2 * 32 * 128;   // two 32x32 fp32 staging boxes per epilogue warp
+constexpr int NUM_THREADS = 256;
+
+struct GemmSmem {
+  static constexpr int A_OFF = 0;
+  static constexpr int B_OFF = STAGES * A_BYTES;
+  static constexpr int EPI_OFF = B_OFF + STAGES * B_BYTES;
+  static constexpr int BAR_OFF = EPI_OFF + 4 * EPI_WARP_BYTES;
+  static constexpr int TOTAL = BAR_OFF + 256 + 1024;   // + alignment slack
+};
+
+// ---------------------------------------------------------------------------
+// C = A . Bt^T + bias, both operands K-major
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gate_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias, int M, int N, int K) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bars = sbase + GemmSmem::BAR_OFF;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bars + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (2 * STAGES + ACC_STAGES + a); };
+  uint32_t* tmem_slot = (uint32_t*)(smem + GemmSmem::BAR_OFF + 8 * (2 * STAGES + 2 * ACC_STAGES));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_n = (N + BN - 1) / BN, num_m = (M + BM - 1) / BM;
+  const int num_tiles = num_m * num_n, num_kb = (K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA); prefetch_tmap(&tmB); prefetch_tmap(&tmC);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < ACC_STAGES; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(smem_u32(tmem_slot), ACC_STAGES * BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {   // ===== TMA producer =====
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / num_n) * BM, n0 = (tile % num_n) * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          mbar_expect_tx(full_bar(stage), A_BYTES + B_BYTES);
+          tma_load_2d(sbase + GemmSmem::A_OFF + stage * A_BYTES, &tmA, full_bar(stage), kb * BK, m0);
+          tma_load_2d(sbase + GemmSmem::B_OFF + stage * B_BYTES, &tmB, full_bar(stage), kb * BK, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {   // ===== MMA issuer =====
+      constexpr uint32_t idesc = make_idesc(BM, BN, 0, 0);
+      int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(acc), aphase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint64_t adesc = make_smem_desc(sbase + GemmSmem::A_OFF + stage * A_BYTES, 16, 1024);
+          const uint64_t bdesc = make_smem_desc(sbase + GemmSmem::B_OFF + stage * B_BYTES, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)   // UMMA_K = 16 bf16 = 32 B inside the 128 B swizzle row
+            umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+          umma_commit(empty_bar(stage));   // frees the smem slot when these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(tfull_bar(acc));
+        if (++acc == ACC_STAGES) { acc = 0; aphase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {   // ===== epilogue =====
+    const int e = warp - 4;
+    uint8_t* ebuf = smem + GemmSmem::EPI_OFF + e * EPI_WARP_BYTES;
+    const uint32_t ebuf_s = smem_u32(ebuf);
+    int acc = 0; uint32_t aphase = 0; int nbuf = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / num_n) * BM, n0 = (tile % num_n) * BN;
+      mbar_wait(tfull_bar(acc), aphase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(32 * e) << 16) + (uint32_t)(acc * BN + c * 32), v);
+        if (lane == 0) tma_store_wait_read<1>();   // the store that last used this staging box is done
+        __syncwarp();
+        const int ncol = n0 + c * 32;
+        uint8_t* box = ebuf + nbuf * 4096;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float4 o;
+          o.x = __uint_as_float(v[4 * q + 0]); o.y = __uint_as_float(v[4 * q + 1]);
+          o.z = __uint_as_float(v[4 * q + 2]); o.w = __uint_as_float(v[4 * q + 3]);
+          if (bias != nullptr) {
+            const int n = ncol + 4 * q;
+            if (n + 3 < N) {
+              const float4 bv = *reinterpret_cast<const float4*>(bias + n);
+              o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+            } else {
+              if (n < N) o.x += bias[n];
+              if (n + 1 < N) o.y += bias[n + 1];
+              if (n + 2 < N) o.z += bias[n + 2];
+            }
+          }
+          // 128B swizzle: 16-byte chunk q of row `lane` lives at chunk q ^ (lane & 7)
+          *reinterpret_cast<float4*>(box + lane * 128 + ((q ^ (lane & 7)) << 4)) = o;
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tmC, ebuf_s + nbuf * 4096, ncol, m0 + 32 * e);
+          tma_store_commit();
+        }
+        nbuf ^= 1;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == ACC_STAGES) { acc = 0; aphase ^= 1; }
+    }
+    if (lane == 0) tma_store_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, ACC_STAGES * BN);
+}
+
+// ---- host side ----------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+int make_map_2d(CUtensorMap* map, CUtensorMapDataType dt, int esize, const void* base, uint64_t inner, uint64_t outer,
+                uint64_t ld_elems, uint32_t box_inner, uint32_t box_outer) {
+  EncodeTiledFn enc = get_encode();
+  DJ_CHECK_ARG(enc != nullptr, "cuTensorMapEncodeTiled entry point not available (no driver?)");
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld_elems * (uint64_t)esize};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DJ_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with %d (inner=%llu outer=%llu ld=%llu)", (int)r,
+               (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld_elems);
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int dj_gate_gemm_bf16(const void* A, int64_t lda, const void* Bt, int64_t ldb, float* C, int64_t ldc,
+                                 const float* bias, int M, int N, int K, void* stream) {
+  DJ_CHECK_ARG(A && Bt && C, "dj_gate_gemm_bf16: NULL pointer");
+  DJ_CHECK_ARG(M > 0 && N > 0 && K > 0, "dj_gate_gemm_bf16: bad shape");
+  DJ_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0 && ldc % 4 == 0 && lda >= K && ldb >= K && ldc >= N,
+               "dj_gate_gemm_bf16: leading dimensions must be 16-byte multiples and cover K/N (lda=%lld ldb=%lld ldc=%lld)",
+               (long long)lda, (long long)ldb, (long long)ldc);
+  DJ_CHECK_ARG(((uintptr_t)A % 16) == 0 && ((uintptr_t)Bt % 16) == 0 && ((uintptr_t)C % 16) == 0 &&
+                   (bias == nullptr || ((uintptr_t)bias % 16) == 0),
+               "dj_gate_gemm_bf16: pointers must be 16-byte aligned");
+  CUtensorMap tmA, tmB, tmC;
+  int rc;
+  if ((rc = make_map_2d(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, BM))) return rc;
+  if ((rc = make_map_2d(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Bt, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BK, BN))) return rc;
+  if ((rc = make_map_2d(&tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, C, (uint64_t)N, (uint64_t)M, (uint64_t)ldc, 32, 32))) return rc;
+  DJ_CUDA(cudaFuncSetAttribute((const void*)gate_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem::TOTAL));
+  const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+  int grid = dj_num_sms();
+  if (grid > tiles) grid = tiles;
+  gate_gemm_kernel<<<grid, NUM_THREADS, GemmSmem::TOTAL, (cudaStream_t)stream>>>(tmA, tmB, tmC, bias, M, N, K);
+  DJ_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int dj_wgrad_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, float* C, int64_t ldc,
+                                  int Ka, int Nb, int64_t M, int64_t a_shift, int64_t a_period, void* stream) {
+  (void)A; (void)lda; (void)B; (void)ldb; (void)C; (void)ldc; (void)Ka; (void)Nb; (void)M; (void)a_shift;
+  (void)a_period; (void)stream;
+  DJ_CHECK_ARG(false, "dj_wgrad_gemm_bf16: not built yet");
+  return -1;
+}

@@ -1,0 +1,302 @@
+// Heads + loss (forward and its own backward), style/conv parameter gradients,
+// fused Nadam.  Replaces model.py:14-20 (primary_loss), model.py:94-95,125
+// (note_dense / volume_dense / Concatenate), the tf.gradients of the front end
+// (model.py:56-58,77-82,113-117,141-142) and keras Nadam (model.py:152).
+#include "dj_common.cuh"
+
+namespace {
+
+constexpr int N_ = DJ_NUM_NOTES, NU_ = DJ_NOTE_UNITS, CK_ = DJ_CONV_K, OU_ = DJ_OCTAVE_UNITS;
+constexpr int PADL_ = (CK_ - 1) / 2;
+constexpr int HEAD_BLOCKS = 512;
+
+__device__ __forceinline__ float bce_term(float t, float o, float& dLdo) {
+  // keras.losses.binary_crossentropy on the TF backend: clip to [1e-7, 1-1e-7],
+  // logit, sigmoid-CE.  Gradient is zero where the clip is active.
+  const float eps = 1e-7f;
+  const float oc = fminf(fmaxf(o, eps), 1.0f - eps);
+  dLdo = (o > eps && o < 1.0f - eps) ? (-t / oc + (1.0f - t) / (1.0f - oc)) : 0.0f;
+  return -(t * logf(oc) + (1.0f - t) * log1pf(-oc));
+}
+
+template <int V>   // V = units / 32 values per lane
+__global__ void __launch_bounds__(256) head_loss_kernel(
+    const float* __restrict__ h, dj_dropout d_h, const float* __restrict__ Wn, const float* __restrict__ bn,
+    const float* __restrict__ Wv, const float* __restrict__ bv, const float* __restrict__ y,
+    float* __restrict__ probs, float* __restrict__ dX, float* __restrict__ partials, int64_t M, float inv_M) {
+  constexpr int UNITS = V * 32;
+  constexpr int PSZ = 3 * UNITS + 4;
+  __shared__ float red[8][PSZ];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float wn0[V], wn1[V], wv[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int u = lane * V + i;
+    wn0[i] = Wn[u * 2]; wn1[i] = Wn[u * 2 + 1]; wv[i] = Wv[u];
+  }
+  const float b0 = bn[0], b1 = bn[1], b2 = bv[0];
+  float g0[V], g1[V], g2[V], gb0 = 0.f, gb1 = 0.f, gb2 = 0.f, lsum = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) g0[i] = g1[i] = g2[i] = 0.f;
+
+  for (int64_t row = (int64_t)blockIdx.x * 8 + warp; row < M; row += (int64_t)gridDim.x * 8) {
+    float x[V];
+#pragma unroll
+    for (int i4 = 0; i4 < V; i4 += 4) {
+      const int u = lane * V + i4;
+      const float4 hv = *reinterpret_cast<const float4*>(h + row * UNITS + u);
+      float m[4];
+      dj_dropmul4(d_h, (uint32_t)(row * UNITS + u), m);
+      x[i4] = hv.x * m[0]; x[i4 + 1] = hv.y * m[1]; x[i4 + 2] = hv.z * m[2]; x[i4 + 3] = hv.w * m[3];
+    }
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      s0 = fmaf(x[i], wn0[i], s0); s1 = fmaf(x[i], wn1[i], s1); s2 = fmaf(x[i], wv[i], s2);
+    }
+    s0 = dj_warp_sum(s0) + b0; s1 = dj_warp_sum(s1) + b1; s2 = dj_warp_sum(s2) + b2;
+    const float p0 = dj_sigmoid(s0), p1 = dj_sigmoid(s1), vol = s2;
+    if (lane == 0) { probs[row * 3] = p0; probs[row * 3 + 1] = p1; probs[row * 3 + 2] = vol; }
+    if (y != nullptr) {
+      const float y0 = y[row * 3], y1 = y[row * 3 + 1], y2 = y[row * 3 + 2];
+      float dl0, dlq;
+      const float l0 = bce_term(y0, p0, dl0);
+      const float q = y0 * p1 + (1.f - y0) * y1;
+      const float l1 = bce_term(y1, q, dlq);
+      const float d = y2 - (y0 * vol + (1.f - y0) * y2);
+      const float da0 = dl0 * p0 * (1.f - p0) * inv_M;
+      const float da1 = dlq * y0 * p1 * (1.f - p1) * inv_M;
+      const float da2 = -2.f * d * y0 * inv_M;
+      if (lane == 0) { lsum += l0 + l1 + d * d; gb0 += da0; gb1 += da1; gb2 += da2; }
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        g0[i] = fmaf(x[i], da0, g0[i]); g1[i] = fmaf(x[i], da1, g1[i]); g2[i] = fmaf(x[i], da2, g2[i]);
+      }
+      if (dX != nullptr) {
+#pragma unroll
+        for (int i4 = 0; i4 < V; i4 += 4) {
+          float4 o;
+          o.x = da0 * wn0[i4] + da1 * wn1[i4] + da2 * wv[i4];
+          o.y = da0 * wn0[i4 + 1] + da1 * wn1[i4 + 1] + da2 * wv[i4 + 1];
+          o.z = da0 * wn0[i4 + 2] + da1 * wn1[i4 + 2] + da2 * wv[i4 + 2];
+          o.w = da0 * wn0[i4 + 3] + da1 * wn1[i4 + 3] + da2 * wv[i4 + 3];
+          *reinterpret_cast<float4*>(dX + row * UNITS + lane * V + i4) = o;
+        }
+      }
+    }
+  }
+  if (y == nullptr || partials == nullptr) return;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int u = lane * V + i;
+    red[warp][u] = g0[i]; red[warp][UNITS + u] = g1[i]; red[warp][2 * UNITS + u] = g2[i];
+  }
+  if (lane == 0) {
+    red[warp][3 * UNITS] = gb0; red[warp][3 * UNITS + 1] = gb1; red[warp][3 * UNITS + 2] = gb2;
+    red[warp][3 * UNITS + 3] = lsum * inv_M;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < PSZ; e += 256) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w][e];
+    partials[(int64_t)blockIdx.x * PSZ + e] = s;
+  }
+}
+
+__global__ void head_finalize_kernel(const float* __restrict__ partials, int units, float* loss_out,
+                                     float* dWn, float* dbn, float* dWv, float* dbv) {
+  const int PSZ = 3 * units + 4;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= PSZ) return;
+  float s = 0.f;
+  for (int b = 0; b < HEAD_BLOCKS; ++b) s += partials[(int64_t)b * PSZ + e];
+  if (e < units) dWn[e * 2] = s;
+  else if (e < 2 * units) dWn[(e - units) * 2 + 1] = s;
+  else if (e < 3 * units) dWv[e - 2 * units] = s;
+  else if (e < 3 * units + 2) dbn[e - 3 * units] = s;
+  else if (e == 3 * units + 2) dbv[0] = s;
+  else loss_out[0] = s;
+}
+
+__global__ void __launch_bounds__(128) style_bwd_reduce_kernel(const float* __restrict__ dA, int64_t ldA, int F,
+                                                               const float* __restrict__ sp, dj_dropout d_sp,
+                                                               float* __restrict__ ds) {
+  const int ld4 = (F + 3) & ~3;
+  const int64_t bt = blockIdx.x;
+  for (int f = threadIdx.x; f < F; f += 128) {
+    float acc = 0.f;
+    for (int n = 0; n < N_; ++n) {
+      const int64_t row = bt * N_ + n;
+      acc = fmaf(dA[row * ldA + f], dj_dropmul(d_sp, (uint32_t)(row * ld4 + f)), acc);
+    }
+    const float s = sp[bt * F + f];
+    ds[bt * F + f] = acc * (1.f - s * s);
+  }
+}
+
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ X, int64_t ldx, int64_t R, int C,
+                                                     float* __restrict__ out, int accumulate) {
+  __shared__ float red[8][33];
+  const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5, c = blockIdx.x * 32 + cl;
+  float s = 0.f;
+  if (c < C)
+    for (int64_t r = rl; r < R; r += 8) s += X[r * ldx + c];
+  red[rl][cl] = s;
+  __syncthreads();
+  if (rl == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][cl];
+    out[c] = accumulate ? out[c] + t : t;
+  }
+}
+
+// conv weight gradient: recompute tanh(conv), form dpre, accumulate x^T.dpre per block
+__global__ void __launch_bounds__(256) conv_bwd_kernel(
+    const float* __restrict__ notes_in, int64_t notes_bstride, int B, int T, const float* __restrict__ Wc,
+    const float* __restrict__ bc, dj_dropout d_notes, dj_dropout d_conv, const float* __restrict__ dA0,
+    int64_t ldA, float* __restrict__ dWc, float* __restrict__ dbc) {
+  __shared__ float Wc_s[CK_ * NU_ * OU_];
+  __shared__ float bc_s[OU_];
+  __shared__ float xs[(N_ + CK_ - 1) * NU_];
+  __shared__ float dpre[N_][OU_];
+  const int tid = threadIdx.x, BT = B * T, o = tid % OU_, q = tid / OU_;
+  for (int i = tid; i < CK_ * NU_ * OU_; i += 256) Wc_s[i] = Wc[i];
+  if (tid < OU_) bc_s[tid] = bc[tid];
+  for (int i = tid; i < (N_ + CK_ - 1) * NU_; i += 256) xs[i] = 0.f;
+  constexpr int KPT = CK_ * NU_ / 4;   // 18 (k,c) pairs per thread
+  float gw[KPT], gb = 0.f;
+#pragma unroll
+  for (int i = 0; i < KPT; ++i) gw[i] = 0.f;
+  __syncthreads();
+  for (int bt = blockIdx.x; bt < BT; bt += gridDim.x) {
+    const int b = bt / T, t = bt % T;
+    if (tid < N_ * NU_) {
+      const int n = tid / NU_, c = tid % NU_;
+      xs[(n + PADL_) * NU_ + c] = notes_in[(int64_t)b * notes_bstride + (int64_t)t * (N_ * NU_) + tid] *
+                                  dj_dropmul(d_notes, (uint32_t)(bt * N_ + n) * 4u + c);
+    }
+    __syncthreads();
+    {
+      float acc[12];
+#pragma unroll
+      for (int j = 0; j < 12; ++j) acc[j] = bc_s[o];
+      for (int kc = 0; kc < CK_ * NU_; ++kc) {
+        const float w = Wc_s[kc * OU_ + o];
+#pragma unroll
+        for (int j = 0; j < 12; ++j) acc[j] = fmaf(xs[(q * 12 + j) * NU_ + kc], w, acc[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 12; ++j) {
+        const int n = q * 12 + j;
+        const int64_t row = (int64_t)bt * N_ + n;
+        const float a = tanhf(acc[j]);
+        dpre[n][o] = dA0[row * ldA + 14 + o] * dj_dropmul(d_conv, (uint32_t)(row * OU_ + o)) * (1.f - a * a);
+      }
+    }
+    __syncthreads();
+    for (int n = 0; n < N_; ++n) {
+      const float d = dpre[n][o];
+      if (q == 0) gb += d;
+#pragma unroll
+      for (int i = 0; i < KPT; ++i) gw[i] = fmaf(xs[n * NU_ + q * KPT + i], d, gw[i]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < KPT; ++i) atomicAdd(dWc + (q * KPT + i) * OU_ + o, gw[i]);
+  if (q == 0) atomicAdd(dbc + o, gb);
+}
+
+__global__ void __launch_bounds__(256) nadam_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                    float* __restrict__ m, float* __restrict__ v, int64_t n,
+                                                    float gscale, float lr, float beta1, float beta2, float eps,
+                                                    float mu_t, float mu_t1, float inv_1m_ms_new,
+                                                    float inv_1m_ms_next, float inv_bias2) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float gi = g[i] * gscale;
+    const float g_prime = gi * inv_1m_ms_new;
+    const float mt = beta1 * m[i] + (1.f - beta1) * gi;
+    const float m_prime = mt * inv_1m_ms_next;
+    const float vt = beta2 * v[i] + (1.f - beta2) * gi * gi;
+    const float v_prime = vt * inv_bias2;
+    const float m_bar = (1.f - mu_t) * g_prime + mu_t1 * m_prime;
+    p[i] = p[i] - lr * m_bar / (sqrtf(v_prime) + eps);
+    m[i] = mt;
+    v[i] = vt;
+  }
+}
+
+}  // namespace
+
+extern "C" int64_t dj_head_partials_size(int units) { return (int64_t)HEAD_BLOCKS * (3 * units + 4); }
+
+extern "C" int dj_head_loss(const float* h, int units, dj_dropout d_h, const float* Wn, const float* bn,
+                            const float* Wv, const float* bv, const float* y_true, float* probs, float* dX,
+                            float* partials, int64_t M, void* stream) {
+  DJ_CHECK_ARG(h && Wn && bn && Wv && bv && probs, "dj_head_loss: NULL pointer");
+  DJ_CHECK_ARG(M > 0 && M * units < (int64_t)4294967296LL, "dj_head_loss: bad M");
+  DJ_CHECK_ARG(y_true == nullptr || partials != nullptr, "dj_head_loss: partials required with y_true");
+  const float inv_M = 1.0f / (float)M;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (units == 128)
+    head_loss_kernel<4><<<HEAD_BLOCKS, 256, 0, st>>>(h, d_h, Wn, bn, Wv, bv, y_true, probs, dX, partials, M, inv_M);
+  else if (units == 256)
+    head_loss_kernel<8><<<HEAD_BLOCKS, 256, 0, st>>>(h, d_h, Wn, bn, Wv, bv, y_true, probs, dX, partials, M, inv_M);
+  else DJ_CHECK_ARG(false, "dj_head_loss: units=%d unsupported (128 or 256)", units);
+  DJ_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int dj_head_finalize(const float* partials, int units, float* loss_out, float* dWn, float* dbn,
+                                float* dWv, float* dbv, void* stream) {
+  DJ_CHECK_ARG(partials && loss_out && dWn && dbn && dWv && dbv, "dj_head_finalize: NULL pointer");
+  const int psz = 3 * units + 4;
+  head_finalize_kernel<<<(psz + 127) / 128, 128, 0, (cudaStream_t)stream>>>(partials, units, loss_out, dWn, dbn, dWv, dbv);
+  DJ_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int dj_style_bwd_reduce(const float* dA, int64_t ldA, int F, const float* sp, dj_dropout d_sp,
+                                   int BT, float* ds, void* stream) {
+  DJ_CHECK_ARG(dA && sp && ds && F > 0 && BT > 0 && ldA >= F, "dj_style_bwd_reduce: bad arguments");
+  style_bwd_reduce_kernel<<<BT, 128, 0, (cudaStream_t)stream>>>(dA, ldA, F, sp, d_sp, ds);
+  DJ_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int dj_colsum(const float* X, int64_t ldx, int64_t R, int C, float* out, int accumulate, void* stream) {
+  DJ_CHECK_ARG(X && out && R > 0 && C > 0 && ldx >= C, "dj_colsum: bad arguments");
+  colsum_kernel<<<(C + 31) / 32, 256, 0, (cudaStream_t)stream>>>(X, ldx, R, C, out, accumulate);
+  DJ_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int dj_conv_bwd(const float* notes_in, int64_t notes_bstride, int B, int T, const float* Wc,
+                           const float* bc, dj_dropout d_notes, dj_dropout d_conv, const float* dA0, int64_t ldA,
+                           float* dWc, float* dbc, void* stream) {
+  DJ_CHECK_ARG(notes_in && Wc && bc && dA0 && dWc && dbc, "dj_conv_bwd: NULL pointer");
+  DJ_CHECK_ARG(B > 0 && T > 0 && ldA >= DJ_FEAT0, "dj_conv_bwd: bad sizes");
+  int grid = dj_num_sms();
+  if (grid > B * T) grid = B * T;
+  conv_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(notes_in, notes_bstride, B, T, Wc, bc, d_notes, d_conv,
+                                                          dA0, ldA, dWc, dbc);
+  DJ_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int dj_nadam_step(float* p, const float* g, float* m, float* v, int64_t n, float gscale, float lr,
+                             float beta1, float beta2, float eps, float mu_t, float mu_t1, float m_sched_new,
+                             float m_sched_next, float bias2, void* stream) {
+  DJ_CHECK_ARG(p && g && m && v && n > 0, "dj_nadam_step: bad arguments");
+  DJ_CHECK_ARG(m_sched_new < 1.f && m_sched_next < 1.f && bias2 > 0.f, "dj_nadam_step: bad schedule scalars");
+  int64_t blocks = (n + 255) / 256;
+  const int maxb = dj_num_sms() * 8;
+  if (blocks > maxb) blocks = maxb;
+  nadam_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, gscale, lr, beta1, beta2, eps, mu_t,
+                                                              mu_t1, 1.f / (1.f - m_sched_new),
+                                                              1.f / (1.f - m_sched_next), 1.f / bias2);
+  DJ_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,430 @@
+// Persistent LSTM recurrence for the DeepJ time axis and note axis.
+//
+// Replaces the sequential part of keras.layers.LSTM at model.py:84 and
+// model.py:120 (the tf.while_loop of h.U matmuls + gate nonlinearities), forward
+// and backward.  Design (B200-first, not the grid-barrier version of SURVEY H4):
+// the independent sequences are tiled over thread-block CLUSTERS; inside a
+// cluster the recurrent matrix U [units, 4*units] is split by hidden unit over
+// the C CTAs and stays resident in shared memory (fp32) for the whole launch;
+// h_t is exchanged through distributed shared memory with ONE cluster barrier
+// per step; the cell state never leaves registers.  No grid-wide barrier exists
+// because sequences in different clusters never interact.
+//
+// Row addressing: all activations are [M, width] with the canonical row order
+// row = (b*T + t)*48 + n; a (sequence, step) pair maps to a row through ScanMap.
+#include <cooperative_groups.h>
+
+#include "dj_common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace {
+
+struct ScanMap {
+  int seq_inner;
+  int64_t outer_stride, inner_stride, step_stride;
+};
+__device__ __forceinline__ int64_t scan_row0(const ScanMap& m, int seq) {
+  return (int64_t)(seq / m.seq_inner) * m.outer_stride + (int64_t)(seq % m.seq_inner) * m.inner_stride;
+}
+__device__ __forceinline__ void cluster_arrive() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void cluster_wait() {
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p));
+}
+
+constexpr int UC = 32;   // hidden units owned by one CTA (=> 128 gate columns)
+
+template <int U, int BS>
+struct FwdSmem {
+  static constexpr int HSTR = U * 4 + 4;            // floats per 4-sequence group (+4: bank skew)
+  static constexpr int HBUF = (BS / 4) * HSTR;      // one h buffer
+  static constexpr int US = U * UC * 4;             // resident U slice
+  static constexpr size_t BYTES = sizeof(float) * (size_t)(US + 2 * HBUF);
+};
+
+// ---------------------------------------------------------------------------
+// forward
+//   thread (sg, ug): sequences 4*sg..4*sg+3 of the tile, hidden units ug and
+//   ug+16 of this CTA's slice, all four gates -> 32 accumulators, c in registers.
+// ---------------------------------------------------------------------------
+template <int U, int C, int BS>
+__global__ void __launch_bounds__((BS / 4) * 16, 1)
+scan_fwd_kernel(float* __restrict__ Z, float* __restrict__ Hout, float* __restrict__ Cout,
+                __nv_bfloat16* __restrict__ Hbf, const float* __restrict__ Uw, int S, int steps,
+                ScanMap map, int hard) {
+  static_assert(U / C == UC, "each CTA owns 32 hidden units");
+  constexpr int NT = (BS / 4) * 16;
+  using SM = FwdSmem<U, BS>;
+  extern __shared__ __align__(16) float smem[];
+  float* Us = smem;               // [U][32 units][4 gates]
+  float* hbuf = smem + SM::US;    // [2][BS/4][U*4+4]
+
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int cid = blockIdx.x / C, ncl = gridDim.x / C;
+  const int tid = threadIdx.x, sg = tid >> 4, ug = tid & 15;
+  const int unit0 = rank * UC;
+
+  for (int idx = tid; idx < SM::US; idx += NT) {
+    const int g = idx & 3, u = (idx >> 2) & 31, k = idx >> 7;
+    Us[idx] = Uw[(size_t)k * 4 * U + g * U + unit0 + u];
+  }
+  float* rbuf[C];
+#pragma unroll
+  for (int r = 0; r < C; ++r) rbuf[r] = cluster.map_shared_rank(hbuf, r);
+  cluster.sync();   // every CTA of the cluster is resident before any remote store
+
+  const int ntiles = (S + BS - 1) / BS;
+  for (int tile = cid; tile < ntiles; tile += ncl) {
+    for (int idx = tid; idx < SM::HBUF; idx += NT) hbuf[idx] = 0.f;   // h_{-1} = 0
+    float c[4][2];
+    bool ok[4];
+    int64_t row0[4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      const int seq = tile * BS + sg * 4 + s;
+      ok[s] = seq < S;
+      row0[s] = scan_row0(map, ok[s] ? seq : 0);
+      c[s][0] = c[s][1] = 0.f;
+    }
+    float zn[4][2][4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s)
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          zn[s][hf][g] = ok[s] ? Z[row0[s] * (4 * U) + g * U + unit0 + hf * 16 + ug] : 0.f;
+    __syncthreads();
+
+    for (int t = 0; t < steps; ++t) {
+      const int cur = t & 1, nxt = cur ^ 1;
+      float acc[4][2][4];
+#pragma unroll
+      for (int s = 0; s < 4; ++s)
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+          for (int g = 0; g < 4; ++g) acc[s][hf][g] = zn[s][hf][g];
+      if (t + 1 < steps) {   // register prefetch of the next step's pre-activations
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+          const int64_t r = row0[s] + (int64_t)(t + 1) * map.step_stride;
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              zn[s][hf][g] = ok[s] ? Z[r * (4 * U) + g * U + unit0 + hf * 16 + ug] : 0.f;
+        }
+      }
+      const float* hb = hbuf + cur * SM::HBUF + sg * SM::HSTR;
+      const float* ua = Us + ug * 4;
+#pragma unroll 4
+      for (int k = 0; k < U; ++k) {
+        const float4 hv = *reinterpret_cast<const float4*>(hb + k * 4);
+        const float4 u0 = *reinterpret_cast<const float4*>(ua + k * (UC * 4));
+        const float4 u1 = *reinterpret_cast<const float4*>(ua + k * (UC * 4) + 64);
+        const float h4[4] = {hv.x, hv.y, hv.z, hv.w};
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+          acc[s][0][0] = fmaf(h4[s], u0.x, acc[s][0][0]);
+          acc[s][0][1] = fmaf(h4[s], u0.y, acc[s][0][1]);
+          acc[s][0][2] = fmaf(h4[s], u0.z, acc[s][0][2]);
+          acc[s][0][3] = fmaf(h4[s], u0.w, acc[s][0][3]);
+          acc[s][1][0] = fmaf(h4[s], u1.x, acc[s][1][0]);
+          acc[s][1][1] = fmaf(h4[s], u1.y, acc[s][1][1]);
+          acc[s][1][2] = fmaf(h4[s], u1.z, acc[s][1][2]);
+          acc[s][1][3] = fmaf(h4[s], u1.w, acc[s][1][3]);
+        }
+      }
+      float hnew[2][4];
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        const int64_t r = row0[s] + (int64_t)t * map.step_stride;
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          const float gi = dj_gate_act(acc[s][hf][0], hard);
+          const float gf = dj_gate_act(acc[s][hf][1], hard);
+          const float gg = tanhf(acc[s][hf][2]);
+          const float go = dj_gate_act(acc[s][hf][3], hard);
+          const float cn = fmaf(gf, c[s][hf], gi * gg);
+          const float hn = go * tanhf(cn);
+          c[s][hf] = cn;
+          hnew[hf][s] = hn;
+          if (ok[s]) {
+            const int col = unit0 + hf * 16 + ug;
+            float* zr = Z + r * (4 * U) + col;
+            zr[0] = gi; zr[U] = gf; zr[2 * U] = gg; zr[3 * U] = go;
+            Hout[r * U + col] = hn;
+            if (Cout != nullptr) Cout[r * U + col] = cn;
+            if (Hbf != nullptr) Hbf[r * U + col] = __float2bfloat16_rn(hn);
+          }
+        }
+      }
+      // all-gather of h_t into every CTA's next buffer (DSMEM, 16 lanes x 16 B contiguous)
+#pragma unroll
+      for (int r = 0; r < C; ++r) {
+        float* dst = rbuf[r] + nxt * SM::HBUF + sg * SM::HSTR + (unit0 + ug) * 4;
+        *reinterpret_cast<float4*>(dst) = make_float4(hnew[0][0], hnew[0][1], hnew[0][2], hnew[0][3]);
+        *reinterpret_cast<float4*>(dst + 64) = make_float4(hnew[1][0], hnew[1][1], hnew[1][2], hnew[1][3]);
+      }
+      cluster.sync();
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// backward (reverse scan).  Per step:
+//   D  dh_rec = sum over the C source CTAs of the partial dz.U^T slots
+//   A  gate derivatives for this CTA's (sequence, unit) pairs -> dz (global + smem)
+//   B  P[s,k] = sum_j dz[s,j] * U[k,col(j)]  over this CTA's 128 gate columns, all k
+//   C  reduce-scatter: P[:, units of CTA d] -> slot[my rank] of CTA d (DSMEM)
+// ---------------------------------------------------------------------------
+template <int U, int C, int BS>
+struct BwdSmem {
+  static constexpr int UT = 128 * U;                     // U^T slice [j][k]
+  static constexpr int DZS = BS + 4;                     // dz row stride (bank skew)
+  static constexpr int DZ = 128 * DZS;
+  static constexpr int SLOT = (BS / 4) * UC * 4;         // one source's contribution
+  static constexpr size_t BYTES = sizeof(float) * (size_t)(UT + DZ + C * SLOT);
+};
+
+template <int U, int C, int BS, typename TZ>
+__global__ void __launch_bounds__((BS / 4) * 16, 1)
+scan_bwd_kernel(const float* __restrict__ G, const float* __restrict__ Cst, const float* __restrict__ dY,
+                int64_t ldY, dj_dropout d_y, const float* __restrict__ Uw, TZ* __restrict__ dZ,
+                float* __restrict__ db, int S, int steps, ScanMap map, int hard) {
+  static_assert(U / C == UC, "each CTA owns 32 hidden units");
+  constexpr int NT = (BS / 4) * 16;
+  constexpr int KQ = U / 64;        // k quads per thread in phase B (4 consecutive k each)
+  using SM = BwdSmem<U, C, BS>;
+  extern __shared__ __align__(16) float smem[];
+  float* UsT = smem;                // [128 j = g*32+u][U k]
+  float* dzb = smem + SM::UT;       // [128 j][BS+4]
+  float* slots = dzb + SM::DZ;      // [C src][BS/4][32 units][4 seqs]
+
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int cid = blockIdx.x / C, ncl = gridDim.x / C;
+  const int tid = threadIdx.x, sg = tid >> 4, ug = tid & 15;
+  const int unit0 = rank * UC;
+
+  for (int idx = tid; idx < SM::UT; idx += NT) {
+    const int k = idx % U, j = idx / U;
+    UsT[idx] = Uw[(size_t)k * 4 * U + (j >> 5) * U + unit0 + (j & 31)];
+  }
+  float* rslots[C];
+#pragma unroll
+  for (int r = 0; r < C; ++r) rslots[r] = cluster.map_shared_rank(slots, r);
+  float dbacc[2][4];
+#pragma unroll
+  for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+    for (int g = 0; g < 4; ++g) dbacc[hf][g] = 0.f;
+  cluster.sync();
+
+  const int ntiles = (S + BS - 1) / BS;
+  for (int tile = cid; tile < ntiles; tile += ncl) {
+    bool ok[4];
+    int64_t row0[4];
+    float dcn[4][2];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      const int seq = tile * BS + sg * 4 + s;
+      ok[s] = seq < S;
+      row0[s] = scan_row0(map, ok[s] ? seq : 0);
+      dcn[s][0] = dcn[s][1] = 0.f;
+    }
+    for (int t = steps - 1; t >= 0; --t) {
+      // ---- D: recurrent gradient arriving from step t+1
+      float dh[4][2];
+#pragma unroll
+      for (int s = 0; s < 4; ++s) dh[s][0] = dh[s][1] = 0.f;
+      if (t != steps - 1) {
+#pragma unroll
+        for (int r = 0; r < C; ++r) {
+          const float* sl = slots + r * SM::SLOT + (sg * UC + ug) * 4;
+          const float4 a = *reinterpret_cast<const float4*>(sl);
+          const float4 b = *reinterpret_cast<const float4*>(sl + 64);
+          dh[0][0] += a.x; dh[1][0] += a.y; dh[2][0] += a.z; dh[3][0] += a.w;
+          dh[0][1] += b.x; dh[1][1] += b.y; dh[2][1] += b.z; dh[3][1] += b.w;
+        }
+      }
+      cluster_arrive();   // my reads of `slots` are done; matched by cluster_wait before phase C
+      // ---- A: elementwise gate backward
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        const int64_t r = row0[s] + (int64_t)t * map.step_stride;
+        const int64_t rp = r - map.step_stride;
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          const int ul = hf * 16 + ug, col = unit0 + ul;
+          float dz[4] = {0.f, 0.f, 0.f, 0.f};
+          if (ok[s]) {
+            const float* gr = G + r * (4 * U) + col;
+            const float gi = gr[0], gf = gr[U], gg = gr[2 * U], go = gr[3 * U];
+            const float ct = Cst[r * U + col];
+            const float cp = (t > 0) ? Cst[rp * U + col] : 0.f;
+            const float dy = dY[r * ldY + col] * dj_dropmul(d_y, (uint32_t)(r * U + col));
+            const float dht = dy + dh[s][hf];
+            const float tc = tanhf(ct);
+            const float d_o = dht * tc;
+            const float dc = fmaf(dht * go, 1.f - tc * tc, dcn[s][hf]);
+            dcn[s][hf] = dc * gf;
+            dz[0] = dc * gg * dj_gate_dact(gi, hard);
+            dz[1] = dc * cp * dj_gate_dact(gf, hard);
+            dz[2] = dc * gi * (1.f - gg * gg);
+            dz[3] = d_o * dj_gate_dact(go, hard);
+            TZ* zr = dZ + r * (4 * U) + col;
+            zr[0] = dj_from_float<TZ>(dz[0]); zr[U] = dj_from_float<TZ>(dz[1]);
+            zr[2 * U] = dj_from_float<TZ>(dz[2]); zr[3 * U] = dj_from_float<TZ>(dz[3]);
+            if (t > 0) {   // warm L2 for the next (earlier) step while phase B runs
+              const int64_t r2 = rp - map.step_stride;
+              prefetch_l2(G + rp * (4 * U) + col);
+              prefetch_l2(dY + rp * ldY + col);
+              if (t > 1) prefetch_l2(Cst + r2 * U + col);
+            }
+          }
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            dbacc[hf][g] += dz[g];
+            dzb[(g * 32 + ul) * SM::DZS + sg * 4 + s] = dz[g];
+          }
+        }
+      }
+      __syncthreads();
+      // ---- B: partial dh_{t-1} over this CTA's 128 gate columns
+      float P[4][KQ][4];
+#pragma unroll
+      for (int s = 0; s < 4; ++s)
+#pragma unroll
+        for (int q = 0; q < KQ; ++q)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) P[s][q][i] = 0.f;
+      if (t > 0) {
+#pragma unroll 2
+        for (int j = 0; j < 128; ++j) {
+          const float4 dv = *reinterpret_cast<const float4*>(dzb + j * SM::DZS + sg * 4);
+          const float d4[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+          for (int q = 0; q < KQ; ++q) {
+            const float4 uv = *reinterpret_cast<const float4*>(UsT + j * U + q * 64 + ug * 4);
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+              P[s][q][0] = fmaf(d4[s], uv.x, P[s][q][0]);
+              P[s][q][1] = fmaf(d4[s], uv.y, P[s][q][1]);
+              P[s][q][2] = fmaf(d4[s], uv.z, P[s][q][2]);
+              P[s][q][3] = fmaf(d4[s], uv.w, P[s][q][3]);
+            }
+          }
+        }
+      }
+      cluster_wait();     // every CTA has consumed last step's slots
+      // ---- C: reduce-scatter.  k = q*64 + ug*4 + i  ->  owner CTA 2q + (ug>=8), unit (ug*4+i)%32
+      if (t > 0) {
+#pragma unroll
+        for (int q = 0; q < KQ; ++q) {
+          float* dst = rslots[2 * q + (ug >> 3)] + rank * SM::SLOT + (sg * UC + (ug & 7) * 4) * 4;
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            *reinterpret_cast<float4*>(dst + i * 4) = make_float4(P[0][q][i], P[1][q][i], P[2][q][i], P[3][q][i]);
+        }
+      }
+      cluster.sync();     // slots complete and dzb free for the next step
+    }
+  }
+  // bias gradient: reduce the per-thread sums over the sequence groups, one atomic per column
+#pragma unroll
+  for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+    for (int g = 0; g < 4; ++g) dzb[(g * 32 + hf * 16 + ug) * SM::DZS + sg] = dbacc[hf][g];
+  __syncthreads();
+  if (tid < 128) {
+    float s = 0.f;
+    for (int q = 0; q < BS / 4; ++q) s += dzb[tid * SM::DZS + q];
+    atomicAdd(db + (tid >> 5) * U + unit0 + (tid & 31), s);
+  }
+}
+
+template <typename K>
+int launch_cluster(K kernel, int C, int nthreads, size_t smem, int nclusters, cudaStream_t st, void** args) {
+  DJ_CUDA(cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (C > 8) DJ_CUDA(cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(nclusters * C);
+  cfg.blockDim = dim3(nthreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  DJ_CUDA(cudaLaunchKernelExC(&cfg, (const void*)kernel, args));
+  return 0;
+}
+
+int pick_clusters(int C, int ntiles) {
+  int ncl = dj_num_sms() / C;
+  if (ncl < 1) ncl = 1;
+  if (ncl > ntiles) ncl = ntiles;
+  // balance: same number of rounds with fewer idle clusters
+  const int rounds = (ntiles + ncl - 1) / ncl;
+  ncl = (ntiles + rounds - 1) / rounds;
+  return ncl;
+}
+
+}  // namespace
+
+extern "C" int dj_lstm_scan_fwd(float* Z, float* h_out, float* c_out, void* h_bf16, const float* Uw, int S,
+                                int steps, int units, int seq_inner, int64_t seq_outer_stride,
+                                int64_t seq_inner_stride, int64_t step_stride, int hard, void* stream) {
+  DJ_CHECK_ARG(Z && h_out && Uw, "dj_lstm_scan_fwd: NULL pointer");
+  DJ_CHECK_ARG(S > 0 && steps > 0 && seq_inner > 0, "dj_lstm_scan_fwd: bad sizes");
+  ScanMap map{seq_inner, seq_outer_stride, seq_inner_stride, step_stride};
+  __nv_bfloat16* hb = (__nv_bfloat16*)h_bf16;
+  void* args[] = {&Z, &h_out, &c_out, &hb, (void*)&Uw, &S, &steps, &map, &hard};
+  cudaStream_t st = (cudaStream_t)stream;
+  if (units == 256) {
+    constexpr int C = 8, BS = 48;
+    return launch_cluster(scan_fwd_kernel<256, C, BS>, C, (BS / 4) * 16, FwdSmem<256, BS>::BYTES,
+                          pick_clusters(C, (S + BS - 1) / BS), st, args);
+  } else if (units == 128) {
+    constexpr int C = 4, BS = 64;
+    return launch_cluster(scan_fwd_kernel<128, C, BS>, C, (BS / 4) * 16, FwdSmem<128, BS>::BYTES,
+                          pick_clusters(C, (S + BS - 1) / BS), st, args);
+  }
+  DJ_CHECK_ARG(false, "dj_lstm_scan_fwd: units=%d unsupported (128 or 256; U must fit cluster shared memory in fp32)", units);
+  return -1;
+}
+
+extern "C" int dj_lstm_scan_bwd(const float* gates, const float* c, const float* dY, int64_t ldY,
+                                dj_dropout d_y, const float* Uw, void* dZ, int dz_dtype, float* db, int S,
+                                int steps, int units, int seq_inner, int64_t seq_outer_stride,
+                                int64_t seq_inner_stride, int64_t step_stride, int hard, void* stream) {
+  DJ_CHECK_ARG(gates && c && dY && Uw && dZ && db, "dj_lstm_scan_bwd: NULL pointer");
+  DJ_CHECK_ARG(S > 0 && steps > 0 && seq_inner > 0 && ldY >= units, "dj_lstm_scan_bwd: bad sizes");
+  DJ_CHECK_ARG(dz_dtype == DJ_F32 || dz_dtype == DJ_BF16, "dj_lstm_scan_bwd: unknown dz dtype %d", dz_dtype);
+  ScanMap map{seq_inner, seq_outer_stride, seq_inner_stride, step_stride};
+  void* args[] = {(void*)&gates, (void*)&c, (void*)&dY, &ldY, &d_y, (void*)&Uw, &dZ, &db, &S, &steps, &map, &hard};
+  cudaStream_t st = (cudaStream_t)stream;
+  if (units == 256) {
+    constexpr int C = 8, BS = 48;
+    const int ncl = pick_clusters(C, (S + BS - 1) / BS);
+    if (dz_dtype == DJ_F32)
+      return launch_cluster(scan_bwd_kernel<256, C, BS, float>, C, (BS / 4) * 16, BwdSmem<256, C, BS>::BYTES, ncl, st, args);
+    return launch_cluster(scan_bwd_kernel<256, C, BS, __nv_bfloat16>, C, (BS / 4) * 16, BwdSmem<256, C, BS>::BYTES, ncl, st, args);
+  } else if (units == 128) {
+    constexpr int C = 4, BS = 64;
+    const int ncl = pick_clusters(C, (S + BS - 1) / BS);
+    if (dz_dtype == DJ_F32)
+      return launch_cluster(scan_bwd_kernel<128, C, BS, float>, C, (BS / 4) * 16, BwdSmem<128, C, BS>::BYTES, ncl, st, args);
+    return launch_cluster(scan_bwd_kernel<128, C, BS, __nv_bfloat16>, C, (BS / 4) * 16, BwdSmem<128, C, BS>::BYTES, ncl, st, args);
+  }
+  DJ_CHECK_ARG(false, "dj_lstm_scan_bwd: units=%d unsupported (128 or 256)", units);
+  return -1;
+}
