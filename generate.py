@@ -1,0 +1,67 @@
+"""Drop-in for the reference's generate.py: `python generate.py [--bars N]
+[--styles i j ...]` and `generate(models, num_bars, styles)` (a generator that
+yields, per timestep, a list of one [48,3] array per sequence,
+generate.py:98-121).  The autoregressive loop itself -- window recompute,
+note-by-note LSTM, temperature, Bernoulli draws -- runs on the GPU
+(music_generator_b200.sampler); the host only supplies the uniform stream that
+np.random.random() would have produced, in the same order."""
+import argparse
+import os
+
+import numpy as np
+
+from constants import *
+from dataset import compute_genre, unclamp_midi
+from util import build_or_load, one_hot
+from music_generator_b200.sampler import generate_events
+
+
+def apply_temperature(prob, temperature):
+    """generate.py:81-91 (host copy for API parity; the device sampler applies
+    the same float32 transform)."""
+    if temperature != 1:
+        x = -np.log(1 / prob - 1)
+        prob = 1 / (1 + np.exp(-x / temperature))
+    return prob
+
+
+def generate(models, num_bars, styles, uniforms=None, default_temp=1):
+    print('Generating with styles:', styles)
+    eng = models[1].engine
+    steps = NOTES_PER_BAR * num_bars
+    if uniforms is None:
+        # worst case 2 draws per (timestep, sequence, note): same values, same order
+        # as the reference's successive np.random.random() calls
+        uniforms = np.random.random_sample(2 * steps * len(styles) * NUM_NOTES)
+    events, _ = generate_events(eng, styles, steps, uniforms, stream_mode=0, default_temp=default_temp)
+    for t in range(steps):
+        yield [events[t, i] for i in range(len(styles))]
+
+
+def write_file(name, results):
+    """generate.py:123-134.  Writing Standard MIDI needs the python-midi package
+    the reference depends on (not installable here); the unclamped piano-roll
+    [T,128,3] that midi_encode would consume is saved instead."""
+    results = zip(*list(results))
+    for i, result in enumerate(results):
+        fpath = os.path.join(SAMPLES_DIR, name + '_' + str(i) + '.npy')
+        print('Writing file', fpath)
+        os.makedirs(os.path.dirname(fpath), exist_ok=True)
+        np.save(fpath, unclamp_midi(np.array(result)))
+
+
+def main():
+    parser = argparse.ArgumentParser(description='Generates music.')
+    parser.add_argument('--bars', default=32, type=int, help='Number of bars to generate')
+    parser.add_argument('--styles', default=None, type=int, nargs='+', help='Styles to mix together')
+    args = parser.parse_args()
+
+    models = build_or_load()
+    styles = [compute_genre(i) for i in range(len(genre))]
+    if args.styles:
+        styles = [np.mean([one_hot(i, NUM_STYLES) for i in args.styles], axis=0)]
+    write_file('output', generate(models, args.bars, styles))
+
+
+if __name__ == '__main__':
+    main()

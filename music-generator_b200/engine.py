@@ -1,0 +1,388 @@
+"""Host-side sequencing of the DeepJ hot path on one B200.
+
+PyTorch is used only for device memory, streams and (in trainer.py)
+torch.distributed; every arithmetic step is a kernel of libdeepj_sm100.so
+called through the C ABI (include/deepj_b200.h).  The engine mirrors the
+reference graph of model.py:128-152 (forward), tf.gradients of it (backward)
+and keras Nadam (model.py:152).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import DJ_BF16, DJ_F32, NO_DROPOUT, Dropout, check
+from .config import ModelConfig, param_shapes, round_up
+
+N = 48
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class Workspace:
+    """Activation / gradient buffers for one (B, T, precision, train) shape."""
+
+    def __init__(self, cfg: ModelConfig, B: int, T: int, bf16: bool, train: bool, dev):
+        self.B, self.T, self.M = B, T, B * T * N
+        M, BT = self.M, B * T
+        f32 = dict(dtype=torch.float32, device=dev)
+        adt = torch.bfloat16 if bf16 else torch.float32
+        self.emb = torch.empty(BT, cfg.style_units, **f32)
+        self.sp, self.A, self.Z, self.h, self.c = [], [], [], [], []
+        self.ld = []
+        for L in cfg.layers():
+            ld = round_up(L["F"], 32)
+            self.ld.append(ld)
+            self.sp.append(torch.empty(BT, L["F"], **f32))
+            self.A.append(torch.empty(M, ld, dtype=adt, device=dev))
+            self.Z.append(torch.empty(M, 4 * L["U"], **f32))
+            self.h.append(torch.empty(M, L["U"], **f32))
+            self.c.append(torch.empty(M, L["U"], **f32) if train else None)
+        self.probs = torch.empty(M, 3, **f32)
+        if train:
+            un = cfg.note_axis_units
+            self.dXtop = torch.empty(M, un, **f32)
+            self.partials = torch.empty(_lib.load().dj_head_partials_size(un), **f32)
+            self.loss = torch.zeros(1, **f32)
+            umax = max(L["U"] for L in cfg.layers())
+            self.dZ = torch.empty(M, 4 * umax, dtype=adt, device=dev)   # reused layer after layer
+            self.dA = [torch.empty(M, ld, **f32) for ld in self.ld]
+            self.ds = [torch.empty(BT, L["F"], **f32) for L in cfg.layers()]
+            self.demb = torch.empty(BT, cfg.style_units, **f32)
+
+
+class Engine:
+    def __init__(self, cfg: ModelConfig = ModelConfig(), device: Optional[torch.device] = None,
+                 precision: str = "bf16", recurrent_activation: str = "hard_sigmoid",
+                 input_dropout: float = 0.2, dropout: float = 0.5):
+        if not torch.cuda.is_available():
+            raise RuntimeError("the DeepJ B200 engine needs a CUDA device; there is no CPU fallback")
+        assert precision in ("bf16", "fp32")
+        self.lib = _lib.load()
+        self.cfg = cfg
+        self.dev = device or torch.device("cuda", torch.cuda.current_device())
+        self.precision = precision
+        self.hard = 1 if recurrent_activation == "hard_sigmoid" else 0
+        self.input_dropout, self.dropout = input_dropout, dropout
+        self.layers = cfg.layers()
+        # ---- flat parameter / gradient / optimizer buffers (one NCCL message)
+        self.shapes = param_shapes(cfg)
+        self.offsets: Dict[str, int] = {}
+        off = 0
+        for k, shp in self.shapes.items():
+            self.offsets[k] = off
+            off += round_up(int(np.prod(shp)), 32)
+        self.flat_size = off
+        self.num_params = sum(int(np.prod(s)) for s in self.shapes.values())
+        f32 = dict(dtype=torch.float32, device=self.dev)
+        self.flat = torch.zeros(off, **f32)
+        self.gflat = torch.zeros(off, **f32)
+        self.m = torch.zeros(off, **f32)
+        self.v = torch.zeros(off, **f32)
+        self.params = {k: self._view(self.flat, k) for k in self.shapes}
+        self.grads = {k: self._view(self.gflat, k) for k in self.shapes}
+        self.iterations, self.m_schedule = 0, 1.0
+        self.nadam = dict(lr=0.002, beta_1=0.9, beta_2=0.999, eps=1e-8, schedule_decay=0.004)
+        self._ws: Dict[tuple, Workspace] = {}
+        self._wbf: Dict[str, torch.Tensor] = {}
+        self._wbf_version = -1
+        self._version = 0
+        self.launches = 0   # kernels of ours enqueued (bench.py reports it)
+        self.profile = None
+        self._tag = ""
+
+    # ------------------------------------------------------------------ params
+    def _view(self, flat, k):
+        shp = self.shapes[k]
+        n = int(np.prod(shp))
+        return flat[self.offsets[k]:self.offsets[k] + n].view(*shp)
+
+    def set_params(self, state: Dict[str, "np.ndarray | torch.Tensor"]) -> None:
+        for k in self.shapes:
+            v = torch.as_tensor(np.asarray(state[k]) if not torch.is_tensor(state[k]) else state[k])
+            if tuple(v.shape) != tuple(self.shapes[k]):
+                raise ValueError(f"{k}: expected shape {self.shapes[k]}, got {tuple(v.shape)}")
+            self.params[k].copy_(v.to(torch.float32))
+        self._version += 1
+
+    def get_params(self) -> Dict[str, np.ndarray]:
+        return {k: v.detach().cpu().numpy().copy() for k, v in self.params.items()}
+
+    def init_params(self, seed: int = 0) -> None:
+        """Keras default initialisers (glorot_uniform / orthogonal / zeros, forget bias 1)."""
+        g = torch.Generator().manual_seed(seed)
+        st = {}
+        for name, shp in self.shapes.items():
+            if name.endswith(".b"):
+                t = torch.zeros(shp, dtype=torch.float64)
+                if ".lstm." in name:
+                    u = shp[0] // 4
+                    t[u:2 * u] = 1.0
+            elif name.endswith("lstm.U"):
+                u = shp[0]
+                blocks = []
+                for _ in range(4):
+                    q, r = torch.linalg.qr(torch.randn(u, u, generator=g, dtype=torch.float64))
+                    blocks.append(q * torch.sign(torch.diagonal(r)))
+                t = torch.cat(blocks, dim=1) * 0.5
+            else:
+                fan_in, fan_out = (shp[0] * shp[1], shp[0] * shp[2]) if len(shp) == 3 else shp
+                lim = math.sqrt(6.0 / (fan_in + fan_out))
+                t = (torch.rand(shp, generator=g, dtype=torch.float64) * 2 - 1) * lim
+            st[name] = t.to(torch.float32)
+        self.set_params(st)
+
+    def _call(self, name, *args):
+        if self.profile is not None:   # debug: per-entry-point device time (CUDA events, serialising)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            check(getattr(self.lib, name)(*args), name)
+            e1.record()
+            self.profile.append((name + self._tag, e0, e1))
+        else:
+            check(getattr(self.lib, name)(*args), name)
+        self.launches += 1
+
+    def profile_summary(self):
+        torch.cuda.synchronize()
+        agg = {}
+        for name, e0, e1 in self.profile:
+            t = e0.elapsed_time(e1)
+            a = agg.setdefault(name, [0, 0.0])
+            a[0] += 1; a[1] += t
+        self.profile = []
+        return agg
+
+    def _refresh_bf16(self):
+        """bf16 copies of the LSTM kernels: transposed [4U, ld] (forward B operand,
+        K-major) and natural [F, 4U] (data-gradient B operand)."""
+        if self._wbf_version == self._version:
+            return
+        for li, L in enumerate(self.layers):
+            W = self.params[f"{L['name']}.lstm.W"]
+            F, U4 = W.shape
+            ld = round_up(F, 32)
+            kt, kn = f"{L['name']}.Wt", f"{L['name']}.Wn"
+            if kt not in self._wbf:
+                self._wbf[kt] = torch.empty(U4, ld, dtype=torch.bfloat16, device=self.dev)
+                self._wbf[kn] = torch.empty(F, U4, dtype=torch.bfloat16, device=self.dev)
+            self._call("dj_cast_bf16", _ptr(W), F, U4, _ptr(self._wbf[kt]), ld, 1, _stream())
+            self._call("dj_cast_bf16", _ptr(W), F, U4, _ptr(self._wbf[kn]), U4, 0, _stream())
+        self._wbf_version = self._version
+
+    # --------------------------------------------------------------- dropout
+    def _drops(self, train: bool, seed: int) -> Dict[int, Dropout]:
+        if not train:
+            return {s: NO_DROPOUT for s in range(1, 13)}
+        out = {}
+        for s in range(1, 13):
+            rate = self.input_dropout if s <= 3 else self.dropout
+            out[s] = _lib.make_dropout(seed, s, rate) if rate > 0 else NO_DROPOUT
+        return out
+
+    def materialize_masks(self, B: int, T: int, seed: int) -> Dict[str, torch.Tensor]:
+        """Debug: the keep masks the kernels will use for (seed), in the oracle's
+        D1..D12 shapes, so a CPU checker can replay the same dropout."""
+        cfg, d = self.cfg, self._drops(True, seed)
+        M = B * T * N
+        shapes = {1: (M, 3), 2: (B * T, cfg.notes_per_bar), 3: (M, 3), 4: (M, cfg.octave_units)}
+        for L in self.layers:
+            shapes[L["site_sp"]] = (M, L["F"])
+            shapes[L["site_out"]] = (M, L["U"])
+        out = {}
+        for s, (rows, F) in shapes.items():
+            t = torch.empty(rows, F, dtype=torch.float32, device=self.dev)
+            self._call("dj_dropout_mask_materialize", d[s], rows, F, _ptr(t), _stream())
+            out[f"D{s}"] = t.view(B, T, F) if s == 2 else t.view(B, T, N, F)
+        return out
+
+    # --------------------------------------------------------------- forward
+    def workspace(self, B: int, T: int, bf16: bool, train: bool) -> Workspace:
+        key = (B, T, bf16, train)
+        if key not in self._ws:
+            self._ws[key] = Workspace(self.cfg, B, T, bf16, train, self.dev)
+        return self._ws[key]
+
+    def _style(self, ws: Workspace, style, bstride, tstride, B, T):
+        cfg, P = self.cfg, self.params
+        n = len(self.layers)
+        Wsd = (C.c_void_p * n)(*[P[f"{L['name']}.sd.W"].data_ptr() for L in self.layers])
+        bsd = (C.c_void_p * n)(*[P[f"{L['name']}.sd.b"].data_ptr() for L in self.layers])
+        Fs = (C.c_int * n)(*[L["F"] for L in self.layers])
+        sp = (C.c_void_p * n)(*[t.data_ptr() for t in ws.sp])
+        self._call("dj_style_fwd", _ptr(style), bstride, tstride, cfg.num_styles, B, T, _ptr(P["style.W"]),
+                   _ptr(P["style.b"]), n, Wsd, bsd, Fs, _ptr(ws.emb), sp, _stream())
+
+    def _gate_gemm(self, li: int, ws: Workspace, bf16: bool, M: int):
+        L, P = self.layers[li], self.params
+        U4, ld = 4 * L["U"], ws.ld[li]
+        bias = P[f"{L['name']}.lstm.b"]
+        if bf16:
+            self._call("dj_gate_gemm_bf16", _ptr(ws.A[li]), ld, _ptr(self._wbf[f"{L['name']}.Wt"]), ld,
+                       _ptr(ws.Z[li]), U4, _ptr(bias), M, U4, ld, _stream())
+        else:
+            self._call("dj_gemm_simt", _ptr(ws.A[li]), DJ_F32, ld, 1, _ptr(P[f"{L['name']}.lstm.W"]), DJ_F32,
+                       U4, 1, _ptr(ws.Z[li]), U4, _ptr(bias), M, U4, L["F"], 0, 0, 0, _stream())
+
+    def _scan_map(self, axis: str, B: int, T: int):
+        if axis == "time":   # sequences (b,n), steps t
+            return dict(S=B * N, steps=T, inner=N, outer=T * N, inner_stride=1, step=N)
+        return dict(S=B * T, steps=N, inner=1, outer=N, inner_stride=0, step=1)   # sequences (b,t), steps n
+
+    def _scan_fwd(self, li: int, ws: Workspace, B: int, T: int, train: bool):
+        L = self.layers[li]
+        m = self._scan_map(L["axis"], B, T)
+        self._call("dj_lstm_scan_fwd", _ptr(ws.Z[li]), _ptr(ws.h[li]), _ptr(ws.c[li]) if train else None, None,
+                   _ptr(self.params[f"{L['name']}.lstm.U"]), m["S"], m["steps"], L["U"], m["inner"], m["outer"],
+                   m["inner_stride"], m["step"], self.hard, _stream())
+
+    def forward_time(self, ws: Workspace, notes, notes_bstride, beat, beat_bstride, B, T, d, bf16, train,
+                     style_done: bool = False, style=None, style_bstride=0, style_tstride=0):
+        """time_axis of model.py:51-89 -> ws.h[1] ([M, Ut] canonical rows)."""
+        P = self.params
+        adt = DJ_BF16 if bf16 else DJ_F32
+        if bf16:
+            self._refresh_bf16()
+        if not style_done:
+            self._style(ws, style, style_bstride, style_tstride, B, T)
+        self._call("dj_frontend_fwd", _ptr(notes), notes_bstride, _ptr(beat), beat_bstride, B, T,
+                   _ptr(P["conv.W"]), _ptr(P["conv.b"]), _ptr(ws.sp[0]), d[1], d[2], d[4], d[5], _ptr(ws.A[0]),
+                   ws.ld[0], adt, _stream())
+        M = B * T * N
+        self._gate_gemm(0, ws, bf16, M)
+        self._scan_fwd(0, ws, B, T, train)
+        L1 = self.layers[1]
+        self._call("dj_layer_input", _ptr(ws.h[0]), self.layers[0]["U"], 0, T * N, d[6], _ptr(ws.sp[1]), L1["F"],
+                   d[7], None, 0, NO_DROPOUT, B, T, _ptr(ws.A[1]), ws.ld[1], adt, _stream())
+        self._gate_gemm(1, ws, bf16, M)
+        self._scan_fwd(1, ws, B, T, train)
+
+    def forward_note(self, ws: Workspace, h_time, h_row0, h_b_rows, chosen, chosen_bstride, B, T, d, bf16,
+                     train, target=None):
+        """note_axis of model.py:91-126 + heads (+ loss partials when target is given)."""
+        P, cfg = self.params, self.cfg
+        adt = DJ_BF16 if bf16 else DJ_F32
+        if bf16:
+            self._refresh_bf16()
+        M = B * T * N
+        L2, L3 = self.layers[2], self.layers[3]
+        self._call("dj_layer_input", _ptr(h_time), cfg.time_axis_units, h_row0, h_b_rows, d[8], _ptr(ws.sp[2]),
+                   L2["F"], d[9], _ptr(chosen), chosen_bstride, d[3], B, T, _ptr(ws.A[2]), ws.ld[2], adt, _stream())
+        self._gate_gemm(2, ws, bf16, M)
+        self._scan_fwd(2, ws, B, T, train)
+        self._call("dj_layer_input", _ptr(ws.h[2]), L2["U"], 0, T * N, d[10], _ptr(ws.sp[3]), L3["F"], d[11],
+                   None, 0, NO_DROPOUT, B, T, _ptr(ws.A[3]), ws.ld[3], adt, _stream())
+        self._gate_gemm(3, ws, bf16, M)
+        self._scan_fwd(3, ws, B, T, train)
+        self._call("dj_head_loss", _ptr(ws.h[3]), cfg.note_axis_units, d[12], _ptr(P["note_dense.W"]),
+                   _ptr(P["note_dense.b"]), _ptr(P["volume_dense.W"]), _ptr(P["volume_dense.b"]),
+                   _ptr(target), _ptr(ws.probs), _ptr(ws.dXtop) if target is not None else None,
+                   _ptr(ws.partials) if target is not None else None, M, _stream())
+
+    def forward(self, notes, chosen, beat, style, target=None, train=False, seed=0, precision=None):
+        """`model([notes, chosen, beat, style])` of model.py:151 on device tensors
+        [B,T,48,3], [B,T,48,3], [B,T,16], [B,T,23] (fp32, contiguous).  Returns
+        the workspace; ws.probs is the [B*T*48, 3] output."""
+        bf16 = (precision or self.precision) == "bf16"
+        B, T = notes.shape[0], notes.shape[1]
+        ws = self.workspace(B, T, bf16, target is not None)
+        d = self._drops(train, seed)
+        self._last = dict(ws=ws, d=d, bf16=bf16, notes=notes, style=style, B=B, T=T)
+        self.forward_time(ws, notes, T * N * 3, beat, T * 16, B, T, d, bf16, target is not None, style=style,
+                          style_bstride=T * self.cfg.num_styles, style_tstride=self.cfg.num_styles)
+        self.forward_note(ws, ws.h[1], 0, T * N, chosen, T * N * 3, B, T, d, bf16, target is not None, target)
+        return ws
+
+    # -------------------------------------------------------------- backward
+    def backward(self):
+        """tf.gradients of primary_loss w.r.t. the 28 weight tensors, for the last
+        forward(target=...).  Fills self.gflat (un-averaged local gradient) and
+        ws.loss."""
+        st = self._last
+        ws, d, bf16, B, T = st["ws"], st["d"], st["bf16"], st["B"], st["T"]
+        P, G, cfg = self.params, self.grads, self.cfg
+        M, BT = B * T * N, B * T
+        zdt = DJ_BF16 if bf16 else DJ_F32
+        self.gflat.zero_()
+        self._call("dj_head_finalize", _ptr(ws.partials), cfg.note_axis_units, _ptr(ws.loss),
+                   _ptr(G["note_dense.W"]), _ptr(G["note_dense.b"]), _ptr(G["volume_dense.W"]),
+                   _ptr(G["volume_dense.b"]), _stream())
+        dY, ldY = ws.dXtop, cfg.note_axis_units
+        first_style = True
+        for li in (3, 2, 1, 0):
+            L = self.layers[li]
+            name, U, F, ld = L["name"], L["U"], L["F"], ws.ld[li]
+            U4 = 4 * U
+            m = self._scan_map(L["axis"], B, T)
+            dZ = ws.dZ.view(-1)[:M * U4].view(M, U4)
+            self._call("dj_lstm_scan_bwd", _ptr(ws.Z[li]), _ptr(ws.c[li]), _ptr(dY), ldY, d[L["site_out"]],
+                       _ptr(P[f"{name}.lstm.U"]), _ptr(dZ), zdt, _ptr(G[f"{name}.lstm.b"]), m["S"], m["steps"], U,
+                       m["inner"], m["outer"], m["inner_stride"], m["step"], self.hard, _stream())
+            # data gradient dA = dZ . W^T
+            if bf16:
+                self._call("dj_gate_gemm_bf16", _ptr(dZ), U4, _ptr(self._wbf[f"{name}.Wn"]), U4, _ptr(ws.dA[li]),
+                           ld, None, M, F, U4, _stream())
+            else:
+                self._call("dj_gemm_simt", _ptr(dZ), DJ_F32, U4, 1, _ptr(P[f"{name}.lstm.W"]), DJ_F32, 1, U4,
+                           _ptr(ws.dA[li]), ld, None, M, F, U4, 0, 0, 0, _stream())
+            # weight gradients: dW = A^T.dZ, dU = H_{step-1}^T.dZ (contraction over the M rows)
+            adt = DJ_BF16 if bf16 else DJ_F32
+            self._call("dj_gemm_simt", _ptr(ws.A[li]), adt, 1, ld, _ptr(dZ), zdt, U4, 1, _ptr(G[f"{name}.lstm.W"]),
+                       U4, None, F, U4, M, 1, 0, 0, _stream())
+            shift, period = (N, T * N) if L["axis"] == "time" else (1, N)
+            self._call("dj_gemm_simt", _ptr(ws.h[li]), DJ_F32, 1, U, _ptr(dZ), zdt, U4, 1,
+                       _ptr(G[f"{name}.lstm.U"]), U4, None, U, U4, M, 1, shift, period, _stream())
+            # style projection backward (model.py:77-82 / 113-117)
+            self._call("dj_style_bwd_reduce", _ptr(ws.dA[li]), ld, F, _ptr(ws.sp[li]), d[L["site_sp"]], BT,
+                       _ptr(ws.ds[li]), _stream())
+            self._call("dj_gemm_simt", _ptr(ws.emb), DJ_F32, 1, cfg.style_units, _ptr(ws.ds[li]), DJ_F32, F, 1,
+                       _ptr(G[f"{name}.sd.W"]), F, None, cfg.style_units, F, BT, 1, 0, 0, _stream())
+            self._call("dj_colsum", _ptr(ws.ds[li]), F, BT, F, _ptr(G[f"{name}.sd.b"]), 0, _stream())
+            self._call("dj_gemm_simt", _ptr(ws.ds[li]), DJ_F32, F, 1, _ptr(P[f"{name}.sd.W"]), DJ_F32, 1, F,
+                       _ptr(ws.demb), cfg.style_units, None, BT, cfg.style_units, F, 0 if first_style else 1, 0, 0,
+                       _stream())
+            first_style = False
+            dY, ldY = ws.dA[li], ld
+        self._call("dj_conv_bwd", _ptr(st["notes"]), T * N * 3, B, T, _ptr(P["conv.W"]), _ptr(P["conv.b"]), d[1],
+                   d[4], _ptr(ws.dA[0]), ws.ld[0], _ptr(G["conv.W"]), _ptr(G["conv.b"]), _stream())
+        ns = cfg.num_styles
+        self._call("dj_gemm_simt", _ptr(st["style"]), DJ_F32, 1, ns, _ptr(ws.demb), DJ_F32, cfg.style_units, 1,
+                   _ptr(G["style.W"]), cfg.style_units, None, ns, cfg.style_units, BT, 1, 0, 0, _stream())
+        self._call("dj_colsum", _ptr(ws.demb), cfg.style_units, BT, cfg.style_units, _ptr(G["style.b"]), 0, _stream())
+        return ws.loss
+
+    # ------------------------------------------------------------- optimizer
+    def nadam_step(self, gscale: float = 1.0):
+        """keras.optimizers.Nadam.get_updates on the flat buffers (model.py:152)."""
+        o = self.nadam
+        t = self.iterations + 1
+        mu_t = o["beta_1"] * (1.0 - 0.5 * (0.96 ** (t * o["schedule_decay"])))
+        mu_t1 = o["beta_1"] * (1.0 - 0.5 * (0.96 ** ((t + 1) * o["schedule_decay"])))
+        ms_new = self.m_schedule * mu_t
+        ms_next = self.m_schedule * mu_t * mu_t1
+        self._call("dj_nadam_step", _ptr(self.flat), _ptr(self.gflat), _ptr(self.m), _ptr(self.v), self.flat_size,
+                   gscale, o["lr"], o["beta_1"], o["beta_2"], o["eps"], mu_t, mu_t1, ms_new, ms_next,
+                   1.0 - o["beta_2"] ** t, _stream())
+        self.iterations, self.m_schedule = t, ms_new
+        self._version += 1
+
+    def train_step(self, notes, chosen, beat, style, target, seed: int, allreduce=None, world: int = 1):
+        """One `fit` batch: forward + primary_loss + backward (+ gradient
+        all-reduce) + Nadam.  Returns the device scalar loss (no sync)."""
+        self.forward(notes, chosen, beat, style, target=target, train=True, seed=seed)
+        loss = self.backward()
+        if allreduce is not None:
+            allreduce(self.gflat)
+        self.nadam_step(1.0 / world)
+        return loss

@@ -1,0 +1,176 @@
+"""The three model objects `build_models` returns (reference model.py:128-169),
+with the slice of the Keras `Model` API the reference's callers use:
+`fit` (train.py:29), `predict` (generate.py:108,114), `load_weights` /
+`save_weights` (util.py:19, train.py:23), `summary` (util.py:16) and
+`get_layer('style')` (visualize.py:13).  NumPy in, NumPy out; all arithmetic
+runs in libdeepj_sm100.so through Engine.
+"""
+from __future__ import annotations
+
+import os
+from typing import Callable, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from .engine import Engine, N, Workspace
+from ._lib import NO_DROPOUT
+
+PREDICT_BATCH = 32   # Keras Model.predict default batch_size; it scopes the pitch_bins scramble
+
+
+def _dev(eng: Engine, a) -> torch.Tensor:
+    return torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32)).to(eng.dev, non_blocking=True)
+
+
+class History:
+    def __init__(self):
+        self.history = {"loss": []}
+
+
+class _Base:
+    def __init__(self, eng: Engine, name: str):
+        self.engine, self.name = eng, name
+
+    # -- weights (Keras HDF5 is unavailable here: h5py is not installed; .npz keyed by tensor name)
+    def save_weights(self, path: str) -> None:
+        os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
+        with open(path, "wb") as f:
+            np.savez(f, **self.engine.get_params())
+
+    def load_weights(self, path: str) -> None:
+        with np.load(path) as z:
+            self.engine.set_params({k: z[k] for k in self.engine.shapes})
+
+    def get_weights(self) -> List[np.ndarray]:
+        return list(self.engine.get_params().values())
+
+    def count_params(self) -> int:
+        return self.engine.num_params
+
+    def summary(self) -> None:
+        print(f'Model "{self.name}" (DeepJ biaxial LSTM, B200 engine, {self.engine.precision} gate GEMMs)')
+        print("-" * 64)
+        for k, s in self.engine.shapes.items():
+            print(f"{k:24s} {str(tuple(s)):>20s} {int(np.prod(s)):>12,d}")
+        print("-" * 64)
+        print(f"Total params: {self.engine.num_params:,d}")
+
+    def get_layer(self, name: str):
+        if name != "style":
+            raise ValueError(f"No such layer: {name}")
+        eng = self.engine
+
+        class _Style:
+            def get_weights(self_inner):
+                p = eng.get_params()
+                return [p["style.W"], p["style.b"]]
+        return _Style()
+
+
+class TrainModel(_Base):
+    """`model` of model.py:151-152 (inputs [notes, chosen, beat, style])."""
+
+    def predict(self, x: Sequence[np.ndarray], batch_size: int = PREDICT_BATCH) -> np.ndarray:
+        notes, chosen, beat, style = x
+        outs = []
+        for s in range(0, len(notes), batch_size):
+            sl = slice(s, s + batch_size)
+            ws = self.engine.forward(_dev(self.engine, notes[sl]), _dev(self.engine, chosen[sl]),
+                                     _dev(self.engine, beat[sl]), _dev(self.engine, style[sl]),
+                                     precision="fp32")
+            b, t = notes[sl].shape[0], notes[sl].shape[1]
+            outs.append(ws.probs.view(b, t, N, 3).cpu().numpy())
+        return np.concatenate(outs, 0)
+
+    def train_on_batch(self, x, y, seed: int = 0, allreduce=None, world: int = 1) -> float:
+        e = self.engine
+        notes, chosen, beat, style = [_dev(e, a) for a in x]
+        target = _dev(e, y[0] if isinstance(y, (list, tuple)) else y)
+        return float(e.train_step(notes, chosen, beat, style, target, seed, allreduce, world).item())
+
+    def fit(self, x, y, epochs: int = 1, callbacks: Optional[list] = None, batch_size: int = 16,
+            shuffle: bool = True, seed: int = 0, verbose: int = 1, allreduce=None, world: int = 1) -> History:
+        """Keras-style epoch loop: shuffled mini-batches (the last one may be
+        short; the pitch_bins scramble is scoped to each batch like in Keras)."""
+        hist = History()
+        y0 = y[0] if isinstance(y, (list, tuple)) else y
+        n = len(x[0])
+        rs = np.random.RandomState(seed)
+        callbacks = callbacks or []
+        for cb in callbacks:
+            cb.set_model(self)
+        step = 0
+        for ep in range(epochs):
+            order = rs.permutation(n) if shuffle else np.arange(n)
+            tot, cnt = 0.0, 0
+            for s in range(0, n, batch_size):
+                idx = order[s:s + batch_size]
+                loss = self.train_on_batch([a[idx] for a in x], y0[idx], seed=seed * 1000003 + step,
+                                           allreduce=allreduce, world=world)
+                tot += loss * len(idx); cnt += len(idx); step += 1
+            logs = {"loss": tot / max(cnt, 1)}
+            hist.history["loss"].append(logs["loss"])
+            if verbose:
+                print(f"Epoch {ep + 1}/{epochs} - loss: {logs['loss']:.4f}")
+            stop = False
+            for cb in callbacks:
+                cb.on_epoch_end(ep, logs)
+                stop = stop or getattr(cb, "stop_training", False)
+            if stop:
+                break
+        return hist
+
+
+class TimeModel(_Base):
+    """`time_model` of model.py:155: [notes, beat, style] -> time_out [G,T,48,Ut]."""
+
+    def predict(self, x: Sequence[np.ndarray], batch_size: int = PREDICT_BATCH) -> np.ndarray:
+        e = self.engine
+        notes, beat, style = x
+        outs = []
+        d = {s: NO_DROPOUT for s in range(1, 13)}
+        for s in range(0, len(notes), batch_size):
+            n_, b_, s_ = [_dev(e, a[s:s + batch_size]) for a in (notes, beat, style)]
+            B, T = n_.shape[0], n_.shape[1]
+            ws = e.workspace(B, T, False, False)
+            e.forward_time(ws, n_, T * N * 3, b_, T * 16, B, T, d, False, False, style=s_,
+                           style_bstride=T * e.cfg.num_styles, style_tstride=e.cfg.num_styles)
+            outs.append(ws.h[1].view(B, T, N, -1).cpu().numpy())
+        return np.concatenate(outs, 0)
+
+
+class NoteModel(_Base):
+    """`note_model` of model.py:157-167: [note_features [G,1,48,Ut], chosen [G,1,48,3],
+    style [G,1,23]] -> [G,1,48,3]."""
+
+    def predict(self, x: Sequence[np.ndarray], batch_size: int = PREDICT_BATCH) -> np.ndarray:
+        e = self.engine
+        feats, chosen, style = x
+        outs = []
+        d = {s: NO_DROPOUT for s in range(1, 13)}
+        for s in range(0, len(feats), batch_size):
+            f_, c_, s_ = [_dev(e, a[s:s + batch_size]) for a in (feats, chosen, style)]
+            B, T = f_.shape[0], f_.shape[1]
+            ws = e.workspace(B, T, False, False)
+            e._style(ws, s_, T * e.cfg.num_styles, e.cfg.num_styles, B, T)
+            e.forward_note(ws, f_.view(B * T * N, -1), 0, T * N, c_, T * N * 3, B, T, d, False, False)
+            outs.append(ws.probs.view(B, T, N, 3).cpu().numpy())
+        return np.concatenate(outs, 0)
+
+
+def primary_loss(y_true: np.ndarray, y_pred: np.ndarray) -> np.ndarray:
+    """Host restatement of model.py:14-20 for callers that want the per-(b,t)
+    loss map of already-computed predictions (the training path computes the
+    loss on device in dj_head_loss)."""
+    y_true = np.asarray(y_true, dtype=np.float32); y_pred = np.asarray(y_pred, dtype=np.float32)
+    eps = np.float32(1e-7)
+
+    def bce(t, o):
+        o = np.clip(o, eps, 1 - eps)
+        return -(t * np.log(o) + (1 - t) * np.log1p(-o)).mean(-1)
+    played = y_true[..., 0]
+    out = bce(y_true[..., 0], y_pred[..., 0])
+    out = out + bce(y_true[..., 1], played * y_pred[..., 1] + (1 - played) * y_true[..., 1])
+    d = y_true[..., 2] - (played * y_pred[..., 2] + (1 - played) * y_true[..., 2])
+    return out + (d * d).mean(-1)

@@ -498,7 +498,7 @@ def generate(p, cfg: Config, styles: Sequence[np.ndarray], num_steps: int, unifo
     gens = [Generation(cfg, s, default_temp) for s in styles]
     G, N, Ut = len(gens), cfg.num_notes, cfg.time_axis_units
     act = recurrent_activation
-    out_steps, prob_steps = [], []
+    out_steps, prob_steps, decision_steps = [], [], []
     with torch.no_grad():
         for t in range(num_steps):
             notes = torch.tensor(np.stack([g.notes_memory for g in gens]), dtype=dtype)
@@ -507,6 +507,7 @@ def generate(p, cfg: Config, styles: Sequence[np.ndarray], num_steps: int, unifo
             feats = time_model_predict(p, cfg, notes, beat, sty, 32, act)[:, -1:, :, :]   # :108-109
             sty1 = sty[:, -1:, :]
             probs_t = np.zeros((G, N, cfg.note_units), dtype=np.float32 if dtype == torch.float32 else np.float64)
+            decisions_t = np.zeros((G, N, cfg.note_units))
             if mode == "literal":
                 for n in range(N):
                     chosen = torch.tensor(np.stack([g.next_note for g in gens])[:, None], dtype=dtype)
@@ -514,6 +515,7 @@ def generate(p, cfg: Config, styles: Sequence[np.ndarray], num_steps: int, unifo
                     for i, g in enumerate(gens):
                         probs_t[i, n] = pred[i, 0, n]
                         g.choose(pred[i][-1], n, rand)
+                        decisions_t[i, n] = g.next_note[n]
                         if forced_events is not None:
                             g.next_note[n] = forced_events[t, i, n]
             else:
@@ -544,12 +546,15 @@ def generate(p, cfg: Config, styles: Sequence[np.ndarray], num_steps: int, unifo
                         row = np.zeros((N, cfg.note_units), dtype=pred_n.dtype)
                         row[n] = pred_n[i]
                         g.choose(row, n, rand)
+                        decisions_t[i, n] = g.next_note[n]
                         if forced_events is not None:
                             g.next_note[n] = forced_events[t, i, n]
             out_steps.append(np.stack([g.end_time(t) for g in gens]))
             prob_steps.append(probs_t)
+            decision_steps.append(decisions_t)
     events = np.stack(out_steps)            # [steps, G, N, 3]
     info = {"uniforms_used": rand.pos, "min_margin": min(g.min_margin for g in gens)}
+    info["decisions"] = np.stack(decision_steps)   # the oracle's own draws (== events unless forced)
     if return_probs:
         info["probs"] = np.stack(prob_steps)
     return events, info

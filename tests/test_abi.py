@@ -1,0 +1,81 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads without a GPU and
+exports every symbol include/deepj_b200.h declares; the host-side mirror of
+the reference interface keeps the reference's names."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import music_generator_b200 as pkg
+    from music_generator_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        pkg.build()
+    return _lib.load()
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "deepj_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(dj_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_every_declared_symbol_is_exported_and_bound(lib):
+    from music_generator_b200 import _lib
+    syms = declared_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/deepj_b200.h but not exported"
+        assert s in _lib.SIGNATURES, f"{s} has no ctypes signature"
+    assert sorted(_lib.SIGNATURES) == syms
+
+
+def test_version_and_error_convention(lib):
+    from music_generator_b200 import _lib
+    assert lib.dj_version() >= 100
+    d = _lib.Dropout()
+    assert lib.dj_make_dropout(7, 4, ctypes.c_float(0.5), ctypes.byref(d)) == 0
+    assert d.mode == 1 and d.thr == 0x80000000 and d.scale == 2.0
+    assert lib.dj_make_dropout(7, 1, ctypes.c_float(0.2), ctypes.byref(d)) == 0 and d.mode == 2
+    assert lib.dj_make_dropout(7, 1, ctypes.c_float(1.5), ctypes.byref(d)) < 0       # invalid argument -> <0
+    assert b"rate" in lib.dj_last_error()
+    # unsupported shape is an error, never a fallback
+    rc = lib.dj_lstm_scan_fwd(None, None, None, None, None, 1, 1, 512, 1, 0, 0, 0, 1, None)
+    assert rc < 0
+
+
+def test_dropout_key_matches_numpy_twin(lib):
+    from music_generator_b200 import _lib
+    import helpers
+    for seed, site in ((7, 4), (123456789012345, 11), (0, 1)):
+        d = _lib.make_dropout(seed, site, 0.5)
+        assert d.key == int(helpers.site_key(seed, site))
+
+
+def test_reference_entry_points_exist():
+    import constants
+    assert constants.NUM_STYLES == 23 and constants.NUM_NOTES == 48 and constants.SEQ_LEN == 128
+    assert constants.TIME_AXIS_UNITS == 256 and constants.NOTE_AXIS_UNITS == 128
+    import dataset, util
+    assert util.one_hot(2, 4).tolist() == [0, 0, 1, 0]
+    assert dataset.compute_beat(17, 16)[1] == 1
+    g = dataset.compute_genre(2)
+    assert np.count_nonzero(g) == 14 and abs(g.sum() - 1) < 1e-12
+    assert dataset.unclamp_midi(np.ones((5, 48, 3))).shape == (5, 84, 3)
+    src = open(os.path.join(ROOT, "model.py")).read()
+    assert "def build_models(time_steps=SEQ_LEN, input_dropout=0.2, dropout=0.5" in src
+
+
+def test_engine_refuses_to_run_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from music_generator_b200.engine import Engine
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        Engine()

@@ -1,0 +1,79 @@
+"""Drop-in for the reference's train.py: `python train.py` builds or loads the
+model and calls `models[0].fit(...)` with best-loss checkpointing and early
+stopping (train.py:18-29).  Under torchrun it trains data-parallel: one process
+per GPU, gradients summed with one NCCL all-reduce of the flat buffer."""
+import argparse
+import os
+
+import numpy as np
+
+from constants import *
+from dataset import synthetic_all
+from util import build_or_load
+
+
+class ModelCheckpoint:
+    """keras.callbacks.ModelCheckpoint(monitor='loss', save_best_only=True,
+    save_weights_only=True) -- train.py:23."""
+
+    def __init__(self, path):
+        self.path, self.best, self.model = path, np.inf, None
+
+    def set_model(self, model):
+        self.model = model
+
+    def on_epoch_end(self, epoch, logs):
+        if logs['loss'] < self.best:
+            self.best = logs['loss']
+            self.model.save_weights(self.path)
+
+
+class EarlyStopping:
+    """keras.callbacks.EarlyStopping(monitor='loss', patience=5) -- train.py:24."""
+
+    def __init__(self, patience=5):
+        self.patience, self.best, self.wait, self.stop_training = patience, np.inf, 0, False
+
+    def set_model(self, model):
+        pass
+
+    def on_epoch_end(self, epoch, logs):
+        if logs['loss'] < self.best:
+            self.best, self.wait = logs['loss'], 0
+        else:
+            self.wait += 1
+            self.stop_training = self.wait >= self.patience
+
+
+def train(models, epochs=1000, num_seqs=256):
+    print('Loading data')
+    # the reference loads a MIDI corpus it does not ship (dataset.load_all);
+    # synthetic piano-rolls of the same shape stand in
+    train_data, train_labels = synthetic_all(num_seqs, SEQ_LEN)
+    allreduce, world, rank = None, 1, 0
+    if 'RANK' in os.environ and int(os.environ.get('WORLD_SIZE', '1')) > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))
+        dist.init_process_group('nccl')
+        world, rank = dist.get_world_size(), dist.get_rank()
+        train_data = [a[rank::world] for a in train_data]
+        train_labels = [a[rank::world] for a in train_labels]
+        allreduce = lambda g: dist.all_reduce(g)
+    cbs = [ModelCheckpoint(MODEL_FILE), EarlyStopping(patience=5)] if rank == 0 else []
+    print('Training')
+    models[0].fit(train_data, train_labels, epochs=epochs, callbacks=cbs, batch_size=BATCH_SIZE,
+                  allreduce=allreduce, world=world, verbose=1 if rank == 0 else 0)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--epochs', type=int, default=1000)
+    ap.add_argument('--num-seqs', type=int, default=256)
+    args = ap.parse_args()
+    models = build_or_load()
+    train(models, args.epochs, args.num_seqs)
+
+
+if __name__ == '__main__':
+    main()
