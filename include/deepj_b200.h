@@ -106,10 +106,10 @@ int dj_gemm_simt(const void* A, int a_dtype, int64_t a_sm, int64_t a_sk, const v
 int dj_gate_gemm_bf16(const void* A, int64_t lda, const void* Bt, int64_t ldb, float* C, int64_t ldc,
                       const float* bias, int M, int N, int K, void* stream);
 /* tcgen05 weight-gradient GEMM (contraction over the M rows, split across CTAs,
- * fp32 atomics):  C[Ka,Nb] += A[M,Ka]^T . B[M,Nb]   (bf16 operands, MN-major)
- *   a_shift/a_period as in dj_gemm_simt (rows shifted by a_shift, zero-filled). */
+ * fp32 global reductions):  C[Ka,Nb] += A[M,Ka]^T . B[M,Nb]   (bf16, MN-major).
+ * The h_{step-1} operand of dU comes pre-shifted from dj_lstm_scan_fwd. */
 int dj_wgrad_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, float* C, int64_t ldc,
-                       int Ka, int Nb, int64_t M, int64_t a_shift, int64_t a_period, void* stream);
+                       int Ka, int Nb, int64_t M, void* stream);
 /* fp32 -> bf16 operand copies: out[r, c] = in[r, c] (c<cols) else 0, out ld = ldo;
  * transpose!=0 writes out[c, r] (ldo >= rows). */
 int dj_cast_bf16(const float* in, int rows, int cols, void* out, int ldo, int transpose, void* stream);
@@ -121,9 +121,11 @@ int dj_cast_bf16(const float* in, int rows, int cols, void* out, int ldo, int tr
  *   Z [M,4*units] fp32: in = x.W+b, out = activated gates i,f,g,o (saved for bwd)
  *   row(seq, step) = (seq/seq_inner)*seq_outer_stride + (seq%seq_inner)*seq_inner_stride
  *                    + step*step_stride
- *   h_out [M,units] fp32; c_out nullable (training only); h_bf16 nullable.
+ *   h_out [M,units] fp32; c_out nullable (training only); h_prev_bf16 nullable:
+ *   bf16 [M,units] receiving h_{step-1} at each row (zeros at step 0) = the A
+ *   operand of the recurrent weight gradient dU = H_{step-1}^T.dZ.
  *   hard != 0: hard_sigmoid gates (Keras < 2.3), else sigmoid. */
-int dj_lstm_scan_fwd(float* Z, float* h_out, float* c_out, void* h_bf16, const float* Uw, int S,
+int dj_lstm_scan_fwd(float* Z, float* h_out, float* c_out, void* h_prev_bf16, const float* Uw, int S,
                      int steps, int units, int seq_inner, int64_t seq_outer_stride,
                      int64_t seq_inner_stride, int64_t step_stride, int hard, void* stream);
 /* reverse scan: consumes gates/c and dY (gradient w.r.t. the DROPPED-OUT layer

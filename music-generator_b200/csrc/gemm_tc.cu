@@ -272,6 +272,131 @@ gate_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 2) tmem_dealloc(tmem_base, ACC_STAGES * BN);
 }
 
+// ---------------------------------------------------------------------------
+// C[Ka,Nb] += A[M,Ka]^T . B[M,Nb]   (weight gradients; both operands MN-major)
+//
+// The contraction runs over the M activation rows, so both operands sit in
+// memory with the NON-contracted index contiguous.  TMA boxes of 64 columns x
+// 64 rows with the 128B swizzle land in smem exactly in UMMA's MN-major SW128
+// canonical layout (8 rows x 128 B atoms; SBO = 1024 B between 8-row groups along
+// K, LBO = one whole box between 64-column groups).  One CTA owns one 128x256
+// output tile and a slice of M; fp32 partial sums leave TMEM through vectorised
+// global reductions (red.global.add.v4.f32).
+// ---------------------------------------------------------------------------
+constexpr int WG_BM = 128, WG_BN = 256, WG_BK = 64, WG_STAGES = 4;
+constexpr int WG_BOX_BYTES = WG_BK * 128;                 // one 64-column box: 8 KB
+constexpr int WG_A_BYTES = (WG_BM / 64) * WG_BOX_BYTES;   // 16 KB
+constexpr int WG_B_BYTES = (WG_BN / 64) * WG_BOX_BYTES;   // 32 KB
+struct WgradSmem {
+  static constexpr int A_OFF = 0;
+  static constexpr int B_OFF = WG_STAGES * WG_A_BYTES;
+  static constexpr int BAR_OFF = B_OFF + WG_STAGES * WG_B_BYTES;
+  static constexpr int TOTAL = BAR_OFF + 256 + 1024;
+};
+
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  float* __restrict__ C, int64_t ldc, int Ka, int Nb, int64_t M, int num_tiles, int kb_per_split) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bars = sbase + WgradSmem::BAR_OFF;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (WG_STAGES + s); };
+  const uint32_t done_bar = bars + 8u * (2 * WG_STAGES);
+  uint32_t* tmem_slot = (uint32_t*)(smem + WgradSmem::BAR_OFF + 8 * (2 * WG_STAGES + 1));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_n = (Nb + WG_BN - 1) / WG_BN;
+  const int tile = blockIdx.x % num_tiles, split = blockIdx.x / num_tiles;
+  const int ka0 = (tile / tiles_n) * WG_BM, nb0 = (tile % tiles_n) * WG_BN;
+  const int total_kb = (int)((M + WG_BK - 1) / WG_BK);
+  const int kb_begin = split * kb_per_split;
+  const int kb_end = min(total_kb, kb_begin + kb_per_split);
+  const int nkb = max(0, kb_end - kb_begin);
+
+  if (warp == 0 && lane == 0) { prefetch_tmap(&tmA); prefetch_tmap(&tmB); }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < WG_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(done_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(smem_u32(tmem_slot), WG_BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {   // ===== TMA producer: 2 boxes of A, 4 boxes of B per stage =====
+      int stage = 0; uint32_t phase = 0;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(empty_bar(stage), phase ^ 1);
+        mbar_expect_tx(full_bar(stage), WG_A_BYTES + WG_B_BYTES);
+        const int r0 = kb * WG_BK;
+#pragma unroll
+        for (int j = 0; j < WG_BM / 64; ++j)
+          tma_load_2d(sbase + WgradSmem::A_OFF + stage * WG_A_BYTES + j * WG_BOX_BYTES, &tmA, full_bar(stage), ka0 + 64 * j, r0);
+#pragma unroll
+        for (int j = 0; j < WG_BN / 64; ++j)
+          tma_load_2d(sbase + WgradSmem::B_OFF + stage * WG_B_BYTES + j * WG_BOX_BYTES, &tmB, full_bar(stage), nb0 + 64 * j, r0);
+        if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && nkb > 0) {   // ===== MMA issuer =====
+      constexpr uint32_t idesc = make_idesc(WG_BM, WG_BN, 1, 1);
+      int stage = 0; uint32_t phase = 0;
+      for (int i = 0; i < nkb; ++i) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        const uint32_t a0 = sbase + WgradSmem::A_OFF + stage * WG_A_BYTES;
+        const uint32_t b0 = sbase + WgradSmem::B_OFF + stage * WG_B_BYTES;
+#pragma unroll
+        for (int k = 0; k < WG_BK / 16; ++k) {   // 16 contraction rows = 2048 B further down the box
+          const uint64_t adesc = make_smem_desc(a0 + k * 2048, WG_BOX_BYTES, 1024);
+          const uint64_t bdesc = make_smem_desc(b0 + k * 2048, WG_BOX_BYTES, 1024);
+          umma_bf16(tmem_base, adesc, bdesc, idesc, (i | k) != 0);
+        }
+        umma_commit(empty_bar(stage));
+        if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(done_bar);
+    }
+  } else if (warp >= 4 && nkb > 0) {   // ===== epilogue: TMEM -> fp32 global reductions =====
+    const int e = warp - 4;
+    mbar_wait(done_bar, 0);
+    tc_fence_after();
+    const int row = ka0 + 32 * e + lane;
+#pragma unroll 1
+    for (int c = 0; c < WG_BN / 32; ++c) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(32 * e) << 16) + (uint32_t)(c * 32), v);
+      if (row < Ka) {
+        float* dst = C + (int64_t)row * ldc + nb0 + c * 32;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int n = nb0 + c * 32 + 4 * q;
+          if (n + 3 < Nb) {
+            red_add_v4(dst + 4 * q, __uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                       __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+          } else {
+            for (int j = 0; j < 4; ++j)
+              if (n + j < Nb) atomicAdd(dst + 4 * q + j, __uint_as_float(v[4 * q + j]));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, WG_BN);
+}
+
 // ---- host side ----------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -331,9 +456,27 @@ extern "C" int dj_gate_gemm_bf16(const void* A, int64_t lda, const void* Bt, int
 }
 
 extern "C" int dj_wgrad_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, float* C, int64_t ldc,
-                                  int Ka, int Nb, int64_t M, int64_t a_shift, int64_t a_period, void* stream) {
-  (void)A; (void)lda; (void)B; (void)ldb; (void)C; (void)ldc; (void)Ka; (void)Nb; (void)M; (void)a_shift;
-  (void)a_period; (void)stream;
-  DJ_CHECK_ARG(false, "dj_wgrad_gemm_bf16: not built yet");
-  return -1;
+                                  int Ka, int Nb, int64_t M, void* stream) {
+  DJ_CHECK_ARG(A && B && C, "dj_wgrad_gemm_bf16: NULL pointer");
+  DJ_CHECK_ARG(Ka > 0 && Nb > 0 && M > 0, "dj_wgrad_gemm_bf16: bad shape");
+  DJ_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0 && ldc % 4 == 0 && lda >= Ka && ldb >= Nb && ldc >= Nb,
+               "dj_wgrad_gemm_bf16: leading dimensions must be 16-byte multiples and cover the widths");
+  DJ_CHECK_ARG(((uintptr_t)A % 16) == 0 && ((uintptr_t)B % 16) == 0 && ((uintptr_t)C % 16) == 0,
+               "dj_wgrad_gemm_bf16: pointers must be 16-byte aligned");
+  CUtensorMap tmA, tmB;
+  int rc;
+  if ((rc = make_map_2d(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, A, (uint64_t)Ka, (uint64_t)M, (uint64_t)lda, 64, WG_BK))) return rc;
+  if ((rc = make_map_2d(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, B, (uint64_t)Nb, (uint64_t)M, (uint64_t)ldb, 64, WG_BK))) return rc;
+  DJ_CUDA(cudaFuncSetAttribute((const void*)wgrad_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WgradSmem::TOTAL));
+  const int tiles = ((Ka + WG_BM - 1) / WG_BM) * ((Nb + WG_BN - 1) / WG_BN);
+  const int total_kb = (int)((M + WG_BK - 1) / WG_BK);
+  int splits = dj_num_sms() / tiles;
+  if (splits < 1) splits = 1;
+  if (splits > total_kb) splits = total_kb;
+  const int kbps = (total_kb + splits - 1) / splits;
+  splits = (total_kb + kbps - 1) / kbps;
+  wgrad_gemm_kernel<<<tiles * splits, NUM_THREADS, WgradSmem::TOTAL, (cudaStream_t)stream>>>(tmA, tmB, C, ldc, Ka, Nb, M,
+                                                                                             tiles, kbps);
+  DJ_LAUNCH_CHECK();
+  return 0;
 }

@@ -39,6 +39,23 @@ __device__ __forceinline__ void prefetch_l2(const void* p) {
 
 constexpr int UC = 32;   // hidden units owned by one CTA (=> 128 gate columns)
 
+// Blackwell packed fp32 FMA (two independent IEEE fp32 FMAs per issue slot, SASS
+// FFMA2): the recurrent h.U product is CUDA-core work (fp32 recurrence, see
+// DESIGN.md) and plain 3-register FFMA issues at half rate on sm_100.
+__device__ __forceinline__ uint64_t pack2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+
 template <int U, int BS>
 struct FwdSmem {
   static constexpr int HSTR = U * 4 + 4;            // floats per 4-sequence group (+4: bank skew)
@@ -104,13 +121,14 @@ scan_fwd_kernel(float* __restrict__ Z, float* __restrict__ Hout, float* __restri
 
     for (int t = 0; t < steps; ++t) {
       const int cur = t & 1, nxt = cur ^ 1;
-      float acc[4][2][4];
+      uint64_t acc2[4][2][2];   // [seq][unit half][gate pair (i,f) / (g,o)]
 #pragma unroll
       for (int s = 0; s < 4; ++s)
 #pragma unroll
-        for (int hf = 0; hf < 2; ++hf)
-#pragma unroll
-          for (int g = 0; g < 4; ++g) acc[s][hf][g] = zn[s][hf][g];
+        for (int hf = 0; hf < 2; ++hf) {
+          acc2[s][hf][0] = pack2(zn[s][hf][0], zn[s][hf][1]);
+          acc2[s][hf][1] = pack2(zn[s][hf][2], zn[s][hf][3]);
+        }
       if (t + 1 < steps) {   // register prefetch of the next step's pre-activations
 #pragma unroll
         for (int s = 0; s < 4; ++s) {
@@ -127,21 +145,25 @@ scan_fwd_kernel(float* __restrict__ Z, float* __restrict__ Hout, float* __restri
 #pragma unroll 4
       for (int k = 0; k < U; ++k) {
         const float4 hv = *reinterpret_cast<const float4*>(hb + k * 4);
-        const float4 u0 = *reinterpret_cast<const float4*>(ua + k * (UC * 4));
-        const float4 u1 = *reinterpret_cast<const float4*>(ua + k * (UC * 4) + 64);
-        const float h4[4] = {hv.x, hv.y, hv.z, hv.w};
+        const ulonglong2 u0 = *reinterpret_cast<const ulonglong2*>(ua + k * (UC * 4));
+        const ulonglong2 u1 = *reinterpret_cast<const ulonglong2*>(ua + k * (UC * 4) + 64);
+        const uint64_t hs[4] = {pack2(hv.x, hv.x), pack2(hv.y, hv.y), pack2(hv.z, hv.z), pack2(hv.w, hv.w)};
 #pragma unroll
         for (int s = 0; s < 4; ++s) {
-          acc[s][0][0] = fmaf(h4[s], u0.x, acc[s][0][0]);
-          acc[s][0][1] = fmaf(h4[s], u0.y, acc[s][0][1]);
-          acc[s][0][2] = fmaf(h4[s], u0.z, acc[s][0][2]);
-          acc[s][0][3] = fmaf(h4[s], u0.w, acc[s][0][3]);
-          acc[s][1][0] = fmaf(h4[s], u1.x, acc[s][1][0]);
-          acc[s][1][1] = fmaf(h4[s], u1.y, acc[s][1][1]);
-          acc[s][1][2] = fmaf(h4[s], u1.z, acc[s][1][2]);
-          acc[s][1][3] = fmaf(h4[s], u1.w, acc[s][1][3]);
+          acc2[s][0][0] = ffma2(hs[s], u0.x, acc2[s][0][0]);
+          acc2[s][0][1] = ffma2(hs[s], u0.y, acc2[s][0][1]);
+          acc2[s][1][0] = ffma2(hs[s], u1.x, acc2[s][1][0]);
+          acc2[s][1][1] = ffma2(hs[s], u1.y, acc2[s][1][1]);
         }
       }
+      float acc[4][2][4];
+#pragma unroll
+      for (int s = 0; s < 4; ++s)
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          unpack2(acc2[s][hf][0], acc[s][hf][0], acc[s][hf][1]);
+          unpack2(acc2[s][hf][1], acc[s][hf][2], acc[s][hf][3]);
+        }
       float hnew[2][4];
 #pragma unroll
       for (int s = 0; s < 4; ++s) {
@@ -162,7 +184,10 @@ scan_fwd_kernel(float* __restrict__ Z, float* __restrict__ Hout, float* __restri
             zr[0] = gi; zr[U] = gf; zr[2 * U] = gg; zr[3 * U] = go;
             Hout[r * U + col] = hn;
             if (Cout != nullptr) Cout[r * U + col] = cn;
-            if (Hbf != nullptr) Hbf[r * U + col] = __float2bfloat16_rn(hn);
+            if (Hbf != nullptr) {   // h_{t} is the "previous h" of step t+1; step 0 sees zeros
+              if (t + 1 < steps) Hbf[(r + map.step_stride) * U + col] = __float2bfloat16_rn(hn);
+              if (t == 0) Hbf[r * U + col] = __float2bfloat16_rn(0.f);
+            }
           }
         }
       }
@@ -299,31 +324,35 @@ scan_bwd_kernel(const float* __restrict__ G, const float* __restrict__ Cst, cons
       }
       __syncthreads();
       // ---- B: partial dh_{t-1} over this CTA's 128 gate columns
-      float P[4][KQ][4];
+      uint64_t P2[4][KQ][2];
 #pragma unroll
       for (int s = 0; s < 4; ++s)
 #pragma unroll
-        for (int q = 0; q < KQ; ++q)
-#pragma unroll
-          for (int i = 0; i < 4; ++i) P[s][q][i] = 0.f;
+        for (int q = 0; q < KQ; ++q) P2[s][q][0] = P2[s][q][1] = 0ull;
       if (t > 0) {
 #pragma unroll 2
         for (int j = 0; j < 128; ++j) {
           const float4 dv = *reinterpret_cast<const float4*>(dzb + j * SM::DZS + sg * 4);
-          const float d4[4] = {dv.x, dv.y, dv.z, dv.w};
+          const uint64_t d2[4] = {pack2(dv.x, dv.x), pack2(dv.y, dv.y), pack2(dv.z, dv.z), pack2(dv.w, dv.w)};
 #pragma unroll
           for (int q = 0; q < KQ; ++q) {
-            const float4 uv = *reinterpret_cast<const float4*>(UsT + j * U + q * 64 + ug * 4);
+            const ulonglong2 uv = *reinterpret_cast<const ulonglong2*>(UsT + j * U + q * 64 + ug * 4);
 #pragma unroll
             for (int s = 0; s < 4; ++s) {
-              P[s][q][0] = fmaf(d4[s], uv.x, P[s][q][0]);
-              P[s][q][1] = fmaf(d4[s], uv.y, P[s][q][1]);
-              P[s][q][2] = fmaf(d4[s], uv.z, P[s][q][2]);
-              P[s][q][3] = fmaf(d4[s], uv.w, P[s][q][3]);
+              P2[s][q][0] = ffma2(d2[s], uv.x, P2[s][q][0]);
+              P2[s][q][1] = ffma2(d2[s], uv.y, P2[s][q][1]);
             }
           }
         }
       }
+      float P[4][KQ][4];
+#pragma unroll
+      for (int s = 0; s < 4; ++s)
+#pragma unroll
+        for (int q = 0; q < KQ; ++q) {
+          unpack2(P2[s][q][0], P[s][q][0], P[s][q][1]);
+          unpack2(P2[s][q][1], P[s][q][2], P[s][q][3]);
+        }
       cluster_wait();     // every CTA has consumed last step's slots
       // ---- C: reduce-scatter.  k = q*64 + ug*4 + i  ->  owner CTA 2q + (ug>=8), unit (ug*4+i)%32
       if (t > 0) {
@@ -380,13 +409,13 @@ int pick_clusters(int C, int ntiles) {
 
 }  // namespace
 
-extern "C" int dj_lstm_scan_fwd(float* Z, float* h_out, float* c_out, void* h_bf16, const float* Uw, int S,
+extern "C" int dj_lstm_scan_fwd(float* Z, float* h_out, float* c_out, void* h_prev_bf16, const float* Uw, int S,
                                 int steps, int units, int seq_inner, int64_t seq_outer_stride,
                                 int64_t seq_inner_stride, int64_t step_stride, int hard, void* stream) {
   DJ_CHECK_ARG(Z && h_out && Uw, "dj_lstm_scan_fwd: NULL pointer");
   DJ_CHECK_ARG(S > 0 && steps > 0 && seq_inner > 0, "dj_lstm_scan_fwd: bad sizes");
   ScanMap map{seq_inner, seq_outer_stride, seq_inner_stride, step_stride};
-  __nv_bfloat16* hb = (__nv_bfloat16*)h_bf16;
+  __nv_bfloat16* hb = (__nv_bfloat16*)h_prev_bf16;
   void* args[] = {&Z, &h_out, &c_out, &hb, (void*)&Uw, &S, &steps, &map, &hard};
   cudaStream_t st = (cudaStream_t)stream;
   if (units == 256) {

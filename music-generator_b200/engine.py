@@ -49,6 +49,9 @@ class Workspace:
             self.Z.append(torch.empty(M, 4 * L["U"], **f32))
             self.h.append(torch.empty(M, L["U"], **f32))
             self.c.append(torch.empty(M, L["U"], **f32) if train else None)
+        # h_{step-1} in bf16: A operand of the tcgen05 recurrent-weight gradient
+        self.hprev = [torch.empty(M, L["U"], dtype=torch.bfloat16, device=dev) if (train and bf16) else None
+                      for L in cfg.layers()]
         self.probs = torch.empty(M, 3, **f32)
         if train:
             un = cfg.note_axis_units
@@ -228,6 +231,7 @@ class Engine:
         L, P = self.layers[li], self.params
         U4, ld = 4 * L["U"], ws.ld[li]
         bias = P[f"{L['name']}.lstm.b"]
+        self._tag = ":" + L["name"]
         if bf16:
             self._call("dj_gate_gemm_bf16", _ptr(ws.A[li]), ld, _ptr(self._wbf[f"{L['name']}.Wt"]), ld,
                        _ptr(ws.Z[li]), U4, _ptr(bias), M, U4, ld, _stream())
@@ -243,9 +247,12 @@ class Engine:
     def _scan_fwd(self, li: int, ws: Workspace, B: int, T: int, train: bool):
         L = self.layers[li]
         m = self._scan_map(L["axis"], B, T)
-        self._call("dj_lstm_scan_fwd", _ptr(ws.Z[li]), _ptr(ws.h[li]), _ptr(ws.c[li]) if train else None, None,
+        self._tag = ":" + L["name"]
+        self._call("dj_lstm_scan_fwd", _ptr(ws.Z[li]), _ptr(ws.h[li]), _ptr(ws.c[li]) if train else None,
+                   _ptr(ws.hprev[li]) if train else None,
                    _ptr(self.params[f"{L['name']}.lstm.U"]), m["S"], m["steps"], L["U"], m["inner"], m["outer"],
                    m["inner_stride"], m["step"], self.hard, _stream())
+        self._tag = ""
 
     def forward_time(self, ws: Workspace, notes, notes_bstride, beat, beat_bstride, B, T, d, bf16, train,
                      style_done: bool = False, style=None, style_bstride=0, style_tstride=0):
@@ -324,6 +331,7 @@ class Engine:
             L = self.layers[li]
             name, U, F, ld = L["name"], L["U"], L["F"], ws.ld[li]
             U4 = 4 * U
+            self._tag = ":bwd:" + name
             m = self._scan_map(L["axis"], B, T)
             dZ = ws.dZ.view(-1)[:M * U4].view(M, U4)
             self._call("dj_lstm_scan_bwd", _ptr(ws.Z[li]), _ptr(ws.c[li]), _ptr(dY), ldY, d[L["site_out"]],
@@ -337,12 +345,17 @@ class Engine:
                 self._call("dj_gemm_simt", _ptr(dZ), DJ_F32, U4, 1, _ptr(P[f"{name}.lstm.W"]), DJ_F32, 1, U4,
                            _ptr(ws.dA[li]), ld, None, M, F, U4, 0, 0, 0, _stream())
             # weight gradients: dW = A^T.dZ, dU = H_{step-1}^T.dZ (contraction over the M rows)
-            adt = DJ_BF16 if bf16 else DJ_F32
-            self._call("dj_gemm_simt", _ptr(ws.A[li]), adt, 1, ld, _ptr(dZ), zdt, U4, 1, _ptr(G[f"{name}.lstm.W"]),
-                       U4, None, F, U4, M, 1, 0, 0, _stream())
-            shift, period = (N, T * N) if L["axis"] == "time" else (1, N)
-            self._call("dj_gemm_simt", _ptr(ws.h[li]), DJ_F32, 1, U, _ptr(dZ), zdt, U4, 1,
-                       _ptr(G[f"{name}.lstm.U"]), U4, None, U, U4, M, 1, shift, period, _stream())
+            if bf16:
+                self._call("dj_wgrad_gemm_bf16", _ptr(ws.A[li]), ld, _ptr(dZ), U4, _ptr(G[f"{name}.lstm.W"]), U4,
+                           F, U4, M, _stream())
+                self._call("dj_wgrad_gemm_bf16", _ptr(ws.hprev[li]), U, _ptr(dZ), U4, _ptr(G[f"{name}.lstm.U"]),
+                           U4, U, U4, M, _stream())
+            else:
+                self._call("dj_gemm_simt", _ptr(ws.A[li]), DJ_F32, 1, ld, _ptr(dZ), zdt, U4, 1,
+                           _ptr(G[f"{name}.lstm.W"]), U4, None, F, U4, M, 1, 0, 0, _stream())
+                shift, period = (N, T * N) if L["axis"] == "time" else (1, N)
+                self._call("dj_gemm_simt", _ptr(ws.h[li]), DJ_F32, 1, U, _ptr(dZ), zdt, U4, 1,
+                           _ptr(G[f"{name}.lstm.U"]), U4, None, U, U4, M, 1, shift, period, _stream())
             # style projection backward (model.py:77-82 / 113-117)
             self._call("dj_style_bwd_reduce", _ptr(ws.dA[li]), ld, F, _ptr(ws.sp[li]), d[L["site_sp"]], BT,
                        _ptr(ws.ds[li]), _stream())
@@ -354,6 +367,7 @@ class Engine:
                        _stream())
             first_style = False
             dY, ldY = ws.dA[li], ld
+        self._tag = ""
         self._call("dj_conv_bwd", _ptr(st["notes"]), T * N * 3, B, T, _ptr(P["conv.W"]), _ptr(P["conv.b"]), d[1],
                    d[4], _ptr(ws.dA[0]), ws.ld[0], _ptr(G["conv.W"]), _ptr(G["conv.b"]), _stream())
         ns = cfg.num_styles

@@ -43,7 +43,8 @@ def test_gemm_simt_layouts(lib, layout):
     a_sm, a_sk = (K, 1) if layout[0] == "n" else (1, M)
     b_sk, b_sn = (N, 1) if layout[1] == "n" else (1, K)
     Cd = torch.zeros(M, N, device="cuda")
-    _lib.check(lib.dj_gemm_simt(P(Ad), 0, a_sm, a_sk, P(Bd), 0, b_sk, b_sn, P(Cd), N, P(bias.cuda()), M, N, K, 0, 0, 0, None))
+    bd = bias.cuda()
+    _lib.check(lib.dj_gemm_simt(P(Ad), 0, a_sm, a_sk, P(Bd), 0, b_sk, b_sn, P(Cd), N, P(bd), M, N, K, 0, 0, 0, None))
     torch.cuda.synchronize()
     assert helpers.rel_err(Cd.cpu().numpy(), ref) < 1e-5
 
@@ -57,13 +58,15 @@ def test_gemm_simt_splitk_shift_and_bf16(lib):
     Xs = torch.zeros_like(X); Xs[1:] = X[:-1]; Xs[::48] = 0
     ref = (Xs.double().t() @ dZ.double()).numpy()
     Cd = torch.zeros(M, N, device="cuda")
-    _lib.check(lib.dj_gemm_simt(P(X.cuda()), 0, 1, M, P(dZ.cuda()), 0, N, 1, P(Cd), N, None, M, N, K, 1, 1, 48, None))
+    Xd, Zd = X.cuda(), dZ.cuda()     # keep device tensors alive: the launches are asynchronous
+    _lib.check(lib.dj_gemm_simt(P(Xd), 0, 1, M, P(Zd), 0, N, 1, P(Cd), N, None, M, N, K, 1, 1, 48, None))
     torch.cuda.synchronize()
     assert helpers.rel_err(Cd.cpu().numpy(), ref) < 1e-4
     Xb, Zb = X.bfloat16(), dZ.bfloat16()
     ref = (Xb.double().t() @ Zb.double()).numpy()
     Cd.zero_()
-    _lib.check(lib.dj_gemm_simt(P(Xb.cuda()), 1, 1, M, P(Zb.cuda()), 1, N, 1, P(Cd), N, None, M, N, K, 1, 0, 0, None))
+    Xbd, Zbd = Xb.cuda(), Zb.cuda()
+    _lib.check(lib.dj_gemm_simt(P(Xbd), 1, 1, M, P(Zbd), 1, N, 1, P(Cd), N, None, M, N, K, 1, 0, 0, None))
     torch.cuda.synchronize()
     assert helpers.rel_err(Cd.cpu().numpy(), ref) < 1e-4
 
@@ -84,11 +87,29 @@ def test_gate_gemm_tcgen05(lib, shape):
     ldc = (N + 3) // 4 * 4
     Cd = torch.full((M, ldc), float("nan"), device="cuda")
     use_bias = N % 4 == 0
-    _lib.check(lib.dj_gate_gemm_bf16(P(Ab.cuda()), lda, P(Bb.cuda()), lda, P(Cd), ldc,
-                                     P(bias.cuda()) if use_bias else None, M, N, lda, None))
+    Ad, Bd, bd = Ab.cuda(), Bb.cuda(), bias.cuda()   # keep alive across the asynchronous launch
+    _lib.check(lib.dj_gate_gemm_bf16(P(Ad), lda, P(Bd), lda, P(Cd), ldc, P(bd) if use_bias else None, M, N, lda, None))
     torch.cuda.synchronize()
     got = Cd.cpu().numpy()[:, :N]
     if not use_bias:
         ref = ref - bias.double().numpy()
     assert np.isfinite(got).all()
     assert helpers.rel_err(got, ref) < 2e-5
+
+
+@pytest.mark.parametrize("shape", [(6144, 128, 512), (98304, 256, 1024), (12288, 94, 1024), (6144 * 3, 259, 512)])
+def test_wgrad_gemm_tcgen05(lib, shape):
+    """C[Ka,Nb] += A[M,Ka]^T.B[M,Nb] on tcgen05 (MN-major operands, split over M)."""
+    from music_generator_b200 import _lib
+    M, Ka, Nb = shape
+    g = torch.Generator().manual_seed(3)
+    lda = (Ka + 31) // 32 * 32
+    A = torch.zeros(M, lda); A[:, :Ka] = torch.randn(M, Ka, generator=g)
+    B = torch.randn(M, Nb, generator=g) * 0.1
+    Ab, Bb = A.bfloat16(), B.bfloat16()
+    C0 = torch.randn(Ka, Nb, generator=g)
+    ref = (C0.double() + Ab[:, :Ka].double().t() @ Bb.double()).numpy()
+    Ad, Bd, Cd = Ab.cuda(), Bb.cuda(), C0.cuda()
+    _lib.check(lib.dj_wgrad_gemm_bf16(P(Ad), lda, P(Bd), Nb, P(Cd), Nb, Ka, Nb, M, None))
+    torch.cuda.synchronize()
+    assert helpers.rel_err(Cd.cpu().numpy(), ref) < 5e-5

@@ -96,8 +96,11 @@ def test_train_step_fp32_matches_oracle_autograd():
     st = O.NadamState()
     p2 = O.nadam_step({k: v.clone() for k, v in p64.items()}, rgrads, st)
     e.nadam_step(1.0)
+    # the first Nadam update is ~lr*sign(g): compare the UPDATE, whose size is lr, not the weight
     for k, v in e.get_params().items():
-        assert helpers.rel_err(v, p2[k].numpy()) < 1e-4, k
+        upd, ref = v - p64[k].numpy(), p2[k].numpy() - p64[k].numpy()
+        assert np.abs(upd - ref).max() < 0.05 * 0.002 * 1.6, k
+        assert helpers.rel_err(v, p2[k].numpy()) < 1e-3, k
 
 
 def test_train_step_fp32_default_window():
@@ -115,6 +118,23 @@ def test_train_matches_golden_fixture():
         g = e.grads[k].cpu().numpy().ravel()
         scale = float(z[f"grad_sum/{k}"][2]) + 1e-30
         assert np.abs(g[:16] - z[f"grad_head/{k}"]).max() / scale < 2e-4, k
+
+
+def test_scan_writes_shifted_h_for_recurrent_wgrad():
+    e = make_engine("bf16")
+    cpu, dev = batch_dev(2, 8)
+    ws = e.forward(*dev[:4], target=dev[4], train=True, seed=3)
+    torch.cuda.synchronize()
+    B, T = 2, 8
+    for li, axis in ((1, "time"), (3, "note")):
+        h = ws.h[li].view(B, T, 48, -1)
+        hp = ws.hprev[li].float().view(B, T, 48, -1)
+        want = torch.zeros_like(h)
+        if axis == "time":
+            want[:, 1:] = h[:, :-1]
+        else:
+            want[:, :, 1:] = h[:, :, :-1]
+        assert torch.equal(hp, want.bfloat16().float()), axis
 
 
 def test_train_step_bf16_within_1e3():
