@@ -1,0 +1,261 @@
+"""bench.py -- the driver's measurement contract for the DeepJ hot path.
+
+  python bench.py --gpus N --steps K --warmup W            (our arm; torchrun for N>1)
+  python bench.py --impl reference --gpus N --steps K --warmup W   (CPU reference arm)
+
+Workload (BASELINE.json configs[2], "DeepJ training, batch 64 synthetic
+sequences, data-parallel with NCCL gradient allreduce"): one step = forward +
+primary_loss + backward + gradient all-reduce + Nadam on 64 synthetic
+[128,48,3] windows PER GPU (weak scaling), default constants.py model, dropout
+on, bf16 gate-GEMM operands / fp32 everything else.  A short generation probe
+(configs[1], 1 style-mixed sequence) is reported under "generation".
+
+The reference's Keras/TensorFlow path cannot run here (not installable, see
+DESIGN.md); `--impl reference` and `cpu_baseline` time the CPU oracle -- a
+restatement of model.py -- on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC, UNIT = "train_seqs_per_sec", "seqs/s"
+BATCH = 64          # per GPU
+REF_SAMPLE_B = 2    # sequences per CPU step (bounded sample of the same workload)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 6:
+                    self.rows.append(f)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def cpu_oracle_rate(steps, warmup, B):
+    """Times the CPU oracle's train step (forward + loss + autograd backward +
+    Nadam) on `B` sequences per step; returns (seqs/s, threads)."""
+    from oracle import deepj_oracle as O
+    cfg = O.Config()
+    p = O.init_params(cfg, 0)
+    batch = O.synthetic_batch(cfg, B, cfg.seq_len, 1234)
+    masks = O.random_masks(cfg, B, cfg.seq_len, 7)
+    st = O.NadamState()
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.time()
+        _, _, grads = O.loss_and_grads(p, cfg, *batch, masks)
+        p = O.nadam_step(p, grads, st)
+        if i >= warmup:
+            times.append(time.time() - t0)
+    return B * len(times) / sum(times), torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    warm = min(args.warmup, 1)
+    steps = max(1, min(args.steps, 6))       # each CPU step is seconds; keep the arm within minutes
+    rate, threads = cpu_oracle_rate(steps, warm, REF_SAMPLE_B)
+    sample = (f"{steps} CPU steps of {REF_SAMPLE_B} sequences (forward+loss+backward+Nadam, fp32 torch-CPU oracle; "
+              f"Keras/TF reference not installable)")
+    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": steps, "warmup": warm, "ms_per_step": 1e3 * REF_SAMPLE_B / rate, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "DeepJ training, default constants.py model, synthetic piano-roll batch",
+                       "batch_per_step": REF_SAMPLE_B, "seq_len": 128},
+            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    import music_generator_b200  # noqa: F401
+    from music_generator_b200.config import ModelConfig
+    from music_generator_b200.engine import Engine
+    from music_generator_b200.sampler import generate_events
+    import dataset
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    B, K, W = args.batch, args.steps, max(args.warmup, 3)
+
+    eng = Engine(ModelConfig(), precision="bf16")
+    eng.init_params(0)
+    x, y = dataset.synthetic_all(B, 128, seed=1234 + rank)
+    host = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in (x[0], x[1], x[2], x[3], y[0])]
+    dev = [h.cuda(non_blocking=True) for h in host]
+    allreduce = (lambda g: dist.all_reduce(g)) if world > 1 else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- device-resident arm (value)
+    for i in range(W):
+        eng.train_step(*dev, seed=i, allreduce=allreduce, world=world)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    DOM = "dj_lstm_scan_bwd:bwd:time1"
+    eng.profile, eng.profile_only = [], {DOM}
+    launches0 = eng.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        loss = eng.train_step(*dev, seed=100 + i, allreduce=allreduce, world=world)
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = eng.launches - launches0
+    dom = eng.profile_summary().get(DOM, [0, 0.0])
+    eng.profile, eng.profile_only = None, None
+    value = world * B * K / (ms * 1e-3)
+
+    # ---------------- end-to-end arm: host buffers in, loss out, every step
+    h2d = sum(h.numel() * h.element_size() for h in host)
+    for i in range(2):
+        d = [h.cuda(non_blocking=True) for h in host]
+        float(eng.train_step(*d, seed=i, allreduce=allreduce, world=world).item())
+    barrier()
+    e0.record()
+    for i in range(K):
+        d = [h.cuda(non_blocking=True) for h in host]
+        lossv = float(eng.train_step(*d, seed=200 + i, allreduce=allreduce, world=world).item())
+    e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    e2e = world * B * K / (ms_e2e * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- roofline of the dominant kernel (time-axis reverse scan, layer 1)
+    # algorithmic bytes per row: gates 16U + c 4U + dY 4U read, dZ(bf16) 8U written, U=256
+    U, M = 256, B * 128 * 48
+    alg_bytes = 32 * U * M
+    peak, how = peaks()
+    dom_ms = dom[1] / max(dom[0], 1)
+    achieved = alg_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else None
+    roofline = {"kernel": "scan_bwd_kernel<256,8,48,bf16> (dj_lstm_scan_bwd, time axis layer 1)", "bound": "hbm",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+                "traffic": None, "peak_source": how, "avg_launch_ms": dom_ms, "launches_timed": dom[0],
+                "algorithmic_bytes_per_launch": alg_bytes,
+                "note": "latency/FMA-bound recurrence, not HBM-bound: see DESIGN.md"}
+
+    # ---------------- generation probe (configs[1])
+    gen = None
+    if not args.no_generation:
+        ge = Engine(ModelConfig(), precision="fp32")
+        ge.init_params(0)
+        sty = np.mean([np.eye(23)[i] for i in (0, 5, 12)], axis=0)
+        gsteps = 32
+        u = np.random.RandomState(42).random_sample(2 * 48 * gsteps)
+        generate_events(ge, [sty], 4, u)
+        torch.cuda.synchronize()
+        t0 = time.time()
+        generate_events(ge, [sty], gsteps, u)
+        torch.cuda.synchronize()
+        gen = {"timesteps_per_s": gsteps / (time.time() - t0), "sequences": 1, "timesteps": gsteps,
+               "workload": "generate.py path, 1 style-mixed sequence, full 128-step window recompute per timestep"}
+
+    # ---------------- CPU baseline on this box's host cores (bounded sample)
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        rate, threads = cpu_oracle_rate(2, 1, REF_SAMPLE_B)
+        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"2 steps of {REF_SAMPLE_B} sequences after 1 warm-up, fp32 torch-CPU oracle of model.py"}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16 gate-GEMM operands, f32 accumulate/recurrence", "data": "synthetic",
+            "config": {"workload": "DeepJ training (BASELINE configs[2]): default constants.py model, "
+                                   "batch 64 synthetic sequences per GPU, fwd+loss+bwd+allreduce+Nadam, dropout on",
+                       "batch_per_gpu": B, "global_batch": B * world, "seq_len": 128, "parallelism": f"dp{world}",
+                       "l2": "per-step working set (>5 GB of activations) exceeds the 126 MB L2; no explicit flush"},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "ms_per_step": ms_e2e / K},
+            "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roofline, "cpu_baseline": cpu,
+            "generation": gen, "loss": lossv}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--no-generation", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -103,6 +103,7 @@ class Engine:
         self._version = 0
         self.launches = 0   # kernels of ours enqueued (bench.py reports it)
         self.profile = None
+        self.profile_only = None
         self._tag = ""
 
     # ------------------------------------------------------------------ params
@@ -147,7 +148,8 @@ class Engine:
         self.set_params(st)
 
     def _call(self, name, *args):
-        if self.profile is not None:   # debug: per-entry-point device time (CUDA events, serialising)
+        if self.profile is not None and (self.profile_only is None or (name + self._tag) in self.profile_only):
+            # per-entry-point device time: CUDA events on the launching stream around the launch
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             check(getattr(self.lib, name)(*args), name)
