@@ -119,12 +119,10 @@ def run_ours(args):
     from music_generator_b200.sampler import generate_events
     import dataset
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    from music_generator_b200 import parallel
+    rank, world, local = parallel.env_world()
     torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    parallel.init_distributed("nccl")
     B, K, W = args.batch, args.steps, max(args.warmup, 3)
 
     eng = Engine(ModelConfig(), precision="bf16")
@@ -132,7 +130,7 @@ def run_ours(args):
     x, y = dataset.synthetic_all(B, 128, seed=1234 + rank)
     host = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in (x[0], x[1], x[2], x[3], y[0])]
     dev = [h.cuda(non_blocking=True) for h in host]
-    allreduce = (lambda g: dist.all_reduce(g)) if world > 1 else None
+    allreduce = parallel.allreduce_flat if world > 1 else None
 
     def barrier():
         if world > 1:
@@ -140,11 +138,7 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def max_over_ranks(ms):
-        if world == 1:
-            return ms
-        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return parallel.max_over_ranks(ms, "cuda")
 
     # ---------------- device-resident arm (value)
     for i in range(W):

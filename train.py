@@ -50,16 +50,14 @@ def train(models, epochs=1000, num_seqs=256):
     # the reference loads a MIDI corpus it does not ship (dataset.load_all);
     # synthetic piano-rolls of the same shape stand in
     train_data, train_labels = synthetic_all(num_seqs, SEQ_LEN)
-    allreduce, world, rank = None, 1, 0
-    if 'RANK' in os.environ and int(os.environ.get('WORLD_SIZE', '1')) > 1:
-        import torch
-        import torch.distributed as dist
-        torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))
-        dist.init_process_group('nccl')
-        world, rank = dist.get_world_size(), dist.get_rank()
-        train_data = [a[rank::world] for a in train_data]
-        train_labels = [a[rank::world] for a in train_labels]
-        allreduce = lambda g: dist.all_reduce(g)
+    from music_generator_b200 import parallel
+    rank, world, _ = parallel.init_distributed()
+    allreduce = None
+    if world > 1:
+        idx = parallel.shard_indices(len(train_data[0]), rank, world)
+        train_data = [a[idx] for a in train_data]
+        train_labels = [a[idx] for a in train_labels]
+        allreduce = parallel.allreduce_flat
     cbs = [ModelCheckpoint(MODEL_FILE), EarlyStopping(patience=5)] if rank == 0 else []
     print('Training')
     models[0].fit(train_data, train_labels, epochs=epochs, callbacks=cbs, batch_size=BATCH_SIZE,
