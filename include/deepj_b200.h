@@ -118,7 +118,9 @@ int dj_cast_bf16(const float* in, int rows, int cols, void* out, int ldo, int tr
  * Persistent thread-block-cluster kernel: the recurrent weights U [units,4*units]
  * stay in shared memory, split by hidden unit over the CTAs of a cluster; h is
  * exchanged through distributed shared memory; cell state lives in registers.
- *   Z [M,4*units] fp32: in = x.W+b, out = activated gates i,f,g,o (saved for bwd)
+ *   Z [M,4*units] fp32: in = x.W+b, out = activated gates i,f,g,o (saved for bwd);
+ *     gate columns are GATE-INTERLEAVED: col = 4*unit + gate (the host converts
+ *     Keras' [i|f|c|o] block order at the API boundary); same for U, dZ, db
  *   row(seq, step) = (seq/seq_inner)*seq_outer_stride + (seq%seq_inner)*seq_inner_stride
  *                    + step*step_stride
  *   h_out [M,units] fp32; c_out nullable (training only); h_prev_bf16 nullable:
@@ -128,6 +130,22 @@ int dj_cast_bf16(const float* in, int rows, int cols, void* out, int ldo, int tr
 int dj_lstm_scan_fwd(float* Z, float* h_out, float* c_out, void* h_prev_bf16, const float* Uw, int S,
                      int steps, int units, int seq_inner, int64_t seq_outer_stride,
                      int64_t seq_inner_stride, int64_t step_stride, int hard, void* stream);
+/* Tensor-core variant of the forward recurrence (training path, bf16 operands for
+ * h.U, fp32 accumulate/state): same contract as dj_lstm_scan_fwd, but U is passed as
+ * Ut_bf16 [4*units, units] (bf16, transposed, gate-interleaved rows) and
+ * h_prev_bf16 is REQUIRED (it doubles as the inter-CTA exchange buffer).  Only the
+ * two maps of the model are supported: units=256 with the time-axis map, units=128
+ * with the note-axis map. */
+int dj_lstm_scan_tc_fwd(float* Z, float* h_out, float* c_out, void* h_prev_bf16, const void* Ut_bf16,
+                        int S, int steps, int units, int seq_inner, int64_t seq_outer_stride,
+                        int64_t seq_inner_stride, int64_t step_stride, int hard, void* stream);
+/* Tensor-core variant of the reverse scan (dz.U^T on tcgen05): U is passed as
+ * Un_bf16 [units, 4*units] (bf16, natural, gate-interleaved columns); dZ is bf16
+ * and doubles as the inter-CTA exchange buffer; db accumulates with fp32 atomics. */
+int dj_lstm_scan_tc_bwd(const float* gates, const float* c, const float* dY, int64_t ldY, dj_dropout d_y,
+                        const void* Un_bf16, void* dZ_bf16, float* db, int S, int steps, int units,
+                        int seq_inner, int64_t seq_outer_stride, int64_t seq_inner_stride,
+                        int64_t step_stride, int hard, void* stream);
 /* reverse scan: consumes gates/c and dY (gradient w.r.t. the DROPPED-OUT layer
  * output, row stride ldY; the kernel applies the mask d_y itself), produces
  * dZ [M,4*units] (dz_dtype) and accumulates db[4*units] (fp32 atomics). */

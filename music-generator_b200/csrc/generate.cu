@@ -62,8 +62,9 @@ __global__ void __launch_bounds__(4 * UN) gen_sample_kernel(
       }
       __syncthreads();
       if (j < UN) {
-        const float gi = dj_gate_act(zbuf[j], hard), gf = dj_gate_act(zbuf[UN + j], hard);
-        const float gg = tanhf(zbuf[2 * UN + j]), go = dj_gate_act(zbuf[3 * UN + j], hard);
+        // gate columns are interleaved: col = 4*unit + gate (i,f,c,o)
+        const float gi = dj_gate_act(zbuf[4 * j], hard), gf = dj_gate_act(zbuf[4 * j + 1], hard);
+        const float gg = tanhf(zbuf[4 * j + 2]), go = dj_gate_act(zbuf[4 * j + 3], hard);
         const float cn = fmaf(gf, c0[gl][j], gi * gg);
         c0[gl][j] = cn;
         const float hn = go * tanhf(cn);
@@ -83,8 +84,8 @@ __global__ void __launch_bounds__(4 * UN) gen_sample_kernel(
       }
       __syncthreads();
       if (j < UN) {
-        const float gi = dj_gate_act(zbuf[j], hard), gf = dj_gate_act(zbuf[UN + j], hard);
-        const float gg = tanhf(zbuf[2 * UN + j]), go = dj_gate_act(zbuf[3 * UN + j], hard);
+        const float gi = dj_gate_act(zbuf[4 * j], hard), gf = dj_gate_act(zbuf[4 * j + 1], hard);
+        const float gg = tanhf(zbuf[4 * j + 2]), go = dj_gate_act(zbuf[4 * j + 3], hard);
         const float cn = fmaf(gf, c1[gl][j], gi * gg);
         c1[gl][j] = cn;
         h1[gl][j] = go * tanhf(cn);

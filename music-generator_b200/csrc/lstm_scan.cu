@@ -12,6 +12,9 @@
 //
 // Row addressing: all activations are [M, width] with the canonical row order
 // row = (b*T + t)*48 + n; a (sequence, step) pair maps to a row through ScanMap.
+// Gate columns use the library-internal GATE-INTERLEAVED order col = 4*unit + gate
+// (gate 0..3 = i,f,c,o), so the four gates of a cell are one 16-byte vector; the
+// host converts from/to the Keras [.., 4U] block order at the API boundary.
 #include <cooperative_groups.h>
 
 #include "dj_common.cuh"
@@ -38,6 +41,17 @@ __device__ __forceinline__ void prefetch_l2(const void* p) {
 }
 
 constexpr int UC = 32;   // hidden units owned by one CTA (=> 128 gate columns)
+
+__device__ __forceinline__ void store_dz4(float* p, const float v[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void store_dz4(__nv_bfloat16* p, const float v[4]) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&a);
+  u.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = u;
+}
 
 // Blackwell packed fp32 FMA (two independent IEEE fp32 FMAs per issue slot, SASS
 // FFMA2): the recurrent h.U product is CUDA-core work (fp32 recurrence, see
@@ -87,10 +101,8 @@ scan_fwd_kernel(float* __restrict__ Z, float* __restrict__ Hout, float* __restri
   const int tid = threadIdx.x, sg = tid >> 4, ug = tid & 15;
   const int unit0 = rank * UC;
 
-  for (int idx = tid; idx < SM::US; idx += NT) {
-    const int g = idx & 3, u = (idx >> 2) & 31, k = idx >> 7;
-    Us[idx] = Uw[(size_t)k * 4 * U + g * U + unit0 + u];
-  }
+  for (int idx = tid; idx < SM::US; idx += NT)   // [k][32 units][4 gates] is a contiguous 512 B run per k
+    Us[idx] = Uw[(size_t)(idx >> 7) * 4 * U + 4 * unit0 + (idx & 127)];
   float* rbuf[C];
 #pragma unroll
   for (int r = 0; r < C; ++r) rbuf[r] = cluster.map_shared_rank(hbuf, r);
@@ -109,14 +121,13 @@ scan_fwd_kernel(float* __restrict__ Z, float* __restrict__ Hout, float* __restri
       row0[s] = scan_row0(map, ok[s] ? seq : 0);
       c[s][0] = c[s][1] = 0.f;
     }
-    float zn[4][2][4];
+    float4 zn[4][2];
 #pragma unroll
     for (int s = 0; s < 4; ++s)
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf)
-#pragma unroll
-        for (int g = 0; g < 4; ++g)
-          zn[s][hf][g] = ok[s] ? Z[row0[s] * (4 * U) + g * U + unit0 + hf * 16 + ug] : 0.f;
+        zn[s][hf] = ok[s] ? *reinterpret_cast<const float4*>(Z + row0[s] * (4 * U) + 4 * (unit0 + hf * 16 + ug))
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
 
     for (int t = 0; t < steps; ++t) {
@@ -126,8 +137,8 @@ scan_fwd_kernel(float* __restrict__ Z, float* __restrict__ Hout, float* __restri
       for (int s = 0; s < 4; ++s)
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
-          acc2[s][hf][0] = pack2(zn[s][hf][0], zn[s][hf][1]);
-          acc2[s][hf][1] = pack2(zn[s][hf][2], zn[s][hf][3]);
+          acc2[s][hf][0] = pack2(zn[s][hf].x, zn[s][hf].y);
+          acc2[s][hf][1] = pack2(zn[s][hf].z, zn[s][hf].w);
         }
       if (t + 1 < steps) {   // register prefetch of the next step's pre-activations
 #pragma unroll
@@ -135,9 +146,8 @@ scan_fwd_kernel(float* __restrict__ Z, float* __restrict__ Hout, float* __restri
           const int64_t r = row0[s] + (int64_t)(t + 1) * map.step_stride;
 #pragma unroll
           for (int hf = 0; hf < 2; ++hf)
-#pragma unroll
-            for (int g = 0; g < 4; ++g)
-              zn[s][hf][g] = ok[s] ? Z[r * (4 * U) + g * U + unit0 + hf * 16 + ug] : 0.f;
+            zn[s][hf] = ok[s] ? *reinterpret_cast<const float4*>(Z + r * (4 * U) + 4 * (unit0 + hf * 16 + ug))
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
       const float* hb = hbuf + cur * SM::HBUF + sg * SM::HSTR;
@@ -180,8 +190,7 @@ scan_fwd_kernel(float* __restrict__ Z, float* __restrict__ Hout, float* __restri
           hnew[hf][s] = hn;
           if (ok[s]) {
             const int col = unit0 + hf * 16 + ug;
-            float* zr = Z + r * (4 * U) + col;
-            zr[0] = gi; zr[U] = gf; zr[2 * U] = gg; zr[3 * U] = go;
+            *reinterpret_cast<float4*>(Z + r * (4 * U) + 4 * col) = make_float4(gi, gf, gg, go);
             Hout[r * U + col] = hn;
             if (Cout != nullptr) Cout[r * U + col] = cn;
             if (Hbf != nullptr) {   // h_{t} is the "previous h" of step t+1; step 0 sees zeros
@@ -240,8 +249,8 @@ scan_bwd_kernel(const float* __restrict__ G, const float* __restrict__ Cst, cons
   const int unit0 = rank * UC;
 
   for (int idx = tid; idx < SM::UT; idx += NT) {
-    const int k = idx % U, j = idx / U;
-    UsT[idx] = Uw[(size_t)k * 4 * U + (j >> 5) * U + unit0 + (j & 31)];
+    const int k = idx % U, j = idx / U;   // j = gate*32 + local unit (smem order); global order is 4*unit + gate
+    UsT[idx] = Uw[(size_t)k * 4 * U + 4 * (unit0 + (j & 31)) + (j >> 5)];
   }
   float* rslots[C];
 #pragma unroll
@@ -291,8 +300,8 @@ scan_bwd_kernel(const float* __restrict__ G, const float* __restrict__ Cst, cons
           const int ul = hf * 16 + ug, col = unit0 + ul;
           float dz[4] = {0.f, 0.f, 0.f, 0.f};
           if (ok[s]) {
-            const float* gr = G + r * (4 * U) + col;
-            const float gi = gr[0], gf = gr[U], gg = gr[2 * U], go = gr[3 * U];
+            const float4 g4 = *reinterpret_cast<const float4*>(G + r * (4 * U) + 4 * col);
+            const float gi = g4.x, gf = g4.y, gg = g4.z, go = g4.w;
             const float ct = Cst[r * U + col];
             const float cp = (t > 0) ? Cst[rp * U + col] : 0.f;
             const float dy = dY[r * ldY + col] * dj_dropmul(d_y, (uint32_t)(r * U + col));
@@ -305,12 +314,10 @@ scan_bwd_kernel(const float* __restrict__ G, const float* __restrict__ Cst, cons
             dz[1] = dc * cp * dj_gate_dact(gf, hard);
             dz[2] = dc * gi * (1.f - gg * gg);
             dz[3] = d_o * dj_gate_dact(go, hard);
-            TZ* zr = dZ + r * (4 * U) + col;
-            zr[0] = dj_from_float<TZ>(dz[0]); zr[U] = dj_from_float<TZ>(dz[1]);
-            zr[2 * U] = dj_from_float<TZ>(dz[2]); zr[3 * U] = dj_from_float<TZ>(dz[3]);
+            store_dz4(dZ + r * (4 * U) + 4 * col, dz);
             if (t > 0) {   // warm L2 for the next (earlier) step while phase B runs
               const int64_t r2 = rp - map.step_stride;
-              prefetch_l2(G + rp * (4 * U) + col);
+              prefetch_l2(G + rp * (4 * U) + 4 * col);
               prefetch_l2(dY + rp * ldY + col);
               if (t > 1) prefetch_l2(Cst + r2 * U + col);
             }
@@ -376,7 +383,7 @@ scan_bwd_kernel(const float* __restrict__ G, const float* __restrict__ Cst, cons
   if (tid < 128) {
     float s = 0.f;
     for (int q = 0; q < BS / 4; ++q) s += dzb[tid * SM::DZS + q];
-    atomicAdd(db + (tid >> 5) * U + unit0 + (tid & 31), s);
+    atomicAdd(db + 4 * (unit0 + (tid & 31)) + (tid >> 5), s);
   }
 }
 

@@ -104,6 +104,7 @@ class Engine:
         self.launches = 0   # kernels of ours enqueued (bench.py reports it)
         self.profile = None
         self.profile_only = None
+        self.tc_scan = True   # bf16 training: recurrence on tcgen05 (False = fp32 CUDA-core scans)
         self._tag = ""
 
     # ------------------------------------------------------------------ params
@@ -112,16 +113,46 @@ class Engine:
         n = int(np.prod(shp))
         return flat[self.offsets[k]:self.offsets[k] + n].view(*shp)
 
+    # The LSTM tensors live on the device in GATE-INTERLEAVED column order
+    # (col = 4*unit + gate) so a cell's four gates are one 16-byte vector; the
+    # Keras block order [i | f | c | o] exists only at this API boundary.
+    @staticmethod
+    def _is_lstm(k: str) -> bool:
+        return ".lstm." in k
+
+    @staticmethod
+    def _to_internal(v: torch.Tensor) -> torch.Tensor:
+        u = v.shape[-1] // 4
+        return v.reshape(*v.shape[:-1], 4, u).transpose(-1, -2).reshape(v.shape).contiguous()
+
+    @staticmethod
+    def _to_keras(v: torch.Tensor) -> torch.Tensor:
+        u = v.shape[-1] // 4
+        return v.reshape(*v.shape[:-1], u, 4).transpose(-1, -2).reshape(v.shape).contiguous()
+
     def set_params(self, state: Dict[str, "np.ndarray | torch.Tensor"]) -> None:
         for k in self.shapes:
             v = torch.as_tensor(np.asarray(state[k]) if not torch.is_tensor(state[k]) else state[k])
             if tuple(v.shape) != tuple(self.shapes[k]):
                 raise ValueError(f"{k}: expected shape {self.shapes[k]}, got {tuple(v.shape)}")
-            self.params[k].copy_(v.to(torch.float32))
+            v = v.to(torch.float32)
+            self.params[k].copy_(self._to_internal(v) if self._is_lstm(k) else v)
         self._version += 1
 
+    def _export(self, views) -> Dict[str, np.ndarray]:
+        out = {}
+        for k, v in views.items():
+            v = v.detach().cpu()
+            out[k] = (self._to_keras(v) if self._is_lstm(k) else v).numpy().copy()
+        return out
+
     def get_params(self) -> Dict[str, np.ndarray]:
-        return {k: v.detach().cpu().numpy().copy() for k, v in self.params.items()}
+        """The 28 tensors in Keras layouts."""
+        return self._export(self.params)
+
+    def get_grads(self) -> Dict[str, np.ndarray]:
+        """Gradients of the last backward() in Keras layouts."""
+        return self._export(self.grads)
 
     def init_params(self, seed: int = 0) -> None:
         """Keras default initialisers (glorot_uniform / orthogonal / zeros, forget bias 1)."""
@@ -184,6 +215,16 @@ class Engine:
                 self._wbf[kn] = torch.empty(F, U4, dtype=torch.bfloat16, device=self.dev)
             self._call("dj_cast_bf16", _ptr(W), F, U4, _ptr(self._wbf[kt]), ld, 1, _stream())
             self._call("dj_cast_bf16", _ptr(W), F, U4, _ptr(self._wbf[kn]), U4, 0, _stream())
+            # recurrent kernel transposed [4U, U]: resident A operand of the tensor-core scan
+            ku = f"{L['name']}.Ut"
+            Um = self.params[f"{L['name']}.lstm.U"]
+            if ku not in self._wbf:
+                self._wbf[ku] = torch.empty(U4, L["U"], dtype=torch.bfloat16, device=self.dev)
+            self._call("dj_cast_bf16", _ptr(Um), L["U"], U4, _ptr(self._wbf[ku]), L["U"], 1, _stream())
+            kun = f"{L['name']}.Un"   # natural [U, 4U]: resident A operand of the tensor-core reverse scan
+            if kun not in self._wbf:
+                self._wbf[kun] = torch.empty(L["U"], U4, dtype=torch.bfloat16, device=self.dev)
+            self._call("dj_cast_bf16", _ptr(Um), L["U"], U4, _ptr(self._wbf[kun]), U4, 0, _stream())
         self._wbf_version = self._version
 
     # --------------------------------------------------------------- dropout
@@ -250,10 +291,15 @@ class Engine:
         L = self.layers[li]
         m = self._scan_map(L["axis"], B, T)
         self._tag = ":" + L["name"]
-        self._call("dj_lstm_scan_fwd", _ptr(ws.Z[li]), _ptr(ws.h[li]), _ptr(ws.c[li]) if train else None,
-                   _ptr(ws.hprev[li]) if train else None,
-                   _ptr(self.params[f"{L['name']}.lstm.U"]), m["S"], m["steps"], L["U"], m["inner"], m["outer"],
-                   m["inner_stride"], m["step"], self.hard, _stream())
+        if train and ws.hprev[li] is not None and self.tc_scan:
+            self._call("dj_lstm_scan_tc_fwd", _ptr(ws.Z[li]), _ptr(ws.h[li]), _ptr(ws.c[li]), _ptr(ws.hprev[li]),
+                       _ptr(self._wbf[f"{L['name']}.Ut"]), m["S"], m["steps"], L["U"], m["inner"], m["outer"],
+                       m["inner_stride"], m["step"], self.hard, _stream())
+        else:
+            self._call("dj_lstm_scan_fwd", _ptr(ws.Z[li]), _ptr(ws.h[li]), _ptr(ws.c[li]) if train else None,
+                       _ptr(ws.hprev[li]) if train else None,
+                       _ptr(self.params[f"{L['name']}.lstm.U"]), m["S"], m["steps"], L["U"], m["inner"], m["outer"],
+                       m["inner_stride"], m["step"], self.hard, _stream())
         self._tag = ""
 
     def forward_time(self, ws: Workspace, notes, notes_bstride, beat, beat_bstride, B, T, d, bf16, train,
@@ -336,9 +382,14 @@ class Engine:
             self._tag = ":bwd:" + name
             m = self._scan_map(L["axis"], B, T)
             dZ = ws.dZ.view(-1)[:M * U4].view(M, U4)
-            self._call("dj_lstm_scan_bwd", _ptr(ws.Z[li]), _ptr(ws.c[li]), _ptr(dY), ldY, d[L["site_out"]],
-                       _ptr(P[f"{name}.lstm.U"]), _ptr(dZ), zdt, _ptr(G[f"{name}.lstm.b"]), m["S"], m["steps"], U,
-                       m["inner"], m["outer"], m["inner_stride"], m["step"], self.hard, _stream())
+            if bf16 and self.tc_scan:
+                self._call("dj_lstm_scan_tc_bwd", _ptr(ws.Z[li]), _ptr(ws.c[li]), _ptr(dY), ldY, d[L["site_out"]],
+                           _ptr(self._wbf[f"{name}.Un"]), _ptr(dZ), _ptr(G[f"{name}.lstm.b"]), m["S"], m["steps"], U,
+                           m["inner"], m["outer"], m["inner_stride"], m["step"], self.hard, _stream())
+            else:
+                self._call("dj_lstm_scan_bwd", _ptr(ws.Z[li]), _ptr(ws.c[li]), _ptr(dY), ldY, d[L["site_out"]],
+                           _ptr(P[f"{name}.lstm.U"]), _ptr(dZ), zdt, _ptr(G[f"{name}.lstm.b"]), m["S"], m["steps"], U,
+                           m["inner"], m["outer"], m["inner_stride"], m["step"], self.hard, _stream())
             # data gradient dA = dZ . W^T
             if bf16:
                 self._call("dj_gate_gemm_bf16", _ptr(dZ), U4, _ptr(self._wbf[f"{name}.Wn"]), U4, _ptr(ws.dA[li]),

@@ -113,3 +113,74 @@ def test_wgrad_gemm_tcgen05(lib, shape):
     _lib.check(lib.dj_wgrad_gemm_bf16(P(Ad), lda, P(Bd), Nb, P(Cd), Nb, Ka, Nb, M, None))
     torch.cuda.synchronize()
     assert helpers.rel_err(Cd.cpu().numpy(), ref) < 5e-5
+
+
+@pytest.mark.parametrize("axis,B,T", [("time", 3, 8), ("note", 2, 40), ("time", 20, 4), ("note", 40, 128)])
+def test_lstm_scan_tcgen05_matches_fp32_scan(lib, axis, B, T):
+    """Tensor-core recurrence (bf16 h.U, fp32 accumulate) against the fp32 CUDA-core
+    recurrence on the same pre-activations."""
+    from music_generator_b200 import _lib
+    g = torch.Generator().manual_seed(5)
+    U = 256 if axis == "time" else 128
+    M = B * T * 48
+    Z0 = torch.randn(M, 4 * U, generator=g)
+    Uw = (torch.randn(U, 4 * U, generator=g) * 0.06).bfloat16().float()     # bf16-representable weights
+    if axis == "time":
+        S, steps, m = B * 48, T, (48, T * 48, 1, 48)
+    else:
+        S, steps, m = B * T, 48, (1, 48, 0, 1)
+    Zr, Zt, Ud = Z0.cuda(), Z0.cuda(), Uw.cuda()
+    Ut = Uw.t().contiguous().bfloat16().cuda()
+    hr, cr = torch.empty(M, U, device="cuda"), torch.empty(M, U, device="cuda")
+    ht, ct = torch.zeros(M, U, device="cuda"), torch.zeros(M, U, device="cuda")
+    hp = torch.full((M, U), 7.0, device="cuda").bfloat16()
+    _lib.check(lib.dj_lstm_scan_fwd(P(Zr), P(hr), P(cr), None, P(Ud), S, steps, U, *m, 1, None))
+    _lib.check(lib.dj_lstm_scan_tc_fwd(P(Zt), P(ht), P(ct), P(hp), P(Ut), S, steps, U, *m, 1, None))
+    torch.cuda.synchronize()
+    dh = (ht - hr).abs()
+    assert torch.isfinite(ht).all()
+    assert float(dh.max()) < 0.03 and float(dh.mean()) < 2e-3, (float(dh.max()), float(dh.mean()))
+    assert float((ct - cr).abs().max()) < 0.06
+    assert float((Zt - Zr).abs().mean()) < 2e-3           # activated gates saved in place
+    # hprev = bf16(h) shifted by one step, zero at step 0
+    h4, p4 = ht.view(B, T, 48, U), hp.float().view(B, T, 48, U)
+    want = torch.zeros_like(h4)
+    if axis == "time":
+        want[:, 1:] = h4[:, :-1]
+    else:
+        want[:, :, 1:] = h4[:, :, :-1]
+    assert torch.equal(p4, want.bfloat16().float())
+
+
+@pytest.mark.parametrize("axis,B,T", [("time", 3, 8), ("note", 2, 40), ("note", 40, 128)])
+def test_lstm_scan_bwd_tcgen05_matches_fp32_scan(lib, axis, B, T):
+    """Reverse scan on tcgen05 (bf16 dz.U^T) against the fp32 CUDA-core reverse scan."""
+    from music_generator_b200 import _lib
+    g = torch.Generator().manual_seed(6)
+    U = 256 if axis == "time" else 128
+    M = B * T * 48
+    Z0 = torch.randn(M, 4 * U, generator=g)
+    Uw = (torch.randn(U, 4 * U, generator=g) * 0.06).bfloat16().float()
+    if axis == "time":
+        S, steps, m = B * 48, T, (48, T * 48, 1, 48)
+    else:
+        S, steps, m = B * T, 48, (1, 48, 0, 1)
+    Z, Ud = Z0.cuda(), Uw.cuda()
+    h, c = torch.empty(M, U, device="cuda"), torch.empty(M, U, device="cuda")
+    _lib.check(lib.dj_lstm_scan_fwd(P(Z), P(h), P(c), None, P(Ud), S, steps, U, *m, 1, None))
+    ld = U + 32
+    dY = (torch.randn(M, ld, generator=g) * 0.1).cuda()
+    d = _lib.make_dropout(11, 6, 0.5)
+    dZr = torch.zeros(M, 4 * U, device="cuda")
+    dbr = torch.zeros(4 * U, device="cuda")
+    _lib.check(lib.dj_lstm_scan_bwd(P(Z), P(c), P(dY), ld, d, P(Ud), P(dZr), 0, P(dbr), S, steps, U, *m, 1, None))
+    Un = Uw.bfloat16().cuda()
+    dZt = torch.zeros(M, 4 * U, device="cuda").bfloat16()
+    dbt = torch.zeros(4 * U, device="cuda")
+    _lib.check(lib.dj_lstm_scan_tc_bwd(P(Z), P(c), P(dY), ld, d, P(Un), P(dZt), P(dbt), S, steps, U, *m, 1, None))
+    torch.cuda.synchronize()
+    a, b = dZt.float().cpu().numpy(), dZr.cpu().numpy()
+    assert np.isfinite(a).all()
+    scale = np.abs(b).max()
+    assert np.abs(a - b).max() / scale < 0.03 and np.abs(a - b).mean() / np.abs(b).mean() < 0.02
+    assert helpers.rel_err(dbt.cpu().numpy(), dbr.cpu().numpy()) < 0.02

@@ -83,8 +83,9 @@ def _train_compare(precision, B, T, tol_loss, tol_grad):
     got = ws.probs.cpu().numpy().reshape(B, T, 48, 3)
     assert np.abs(got - rprobs.numpy()).max() < max(tol_loss, 2e-5) * 2
     worst = {}
+    ggpu = e.get_grads()
     for k, g in rgrads.items():
-        worst[k] = helpers.rel_err(e.grads[k].cpu().numpy(), g.numpy())
+        worst[k] = helpers.rel_err(ggpu[k], g.numpy())
     bad = {k: v for k, v in worst.items() if v > tol_grad}
     assert not bad, bad
     return e, p64, rgrads
@@ -114,8 +115,8 @@ def test_train_matches_golden_fixture():
     e.forward(*dev[:4], target=dev[4], train=True, seed=7)
     loss = float(e.backward().item())
     assert abs(loss - float(z["train_loss"])) / float(z["train_loss"]) < 1e-5
-    for k in e.grads:
-        g = e.grads[k].cpu().numpy().ravel()
+    for k, gk in e.get_grads().items():
+        g = gk.ravel()
         scale = float(z[f"grad_sum/{k}"][2]) + 1e-30
         assert np.abs(g[:16] - z[f"grad_head/{k}"]).max() / scale < 2e-4, k
 
