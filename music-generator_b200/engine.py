@@ -282,6 +282,11 @@ class Engine:
             self._call("dj_gemm_simt", _ptr(ws.A[li]), DJ_F32, ld, 1, _ptr(P[f"{L['name']}.lstm.W"]), DJ_F32,
                        U4, 1, _ptr(ws.Z[li]), U4, _ptr(bias), M, U4, L["F"], 0, 0, 0, _stream())
 
+    def _tc_ok(self, B: int, T: int) -> bool:
+        """The tensor-core scans work on whole tiles: 48 time-axis sequences (always whole: B*48) and
+        64 note-axis sequences (B*T % 64 == 0); other shapes use the fp32 CUDA-core scans."""
+        return self.tc_scan and (B * T) % 64 == 0
+
     def _scan_map(self, axis: str, B: int, T: int):
         if axis == "time":   # sequences (b,n), steps t
             return dict(S=B * N, steps=T, inner=N, outer=T * N, inner_stride=1, step=N)
@@ -291,7 +296,7 @@ class Engine:
         L = self.layers[li]
         m = self._scan_map(L["axis"], B, T)
         self._tag = ":" + L["name"]
-        if train and ws.hprev[li] is not None and self.tc_scan:
+        if train and ws.hprev[li] is not None and self._tc_ok(B, T):
             self._call("dj_lstm_scan_tc_fwd", _ptr(ws.Z[li]), _ptr(ws.h[li]), _ptr(ws.c[li]), _ptr(ws.hprev[li]),
                        _ptr(self._wbf[f"{L['name']}.Ut"]), m["S"], m["steps"], L["U"], m["inner"], m["outer"],
                        m["inner_stride"], m["step"], self.hard, _stream())
@@ -382,7 +387,7 @@ class Engine:
             self._tag = ":bwd:" + name
             m = self._scan_map(L["axis"], B, T)
             dZ = ws.dZ.view(-1)[:M * U4].view(M, U4)
-            if bf16 and self.tc_scan:
+            if bf16 and self._tc_ok(B, T):
                 self._call("dj_lstm_scan_tc_bwd", _ptr(ws.Z[li]), _ptr(ws.c[li]), _ptr(dY), ldY, d[L["site_out"]],
                            _ptr(self._wbf[f"{name}.Un"]), _ptr(dZ), _ptr(G[f"{name}.lstm.b"]), m["S"], m["steps"], U,
                            m["inner"], m["outer"], m["inner_stride"], m["step"], self.hard, _stream())

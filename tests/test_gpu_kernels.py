@@ -115,7 +115,7 @@ def test_wgrad_gemm_tcgen05(lib, shape):
     assert helpers.rel_err(Cd.cpu().numpy(), ref) < 5e-5
 
 
-@pytest.mark.parametrize("axis,B,T", [("time", 3, 8), ("note", 2, 40), ("time", 20, 4), ("note", 40, 128)])
+@pytest.mark.parametrize("axis,B,T", [("time", 3, 8), ("note", 2, 32), ("time", 20, 4), ("note", 40, 128)])
 def test_lstm_scan_tcgen05_matches_fp32_scan(lib, axis, B, T):
     """Tensor-core recurrence (bf16 h.U, fp32 accumulate) against the fp32 CUDA-core
     recurrence on the same pre-activations."""
@@ -152,7 +152,7 @@ def test_lstm_scan_tcgen05_matches_fp32_scan(lib, axis, B, T):
     assert torch.equal(p4, want.bfloat16().float())
 
 
-@pytest.mark.parametrize("axis,B,T", [("time", 3, 8), ("note", 2, 40), ("note", 40, 128)])
+@pytest.mark.parametrize("axis,B,T", [("time", 3, 8), ("note", 2, 32), ("note", 40, 128)])
 def test_lstm_scan_bwd_tcgen05_matches_fp32_scan(lib, axis, B, T):
     """Reverse scan on tcgen05 (bf16 dz.U^T) against the fp32 CUDA-core reverse scan."""
     from music_generator_b200 import _lib
