@@ -146,7 +146,7 @@ def run_ours(args):
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
-    DOM = "dj_lstm_scan_bwd:bwd:time1"
+    DOM = "dj_lstm_scan_tc_bwd:bwd:time1"
     eng.profile, eng.profile_only = [], {DOM}
     launches0 = eng.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -190,11 +190,11 @@ def run_ours(args):
     peak, how = peaks()
     dom_ms = dom[1] / max(dom[0], 1)
     achieved = alg_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else None
-    roofline = {"kernel": "scan_bwd_kernel<256,8,48,bf16> (dj_lstm_scan_bwd, time axis layer 1)", "bound": "hbm",
+    roofline = {"kernel": "scan_tc_bwd_kernel<256,48> (dj_lstm_scan_tc_bwd, time-axis layer 1 reverse scan)", "bound": "hbm",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                 "traffic": None, "peak_source": how, "avg_launch_ms": dom_ms, "launches_timed": dom[0],
                 "algorithmic_bytes_per_launch": alg_bytes,
-                "note": "latency/FMA-bound recurrence, not HBM-bound: see DESIGN.md"}
+                "note": "sequential recurrence: bound by the per-step barrier/TMA/MMA latency chain, see DESIGN.md"}
 
     # ---------------- generation probe (configs[1])
     gen = None
@@ -211,6 +211,16 @@ def run_ours(args):
         torch.cuda.synchronize()
         gen = {"timesteps_per_s": gsteps / (time.time() - t0), "sequences": 1, "timesteps": gsteps,
                "workload": "generate.py path, 1 style-mixed sequence, full 128-step window recompute per timestep"}
+        # configs[3] per-GPU share: 128 independent sequences (4 predict-chunks of 32), indexed uniform stream
+        Gb, bsteps = 128, 4
+        stys = [np.eye(23)[i % 23] for i in range(Gb)]
+        ub = np.random.RandomState(7).random_sample((bsteps, Gb, 48, 2))
+        generate_events(ge, stys, 1, ub[:1], stream_mode=1)
+        torch.cuda.synchronize()
+        t0 = time.time()
+        generate_events(ge, stys, bsteps, ub, stream_mode=1)
+        torch.cuda.synchronize()
+        gen["batched"] = {"sequences": Gb, "timesteps": bsteps, "timesteps_per_s": Gb * bsteps / (time.time() - t0)}
 
     # ---------------- CPU baseline on this box's host cores (bounded sample)
     cpu = None

@@ -17,6 +17,8 @@ import torch
 from ._lib import DJ_F32, NO_DROPOUT
 from .engine import Engine, N, Workspace, _ptr, _stream
 
+PREDICT_CHUNK = 32   # keras Model.predict default batch_size
+
 
 class DeviceGeneration:
     """State of G `MusicGeneration` objects (generate.py:17-30) held in HBM."""
@@ -39,7 +41,7 @@ class DeviceGeneration:
         self.events = torch.zeros(G, N, 3, **f32)
         self.margin = torch.full((G,), 1e300, dtype=torch.float64, device=dev)
         self.cursor = torch.zeros(1, dtype=torch.int64, device=dev)
-        self.ws_time = eng.workspace(G, L, False, False)
+        self.ws_time = Workspace(cfg, G, L, False, False, dev)
         self.ws_note = Workspace(cfg, G, 1, False, False, dev)
         self.zero_chosen = torch.zeros(G, 1, N, 3, **f32)
         self.probs = torch.zeros(num_steps, G, N, 3, **f32)
@@ -94,18 +96,24 @@ def generate_events(eng: Engine, styles: Sequence[np.ndarray], num_steps: int, u
     are made and recorded but the forced event is what enters the window.
     Returns (events [steps,G,48,3], info dict with probs / min_margin / uniforms_used).
     """
-    gen = DeviceGeneration(eng, styles, num_steps, default_temp)
+    G = len(styles)
     u = torch.tensor(np.ascontiguousarray(uniforms, dtype=np.float64), device=eng.dev)
     if stream_mode == 1:
-        assert u.shape == (num_steps, gen.G, N, 2), u.shape
+        assert u.shape == (num_steps, G, N, 2), u.shape
+        # Keras predict() runs 32 sequences at a time and that chunk scopes the pitch_bins
+        # scramble (model.py:43-49), so larger batches are generated chunk by chunk
+        chunks = [(s, min(s + PREDICT_CHUNK, G)) for s in range(0, G, PREDICT_CHUNK)]
+    else:
+        if G > PREDICT_CHUNK:
+            raise ValueError("reference stream order supports at most %d sequences" % PREDICT_CHUNK)
+        chunks = [(0, G)]
+    gens = [DeviceGeneration(eng, styles[a:b], num_steps, default_temp) for a, b in chunks]
+    us = [u if stream_mode == 0 else u[:, a:b].contiguous() for a, b in chunks]
     forced = None if forced_events is None else torch.tensor(forced_events, dtype=torch.float32, device=eng.dev)
-    sampled = []
     for t in range(num_steps):
-        gen.step(t, u, stream_mode, None if forced is None else forced[t])
-        if forced is not None:
-            sampled.append(gen.events.clone())
-    info = dict(probs=gen.probs.cpu().numpy(), min_margin=float(gen.margin.min().item()),
-                uniforms_used=int(gen.cursor.item()))
-    if forced is not None:
-        info["sampled"] = torch.stack(sampled).cpu().numpy()
-    return gen.results(), info
+        for gen, uc, (a, b) in zip(gens, us, chunks):
+            gen.step(t, uc, stream_mode, None if forced is None else forced[t, a:b])
+    info = dict(probs=np.concatenate([g.probs.cpu().numpy() for g in gens], axis=1),
+                min_margin=min(float(g.margin.min().item()) for g in gens),
+                uniforms_used=int(gens[0].cursor.item()))
+    return np.concatenate([g.results() for g in gens], axis=1), info

@@ -196,3 +196,30 @@ def test_generation_three_genres_reference_stream_order():
     oev, oinfo = O.generate(p32, CFG, styles, steps, u, mode="incremental", forced_events=ev)
     assert np.array_equal(oinfo["decisions"][..., :2], ev[..., :2])
     assert info["uniforms_used"] == oinfo["uniforms_used"]
+
+
+def test_generation_indexed_stream_chunks_of_32():
+    """Batched generation (BASELINE configs[3] shape): indexed uniforms U[t,g,n,2]; sequences are
+    processed in predict-chunks of 32, so chunk k must equal a stand-alone run of those 32."""
+    from music_generator_b200.sampler import generate_events
+    e = make_engine("fp32")
+    G, steps = 40, 2
+    styles = [np.eye(23)[i % 23] for i in range(G)]
+    u = np.random.RandomState(9).random_sample((steps, G, 48, 2))
+    ev, info = generate_events(e, styles, steps, u, stream_mode=1)
+    assert ev.shape == (steps, G, 48, 3)
+    ev2, _ = generate_events(e, styles[32:], steps, u[:, 32:], stream_mode=1)
+    assert np.array_equal(ev[:, 32:], ev2)
+    assert np.all(ev[..., 1] <= ev[..., 0])
+    # a single sequence with its own uniforms laid out in reference order reproduces the reference-stream run
+    # (one sequence: the chunk is the sequence, so the pitch_bins scramble agrees)
+    u1 = np.random.RandomState(10).random_sample((steps, 1, 48, 2))
+    ev_i, _ = generate_events(e, styles[:1], steps, u1, stream_mode=1)
+    flat = []
+    for t in range(steps):
+        for n in range(48):
+            flat.append(u1[t, 0, n, 0])
+            if ev_i[t, 0, n, 0] == 1:
+                flat.append(u1[t, 0, n, 1])
+    ev_r, info_r = generate_events(e, styles[:1], steps, np.array(flat + [0.5] * 8), stream_mode=0)
+    assert np.array_equal(ev_i, ev_r) and info_r["uniforms_used"] == len(flat)
