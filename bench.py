@@ -111,7 +111,30 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+class StdoutToStderr:
+    """NCCL prints its version banner on the C-level stdout at first use; the contract is ONE JSON line
+    on stdout, so everything before the final print goes to stderr."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *a):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 def run_ours(args):
+    with StdoutToStderr():
+        line = _run_ours(args)
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+def _run_ours(args):
     import torch.distributed as dist
     import music_generator_b200  # noqa: F401
     from music_generator_b200.config import ModelConfig
@@ -181,7 +204,7 @@ def run_ours(args):
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
-        return
+        return None
 
     # ---------------- roofline of the dominant kernel (time-axis reverse scan, layer 1)
     # algorithmic bytes per row: gates 16U + c 4U + dY 4U read, dZ(bf16) 8U written, U=256
@@ -240,9 +263,9 @@ def run_ours(args):
                     "ms_per_step": ms_e2e / K},
             "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roofline, "cpu_baseline": cpu,
             "generation": gen, "loss": lossv}
-    print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    return line
 
 
 def main():

@@ -135,20 +135,23 @@ __global__ void __launch_bounds__(128) style_bwd_reduce_kernel(const float* __re
   }
 }
 
+// grid (column blocks of 32, row slices): each block sums its slice, one atomic per column per block
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ X, int64_t ldx, int64_t R, int C,
-                                                     float* __restrict__ out, int accumulate) {
+                                                     float* __restrict__ out) {
   __shared__ float red[8][33];
   const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5, c = blockIdx.x * 32 + cl;
+  const int64_t per = (R + gridDim.y - 1) / gridDim.y;
+  const int64_t r0 = (int64_t)blockIdx.y * per, r1 = (r0 + per < R) ? r0 + per : R;
   float s = 0.f;
   if (c < C)
-    for (int64_t r = rl; r < R; r += 8) s += X[r * ldx + c];
+    for (int64_t r = r0 + rl; r < r1; r += 8) s += X[r * ldx + c];
   red[rl][cl] = s;
   __syncthreads();
   if (rl == 0 && c < C) {
     float t = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) t += red[i][cl];
-    out[c] = accumulate ? out[c] + t : t;
+    atomicAdd(out + c, t);
   }
 }
 
@@ -268,7 +271,11 @@ extern "C" int dj_style_bwd_reduce(const float* dA, int64_t ldA, int F, const fl
 
 extern "C" int dj_colsum(const float* X, int64_t ldx, int64_t R, int C, float* out, int accumulate, void* stream) {
   DJ_CHECK_ARG(X && out && R > 0 && C > 0 && ldx >= C, "dj_colsum: bad arguments");
-  colsum_kernel<<<(C + 31) / 32, 256, 0, (cudaStream_t)stream>>>(X, ldx, R, C, out, accumulate);
+  if (!accumulate) DJ_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)C, (cudaStream_t)stream));
+  int slices = (int)((R + 127) / 128);
+  if (slices > 64) slices = 64;
+  if (slices < 1) slices = 1;
+  colsum_kernel<<<dim3((C + 31) / 32, slices), 256, 0, (cudaStream_t)stream>>>(X, ldx, R, C, out);
   DJ_LAUNCH_CHECK();
   return 0;
 }
@@ -278,7 +285,7 @@ extern "C" int dj_conv_bwd(const float* notes_in, int64_t notes_bstride, int B, 
                            float* dWc, float* dbc, void* stream) {
   DJ_CHECK_ARG(notes_in && Wc && bc && dA0 && dWc && dbc, "dj_conv_bwd: NULL pointer");
   DJ_CHECK_ARG(B > 0 && T > 0 && ldA >= DJ_FEAT0, "dj_conv_bwd: bad sizes");
-  int grid = dj_num_sms();
+  int grid = dj_num_sms() * 4;   // 31 KB smem, 256 threads: 4 resident blocks hide the per-(b,t) barriers
   if (grid > B * T) grid = B * T;
   conv_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(notes_in, notes_bstride, B, T, Wc, bc, d_notes, d_conv,
                                                           dA0, ldA, dWc, dbc);

@@ -176,6 +176,12 @@ scan_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
         acc_phase ^= 1;
         tc_fence_after();
       }
+      if (t + 1 < steps && lane < 16) {   // warm L2 with the next step's x.W rows (this warp's 128-byte segments)
+#pragma unroll
+        for (int ci = 0; ci < NCH; ++ci)
+          asm volatile("prefetch.global.L2 [%0];\n" ::"l"(Z + (size_t)(rowb[ci] + lane * sstr + (t + 1) * tstr) * (4 * U) +
+                                                              128 * rank + 32 * q));
+      }
 #pragma unroll
       for (int ci = 0; ci < NCH; ++ci) {
         float v[16];
@@ -395,13 +401,16 @@ scan_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
     float dbacc[4] = {0.f, 0.f, 0.f, 0.f};
     float dcn[CPL], ct[CPL], cpv[CPL], dyv[CPL];
     float4 gv[CPL];
+    // Pure loads only: anything computed on a just-loaded value would serialise the loads (each use
+    // waits for its own DRAM round trip).  Masks and the t==0 special case are applied at use time.
     auto issue_loads = [&](int t) {       // everything of step t that does not depend on the recurrence
+      const uint32_t tp = (t > 0) ? (uint32_t)(t - 1) : 0u;      // clamped: row of c_{t-1} (ignored at t == 0)
 #pragma unroll
       for (int j = 0; j < CPL; ++j) {
         const uint32_t r = row00 + j * sstr + (uint32_t)t * tstr;
-        gv[j] = *reinterpret_cast<const float4*>(G + (size_t)r * (4 * U) + 4 * col);
-        cpv[j] = (t > 0) ? Cst[(size_t)(r - tstr) * U + col] : 0.f;
-        dyv[j] = dY[(size_t)r * ldY + col] * dj_dropmul(d_y, r * U + col);
+        gv[j] = __ldg(reinterpret_cast<const float4*>(G + (size_t)r * (4 * U) + 4 * col));
+        cpv[j] = __ldg(Cst + (size_t)(row00 + j * sstr + tp * tstr) * U + col);
+        dyv[j] = __ldg(dY + (size_t)r * ldY + col);
       }
     };
 #pragma unroll
@@ -435,13 +444,14 @@ scan_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
       for (int j = 0; j < CPL; ++j) {
         const uint32_t r = row00 + j * sstr + (uint32_t)t * tstr;
         const float4 g4 = gv[j];
-        const float dht = dyv[j] + dh[j];
+        const float cprev = (t > 0) ? cpv[j] : 0.f;
+        const float dht = fmaf(dyv[j], dj_dropmul(d_y, r * U + col), dh[j]);
         const float tc = fast_tanh(ct[j]);
         const float d_o = dht * tc;
         const float dc = fmaf(dht * g4.w, 1.f - tc * tc, dcn[j]);
         dcn[j] = dc * g4.y;
         const float dz0 = dc * g4.z * dj_gate_dact(g4.x, hard);
-        const float dz1 = dc * cpv[j] * dj_gate_dact(g4.y, hard);
+        const float dz1 = dc * cprev * dj_gate_dact(g4.y, hard);
         const float dz2 = dc * g4.x * (1.f - g4.z * g4.z);
         const float dz3 = d_o * dj_gate_dact(g4.w, hard);
         __nv_bfloat162 lo = __floats2bfloat162_rn(dz0, dz1), hi = __floats2bfloat162_rn(dz2, dz3);
@@ -450,7 +460,7 @@ scan_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
         pk.y = *reinterpret_cast<uint32_t*>(&hi);
         *reinterpret_cast<uint2*>(dZ + (size_t)r * (4 * U) + 4 * col) = pk;
         dbacc[0] += dz0; dbacc[1] += dz1; dbacc[2] += dz2; dbacc[3] += dz3;
-        ct[j] = cpv[j];                   // c_{t-1} is the cell state of the next (earlier) step
+        ct[j] = cprev;                    // c_{t-1} is the cell state of the next (earlier) step
       }
       if (t > 0) issue_loads(t - 1);      // in flight across the fence / barrier / TMA / MMA of the step boundary
       tc_fence_before();

@@ -419,7 +419,7 @@ class Engine:
                        _ptr(ws.ds[li]), _stream())
             self._call("dj_gemm_simt", _ptr(ws.emb), DJ_F32, 1, cfg.style_units, _ptr(ws.ds[li]), DJ_F32, F, 1,
                        _ptr(G[f"{name}.sd.W"]), F, None, cfg.style_units, F, BT, 1, 0, 0, _stream())
-            self._call("dj_colsum", _ptr(ws.ds[li]), F, BT, F, _ptr(G[f"{name}.sd.b"]), 0, _stream())
+            self._call("dj_colsum", _ptr(ws.ds[li]), F, BT, F, _ptr(G[f"{name}.sd.b"]), 1, _stream())
             self._call("dj_gemm_simt", _ptr(ws.ds[li]), DJ_F32, F, 1, _ptr(P[f"{name}.sd.W"]), DJ_F32, 1, F,
                        _ptr(ws.demb), cfg.style_units, None, BT, cfg.style_units, F, 0 if first_style else 1, 0, 0,
                        _stream())
@@ -431,7 +431,7 @@ class Engine:
         ns = cfg.num_styles
         self._call("dj_gemm_simt", _ptr(st["style"]), DJ_F32, 1, ns, _ptr(ws.demb), DJ_F32, cfg.style_units, 1,
                    _ptr(G["style.W"]), cfg.style_units, None, ns, cfg.style_units, BT, 1, 0, 0, _stream())
-        self._call("dj_colsum", _ptr(ws.demb), cfg.style_units, BT, cfg.style_units, _ptr(G["style.b"]), 0, _stream())
+        self._call("dj_colsum", _ptr(ws.demb), cfg.style_units, BT, cfg.style_units, _ptr(G["style.b"]), 1, _stream())
         return ws.loss
 
     # ------------------------------------------------------------- optimizer
