@@ -113,6 +113,9 @@ int dj_wgrad_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, f
 /* fp32 -> bf16 operand copies: out[r, c] = in[r, c] (c<cols) else 0, out ld = ldo;
  * transpose!=0 writes out[c, r] (ldo >= rows). */
 int dj_cast_bf16(const float* in, int rows, int cols, void* out, int ldo, int transpose, void* stream);
+/* the same for up to 16 tensors in one launch (all operand copies of a training step) */
+int dj_cast_bf16_multi(int n, const float* const* in, const int* rows, const int* cols, void* const* out,
+                       const int* ldo, const int* transpose, void* stream);
 
 /* ---- recurrence (the sequential part of keras LSTM, model.py:84,120) ---------
  * Persistent thread-block-cluster kernel: the recurrent weights U [units,4*units]

@@ -248,6 +248,28 @@ __global__ void cast_bf16_kernel(const float* __restrict__ in, int rows, int col
   }
 }
 
+struct CastBatch {
+  const float* in[16];
+  __nv_bfloat16* out[16];
+  int rows[16], cols[16], ldo[16], transpose[16];
+};
+// all bf16 operand copies of a step in one launch: blockIdx.y selects the tensor
+__global__ void cast_bf16_multi_kernel(CastBatch b) {
+  const int e = blockIdx.y;
+  const float* __restrict__ in = b.in[e];
+  __nv_bfloat16* __restrict__ out = b.out[e];
+  const int rows = b.rows[e], cols = b.cols[e], ldo = b.ldo[e], tr = b.transpose[e];
+  const int orows = tr ? cols : rows;
+  const int64_t total = (int64_t)orows * ldo;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ro = (int)(i / ldo), co = (int)(i % ldo);
+    float v = 0.f;
+    if (!tr) { if (co < cols) v = in[(int64_t)ro * cols + co]; }
+    else { if (co < rows) v = in[(int64_t)co * cols + ro]; }
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+
 inline int grid_for(int64_t total, int threads, int max_blocks) {
   int64_t b = (total + threads - 1) / threads;
   if (b < 1) b = 1;
@@ -349,6 +371,21 @@ extern "C" int dj_cast_bf16(const float* in, int rows, int cols, void* out, int 
   DJ_CHECK_ARG(ldo >= (transpose ? rows : cols), "dj_cast_bf16: ldo %d too small", ldo);
   cast_bf16_kernel<<<grid_for((int64_t)orows * ldo, 256, dj_num_sms() * 8), 256, 0, (cudaStream_t)stream>>>(
       in, rows, cols, (__nv_bfloat16*)out, ldo, transpose, orows);
+  DJ_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int dj_cast_bf16_multi(int n, const float* const* in, const int* rows, const int* cols, void* const* out,
+                                  const int* ldo, const int* transpose, void* stream) {
+  DJ_CHECK_ARG(n > 0 && n <= 16 && in && rows && cols && out && ldo && transpose, "dj_cast_bf16_multi: bad arguments");
+  CastBatch b{};
+  for (int i = 0; i < n; ++i) {
+    DJ_CHECK_ARG(in[i] && out[i] && rows[i] > 0 && cols[i] > 0 && ldo[i] >= (transpose[i] ? rows[i] : cols[i]),
+                 "dj_cast_bf16_multi: entry %d invalid", i);
+    b.in[i] = in[i]; b.out[i] = (__nv_bfloat16*)out[i];
+    b.rows[i] = rows[i]; b.cols[i] = cols[i]; b.ldo[i] = ldo[i]; b.transpose[i] = transpose[i];
+  }
+  cast_bf16_multi_kernel<<<dim3(64, n), 256, 0, (cudaStream_t)stream>>>(b);
   DJ_LAUNCH_CHECK();
   return 0;
 }

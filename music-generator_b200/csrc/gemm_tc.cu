@@ -19,14 +19,17 @@ namespace {
 constexpr int BM = 128, BN = 128, BK = 64;
 constexpr int STAGES = 4, ACC_STAGES = 2;
 constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
-constexpr int EPI_WARP_BYTES = 2 * 32 * 128;   // two 32x32 fp32 staging boxes per epilogue warp
+constexpr int EPI_BOXES = 4;                     // 32x32 fp32 staging boxes per epilogue warp (TMA stores in flight)
+constexpr int EPI_WARP_BYTES = EPI_BOXES * 32 * 128;
 constexpr int NUM_THREADS = 256;
 
+constexpr int MAX_BIAS_N = 2048;                  // bias is staged in shared memory once per CTA
 struct GemmSmem {
   static constexpr int A_OFF = 0;
   static constexpr int B_OFF = STAGES * A_BYTES;
   static constexpr int EPI_OFF = B_OFF + STAGES * B_BYTES;
-  static constexpr int BAR_OFF = EPI_OFF + 4 * EPI_WARP_BYTES;
+  static constexpr int BIAS_OFF = EPI_OFF + 4 * EPI_WARP_BYTES;
+  static constexpr int BAR_OFF = BIAS_OFF + MAX_BIAS_N * 4;
   static constexpr int TOTAL = BAR_OFF + 256 + 1024;   // + alignment slack
 };
 
@@ -59,6 +62,9 @@ gate_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(smem_u32(tmem_slot), ACC_STAGES * BN);
+  float* bias_s = reinterpret_cast<float*>(smem + GemmSmem::BIAS_OFF);
+  if (bias != nullptr)   // one global read of the bias per CTA; the epilogue then reads it from shared memory
+    for (int i = threadIdx.x; i < ((N + 127) / 128) * 128; i += NUM_THREADS) bias_s[i] = (i < N) ? bias[i] : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -114,7 +120,7 @@ gate_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(32 * e) << 16) + (uint32_t)(acc * BN + c * 32), v);
-        if (lane == 0) tma_store_wait_read<1>();   // the store that last used this staging box is done
+        if (lane == 0) tma_store_wait_read<EPI_BOXES - 1>();   // the store that last used this staging box is done
         __syncwarp();
         const int ncol = n0 + c * 32;
         uint8_t* box = ebuf + nbuf * 4096;
@@ -124,15 +130,8 @@ gate_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           o.x = __uint_as_float(v[4 * q + 0]); o.y = __uint_as_float(v[4 * q + 1]);
           o.z = __uint_as_float(v[4 * q + 2]); o.w = __uint_as_float(v[4 * q + 3]);
           if (bias != nullptr) {
-            const int n = ncol + 4 * q;
-            if (n + 3 < N) {
-              const float4 bv = *reinterpret_cast<const float4*>(bias + n);
-              o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
-            } else {
-              if (n < N) o.x += bias[n];
-              if (n + 1 < N) o.y += bias[n + 1];
-              if (n + 2 < N) o.z += bias[n + 2];
-            }
+            const float4 bv = *reinterpret_cast<const float4*>(bias_s + ncol + 4 * q);   // broadcast smem read
+            o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
           }
           // 128B swizzle: 16-byte chunk q of row `lane` lives at chunk q ^ (lane & 7)
           *reinterpret_cast<float4*>(box + lane * 128 + ((q ^ (lane & 7)) << 4)) = o;
@@ -143,7 +142,7 @@ gate_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           tma_store_2d(&tmC, ebuf_s + nbuf * 4096, ncol, m0 + 32 * e);
           tma_store_commit();
         }
-        nbuf ^= 1;
+        nbuf = (nbuf + 1) % EPI_BOXES;
       }
       tc_fence_before();
       __syncwarp();
@@ -291,6 +290,7 @@ extern "C" int dj_gate_gemm_bf16(const void* A, int64_t lda, const void* Bt, int
   DJ_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0 && ldc % 4 == 0 && lda >= K && ldb >= K && ldc >= N,
                "dj_gate_gemm_bf16: leading dimensions must be 16-byte multiples and cover K/N (lda=%lld ldb=%lld ldc=%lld)",
                (long long)lda, (long long)ldb, (long long)ldc);
+  DJ_CHECK_ARG(bias == nullptr || N <= MAX_BIAS_N, "dj_gate_gemm_bf16: N=%d exceeds the bias staging capacity %d", N, MAX_BIAS_N);
   DJ_CHECK_ARG(((uintptr_t)A % 16) == 0 && ((uintptr_t)Bt % 16) == 0 && ((uintptr_t)C % 16) == 0 &&
                    (bias == nullptr || ((uintptr_t)bias % 16) == 0),
                "dj_gate_gemm_bf16: pointers must be 16-byte aligned");

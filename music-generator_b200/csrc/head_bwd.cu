@@ -39,48 +39,65 @@ __global__ void __launch_bounds__(256) head_loss_kernel(
 #pragma unroll
   for (int i = 0; i < V; ++i) g0[i] = g1[i] = g2[i] = 0.f;
 
-  for (int64_t row = (int64_t)blockIdx.x * 8 + warp; row < M; row += (int64_t)gridDim.x * 8) {
-    float x[V];
+  // RB rows per warp iteration: all their loads are issued before any is used (memory-level parallelism)
+  constexpr int RB = 4;
+  for (int64_t row0 = ((int64_t)blockIdx.x * 8 + warp) * RB; row0 < M; row0 += (int64_t)gridDim.x * 8 * RB) {
+    float4 hv[RB][V / 4];
+    float yv[RB][3];
 #pragma unroll
-    for (int i4 = 0; i4 < V; i4 += 4) {
-      const int u = lane * V + i4;
-      const float4 hv = *reinterpret_cast<const float4*>(h + row * UNITS + u);
-      float m[4];
-      dj_dropmul4(d_h, (uint32_t)(row * UNITS + u), m);
-      x[i4] = hv.x * m[0]; x[i4 + 1] = hv.y * m[1]; x[i4 + 2] = hv.z * m[2]; x[i4 + 3] = hv.w * m[3];
-    }
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    for (int rb = 0; rb < RB; ++rb) {
+      const int64_t row = (row0 + rb < M) ? row0 + rb : M - 1;
 #pragma unroll
-    for (int i = 0; i < V; ++i) {
-      s0 = fmaf(x[i], wn0[i], s0); s1 = fmaf(x[i], wn1[i], s1); s2 = fmaf(x[i], wv[i], s2);
+      for (int i4 = 0; i4 < V; i4 += 4)
+        hv[rb][i4 / 4] = __ldg(reinterpret_cast<const float4*>(h + row * UNITS + lane * V + i4));
+      if (y != nullptr) { yv[rb][0] = __ldg(y + row * 3); yv[rb][1] = __ldg(y + row * 3 + 1); yv[rb][2] = __ldg(y + row * 3 + 2); }
     }
-    s0 = dj_warp_sum(s0) + b0; s1 = dj_warp_sum(s1) + b1; s2 = dj_warp_sum(s2) + b2;
-    const float p0 = dj_sigmoid(s0), p1 = dj_sigmoid(s1), vol = s2;
-    if (lane == 0) { probs[row * 3] = p0; probs[row * 3 + 1] = p1; probs[row * 3 + 2] = vol; }
-    if (y != nullptr) {
-      const float y0 = y[row * 3], y1 = y[row * 3 + 1], y2 = y[row * 3 + 2];
-      float dl0, dlq;
-      const float l0 = bce_term(y0, p0, dl0);
-      const float q = y0 * p1 + (1.f - y0) * y1;
-      const float l1 = bce_term(y1, q, dlq);
-      const float d = y2 - (y0 * vol + (1.f - y0) * y2);
-      const float da0 = dl0 * p0 * (1.f - p0) * inv_M;
-      const float da1 = dlq * y0 * p1 * (1.f - p1) * inv_M;
-      const float da2 = -2.f * d * y0 * inv_M;
-      if (lane == 0) { lsum += l0 + l1 + d * d; gb0 += da0; gb1 += da1; gb2 += da2; }
+#pragma unroll
+    for (int rb = 0; rb < RB; ++rb) {
+      const int64_t row = row0 + rb;
+      if (row >= M) break;
+      float x[V];
+#pragma unroll
+      for (int i4 = 0; i4 < V; i4 += 4) {
+        const int u = lane * V + i4;
+        float m[4];
+        dj_dropmul4(d_h, (uint32_t)(row * UNITS + u), m);
+        x[i4] = hv[rb][i4 / 4].x * m[0]; x[i4 + 1] = hv[rb][i4 / 4].y * m[1];
+        x[i4 + 2] = hv[rb][i4 / 4].z * m[2]; x[i4 + 3] = hv[rb][i4 / 4].w * m[3];
+      }
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f;
 #pragma unroll
       for (int i = 0; i < V; ++i) {
-        g0[i] = fmaf(x[i], da0, g0[i]); g1[i] = fmaf(x[i], da1, g1[i]); g2[i] = fmaf(x[i], da2, g2[i]);
+        s0 = fmaf(x[i], wn0[i], s0); s1 = fmaf(x[i], wn1[i], s1); s2 = fmaf(x[i], wv[i], s2);
       }
-      if (dX != nullptr) {
+      s0 = dj_warp_sum(s0) + b0; s1 = dj_warp_sum(s1) + b1; s2 = dj_warp_sum(s2) + b2;
+      const float p0 = dj_sigmoid(s0), p1 = dj_sigmoid(s1), vol = s2;
+      if (lane == 0) { probs[row * 3] = p0; probs[row * 3 + 1] = p1; probs[row * 3 + 2] = vol; }
+      if (y != nullptr) {
+        const float y0 = yv[rb][0], y1 = yv[rb][1], y2 = yv[rb][2];
+        float dl0, dlq;
+        const float l0 = bce_term(y0, p0, dl0);
+        const float q = y0 * p1 + (1.f - y0) * y1;
+        const float l1 = bce_term(y1, q, dlq);
+        const float d = y2 - (y0 * vol + (1.f - y0) * y2);
+        const float da0 = dl0 * p0 * (1.f - p0) * inv_M;
+        const float da1 = dlq * y0 * p1 * (1.f - p1) * inv_M;
+        const float da2 = -2.f * d * y0 * inv_M;
+        if (lane == 0) { lsum += l0 + l1 + d * d; gb0 += da0; gb1 += da1; gb2 += da2; }
 #pragma unroll
-        for (int i4 = 0; i4 < V; i4 += 4) {
-          float4 o;
-          o.x = da0 * wn0[i4] + da1 * wn1[i4] + da2 * wv[i4];
-          o.y = da0 * wn0[i4 + 1] + da1 * wn1[i4 + 1] + da2 * wv[i4 + 1];
-          o.z = da0 * wn0[i4 + 2] + da1 * wn1[i4 + 2] + da2 * wv[i4 + 2];
-          o.w = da0 * wn0[i4 + 3] + da1 * wn1[i4 + 3] + da2 * wv[i4 + 3];
-          *reinterpret_cast<float4*>(dX + row * UNITS + lane * V + i4) = o;
+        for (int i = 0; i < V; ++i) {
+          g0[i] = fmaf(x[i], da0, g0[i]); g1[i] = fmaf(x[i], da1, g1[i]); g2[i] = fmaf(x[i], da2, g2[i]);
+        }
+        if (dX != nullptr) {
+#pragma unroll
+          for (int i4 = 0; i4 < V; i4 += 4) {
+            float4 o;
+            o.x = da0 * wn0[i4] + da1 * wn1[i4] + da2 * wv[i4];
+            o.y = da0 * wn0[i4 + 1] + da1 * wn1[i4 + 1] + da2 * wv[i4 + 1];
+            o.z = da0 * wn0[i4 + 2] + da1 * wn1[i4 + 2] + da2 * wv[i4 + 2];
+            o.w = da0 * wn0[i4 + 3] + da1 * wn1[i4 + 3] + da2 * wv[i4 + 3];
+            *reinterpret_cast<float4*>(dX + row * UNITS + lane * V + i4) = o;
+          }
         }
       }
     }

@@ -205,26 +205,26 @@ class Engine:
         K-major) and natural [F, 4U] (data-gradient B operand)."""
         if self._wbf_version == self._version:
             return
+        ents = []   # (src, rows, cols, dst, ldo, transpose)
         for li, L in enumerate(self.layers):
             W = self.params[f"{L['name']}.lstm.W"]
-            F, U4 = W.shape
-            ld = round_up(F, 32)
-            kt, kn = f"{L['name']}.Wt", f"{L['name']}.Wn"
-            if kt not in self._wbf:
-                self._wbf[kt] = torch.empty(U4, ld, dtype=torch.bfloat16, device=self.dev)
-                self._wbf[kn] = torch.empty(F, U4, dtype=torch.bfloat16, device=self.dev)
-            self._call("dj_cast_bf16", _ptr(W), F, U4, _ptr(self._wbf[kt]), ld, 1, _stream())
-            self._call("dj_cast_bf16", _ptr(W), F, U4, _ptr(self._wbf[kn]), U4, 0, _stream())
-            # recurrent kernel transposed [4U, U]: resident A operand of the tensor-core scan
-            ku = f"{L['name']}.Ut"
             Um = self.params[f"{L['name']}.lstm.U"]
-            if ku not in self._wbf:
-                self._wbf[ku] = torch.empty(U4, L["U"], dtype=torch.bfloat16, device=self.dev)
-            self._call("dj_cast_bf16", _ptr(Um), L["U"], U4, _ptr(self._wbf[ku]), L["U"], 1, _stream())
-            kun = f"{L['name']}.Un"   # natural [U, 4U]: resident A operand of the tensor-core reverse scan
-            if kun not in self._wbf:
-                self._wbf[kun] = torch.empty(L["U"], U4, dtype=torch.bfloat16, device=self.dev)
-            self._call("dj_cast_bf16", _ptr(Um), L["U"], U4, _ptr(self._wbf[kun]), U4, 0, _stream())
+            F, U4 = W.shape
+            U, ld = L["U"], round_up(F, 32)
+            n = L["name"]
+            if f"{n}.Wt" not in self._wbf:
+                bf = dict(dtype=torch.bfloat16, device=self.dev)
+                self._wbf[f"{n}.Wt"] = torch.empty(U4, ld, **bf)   # W^T  [4U, ld]: forward B operand (K-major)
+                self._wbf[f"{n}.Wn"] = torch.empty(F, U4, **bf)    # W    [F, 4U]: data-gradient B operand
+                self._wbf[f"{n}.Ut"] = torch.empty(U4, U, **bf)    # U^T  [4U, U]: resident A operand, forward scan
+                self._wbf[f"{n}.Un"] = torch.empty(U, U4, **bf)    # U    [U, 4U]: resident A operand, reverse scan
+            ents += [(W, F, U4, self._wbf[f"{n}.Wt"], ld, 1), (W, F, U4, self._wbf[f"{n}.Wn"], U4, 0),
+                     (Um, U, U4, self._wbf[f"{n}.Ut"], U, 1), (Um, U, U4, self._wbf[f"{n}.Un"], U4, 0)]
+        k = len(ents)
+        self._call("dj_cast_bf16_multi", k, (C.c_void_p * k)(*[e[0].data_ptr() for e in ents]),
+                   (C.c_int * k)(*[e[1] for e in ents]), (C.c_int * k)(*[e[2] for e in ents]),
+                   (C.c_void_p * k)(*[e[3].data_ptr() for e in ents]), (C.c_int * k)(*[e[4] for e in ents]),
+                   (C.c_int * k)(*[e[5] for e in ents]), _stream())
         self._wbf_version = self._version
 
     # --------------------------------------------------------------- dropout
