@@ -532,10 +532,16 @@ extern "C" int dj_lstm_scan_tc_fwd(float* Z, float* h_out, float* c_out, void* h
     // time axis: sequences (b, n), rows of one b are contiguous at each step
     DJ_CHECK_ARG(seq_inner == 48 && seq_inner_stride == 1 && step_stride == 48 && S % 48 == 0,
                  "dj_lstm_scan_tc_fwd: units=256 expects the time-axis map (seq=(b,n))");
+    // 2 CTAs/SM x 16 resident 8-CTA clusters = 32 tile slots: beyond that, double the tile (two batch
+    // elements per cluster) so the whole layer still runs as one wave of step chains
+    if (S % 96 == 0 && S / 48 > 32)
+      return launch_tc_fwd<256, 96>(Ut_bf16, Z, h_out, c_out, h_prev_bf16, S, steps, map, 1, hard, st);
     return launch_tc_fwd<256, 48>(Ut_bf16, Z, h_out, c_out, h_prev_bf16, S, steps, map, 1, hard, st);
   } else if (units == 128) {
     DJ_CHECK_ARG(seq_inner == 1 && seq_outer_stride == 48 && step_stride == 1 && steps <= 48,
                  "dj_lstm_scan_tc_fwd: units=128 expects the note-axis map (seq=(b,t))");
+    if (S % 128 == 0 && S / 64 > 74)
+      return launch_tc_fwd<128, 128>(Ut_bf16, Z, h_out, c_out, h_prev_bf16, S, steps, map, 0, hard, st);
     return launch_tc_fwd<128, 64>(Ut_bf16, Z, h_out, c_out, h_prev_bf16, S, steps, map, 0, hard, st);
   }
   DJ_CHECK_ARG(false, "dj_lstm_scan_tc_fwd: units=%d unsupported (128 or 256)", units);
