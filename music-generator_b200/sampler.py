@@ -18,6 +18,7 @@ from ._lib import DJ_F32, NO_DROPOUT
 from .engine import Engine, N, Workspace, _ptr, _stream
 
 PREDICT_CHUNK = 32   # keras Model.predict default batch_size
+REFERENCE_STREAM_MAX = 8   # sequences one sampler cluster walks in np.random call order (generate.py default: 3)
 
 
 class DeviceGeneration:
@@ -104,8 +105,8 @@ def generate_events(eng: Engine, styles: Sequence[np.ndarray], num_steps: int, u
         # scramble (model.py:43-49), so larger batches are generated chunk by chunk
         chunks = [(s, min(s + PREDICT_CHUNK, G)) for s in range(0, G, PREDICT_CHUNK)]
     else:
-        if G > PREDICT_CHUNK:
-            raise ValueError("reference stream order supports at most %d sequences" % PREDICT_CHUNK)
+        if G > REFERENCE_STREAM_MAX:
+            raise ValueError("reference stream order supports at most %d sequences" % REFERENCE_STREAM_MAX)
         chunks = [(0, G)]
     gens = [DeviceGeneration(eng, styles[a:b], num_steps, default_temp) for a, b in chunks]
     us = [u if stream_mode == 0 else u[:, a:b].contiguous() for a, b in chunks]
