@@ -215,7 +215,9 @@ def _run_ours(args):
     achieved = alg_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else None
     roofline = {"kernel": "scan_tc_bwd_kernel<256,48> (dj_lstm_scan_tc_bwd, time-axis layer 1 reverse scan)", "bound": "hbm",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                "traffic": None, "peak_source": how, "avg_launch_ms": dom_ms, "launches_timed": dom[0],
+                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape from the ncu --set full
+                # capture summarised in profiles/r01_scan_tc_bwd_time.md (2.417 GB + 0.785 GB per launch)
+                "traffic": 3.202e9 if B == 64 else None, "peak_source": how, "avg_launch_ms": dom_ms, "launches_timed": dom[0],
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "note": "sequential recurrence: bound by the per-step barrier/TMA/MMA latency chain, see DESIGN.md"}
 

@@ -266,6 +266,7 @@ int launch_tc_fwd(const void* Ut_bf, float* Z, float* h_out, float* c_out, void*
   }
   auto kernel = scan_tc_fwd_kernel<U, BS>;
   DJ_CUDA(cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
+  if (C > 8) DJ_CUDA(cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((S / BS) * C);   // one cluster per tile; the hardware keeps 2 CTAs resident per SM
   cfg.blockDim = dim3(TC_THREADS);
@@ -290,9 +291,11 @@ int launch_tc_fwd(const void* Ut_bf, float* Z, float* h_out, float* c_out, void*
 //   multicast from the dZ buffer in L2 (dZ must be written anyway for the weight
 //   gradients).  M = 64 accumulators sit in lanes 0..15 of each TMEM quarter.
 // ---------------------------------------------------------------------------
-template <int U, int BS>
+// UPC = hidden units owned by one CTA: 64 (M = 64 fully used) or 32 (U = 512: only 32 rows of U fit; the
+// M = 64 MMA then reads 32 further rows of the next K atom, whose accumulator rows are never read).
+template <int U, int BS, int UPC>
 struct TcBwdSmem {
-  static constexpr int A_BYTES = 64 * 4 * U * 2;
+  static constexpr int A_BYTES = UPC * 4 * U * 2;
   static constexpr int B_BYTES = BS * 4 * U * 2;
   static constexpr int A_OFF = 0, B_OFF = A_BYTES, BAR_OFF = A_BYTES + B_BYTES;
   static constexpr int TOTAL = BAR_OFF + 64 + 1024;
@@ -308,20 +311,22 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t v[8]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
 
-template <int U, int BS>
+template <int U, int BS, int UPC>
 __global__ void __launch_bounds__(TCB_THREADS, (U == 128 && BS <= 32) ? 2 : 1)
 scan_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmZ,
                    const float* __restrict__ G, const float* __restrict__ Cst, const float* __restrict__ dY,
                    uint32_t ldY, dj_dropout d_y, __nv_bfloat16* __restrict__ dZ, float* __restrict__ db,
                    int steps, TcMap map, int hard) {
-  constexpr int C = U / 64;             // cluster size
+  constexpr int C = U / UPC;            // cluster size
   constexpr int KA = 4 * U / 64;        // K atoms of the contraction (gate columns)
+  constexpr int ATOM = UPC * 128;       // bytes of one resident K atom of U (UPC rows x 128 B)
+  static_assert(UPC == 64 || UPC == 32, "units per CTA");
   constexpr int KPC = KA / C;           // atoms each CTA multicasts per step
   constexpr int WC = BS / 2;            // accumulator columns (sequences) per epilogue warp
   constexpr int CPL = BS / 4;           // cells per lane
   constexpr uint32_t TMEM_COLS = BS <= 32 ? 32 : BS <= 64 ? 64 : BS <= 128 ? 128 : 256;
   static_assert(WC % 8 == 0, "warp column range is loaded in 8-column pieces");
-  using SM = TcBwdSmem<U, BS>;
+  using SM = TcBwdSmem<U, BS, UPC>;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -354,7 +359,7 @@ scan_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
     if (lane == 0) {   // resident A operand: rows [64*rank, +64) of U, all 4U columns
       mbar_expect_tx(bar_a, SM::A_BYTES);
       for (int ja = 0; ja < KA; ++ja)
-        tma_load_2d(sbase + SM::A_OFF + ja * 8192, &tmU, bar_a, ja * 64, 64 * rank);
+        tma_load_2d(sbase + SM::A_OFF + ja * ATOM, &tmU, bar_a, ja * 64, UPC * rank);
     }
     uint32_t z_phase = 0;
     for (int t = steps - 1; t >= 0; --t) {
@@ -368,7 +373,7 @@ scan_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
         for (int ja = 0; ja < KA; ++ja)
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const uint64_t adesc = make_smem_desc(sbase + SM::A_OFF + ja * 8192 + k * 32, 16, 1024);
+            const uint64_t adesc = make_smem_desc(sbase + SM::A_OFF + ja * ATOM + k * 32, 16, 1024);
             const uint64_t bdesc = make_smem_desc(sbase + SM::B_OFF + ja * (BS * 128) + k * 32, 16, 1024);
             umma_bf16(tmem_base, adesc, bdesc, idesc, (ja | k) != 0);
           }
@@ -382,7 +387,9 @@ scan_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
         mbar_expect_tx(bar_z, SM::B_BYTES);
         for (int i = 0; i < KPC; ++i) {
           const int ja = rank * KPC + i;
-          tma_load_3d_mc(sbase + SM::B_OFF + ja * (BS * 128), &tmZ, bar_z, ja * 64, t * map.step1, tile * map.base2,
+          // tile -> TMA coordinates: off2 tiles per batch element on the time axis, 1 on the note axis
+          tma_load_3d_mc(sbase + SM::B_OFF + ja * (BS * 128), &tmZ, bar_z, ja * 64,
+                         t * map.step1 + (tile % map.off2) * map.off1, (tile / map.off2) * map.base2,
                          (uint16_t)((1u << C) - 1u));
         }
       }
@@ -394,7 +401,8 @@ scan_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
     const int q = warp & 3;
     const int w2 = (warp - 1) >> 2;
     const int sh = lane >> 4;
-    const uint32_t col = 64 * rank + 16 * q + (lane & 15);        // global hidden unit
+    const uint32_t col = UPC * rank + 16 * q + (lane & 15);       // global hidden unit
+    const bool active = (16 * q < UPC);                            // UPC = 32: only TMEM quarters 0,1 hold real rows
     const uint32_t sstr = (uint32_t)map.seq_stride, tstr = (uint32_t)map.step_stride;
     const uint32_t n0 = w2 * WC + sh * CPL;                        // first sequence (in the tile) of this lane
     const uint32_t row00 = (uint32_t)tc_row0(map, tile * BS) + n0 * sstr;
@@ -405,6 +413,7 @@ scan_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
     // waits for its own DRAM round trip).  Masks and the t==0 special case are applied at use time.
     auto issue_loads = [&](int t) {       // everything of step t that does not depend on the recurrence
       const uint32_t tp = (t > 0) ? (uint32_t)(t - 1) : 0u;      // clamped: row of c_{t-1} (ignored at t == 0)
+      if (!active) return;
 #pragma unroll
       for (int j = 0; j < CPL; ++j) {
         const uint32_t r = row00 + j * sstr + (uint32_t)t * tstr;
@@ -416,7 +425,8 @@ scan_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
 #pragma unroll
     for (int j = 0; j < CPL; ++j) {
       dcn[j] = 0.f;
-      ct[j] = Cst[(size_t)(row00 + j * sstr + (uint32_t)(steps - 1) * tstr) * U + col];
+      ct[j] = active ? Cst[(size_t)(row00 + j * sstr + (uint32_t)(steps - 1) * tstr) * U + col] : 0.f;
+      gv[j] = make_float4(0.f, 0.f, 0.f, 0.f); cpv[j] = 0.f; dyv[j] = 0.f;
     }
     issue_loads(steps - 1);
     uint32_t acc_phase = 0;
@@ -442,6 +452,7 @@ scan_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
       }
 #pragma unroll
       for (int j = 0; j < CPL; ++j) {
+        if (!active) break;
         const uint32_t r = row00 + j * sstr + (uint32_t)t * tstr;
         const float4 g4 = gv[j];
         const float cprev = (t > 0) ? cpv[j] : 0.f;
@@ -468,42 +479,45 @@ scan_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
       cl_arrive();
       cl_wait();
     }
+    if (active) {
 #pragma unroll
-    for (int gq = 0; gq < 4; ++gq) atomicAdd(db + 4 * col + gq, dbacc[gq]);
+      for (int gq = 0; gq < 4; ++gq) atomicAdd(db + 4 * col + gq, dbacc[gq]);
+    }
   }
   tc_fence_before();
   cluster.sync();
   if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-template <int U, int BS>
+template <int U, int BS, int UPC, bool AXIS_TIME>
 int launch_tc_bwd(const void* Un_bf, const float* gates, const float* c, const float* dY, int64_t ldY, dj_dropout d_y,
-                  void* dZ, float* db, int S, int steps, const TcMap& map_in, int axis_time, int hard, cudaStream_t st) {
-  constexpr int C = U / 64;
-  using SM = TcBwdSmem<U, BS>;
+                  void* dZ, float* db, int S, int steps, const TcMap& map_in, int hard, cudaStream_t st) {
+  constexpr int C = U / UPC;
+  using SM = TcBwdSmem<U, BS, UPC>;
   DJ_CHECK_ARG(S % BS == 0, "dj_lstm_scan_tc_bwd: the number of sequences (%d) must be a multiple of %d", S, BS);
   TcMap map = map_in;
   CUtensorMap tmU, tmZ;
   int rc;
-  if ((rc = make_map_2d(&tmU, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Un_bf, (uint64_t)4 * U, (uint64_t)U, (uint64_t)4 * U, 64, 64)))
+  if ((rc = make_map_2d(&tmU, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Un_bf, (uint64_t)4 * U, (uint64_t)U, (uint64_t)4 * U, 64, UPC)))
     return rc;
-  if (axis_time) {
-    static_assert(BS % 48 == 0 || U != 256, "time-axis tiles are whole batch elements");
+  if (AXIS_TIME) {   // dZ viewed as [b][t*48+n][4U]; a tile is BS consecutive notes of one batch element
+    static_assert(!AXIS_TIME || 48 % BS == 0, "time-axis tiles divide a batch element");
     const uint64_t rows_per_b = (uint64_t)map.outer_stride, B = (uint64_t)(S / 48);
     const uint64_t dims[3] = {(uint64_t)4 * U, rows_per_b, B}, str[2] = {(uint64_t)4 * U, rows_per_b * 4 * U};
-    const uint32_t box[3] = {64, 48, (uint32_t)(BS / 48)};
+    const uint32_t box[3] = {64, (uint32_t)BS, 1};
     if ((rc = make_map(&tmZ, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dZ, 3, dims, str, box))) return rc;
-    map.step1 = 48; map.off1 = 0; map.base2 = BS / 48; map.off2 = 0;
+    map.step1 = 48; map.off1 = BS; map.base2 = 1; map.off2 = 48 / BS;
     map.seq_stride = map.inner_stride;
-  } else {
+  } else {           // dZ viewed as [seq][n][4U]
     const uint64_t dims[3] = {(uint64_t)4 * U, 48, (uint64_t)S}, str[2] = {(uint64_t)4 * U, (uint64_t)48 * 4 * U};
     const uint32_t box[3] = {64, 1, (uint32_t)BS};
     if ((rc = make_map(&tmZ, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dZ, 3, dims, str, box))) return rc;
-    map.step1 = 1; map.off1 = 0; map.base2 = BS; map.off2 = 0;
+    map.step1 = 1; map.off1 = 0; map.base2 = BS; map.off2 = 1;
     map.seq_stride = map.outer_stride;
   }
-  auto kernel = scan_tc_bwd_kernel<U, BS>;
+  auto kernel = scan_tc_bwd_kernel<U, BS, UPC>;
   DJ_CUDA(cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
+  if (C > 8) DJ_CUDA(cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((S / BS) * C);   // one cluster per tile
   cfg.blockDim = dim3(TCB_THREADS);
@@ -528,23 +542,25 @@ extern "C" int dj_lstm_scan_tc_fwd(float* Z, float* h_out, float* c_out, void* h
   DJ_CHECK_ARG(S > 0 && steps > 0, "dj_lstm_scan_tc_fwd: bad sizes");
   TcMap map{seq_inner, seq_outer_stride, seq_inner_stride, step_stride, 0, 0, 0, 0, 0};
   cudaStream_t st = (cudaStream_t)stream;
-  if (units == 256) {
-    // time axis: sequences (b, n), rows of one b are contiguous at each step
-    DJ_CHECK_ARG(seq_inner == 48 && seq_inner_stride == 1 && step_stride == 48 && S % 48 == 0,
-                 "dj_lstm_scan_tc_fwd: units=256 expects the time-axis map (seq=(b,n))");
+  const bool time_map = (seq_inner == 48 && seq_inner_stride == 1 && step_stride == 48 && S % 48 == 0);
+  const bool note_map = (seq_inner == 1 && seq_outer_stride == 48 && step_stride == 1 && steps <= 48);
+  DJ_CHECK_ARG(time_map || note_map, "dj_lstm_scan_tc_fwd: only the time-axis (seq=(b,n)) and note-axis (seq=(b,t)) maps are supported");
+  if (time_map && units == 256) {
     // 2 CTAs/SM x 16 resident 8-CTA clusters = 32 tile slots: beyond that, double the tile (two batch
     // elements per cluster) so the whole layer still runs as one wave of step chains
     if (S % 96 == 0 && S / 48 > 32)
       return launch_tc_fwd<256, 96>(Ut_bf16, Z, h_out, c_out, h_prev_bf16, S, steps, map, 1, hard, st);
     return launch_tc_fwd<256, 48>(Ut_bf16, Z, h_out, c_out, h_prev_bf16, S, steps, map, 1, hard, st);
-  } else if (units == 128) {
-    DJ_CHECK_ARG(seq_inner == 1 && seq_outer_stride == 48 && step_stride == 1 && steps <= 48,
-                 "dj_lstm_scan_tc_fwd: units=128 expects the note-axis map (seq=(b,t))");
+  } else if (time_map && units == 512) {   // scaled model (BASELINE configs[4]): 16-CTA clusters
+    return launch_tc_fwd<512, 48>(Ut_bf16, Z, h_out, c_out, h_prev_bf16, S, steps, map, 1, hard, st);
+  } else if (note_map && units == 128) {
     if (S % 128 == 0 && S / 64 > 74)
       return launch_tc_fwd<128, 128>(Ut_bf16, Z, h_out, c_out, h_prev_bf16, S, steps, map, 0, hard, st);
     return launch_tc_fwd<128, 64>(Ut_bf16, Z, h_out, c_out, h_prev_bf16, S, steps, map, 0, hard, st);
+  } else if (note_map && units == 256) {   // scaled model, note axis
+    return launch_tc_fwd<256, 64>(Ut_bf16, Z, h_out, c_out, h_prev_bf16, S, steps, map, 0, hard, st);
   }
-  DJ_CHECK_ARG(false, "dj_lstm_scan_tc_fwd: units=%d unsupported (128 or 256)", units);
+  DJ_CHECK_ARG(false, "dj_lstm_scan_tc_fwd: units=%d unsupported on this axis (time: 256/512, note: 128/256)", units);
   return -1;
 }
 
@@ -556,15 +572,17 @@ extern "C" int dj_lstm_scan_tc_bwd(const float* gates, const float* c, const flo
   DJ_CHECK_ARG(S > 0 && steps > 0 && ldY >= units, "dj_lstm_scan_tc_bwd: bad sizes");
   TcMap map{seq_inner, seq_outer_stride, seq_inner_stride, step_stride, 0, 0, 0, 0, 0};
   cudaStream_t st = (cudaStream_t)stream;
-  if (units == 256) {
-    DJ_CHECK_ARG(seq_inner == 48 && seq_inner_stride == 1 && step_stride == 48 && S % 48 == 0,
-                 "dj_lstm_scan_tc_bwd: units=256 expects the time-axis map (seq=(b,n))");
-    return launch_tc_bwd<256, 48>(Un_bf16, gates, c, dY, ldY, d_y, dZ_bf16, db, S, steps, map, 1, hard, st);
-  } else if (units == 128) {
-    DJ_CHECK_ARG(seq_inner == 1 && seq_outer_stride == 48 && step_stride == 1 && steps <= 48,
-                 "dj_lstm_scan_tc_bwd: units=128 expects the note-axis map (seq=(b,t))");
-    return launch_tc_bwd<128, 32>(Un_bf16, gates, c, dY, ldY, d_y, dZ_bf16, db, S, steps, map, 0, hard, st);
-  }
-  DJ_CHECK_ARG(false, "dj_lstm_scan_tc_bwd: units=%d unsupported (128 or 256)", units);
+  const bool time_map = (seq_inner == 48 && seq_inner_stride == 1 && step_stride == 48 && S % 48 == 0);
+  const bool note_map = (seq_inner == 1 && seq_outer_stride == 48 && step_stride == 1 && steps <= 48);
+  DJ_CHECK_ARG(time_map || note_map, "dj_lstm_scan_tc_bwd: only the time-axis (seq=(b,n)) and note-axis (seq=(b,t)) maps are supported");
+  if (time_map && units == 256)
+    return launch_tc_bwd<256, 48, 64, true>(Un_bf16, gates, c, dY, ldY, d_y, dZ_bf16, db, S, steps, map, hard, st);
+  if (time_map && units == 512)   // scaled model: 32 units per CTA, 16-CTA clusters, a third of a batch element per tile
+    return launch_tc_bwd<512, 16, 32, true>(Un_bf16, gates, c, dY, ldY, d_y, dZ_bf16, db, S, steps, map, hard, st);
+  if (note_map && units == 128)
+    return launch_tc_bwd<128, 32, 64, false>(Un_bf16, gates, c, dY, ldY, d_y, dZ_bf16, db, S, steps, map, hard, st);
+  if (note_map && units == 256)   // scaled model, note axis
+    return launch_tc_bwd<256, 32, 64, false>(Un_bf16, gates, c, dY, ldY, d_y, dZ_bf16, db, S, steps, map, hard, st);
+  DJ_CHECK_ARG(false, "dj_lstm_scan_tc_bwd: units=%d unsupported on this axis (time: 256/512, note: 128/256)", units);
   return -1;
 }

@@ -115,13 +115,14 @@ def test_wgrad_gemm_tcgen05(lib, shape):
     assert helpers.rel_err(Cd.cpu().numpy(), ref) < 5e-5
 
 
-@pytest.mark.parametrize("axis,B,T", [("time", 3, 8), ("note", 2, 32), ("time", 20, 4), ("note", 40, 128)])
+@pytest.mark.parametrize("axis,B,T", [("time", 3, 8), ("note", 2, 32), ("time", 20, 4), ("note", 40, 128),
+                                      ("note256", 2, 32)])
 def test_lstm_scan_tcgen05_matches_fp32_scan(lib, axis, B, T):
     """Tensor-core recurrence (bf16 h.U, fp32 accumulate) against the fp32 CUDA-core
     recurrence on the same pre-activations."""
     from music_generator_b200 import _lib
     g = torch.Generator().manual_seed(5)
-    U = 256 if axis == "time" else 128
+    U = 256 if axis in ("time", "note256") else 128
     M = B * T * 48
     Z0 = torch.randn(M, 4 * U, generator=g)
     Uw = (torch.randn(U, 4 * U, generator=g) * 0.06).bfloat16().float()     # bf16-representable weights
@@ -152,12 +153,12 @@ def test_lstm_scan_tcgen05_matches_fp32_scan(lib, axis, B, T):
     assert torch.equal(p4, want.bfloat16().float())
 
 
-@pytest.mark.parametrize("axis,B,T", [("time", 3, 8), ("note", 2, 32), ("note", 40, 128)])
+@pytest.mark.parametrize("axis,B,T", [("time", 3, 8), ("note", 2, 32), ("note", 40, 128), ("note256", 2, 32)])
 def test_lstm_scan_bwd_tcgen05_matches_fp32_scan(lib, axis, B, T):
     """Reverse scan on tcgen05 (bf16 dz.U^T) against the fp32 CUDA-core reverse scan."""
     from music_generator_b200 import _lib
     g = torch.Generator().manual_seed(6)
-    U = 256 if axis == "time" else 128
+    U = 256 if axis in ("time", "note256") else 128
     M = B * T * 48
     Z0 = torch.randn(M, 4 * U, generator=g)
     Uw = (torch.randn(U, 4 * U, generator=g) * 0.06).bfloat16().float()

@@ -14,10 +14,10 @@ CFG = O.Config()
 GOLD = os.path.join(os.path.dirname(__file__), "golden", "deepj_small.npz")
 
 
-def make_engine(precision="fp32", seed=0):
+def make_engine(precision="fp32", seed=0, **cfg_kw):
     from music_generator_b200.config import ModelConfig
     from music_generator_b200.engine import Engine
-    e = Engine(ModelConfig(), precision=precision)
+    e = Engine(ModelConfig(**cfg_kw), precision=precision)
     e.init_params(seed)
     return e
 
@@ -66,10 +66,11 @@ def test_forward_matches_golden_fixture():
     assert np.abs(got - z["predict_probs"]).max() < 2e-5
 
 
-def _train_compare(precision, B, T, tol_loss, tol_grad):
-    e = make_engine(precision)
+def _train_compare(precision, B, T, tol_loss, tol_grad, CFG=CFG, **cfg_kw):
+    e = make_engine(precision, **cfg_kw)
     p64 = helpers.to_oracle_params(e.get_params())
-    cpu, dev = batch_dev(B, T)
+    b = O.synthetic_batch(CFG, B, T, 1234, torch.float32)
+    cpu, dev = b, [t.cuda().contiguous() for t in b]
     seed = 7
     ws = e.forward(*dev[:4], target=dev[4], train=True, seed=seed)
     loss = float(e.backward().item())
@@ -142,6 +143,18 @@ def test_train_step_bf16_within_1e3():
     """north_star tolerance: probabilities and losses within 1e-3 relative with
     bf16 operands in the gate GEMMs only (fp32 accumulate, fp32 recurrence)."""
     _train_compare("bf16", 2, 128, 1e-3, 3e-2)
+
+
+def test_train_step_bf16_odd_shape_uses_fp32_scans():
+    """Batch shapes that are not whole tensor-core tiles (B*T % 64 != 0) run the CUDA-core scans
+    with the tcgen05 GEMMs; same tolerance."""
+    _train_compare("bf16", 3, 5, 1e-3, 3e-2)
+
+
+def test_scaled_model_bf16_train_step():
+    """BASELINE configs[4]: 2x hidden units (512 time / 256 note): 16-CTA clusters on the time axis."""
+    cfg = O.Config(time_axis_units=512, note_axis_units=256)
+    _train_compare("bf16", 1, 64, 1e-3, 3e-2, CFG=cfg, time_axis_units=512, note_axis_units=256)
 
 
 def test_keras_like_predict_api():
