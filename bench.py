@@ -147,10 +147,14 @@ def _run_ours(args):
     torch.cuda.set_device(local)
     parallel.init_distributed("nccl")
     B, K, W = args.batch, args.steps, max(args.warmup, 3)
-
-    eng = Engine(ModelConfig(), precision="bf16")
+    scaled = args.workload == "scaled"
+    T = 512 if scaled else 128
+    mcfg = ModelConfig(time_axis_units=512, note_axis_units=256, seq_len=512) if scaled else ModelConfig()
+    if scaled and args.batch == BATCH:
+        B = 16                                   # BASELINE configs[4]: 2x hidden units, 4x sequence length, B=16/GPU
+    eng = Engine(mcfg, precision="bf16")
     eng.init_params(0)
-    x, y = dataset.synthetic_all(B, 128, seed=1234 + rank)
+    x, y = dataset.synthetic_all(B, T, seed=1234 + rank)
     host = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in (x[0], x[1], x[2], x[3], y[0])]
     dev = [h.cuda(non_blocking=True) for h in host]
     allreduce = parallel.allreduce_flat if world > 1 else None
@@ -208,22 +212,23 @@ def _run_ours(args):
 
     # ---------------- roofline of the dominant kernel (time-axis reverse scan, layer 1)
     # algorithmic bytes per row: gates 16U + c 4U + dY 4U read, dZ(bf16) 8U written, U=256
-    U, M = 256, B * 128 * 48
+    U, M = mcfg.time_axis_units, B * T * 48
     alg_bytes = 32 * U * M
     peak, how = peaks()
     dom_ms = dom[1] / max(dom[0], 1)
     achieved = alg_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else None
-    roofline = {"kernel": "scan_tc_bwd_kernel<256,48> (dj_lstm_scan_tc_bwd, time-axis layer 1 reverse scan)", "bound": "hbm",
+    kname = "scan_tc_bwd_kernel<512,16,32>" if scaled else "scan_tc_bwd_kernel<256,48,64>"
+    roofline = {"kernel": kname + " (dj_lstm_scan_tc_bwd, time-axis layer 1 reverse scan)", "bound": "hbm",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                 # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape from the ncu --set full
                 # capture summarised in profiles/r01_scan_tc_bwd_time.md (2.417 GB + 0.785 GB per launch)
-                "traffic": 3.202e9 if B == 64 else None, "peak_source": how, "avg_launch_ms": dom_ms, "launches_timed": dom[0],
+                "traffic": 3.202e9 if (B == 64 and not scaled) else None, "peak_source": how, "avg_launch_ms": dom_ms, "launches_timed": dom[0],
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "note": "sequential recurrence: bound by the per-step barrier/TMA/MMA latency chain, see DESIGN.md"}
 
     # ---------------- generation probe (configs[1])
     gen = None
-    if not args.no_generation:
+    if not args.no_generation and not scaled:
         ge = Engine(ModelConfig(), precision="fp32")
         ge.init_params(0)
         sty = np.mean([np.eye(23)[i] for i in (0, 5, 12)], axis=0)
@@ -257,9 +262,11 @@ def _run_ours(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16 gate-GEMM operands, f32 accumulate/recurrence", "data": "synthetic",
-            "config": {"workload": "DeepJ training (BASELINE configs[2]): default constants.py model, "
-                                   "batch 64 synthetic sequences per GPU, fwd+loss+bwd+allreduce+Nadam, dropout on",
-                       "batch_per_gpu": B, "global_batch": B * world, "seq_len": 128, "parallelism": f"dp{world}",
+            "config": {"workload": ("Scaled biaxial LSTM (BASELINE configs[4]): 512/256 units, 512-step windows, "
+                                    "synthetic batch per GPU, fwd+loss+bwd+allreduce+Nadam, dropout on") if scaled else
+                                   ("DeepJ training (BASELINE configs[2]): default constants.py model, "
+                                    "batch 64 synthetic sequences per GPU, fwd+loss+bwd+allreduce+Nadam, dropout on"),
+                       "batch_per_gpu": B, "global_batch": B * world, "seq_len": T, "parallelism": f"dp{world}",
                        "l2": "per-step working set (>5 GB of activations) exceeds the 126 MB L2; no explicit flush"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / K},
@@ -277,6 +284,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--workload", default="default", choices=["default", "scaled"])
     ap.add_argument("--no-generation", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -38,6 +38,27 @@ def generate(models, num_bars, styles, uniforms=None, default_temp=1):
         yield [events[t, i] for i in range(len(styles))]
 
 
+def generate_batch(models, num_bars, styles, seed=0, default_temp=1):
+    """Many independent style-conditioned sequences (BASELINE configs[3]): every (timestep, sequence,
+    note) owns its two uniforms U[t,g,n,:] -- drawn from RandomState(seed) for the WHOLE batch -- so the
+    result does not depend on how the sequences are sharded.  Under torchrun each rank generates the
+    sequences rank, rank+world, ... (multiples of the 32-sequence predict chunk keep the pitch-bins scope
+    of a single-GPU run); no collective is involved.  Returns (indices, events[steps, len(indices), 48, 3])."""
+    from music_generator_b200 import parallel
+    rank, world, local = parallel.env_world()
+    eng = models[1].engine
+    steps = NOTES_PER_BAR * num_bars
+    G = len(styles)
+    u = np.random.RandomState(seed).random_sample((steps, G, NUM_NOTES, 2))
+    chunk = 32
+    mine = [g for g in range(G) if (g // chunk) % world == rank]
+    if not mine:
+        return mine, np.zeros((steps, 0, NUM_NOTES, NOTE_UNITS), dtype=np.float32)
+    events, _ = generate_events(eng, [styles[g] for g in mine], steps, np.ascontiguousarray(u[:, mine]),
+                                stream_mode=1, default_temp=default_temp)
+    return mine, events
+
+
 def write_file(name, results):
     """generate.py:123-134.  Writing Standard MIDI needs the python-midi package
     the reference depends on (not installable here); the unclamped piano-roll
@@ -54,7 +75,13 @@ def main():
     parser = argparse.ArgumentParser(description='Generates music.')
     parser.add_argument('--bars', default=32, type=int, help='Number of bars to generate')
     parser.add_argument('--styles', default=None, type=int, nargs='+', help='Styles to mix together')
+    parser.add_argument('--batch', default=0, type=int,
+                        help='Generate this many independent sequences (sharded over ranks under torchrun)')
     args = parser.parse_args()
+    if args.batch:
+        import torch
+        from music_generator_b200 import parallel
+        torch.cuda.set_device(parallel.env_world()[2])
 
     models = build_or_load()
     styles = [compute_genre(i) for i in range(len(genre))]
