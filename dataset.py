@@ -30,6 +30,40 @@ def clamp_midi(sequence):
     return sequence[:, MIN_NOTE:MAX_NOTE, :]
 
 
+def stagger(data, time_steps):
+    """Windows of `time_steps` every NOTES_PER_BAR steps over the sequence left-padded with
+    `time_steps` silent frames; labels are the same windows one step later (dataset.py:28-37)."""
+    data = list(data)
+    padded = [np.zeros_like(data[0])] * time_steps + data
+    starts = range(0, len(padded) - time_steps, NOTES_PER_BAR)
+    return [padded[i:i + time_steps] for i in starts], [padded[i + 1:i + time_steps + 1] for i in starts]
+
+
+def load_all(styles, batch_size, time_steps):
+    """MIDI corpus -> ([notes, target, beat, style], [target]) training arrays (dataset.py:39-76).
+    One style id per composer directory; files shorter than a window are skipped."""
+    from concurrent.futures import ThreadPoolExecutor
+    from midi_util import load_midi
+    from util import get_all_files
+    notes, targets, beats, style_rows = [], [], [], []
+    composers = [d for group in styles for d in group]
+    for style_id, directory in enumerate(composers):
+        hot = one_hot(style_id, NUM_STYLES)
+        with ThreadPoolExecutor() as pool:           # the reference decodes files on a thread pool, in order
+            seqs = list(pool.map(load_midi, get_all_files([directory])))
+        for seq in seqs:
+            if len(seq) < time_steps:
+                continue
+            seq = clamp_midi(seq)
+            x, y = stagger(seq, time_steps)
+            notes += x
+            targets += y
+            beats += stagger([compute_beat(i, NOTES_PER_BAR) for i in range(len(seq))], time_steps)[0]
+            style_rows += stagger([hot] * len(seq), time_steps)[0]
+    notes, targets = np.array(notes), np.array(targets)
+    return [notes, targets, np.array(beats), np.array(style_rows)], [targets]
+
+
 def synthetic_all(num_seqs, time_steps=SEQ_LEN, seed=1234):
     """Synthetic stand-in with the shapes/semantics of load_all's return value
     (dataset.py:72-76): ([notes, target, beat, style], [target])."""

@@ -13,6 +13,8 @@ import numpy as np
 from constants import *
 from dataset import compute_genre, unclamp_midi
 from util import build_or_load, one_hot
+from midi_util import midi_encode
+from music_generator_b200 import smf as midi
 from music_generator_b200.sampler import generate_events
 
 
@@ -60,15 +62,14 @@ def generate_batch(models, num_bars, styles, seed=0, default_temp=1):
 
 
 def write_file(name, results):
-    """generate.py:123-134.  Writing Standard MIDI needs the python-midi package
-    the reference depends on (not installable here); the unclamped piano-roll
-    [T,128,3] that midi_encode would consume is saved instead."""
+    """generate.py:123-134: one .mid per generated sequence (unclamp to the 128-pitch
+    roll, midi_encode, write a Standard MIDI File)."""
     results = zip(*list(results))
     for i, result in enumerate(results):
-        fpath = os.path.join(SAMPLES_DIR, name + '_' + str(i) + '.npy')
+        fpath = os.path.join(SAMPLES_DIR, name + '_' + str(i) + '.mid')
         print('Writing file', fpath)
         os.makedirs(os.path.dirname(fpath), exist_ok=True)
-        np.save(fpath, unclamp_midi(np.array(result)))
+        midi.write_midifile(fpath, midi_encode(unclamp_midi(np.array(result))))
 
 
 def main():

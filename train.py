@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 from constants import *
-from dataset import synthetic_all
+from dataset import load_all, synthetic_all
 from util import build_or_load
 
 
@@ -47,9 +47,12 @@ class EarlyStopping:
 
 def train(models, epochs=1000, num_seqs=256):
     print('Loading data')
-    # the reference loads a MIDI corpus it does not ship (dataset.load_all);
-    # synthetic piano-rolls of the same shape stand in
-    train_data, train_labels = synthetic_all(num_seqs, SEQ_LEN)
+    # the reference trains on a MIDI corpus under data/ that it does not ship (README.md:20); use it when it is
+    # there, otherwise synthetic piano-rolls of the same shape stand in
+    if any(os.path.isdir(d) for group in styles for d in group):
+        train_data, train_labels = load_all(styles, BATCH_SIZE, SEQ_LEN)
+    else:
+        train_data, train_labels = synthetic_all(num_seqs, SEQ_LEN)
     from music_generator_b200 import parallel
     rank, world, _ = parallel.init_distributed()
     allreduce = None

@@ -1,4 +1,6 @@
-"""Host helpers on the entry path (reference util.py:8-23)."""
+"""Host helpers on the entry path (reference util.py:8-33)."""
+import os
+
 import numpy as np
 
 from constants import *
@@ -23,3 +25,12 @@ def build_or_load(allow_load=True):
         except Exception:
             print('Unable to load model from file.')
     return models
+
+
+def get_all_files(paths):
+    """Every .mid under the given directories (reference util.py:25-33)."""
+    found = []
+    for path in paths:
+        for root, _, files in os.walk(path):
+            found += [os.path.join(root, f) for f in sorted(files) if f.endswith('.mid')]
+    return [f for f in found if os.path.isfile(f)]
