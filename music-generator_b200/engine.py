@@ -58,8 +58,9 @@ class Workspace:
             self.dXtop = torch.empty(M, un, **f32)
             self.partials = torch.empty(_lib.load().dj_head_partials_size(un), **f32)
             self.loss = torch.zeros(1, **f32)
-            umax = max(L["U"] for L in cfg.layers())
-            self.dZ = torch.empty(M, 4 * umax, dtype=adt, device=dev)   # reused layer after layer
+            # one dZ per layer: the weight-gradient GEMMs of layer l run on a second stream while the
+            # reverse scan of layer l-1 is already writing its own dZ
+            self.dZ = [torch.empty(M, 4 * L["U"], dtype=adt, device=dev) for L in cfg.layers()]
             self.dA = [torch.empty(M, ld, **f32) for ld in self.ld]
             self.ds = [torch.empty(BT, L["F"], **f32) for L in cfg.layers()]
             self.demb = torch.empty(BT, cfg.style_units, **f32)
@@ -105,6 +106,10 @@ class Engine:
         self.profile = None
         self.profile_only = None
         self.tc_scan = True   # bf16 training: recurrence on tcgen05 (False = fp32 CUDA-core scans)
+        # backward runs on two streams: the dependency chain (reverse scan -> data gradient -> next layer's
+        # reverse scan) on a high-priority stream, the weight / style / conv gradients behind it on the caller's
+        self.overlap = True
+        self._hi = None
         self._tag = ""
 
     # ------------------------------------------------------------------ params
@@ -378,6 +383,13 @@ class Engine:
         self._call("dj_head_finalize", _ptr(ws.partials), cfg.note_axis_units, _ptr(ws.loss),
                    _ptr(G["note_dense.W"]), _ptr(G["note_dense.b"]), _ptr(G["volume_dense.W"]),
                    _ptr(G["volume_dense.b"]), _stream())
+        main = torch.cuda.current_stream()
+        two = self.overlap and self.profile is None
+        if two and self._hi is None:
+            self._hi = torch.cuda.Stream(device=self.dev, priority=-1)
+        chain = self._hi if two else main
+        if two:
+            chain.wait_stream(main)           # forward, zeroed gradients
         dY, ldY = ws.dXtop, cfg.note_axis_units
         first_style = True
         for li in (3, 2, 1, 0):
@@ -386,23 +398,33 @@ class Engine:
             U4 = 4 * U
             self._tag = ":bwd:" + name
             m = self._scan_map(L["axis"], B, T)
-            dZ = ws.dZ.view(-1)[:M * U4].view(M, U4)
-            if bf16 and self._tc_ok(B, T):
-                self._call("dj_lstm_scan_tc_bwd", _ptr(ws.Z[li]), _ptr(ws.c[li]), _ptr(dY), ldY, d[L["site_out"]],
-                           _ptr(self._wbf[f"{name}.Un"]), _ptr(dZ), _ptr(G[f"{name}.lstm.b"]), m["S"], m["steps"], U,
-                           m["inner"], m["outer"], m["inner_stride"], m["step"], self.hard, _stream())
-            else:
-                self._call("dj_lstm_scan_bwd", _ptr(ws.Z[li]), _ptr(ws.c[li]), _ptr(dY), ldY, d[L["site_out"]],
-                           _ptr(P[f"{name}.lstm.U"]), _ptr(dZ), zdt, _ptr(G[f"{name}.lstm.b"]), m["S"], m["steps"], U,
-                           m["inner"], m["outer"], m["inner_stride"], m["step"], self.hard, _stream())
-            # data gradient dA = dZ . W^T
-            if bf16:
-                self._call("dj_gate_gemm_bf16", _ptr(dZ), U4, _ptr(self._wbf[f"{name}.Wn"]), U4, _ptr(ws.dA[li]),
-                           ld, None, M, F, U4, _stream())
-            else:
-                self._call("dj_gemm_simt", _ptr(dZ), DJ_F32, U4, 1, _ptr(P[f"{name}.lstm.W"]), DJ_F32, 1, U4,
-                           _ptr(ws.dA[li]), ld, None, M, F, U4, 0, 0, 0, _stream())
-            # weight gradients: dW = A^T.dZ, dU = H_{step-1}^T.dZ (contraction over the M rows)
+            dZ = ws.dZ[li]
+            with torch.cuda.stream(chain):
+                # ---- critical chain: reverse scan, then the data gradient the next layer's scan consumes
+                if bf16 and self._tc_ok(B, T):
+                    self._call("dj_lstm_scan_tc_bwd", _ptr(ws.Z[li]), _ptr(ws.c[li]), _ptr(dY), ldY, d[L["site_out"]],
+                               _ptr(self._wbf[f"{name}.Un"]), _ptr(dZ), _ptr(G[f"{name}.lstm.b"]), m["S"], m["steps"],
+                               U, m["inner"], m["outer"], m["inner_stride"], m["step"], self.hard, _stream())
+                else:
+                    self._call("dj_lstm_scan_bwd", _ptr(ws.Z[li]), _ptr(ws.c[li]), _ptr(dY), ldY, d[L["site_out"]],
+                               _ptr(P[f"{name}.lstm.U"]), _ptr(dZ), zdt, _ptr(G[f"{name}.lstm.b"]), m["S"], m["steps"],
+                               U, m["inner"], m["outer"], m["inner_stride"], m["step"], self.hard, _stream())
+                ev_scan = torch.cuda.Event() if two else None
+                if two:
+                    ev_scan.record(chain)
+                # data gradient dA = dZ . W^T
+                if bf16:
+                    self._call("dj_gate_gemm_bf16", _ptr(dZ), U4, _ptr(self._wbf[f"{name}.Wn"]), U4, _ptr(ws.dA[li]),
+                               ld, None, M, F, U4, _stream())
+                else:
+                    self._call("dj_gemm_simt", _ptr(dZ), DJ_F32, U4, 1, _ptr(P[f"{name}.lstm.W"]), DJ_F32, 1, U4,
+                               _ptr(ws.dA[li]), ld, None, M, F, U4, 0, 0, 0, _stream())
+                ev_dgrad = torch.cuda.Event() if two else None
+                if two:
+                    ev_dgrad.record(chain)
+            # ---- off the chain (caller's stream): weight gradients dW = A^T.dZ, dU = H_{step-1}^T.dZ
+            if two:
+                main.wait_event(ev_scan)
             if bf16:
                 self._call("dj_wgrad_gemm_bf16", _ptr(ws.A[li]), ld, _ptr(dZ), U4, _ptr(G[f"{name}.lstm.W"]), U4,
                            F, U4, M, _stream())
@@ -414,7 +436,9 @@ class Engine:
                 shift, period = (N, T * N) if L["axis"] == "time" else (1, N)
                 self._call("dj_gemm_simt", _ptr(ws.h[li]), DJ_F32, 1, U, _ptr(dZ), zdt, U4, 1,
                            _ptr(G[f"{name}.lstm.U"]), U4, None, U, U4, M, 1, shift, period, _stream())
-            # style projection backward (model.py:77-82 / 113-117)
+            # style projection backward (model.py:77-82 / 113-117) needs dA of this layer
+            if two:
+                main.wait_event(ev_dgrad)
             self._call("dj_style_bwd_reduce", _ptr(ws.dA[li]), ld, F, _ptr(ws.sp[li]), d[L["site_sp"]], BT,
                        _ptr(ws.ds[li]), _stream())
             self._call("dj_gemm_simt", _ptr(ws.emb), DJ_F32, 1, cfg.style_units, _ptr(ws.ds[li]), DJ_F32, F, 1,
@@ -432,6 +456,8 @@ class Engine:
         self._call("dj_gemm_simt", _ptr(st["style"]), DJ_F32, 1, ns, _ptr(ws.demb), DJ_F32, cfg.style_units, 1,
                    _ptr(G["style.W"]), cfg.style_units, None, ns, cfg.style_units, BT, 1, 0, 0, _stream())
         self._call("dj_colsum", _ptr(ws.demb), cfg.style_units, BT, cfg.style_units, _ptr(G["style.b"]), 1, _stream())
+        if two:
+            main.wait_stream(chain)
         return ws.loss
 
     # ------------------------------------------------------------- optimizer
