@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import Dict, List, Optional
 
 import numpy as np
@@ -108,7 +109,7 @@ class Engine:
         self.tc_scan = True   # bf16 training: recurrence on tcgen05 (False = fp32 CUDA-core scans)
         # backward runs on two streams: the dependency chain (reverse scan -> data gradient -> next layer's
         # reverse scan) on a high-priority stream, the weight / style / conv gradients behind it on the caller's
-        self.overlap = True
+        self.overlap = os.environ.get("DJ_NO_OVERLAP", "") == ""
         self._hi = None
         self._tag = ""
 
@@ -384,7 +385,7 @@ class Engine:
                    _ptr(G["note_dense.W"]), _ptr(G["note_dense.b"]), _ptr(G["volume_dense.W"]),
                    _ptr(G["volume_dense.b"]), _stream())
         main = torch.cuda.current_stream()
-        two = self.overlap and self.profile is None
+        two = self.overlap and (self.profile is None or self.profile_only is not None)   # full profiling serialises
         if two and self._hi is None:
             self._hi = torch.cuda.Stream(device=self.dev, priority=-1)
         chain = self._hi if two else main
