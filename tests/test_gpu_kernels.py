@@ -153,7 +153,8 @@ def test_lstm_scan_tcgen05_matches_fp32_scan(lib, axis, B, T):
     assert torch.equal(p4, want.bfloat16().float())
 
 
-@pytest.mark.parametrize("axis,B,T", [("time", 3, 8), ("note", 2, 32), ("note", 40, 128), ("note256", 2, 32)])
+@pytest.mark.parametrize("axis,B,T", [("time", 3, 8), ("note", 2, 32), ("note", 40, 128), ("note256", 2, 32),
+                                      ("time", 40, 6)])   # 40 batch elements: the streaming 96-sequence-tile variant
 def test_lstm_scan_bwd_tcgen05_matches_fp32_scan(lib, axis, B, T):
     """Reverse scan on tcgen05 (bf16 dz.U^T) against the fp32 CUDA-core reverse scan."""
     from music_generator_b200 import _lib
