@@ -8,6 +8,17 @@
 namespace {
 
 // ---- PTX wrappers -----------------------------------------------------------
+// One lane of a CONVERGED warp.  Single-thread instructions (tcgen05.mma, TMA) are issued under this
+// predicate rather than `lane == 0`: with a warp-uniform branch around it the compiler keeps descriptors in
+// uniform registers; under a divergent `lane == 0` branch it wraps every UTCHMMA in an ELECT/R2UR loop
+// (~65 cycles per MMA instead of the MMA's own 24-48).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+  return pred != 0;
+}
+// warp index as a provably warp-uniform value
+__device__ __forceinline__ int uniform_warp_id() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -122,6 +133,14 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, 
 
 
 // cluster-wide helpers
+__device__ __forceinline__ void tma_load_4d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                               int c3, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+      "[%0], [%1, {%3, %4, %5, %6}], [%2], %7;\n" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(cta_mask)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_3d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
                                                uint16_t cta_mask) {
   asm volatile(
@@ -130,7 +149,11 @@ __device__ __forceinline__ void tma_load_3d_mc(uint32_t dst, const CUtensorMap* 
       "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "h"(cta_mask)
       : "memory");
 }
+#ifdef DJ_FENCE_GLOBAL
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async.global;\n" ::: "memory"); }
+#else
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
+#endif
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t v[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -159,14 +182,15 @@ inline EncodeTiledFn get_encode() {
   return fn;
 }
 
-// rank-2 or rank-3 tiled map, 128B swizzle, zero OOB fill.  dims/box innermost first;
+// rank-2..5 tiled map, 128B swizzle, zero OOB fill.  dims/box innermost first;
 // strides_elems[i] = stride of dimension i+1 in elements.
 inline int make_map(CUtensorMap* map, CUtensorMapDataType dt, int esize, const void* base, int rank,
                     const uint64_t* dims, const uint64_t* strides_elems, const uint32_t* box) {
   EncodeTiledFn enc = get_encode();
   DJ_CHECK_ARG(enc != nullptr, "cuTensorMapEncodeTiled entry point not available (no driver?)");
-  cuuint64_t d[3] = {1, 1, 1}, st[2] = {0, 0};
-  cuuint32_t bx[3] = {1, 1, 1}, es[3] = {1, 1, 1};
+  DJ_CHECK_ARG(rank >= 1 && rank <= 5, "tensor map rank %d", rank);
+  cuuint64_t d[5] = {1, 1, 1, 1, 1}, st[4] = {0, 0, 0, 0};
+  cuuint32_t bx[5] = {1, 1, 1, 1, 1}, es[5] = {1, 1, 1, 1, 1};
   for (int i = 0; i < rank; ++i) { d[i] = dims[i]; bx[i] = box[i]; }
   for (int i = 0; i + 1 < rank; ++i) st[i] = strides_elems[i] * (uint64_t)esize;
   CUresult r = enc(map, dt, (cuuint32_t)rank, const_cast<void*>(base), d, st, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,

@@ -22,10 +22,34 @@
 // `hprev` is needed anyway as the A operand of dU = H_{t-1}^T.dZ, so the all-gather
 // costs no extra HBM traffic and avoids the ~20 B/clk DSMEM store path.
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include "dj_tc.cuh"
 
 namespace cg = cooperative_groups;
+
+#ifdef DJ_TRACE
+// debug build only (tools/scan_trace.py): per-step clock64() stamps of one CTA's issuer and epilogue lanes
+__device__ long long* g_dj_trace = nullptr;
+extern "C" int dj_debug_trace_set(void* buf) {
+  return (int)cudaMemcpyToSymbol(g_dj_trace, &buf, sizeof(buf));
+}
+#define DJ_TR(t, k)                                                                                   \
+  do {                                                                                                \
+    if (g_dj_trace != nullptr && (blockIdx.x == 0 || blockIdx.x == gridDim.x / 2 + 1))                \
+      g_dj_trace[(((blockIdx.x == 0) ? 0 : 1) * 512 + (t)) * 16 + (k)] = clock64();                   \
+  } while (0)
+#define DJ_TRV(t, k, v)                                                                               \
+  do {                                                                                                \
+    if (g_dj_trace != nullptr && (blockIdx.x == 0 || blockIdx.x == gridDim.x / 2 + 1))                \
+      g_dj_trace[(((blockIdx.x == 0) ? 0 : 1) * 512 + (t)) * 16 + (k)] = (v);                         \
+  } while (0)
+#define DJ_CLK() clock64()
+#else
+#define DJ_TR(t, k) do {} while (0)
+#define DJ_TRV(t, k, v) do {} while (0)
+#define DJ_CLK() 0ll
+#endif
 
 namespace {
 
@@ -48,13 +72,25 @@ struct TcFwdSmem {
   static constexpr int TOTAL = BAR_OFF + 32;          // no static smem: two CTAs must fit one SM
 };
 
+// single-instruction MUFU forms (ftz: no denormal range fix-up around ex2, no Newton step after rcp)
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_ftz(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;\n" : "=f"(y) : "f"(x));
+  return y;
+}
+// tanh(x) = 1 - 2 / (e^{2x} + 1): exact limits at +-inf (ex2 -> inf / 0), 5 instructions
 __device__ __forceinline__ float fast_tanh(float x) {
-  const float e = __expf(2.0f * x);
-  return 1.0f - __fdividef(2.0f, e + 1.0f);
+  return fmaf(-2.0f, rcp_ftz(ex2_ftz(x * 2.885390081777927f) + 1.0f), 1.0f);
 }
 __device__ __forceinline__ float hard_sig_sat(float x) { return __saturatef(fmaf(x, 0.2f, 0.5f)); }
-__device__ __forceinline__ float gate_act_fast(float x, int hard) {
-  return hard ? hard_sig_sat(x) : __fdividef(1.0f, 1.0f + __expf(-x));
+template <bool HARD> __device__ __forceinline__ float gate_act_fast(float x) {
+  if constexpr (HARD) return hard_sig_sat(x);
+  else return rcp_ftz(1.0f + ex2_ftz(x * -1.4426950408889634f));
 }
 __device__ __forceinline__ int64_t tc_row0(const TcMap& m, int seq) {
   return (int64_t)(seq / m.seq_inner) * m.outer_stride + (int64_t)(seq % m.seq_inner) * m.inner_stride;
@@ -68,11 +104,15 @@ __device__ __forceinline__ void cl_wait() { asm volatile("barrier.cluster.wait.a
 // slower per step on B200: DSMEM stores are the slow path.)  Two CTAs of different
 // clusters share an SM so one tile's barrier / TMA / MMA latency chain is covered by the
 // other tile's epilogue; the next pre-activations are always in flight in registers.
-template <int U, int BS>
+// TIME: sequences (b, n) stepping t (sequence stride 1 row, step stride 48 rows); else the note axis:
+// sequences (b, t) stepping n (sequence stride 48 rows, step stride 1).  Both strides and the gate
+// activation are compile-time so every row offset inside a chunk is an immediate.
+template <int U, int BS, bool TIME, bool HARD, int NB>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 scan_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmH,
                    float* __restrict__ Z, float* __restrict__ Hout, float* __restrict__ Cout,
-                   __nv_bfloat16* __restrict__ Hprev, int steps, TcMap map, int hard) {
+                   __nv_bfloat16* __restrict__ Hprev, int steps, TcMap map) {
+  constexpr uint32_t SSTR = TIME ? 1u : 48u, TSTR = TIME ? 48u : 1u;
   constexpr int C = U / 32;            // cluster size
   constexpr int KA = U / 64;           // 64-wide K atoms
   constexpr int RH = BS / 2;           // rows per multicast slice
@@ -90,7 +130,7 @@ scan_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   const int tile = blockIdx.x / C;     // one tile of BS sequences per cluster
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_id(), lane = threadIdx.x & 31;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -110,41 +150,49 @@ scan_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
 
   if (warp == 0) {
     // ================= TMA (once) + MMA issuer =================
-    if (lane == 0) {   // resident A operand: rows [128*rank, +128) of U^T
+    // the whole warp walks the loop converged; single-thread work sits under elect_one()
+    if (elect_one()) {   // resident A operand: rows [128*rank, +128) of U^T
       mbar_expect_tx(bar_a, SM::A_BYTES);
 #pragma unroll
       for (int ka = 0; ka < KA; ++ka)
         tma_load_2d(sbase + SM::A_OFF + ka * 16384, &tmU, bar_a, ka * 64, 128 * rank);
     }
+    __syncwarp();
     uint32_t h_phase = 0;
     for (int t = 0; t < steps; ++t) {
-      if (lane == 0 && t > 0) {
+      if (t > 0) {
         if (t == 1) mbar_wait(bar_a, 0);
         mbar_wait(bar_h, h_phase);
+        DJ_TR(t, 0);
         h_phase ^= 1;
         tc_fence_after();
-        constexpr uint32_t idesc = make_idesc(128, BS, 0, 0);
+        if (elect_one()) {
+          constexpr uint32_t idesc = make_idesc(128, BS, 0, 0);
+          const uint64_t adesc0 = make_smem_desc(sbase + SM::A_OFF, 16, 1024);
+          const uint64_t bdesc0 = make_smem_desc(sbase + SM::H_OFF, 16, 1024);
 #pragma unroll
-        for (int ka = 0; ka < KA; ++ka)
+          for (int ka = 0; ka < KA; ++ka)
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t adesc = make_smem_desc(sbase + SM::A_OFF + ka * 16384 + k * 32, 16, 1024);
-            const uint64_t bdesc = make_smem_desc(sbase + SM::H_OFF + ka * (BS * 128) + k * 32, 16, 1024);
-            umma_bf16(tmem_base, adesc, bdesc, idesc, (ka | k) != 0);
-          }
-        umma_commit(bar_acc);
+            for (int k = 0; k < 4; ++k)   // descriptor start addresses are in 16-byte units
+              umma_bf16(tmem_base, adesc0 + (uint64_t)((ka * 16384 + k * 32) >> 4),
+                        bdesc0 + (uint64_t)((ka * (BS * 128) + k * 32) >> 4), idesc, (ka | k) != 0);
+          umma_commit(bar_acc);
+          DJ_TR(t, 1);
+        }
+        __syncwarp();
       }
-      __syncwarp();
       cl_arrive();
-      cl_wait();     // every CTA of the cluster has published its slice of h_t
-      if (lane == 0 && t + 1 < steps) {
-        fence_proxy_async_all();
+      cl_wait();     // every CTA of the cluster has published its slice of h_t (and fenced it for the async proxy)
+      DJ_TR(t, 2);
+      if (t + 1 < steps && elect_one()) {
         mbar_expect_tx(bar_h, SM::H_BYTES);
         const int ka = rank >> 1, hh = rank & 1;
         tma_load_3d_mc(sbase + SM::H_OFF + ka * (BS * 128) + hh * (RH * 128), &tmH, bar_h, ka * 64,
                        (t + 1) * map.step1 + hh * map.off1, tile * map.base2 + hh * map.off2,
                        (uint16_t)((1u << C) - 1u));
+        DJ_TR(t, 3);
       }
+      __syncwarp();
     }
   } else {
     // ================= epilogue warps =================
@@ -153,7 +201,6 @@ scan_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
     const int g = lane & 3;                 // gate held before the transpose / sequence slot after it
     const uint32_t col = 32 * rank + 8 * q + up;          // global hidden unit
     const uint32_t zc = 128 * rank + 32 * q + lane;       // gate-interleaved column this lane reads
-    const uint32_t sstr = (uint32_t)map.seq_stride, tstr = (uint32_t)map.step_stride;
     float cst[NCH][4];
     uint32_t rowb[NCH];                     // row of each chunk's first sequence at step 0
 #pragma unroll
@@ -162,13 +209,17 @@ scan_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
       for (int j = 0; j < 4; ++j) cst[i][j] = 0.f;
       rowb[i] = (uint32_t)tc_row0(map, tile * BS + i * 16);   // a 16-chunk never straddles a batch element
     }
-    float zreg[16];
+    // x.W pre-activations are prefetched NB chunks ahead into registers (NB divides NCH, so after
+    // unrolling every buffer index is static)
+    static_assert(NCH % NB == 0, "prefetch ring must divide the chunk count");
+    float zreg[NB][16];
     auto load_z = [&](int ci, uint32_t t) {
-      const float* zp = Z + (size_t)(rowb[ci] + t * tstr) * (4 * U) + zc;
+      const float* zp = Z + (size_t)(rowb[ci] + t * TSTR) * (4 * U) + zc;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) zreg[j] = zp[(size_t)(j * sstr) * (4 * U)];
+      for (int j = 0; j < 16; ++j) zreg[ci % NB][j] = zp[(size_t)j * SSTR * (4 * U)];
     };
-    load_z(0, 0);
+#pragma unroll
+    for (int ci = 0; ci < NB; ++ci) load_z(ci, 0);
     uint32_t acc_phase = 0;
     for (int t = 0; t < steps; ++t) {
       if (t > 0) {
@@ -176,28 +227,46 @@ scan_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
         acc_phase ^= 1;
         tc_fence_after();
       }
+      if (warp == 1 && lane == 0) DJ_TR(t, 8);
       if (t + 1 < steps && lane < 16) {   // warm L2 with the next step's x.W rows (this warp's 128-byte segments)
 #pragma unroll
         for (int ci = 0; ci < NCH; ++ci)
-          asm volatile("prefetch.global.L2 [%0];\n" ::"l"(Z + (size_t)(rowb[ci] + lane * sstr + (t + 1) * tstr) * (4 * U) +
+          asm volatile("prefetch.global.L2 [%0];\n" ::"l"(Z + (size_t)(rowb[ci] + lane * SSTR + (t + 1) * TSTR) * (4 * U) +
                                                               128 * rank + 32 * q));
       }
+      long long trs[4] = {0, 0, 0, 0};
+      const bool not_last = (t + 1 < steps);
 #pragma unroll
       for (int ci = 0; ci < NCH; ++ci) {
         float v[16];
+        const long long c0 = DJ_CLK();
+        long long c1 = c0;
         if (t > 0) {
           uint32_t acc[16];
           tmem_ld16(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(ci * 16), acc);
+          c1 = DJ_CLK();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]) + zreg[j];
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]) + zreg[ci % NB][j];
         } else {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = zreg[j];
+          for (int j = 0; j < 16; ++j) v[j] = zreg[ci % NB][j];
         }
-        // keep the next pre-activations in flight: next chunk of this step, or chunk 0 of the next
-        // step (which then overlaps the fence + cluster barrier + TMA + MMA of the step boundary)
-        if (ci + 1 < NCH) load_z(ci + 1, t);
-        else if (t + 1 < steps) load_z(0, t + 1);
+#ifdef DJ_TRACE
+        asm volatile("" ::"f"(v[0]), "f"(v[5]), "f"(v[10]), "f"(v[15]) : "memory");
+#endif
+        const long long c2 = DJ_CLK();
+        // refill the buffer just consumed: NB chunks ahead, wrapping into the next step (those loads
+        // then overlap the fence + cluster barrier + TMA + MMA of the step boundary)
+        if (ci + NB < NCH) load_z(ci + NB, t);
+        else if (not_last) load_z(ci + NB - NCH, t + 1);
+        const long long c3 = DJ_CLK();
+        // this lane's cell after the transpose: sequence 16*ci + 4*blk + g, unit `col`
+        const uint32_t row_c = rowb[ci] + (uint32_t)g * SSTR + (uint32_t)t * TSTR;
+        float* const zg = Z + (size_t)row_c * (4 * U) + 4 * col;
+        const size_t o1 = (size_t)row_c * U + col;
+        float* const hp = Hout + o1;
+        float* const cp = Cout + o1;                       // only dereferenced when Cout != nullptr
+        __nv_bfloat16* const hb = Hprev + o1;
 #pragma unroll
         for (int blk = 0; blk < 4; ++blk) {
           // 4x4 transpose across the 4 lanes of a unit: lane g ends with i,f,g,o of sequence 4*blk+g
@@ -208,29 +277,35 @@ scan_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
           const float b0 = odd ? x1 : a0, b1 = odd ? a1 : x1, b2 = odd ? x2 : a2, b3 = odd ? a3 : x2;
           const float y0 = __shfl_xor_sync(0xffffffffu, hi ? b0 : b2, 2);
           const float y1 = __shfl_xor_sync(0xffffffffu, hi ? b1 : b3, 2);
-          const float zi = hi ? y0 : b0, zf = hi ? y1 : b1, zg = hi ? b2 : y0, zo = hi ? b3 : y1;
+          const float zi = hi ? y0 : b0, zf = hi ? y1 : b1, zg_ = hi ? b2 : y0, zo = hi ? b3 : y1;
 
-          const float gi = gate_act_fast(zi, hard), gf = gate_act_fast(zf, hard);
-          const float gg = fast_tanh(zg), go = gate_act_fast(zo, hard);
+          const float gi = gate_act_fast<HARD>(zi), gf = gate_act_fast<HARD>(zf);
+          const float gg = fast_tanh(zg_), go = gate_act_fast<HARD>(zo);
           const float cn = fmaf(gf, cst[ci][blk], gi * gg);
           const float hn = go * fast_tanh(cn);
           cst[ci][blk] = cn;
-          const __nv_bfloat16 hb16 = __float2bfloat16_rn(hn);
 
-          const uint32_t row = rowb[ci] + (4 * blk + g) * sstr + t * tstr;
-          const uint32_t o1 = row * U + col;
+          constexpr size_t RO = (size_t)4 * SSTR;          // rows between consecutive blocks
           // h_t (bf16) at the NEXT step's row: the A operand of dU = H_{t-1}^T.dZ
-          if (t + 1 < steps) Hprev[o1 + tstr * U] = hb16;
-          if (t == 0) Hprev[o1] = __float2bfloat16_rn(0.f);
-          *reinterpret_cast<float4*>(Z + (size_t)row * (4 * U) + 4 * col) = make_float4(gi, gf, gg, go);
-          Hout[o1] = hn;
-          if (Cout != nullptr) Cout[o1] = cn;
+          if (not_last) hb[(blk * RO + TSTR) * U] = __float2bfloat16_rn(hn);
+          if (t == 0) hb[blk * RO * U] = __float2bfloat16_rn(0.f);
+          *reinterpret_cast<float4*>(zg + blk * RO * (4 * U)) = make_float4(gi, gf, gg, go);
+          hp[blk * RO * U] = hn;
+          if (Cout != nullptr) cp[blk * RO * U] = cn;
         }
+        const long long c4 = DJ_CLK();
+        trs[0] += c1 - c0; trs[1] += c2 - c1; trs[2] += c3 - c2; trs[3] += c4 - c3;
+      }
+      if (warp == 1 && lane == 0) {
+        DJ_TR(t, 9);
+        DJ_TRV(t, 12, trs[0]); DJ_TRV(t, 13, trs[1]); DJ_TRV(t, 14, trs[2]); DJ_TRV(t, 15, trs[3]);
       }
       tc_fence_before();
       fence_proxy_async_all();   // generic-proxy global stores of h_t -> visible to the TMA (async proxy) reads
+      if (warp == 1 && lane == 0) DJ_TR(t, 10);
       cl_arrive();
       cl_wait();
+      if (warp == 1 && lane == 0) DJ_TR(t, 11);
     }
   }
   tc_fence_before();
@@ -238,9 +313,9 @@ scan_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
   if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-template <int U, int BS>
-int launch_tc_fwd(const void* Ut_bf, float* Z, float* h_out, float* c_out, void* hprev, int S, int steps,
-                  const TcMap& map_in, int axis_time, int hard, cudaStream_t st) {
+template <int U, int BS, bool TIME, bool HARD, int NB>
+int launch_tc_fwd_inst(const void* Ut_bf, float* Z, float* h_out, float* c_out, void* hprev, int S, int steps,
+                       const TcMap& map_in, cudaStream_t st) {
   constexpr int C = U / 32;
   using SM = TcFwdSmem<U, BS>;
   DJ_CHECK_ARG(S % BS == 0, "dj_lstm_scan_tc_fwd: the number of sequences (%d) must be a multiple of %d", S, BS);
@@ -250,7 +325,7 @@ int launch_tc_fwd(const void* Ut_bf, float* Z, float* h_out, float* c_out, void*
   if ((rc = make_map_2d(&tmU, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Ut_bf, (uint64_t)U, (uint64_t)4 * U, (uint64_t)U, 64, 128)))
     return rc;
   constexpr int RH = BS / 2;
-  if (axis_time) {   // hprev viewed as [b][t*48+n][U]
+  if (TIME) {   // hprev viewed as [b][t*48+n][U]
     const uint64_t rows_per_b = (uint64_t)map.outer_stride, B = (uint64_t)(S / 48);
     const uint64_t dims[3] = {(uint64_t)U, rows_per_b, B}, str[2] = {(uint64_t)U, rows_per_b * U};
     const uint32_t box[3] = {64, (uint32_t)(RH <= 48 ? RH : 48), (uint32_t)(RH <= 48 ? 1 : RH / 48)};
@@ -264,7 +339,7 @@ int launch_tc_fwd(const void* Ut_bf, float* Z, float* h_out, float* c_out, void*
     map.step1 = 1; map.off1 = 0; map.base2 = BS; map.off2 = RH;
     map.seq_stride = map.outer_stride;
   }
-  auto kernel = scan_tc_fwd_kernel<U, BS>;
+  auto kernel = scan_tc_fwd_kernel<U, BS, TIME, HARD, NB>;
   DJ_CUDA(cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
   if (C > 8) DJ_CUDA(cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   cudaLaunchConfig_t cfg{};
@@ -277,8 +352,39 @@ int launch_tc_fwd(const void* Ut_bf, float* Z, float* h_out, float* c_out, void*
   at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
   __nv_bfloat16* hp = (__nv_bfloat16*)hprev;
-  DJ_CUDA(cudaLaunchKernelEx(&cfg, kernel, tmU, tmH, Z, h_out, c_out, hp, steps, map, hard));
+  DJ_CUDA(cudaLaunchKernelEx(&cfg, kernel, tmU, tmH, Z, h_out, c_out, hp, steps, map));
   return 0;
+}
+
+// prefetch depth of the x.W pre-activations, in 16-sequence chunks (DJ_FWD_NB overrides for experiments)
+inline int fwd_prefetch_depth(int nch, int dflt) {
+  static int env = -1;
+  if (env < 0) {
+    const char* e = getenv("DJ_FWD_NB");
+    env = e ? atoi(e) : 0;
+  }
+  const int nb = env > 0 ? env : dflt;
+  return (nb >= 1 && nb <= 3 && nch % nb == 0) ? nb : dflt;
+}
+
+template <int U, int BS, bool TIME>
+int launch_tc_fwd(const void* Ut_bf, float* Z, float* h_out, float* c_out, void* hprev, int S, int steps,
+                  const TcMap& map, int /*axis_time*/, int hard, cudaStream_t st) {
+  constexpr int NCH = BS / 16;
+  constexpr int NB_DEF = 1;
+  const int nb = fwd_prefetch_depth(NCH, NB_DEF);
+#define DJ_FWD_CASE(NBV)                                                                                        \
+  if constexpr (NCH % NBV == 0) {                                                                               \
+    if (nb == NBV)                                                                                              \
+      return hard ? launch_tc_fwd_inst<U, BS, TIME, true, NBV>(Ut_bf, Z, h_out, c_out, hprev, S, steps, map, st) \
+                  : launch_tc_fwd_inst<U, BS, TIME, false, NBV>(Ut_bf, Z, h_out, c_out, hprev, S, steps, map, st); \
+  }
+  DJ_FWD_CASE(1)
+  DJ_FWD_CASE(2)
+  DJ_FWD_CASE(3)
+#undef DJ_FWD_CASE
+  DJ_CHECK_ARG(false, "dj_lstm_scan_tc_fwd: no kernel instance for prefetch depth %d", nb);
+  return -1;
 }
 
 // ---------------------------------------------------------------------------
@@ -311,7 +417,7 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t v[8]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
 
-template <int U, int BS, int UPC>
+template <int U, int BS, int UPC, bool AXIS_TIME>
 __global__ void __launch_bounds__(TCB_THREADS, (U == 128 && BS <= 32) ? 2 : 1)
 scan_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmZ,
                    const float* __restrict__ G, const float* __restrict__ Cst, const float* __restrict__ dY,
@@ -337,7 +443,7 @@ scan_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   const int tile = blockIdx.x / C;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_id(), lane = threadIdx.x & 31;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -356,43 +462,51 @@ scan_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
 
   if (warp == 0) {
     // ================= TMA + MMA issuer: dh_t = U . dz_{t+1}^T =================
-    if (lane == 0) {   // resident A operand: rows [64*rank, +64) of U, all 4U columns
+    // the whole warp walks the loop converged; single-thread work sits under elect_one()
+    if (elect_one()) {   // resident A operand: rows [UPC*rank, +UPC) of U, all 4U columns
       mbar_expect_tx(bar_a, SM::A_BYTES);
       for (int ja = 0; ja < KA; ++ja)
         tma_load_2d(sbase + SM::A_OFF + ja * ATOM, &tmU, bar_a, ja * 64, UPC * rank);
     }
+    __syncwarp();
     uint32_t z_phase = 0;
     for (int t = steps - 1; t >= 0; --t) {
-      if (lane == 0 && t != steps - 1) {
+      if (t != steps - 1) {
         if (t == steps - 2) mbar_wait(bar_a, 0);
         mbar_wait(bar_z, z_phase);
+        DJ_TR(t, 0);
         z_phase ^= 1;
         tc_fence_after();
-        constexpr uint32_t idesc = make_idesc(64, BS, 0, 0);
-#pragma unroll 4
-        for (int ja = 0; ja < KA; ++ja)
+        if (elect_one()) {
+          constexpr uint32_t idesc = make_idesc(64, BS, 0, 0);
+          const uint64_t adesc0 = make_smem_desc(sbase + SM::A_OFF, 16, 1024);
+          const uint64_t bdesc0 = make_smem_desc(sbase + SM::B_OFF, 16, 1024);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t adesc = make_smem_desc(sbase + SM::A_OFF + ja * ATOM + k * 32, 16, 1024);
-            const uint64_t bdesc = make_smem_desc(sbase + SM::B_OFF + ja * (BS * 128) + k * 32, 16, 1024);
-            umma_bf16(tmem_base, adesc, bdesc, idesc, (ja | k) != 0);
-          }
-        umma_commit(bar_acc);
+          for (int ja = 0; ja < KA; ++ja)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)   // descriptor start addresses are in 16-byte units
+              umma_bf16(tmem_base, adesc0 + (uint64_t)((ja * ATOM + k * 32) >> 4),
+                        bdesc0 + (uint64_t)((ja * (BS * 128) + k * 32) >> 4), idesc, (ja | k) != 0);
+          umma_commit(bar_acc);
+          DJ_TR(t, 1);
+        }
+        __syncwarp();
       }
-      __syncwarp();
       cl_arrive();
       cl_wait();
-      if (lane == 0 && t > 0) {   // all-gather dz_t: this CTA multicasts KPC of the KA column atoms
-        fence_proxy_async_all();
+      DJ_TR(t, 2);
+      // all-gather dz_t: this CTA multicasts KPC of the KA column atoms.  The writers fenced their
+      // generic-proxy stores (fence.proxy.async) before arriving on the cluster barrier.
+      if (t > 0 && elect_one()) {
         mbar_expect_tx(bar_z, SM::B_BYTES);
-        for (int i = 0; i < KPC; ++i) {
-          const int ja = rank * KPC + i;
-          // tile -> TMA coordinates: off2 tiles per batch element on the time axis, 1 on the note axis
-          tma_load_3d_mc(sbase + SM::B_OFF + ja * (BS * 128), &tmZ, bar_z, ja * 64,
-                         t * map.step1 + (tile % map.off2) * map.off1, (tile / map.off2) * map.base2,
-                         (uint16_t)((1u << C) - 1u));
-        }
+        // one 4-D box {64 columns, BS rows, KPC atoms, 1}: lands as KPC consecutive [BS x 128 B] swizzled atoms.
+        // map.step1/off1: row coordinate = t*step1 + (tile % off2)*off1; map.base2: outer coordinate per tile group
+        tma_load_4d_mc(sbase + SM::B_OFF + rank * KPC * (BS * 128), &tmZ, bar_z, 0,
+                       AXIS_TIME ? t * 48 + (tile % map.off2) * BS : tile * BS, rank * KPC,
+                       AXIS_TIME ? tile / map.off2 : t, (uint16_t)((1u << C) - 1u));
+        DJ_TR(t, 3);
       }
+      __syncwarp();
     }
   } else {
     // ================= epilogue: gate derivatives =================
@@ -436,11 +550,13 @@ scan_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
         mbar_wait(bar_acc, acc_phase);
         acc_phase ^= 1;
         tc_fence_after();
+        if (warp == 1 && lane == 0) DJ_TR(t, 8);
         uint32_t acc[WC];
 #pragma unroll
         for (int p8 = 0; p8 < WC / 8; ++p8)
           tmem_ld8(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(w2 * WC + p8 * 8), acc + p8 * 8);
         tmem_ld_wait();
+        if (warp == 1 && lane == 0) DJ_TR(t, 12);
 #pragma unroll
         for (int j = 0; j < CPL; ++j) {
           const float up = __shfl_sync(0xffffffffu, __uint_as_float(acc[CPL + j]), lane & 15);
@@ -473,11 +589,15 @@ scan_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
         dbacc[0] += dz0; dbacc[1] += dz1; dbacc[2] += dz2; dbacc[3] += dz3;
         ct[j] = cprev;                    // c_{t-1} is the cell state of the next (earlier) step
       }
-      if (t > 0) issue_loads(t - 1);      // in flight across the fence / barrier / TMA / MMA of the step boundary
+      if (warp == 1 && lane == 0) DJ_TR(t, 9);
       tc_fence_before();
       fence_proxy_async_all();            // dz_t (generic-proxy global stores) -> TMA (async proxy) reads
-      cl_arrive();
+      if (warp == 1 && lane == 0) DJ_TR(t, 13);
+      cl_arrive();                        // publish first: the other CTAs' chain only needs dz_t ...
+      if (warp == 1 && lane == 0) DJ_TR(t, 10);
+      if (t > 0) issue_loads(t - 1);      // ... these land during the barrier / TMA / MMA of the step boundary
       cl_wait();
+      if (warp == 1 && lane == 0) DJ_TR(t, 11);
     }
     if (active) {
 #pragma unroll
@@ -500,22 +620,23 @@ int launch_tc_bwd(const void* Un_bf, const float* gates, const float* c, const f
   int rc;
   if ((rc = make_map_2d(&tmU, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Un_bf, (uint64_t)4 * U, (uint64_t)U, (uint64_t)4 * U, 64, UPC)))
     return rc;
-  if (AXIS_TIME) {   // dZ viewed as [b][t*48+n][4U]; a tile is BS consecutive notes of one batch element
+  constexpr int KA = 4 * U / 64, KPC = KA / C;
+  if (AXIS_TIME) {   // dZ viewed as [b][t*48+n][atom][64]; a tile is BS consecutive notes of one batch element
     static_assert(!AXIS_TIME || 48 % BS == 0, "time-axis tiles divide a batch element");
     const uint64_t rows_per_b = (uint64_t)map.outer_stride, B = (uint64_t)(S / 48);
-    const uint64_t dims[3] = {(uint64_t)4 * U, rows_per_b, B}, str[2] = {(uint64_t)4 * U, rows_per_b * 4 * U};
-    const uint32_t box[3] = {64, (uint32_t)BS, 1};
-    if ((rc = make_map(&tmZ, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dZ, 3, dims, str, box))) return rc;
+    const uint64_t dims[4] = {64, rows_per_b, (uint64_t)KA, B}, str[3] = {(uint64_t)4 * U, 64, rows_per_b * 4 * U};
+    const uint32_t box[4] = {64, (uint32_t)BS, (uint32_t)KPC, 1};
+    if ((rc = make_map(&tmZ, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dZ, 4, dims, str, box))) return rc;
     map.step1 = 48; map.off1 = BS; map.base2 = 1; map.off2 = 48 / BS;
     map.seq_stride = map.inner_stride;
-  } else {           // dZ viewed as [seq][n][4U]
-    const uint64_t dims[3] = {(uint64_t)4 * U, 48, (uint64_t)S}, str[2] = {(uint64_t)4 * U, (uint64_t)48 * 4 * U};
-    const uint32_t box[3] = {64, 1, (uint32_t)BS};
-    if ((rc = make_map(&tmZ, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dZ, 3, dims, str, box))) return rc;
+  } else {           // dZ viewed as [n][atom][seq][64] (strides: seq 48*4U, atom 64, n 4U)
+    const uint64_t dims[4] = {64, (uint64_t)S, (uint64_t)KA, 48}, str[3] = {(uint64_t)48 * 4 * U, 64, (uint64_t)4 * U};
+    const uint32_t box[4] = {64, (uint32_t)BS, (uint32_t)KPC, 1};
+    if ((rc = make_map(&tmZ, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dZ, 4, dims, str, box))) return rc;
     map.step1 = 1; map.off1 = 0; map.base2 = BS; map.off2 = 1;
     map.seq_stride = map.outer_stride;
   }
-  auto kernel = scan_tc_bwd_kernel<U, BS, UPC>;
+  auto kernel = scan_tc_bwd_kernel<U, BS, UPC, AXIS_TIME>;
   DJ_CUDA(cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
   if (C > 8) DJ_CUDA(cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   cudaLaunchConfig_t cfg{};
@@ -549,16 +670,16 @@ extern "C" int dj_lstm_scan_tc_fwd(float* Z, float* h_out, float* c_out, void* h
     // 2 CTAs/SM x 16 resident 8-CTA clusters = 32 tile slots: beyond that, double the tile (two batch
     // elements per cluster) so the whole layer still runs as one wave of step chains
     if (S % 96 == 0 && S / 48 > 32)
-      return launch_tc_fwd<256, 96>(Ut_bf16, Z, h_out, c_out, h_prev_bf16, S, steps, map, 1, hard, st);
-    return launch_tc_fwd<256, 48>(Ut_bf16, Z, h_out, c_out, h_prev_bf16, S, steps, map, 1, hard, st);
+      return launch_tc_fwd<256, 96, true>(Ut_bf16, Z, h_out, c_out, h_prev_bf16, S, steps, map, 1, hard, st);
+    return launch_tc_fwd<256, 48, true>(Ut_bf16, Z, h_out, c_out, h_prev_bf16, S, steps, map, 1, hard, st);
   } else if (time_map && units == 512) {   // scaled model (BASELINE configs[4]): 16-CTA clusters
-    return launch_tc_fwd<512, 48>(Ut_bf16, Z, h_out, c_out, h_prev_bf16, S, steps, map, 1, hard, st);
+    return launch_tc_fwd<512, 48, true>(Ut_bf16, Z, h_out, c_out, h_prev_bf16, S, steps, map, 1, hard, st);
   } else if (note_map && units == 128) {
     if (S % 128 == 0 && S / 64 > 74)
-      return launch_tc_fwd<128, 128>(Ut_bf16, Z, h_out, c_out, h_prev_bf16, S, steps, map, 0, hard, st);
-    return launch_tc_fwd<128, 64>(Ut_bf16, Z, h_out, c_out, h_prev_bf16, S, steps, map, 0, hard, st);
+      return launch_tc_fwd<128, 128, false>(Ut_bf16, Z, h_out, c_out, h_prev_bf16, S, steps, map, 0, hard, st);
+    return launch_tc_fwd<128, 64, false>(Ut_bf16, Z, h_out, c_out, h_prev_bf16, S, steps, map, 0, hard, st);
   } else if (note_map && units == 256) {   // scaled model, note axis
-    return launch_tc_fwd<256, 64>(Ut_bf16, Z, h_out, c_out, h_prev_bf16, S, steps, map, 0, hard, st);
+    return launch_tc_fwd<256, 64, false>(Ut_bf16, Z, h_out, c_out, h_prev_bf16, S, steps, map, 0, hard, st);
   }
   DJ_CHECK_ARG(false, "dj_lstm_scan_tc_fwd: units=%d unsupported on this axis (time: 256/512, note: 128/256)", units);
   return -1;
