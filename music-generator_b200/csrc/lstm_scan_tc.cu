@@ -61,15 +61,23 @@ struct TcMap {
   int64_t seq_stride;                  // row distance of consecutive sequences inside a 16-chunk
 };
 
-constexpr int TC_EPI_WARPS = 4;
-constexpr int TC_THREADS = 32 * (1 + TC_EPI_WARPS);
+constexpr int TC_EPI_WARPS = 8;       // two per TMEM lane quarter
+constexpr int TC_THREADS = 32 * (2 + TC_EPI_WARPS);   // warp 0 and warp 9 each drive one half-tile's chain
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t v[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
 
 template <int U, int BS>
 struct TcFwdSmem {
   static constexpr int A_BYTES = 128 * U * 2;
   static constexpr int H_BYTES = BS * U * 2;
   static constexpr int A_OFF = 0, H_OFF = A_BYTES, BAR_OFF = A_BYTES + H_BYTES;
-  static constexpr int TOTAL = BAR_OFF + 32;          // no static smem: two CTAs must fit one SM
+  static constexpr int TOTAL = BAR_OFF + 96;          // no static smem: two CTAs must fit one SM
 };
 
 // single-instruction MUFU forms (ftz: no denormal range fix-up around ex2, no Newton step after rcp)
@@ -107,7 +115,19 @@ __device__ __forceinline__ void cl_wait() { asm volatile("barrier.cluster.wait.a
 // TIME: sequences (b, n) stepping t (sequence stride 1 row, step stride 48 rows); else the note axis:
 // sequences (b, t) stepping n (sequence stride 48 rows, step stride 1).  Both strides and the gate
 // activation are compile-time so every row offset inside a chunk is an immediate.
-template <int U, int BS, bool TIME, bool HARD, int NB>
+//
+// Warp roles: warps 0 and 9 issue (TMA, MMA) and publish, one half-tile each; warps 1..8 are the epilogue,
+// two per TMEM lane quarter, each taking 8 of the 16 sequences of every chunk.
+//
+// NS = 2 software-pipelines the tile as two half-tiles that alternate through the same epilogue warps:
+// while they do the gate math of half B, half A's publish -> all-gather -> MMA chain is in flight.
+// Per half-step the hand-offs are mbarriers, not the hardware cluster barrier:
+//   epilogue warps  --done[hf] (count 8, release.cta)-->  issuer
+//   issuer: ONE gpu-scope release for the whole CTA (the pattern of a grid barrier: CTA-level sync, then
+//           one thread's fence publishes everybody's stores), then a remote arrive on pub[hf] of all C CTAs
+//   pub[hf] complete (count C) -> this CTA's multicast TMA of its slice of h_t -> bar_h[hf] -> MMA -> bar_acc[hf]
+// so the epilogue warps never execute a gpu-scope membar or a cluster barrier.
+template <int U, int BS, bool TIME, bool HARD, int NB, int NS>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 scan_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmH,
                    float* __restrict__ Z, float* __restrict__ Hout, float* __restrict__ Cout,
@@ -117,6 +137,10 @@ scan_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
   constexpr int KA = U / 64;           // 64-wide K atoms
   constexpr int RH = BS / 2;           // rows per multicast slice
   constexpr int NCH = BS / 16;         // 16-sequence chunks per tile
+  constexpr int HB = BS / NS;          // sequences per half-tile (= MMA N)
+  constexpr int NCHH = NCH / NS;       // chunks per half-tile
+  static_assert(NS == 1 || NS == 2, "one tile or two half-tiles");
+  static_assert(NS == 1 || (NCH % 2 == 0), "half-tiles are whole 16-sequence chunks");
   static_assert(C == 2 * KA && RH % 8 == 0, "slices = K atoms x 2 row halves");
   constexpr uint32_t TMEM_COLS = BS <= 32 ? 32 : BS <= 64 ? 64 : BS <= 128 ? 128 : 256;
   static_assert(BS % 16 == 0 && BS <= 256, "tile shape");
@@ -124,8 +148,10 @@ scan_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
 
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
-  const uint32_t bar_a = sbase + SM::BAR_OFF, bar_acc = bar_a + 8, bar_h = bar_a + 16;
-  volatile uint32_t* tmem_slot_p = (volatile uint32_t*)(smem + SM::BAR_OFF + 24);
+  // barriers: a | acc[2] | h[2] | done[2] | pub[2] | tmem slot
+  const uint32_t bar_a = sbase + SM::BAR_OFF, bar_acc0 = bar_a + 8, bar_h0 = bar_a + 24, bar_done0 = bar_a + 40,
+                 bar_pub0 = bar_a + 56;
+  volatile uint32_t* tmem_slot_p = (volatile uint32_t*)(smem + SM::BAR_OFF + 72);
 
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
@@ -136,176 +162,180 @@ scan_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
     if (lane == 0) {
       if (sbase & 1023u) { printf("deepj scan_tc_fwd: dynamic smem not 1024-aligned\n"); __trap(); }
       prefetch_tmap(&tmU); prefetch_tmap(&tmH);
-      mbar_init(bar_a, 1); mbar_init(bar_acc, 1); mbar_init(bar_h, 1);
+      mbar_init(bar_a, 1);
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        mbar_init(bar_acc0 + 8 * hf, 1); mbar_init(bar_h0 + 8 * hf, 1);
+        mbar_init(bar_done0 + 8 * hf, TC_EPI_WARPS); mbar_init(bar_pub0 + 8 * hf, C);
+      }
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc(sbase + SM::BAR_OFF + 24, TMEM_COLS);
+    tmem_alloc(sbase + SM::BAR_OFF + 72, TMEM_COLS);
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_p;
-  cluster.sync();   // peers' barriers are initialised before any multicast can target them
+  cluster.sync();   // peers' barriers are initialised before any multicast / remote arrive can target them
 
-  if (warp == 0) {
-    // ================= TMA (once) + MMA issuer =================
+  if (warp == 0 || warp == 1 + TC_EPI_WARPS) {
+    // ================= issuer + publisher of half-tile hf =================
     // the whole warp walks the loop converged; single-thread work sits under elect_one()
-    if (elect_one()) {   // resident A operand: rows [128*rank, +128) of U^T
+    const int hf = (warp == 0) ? 0 : 1;
+    if (warp == 0 && elect_one()) {   // resident A operand: rows [128*rank, +128) of U^T
       mbar_expect_tx(bar_a, SM::A_BYTES);
 #pragma unroll
       for (int ka = 0; ka < KA; ++ka)
         tma_load_2d(sbase + SM::A_OFF + ka * 16384, &tmU, bar_a, ka * 64, 128 * rank);
     }
     __syncwarp();
-    uint32_t h_phase = 0;
-    for (int t = 0; t < steps; ++t) {
-      if (t > 0) {
-        if (t == 1) mbar_wait(bar_a, 0);
-        mbar_wait(bar_h, h_phase);
-        DJ_TR(t, 0);
-        h_phase ^= 1;
+    const int my_ka = rank >> 1, my_hh = rank & 1;       // the slice of h_t this CTA multicasts
+    const uint32_t bar_done = bar_done0 + 8 * hf, bar_pub = bar_pub0 + 8 * hf, bar_h = bar_h0 + 8 * hf,
+                   bar_acc = bar_acc0 + 8 * hf;
+    if (hf < NS) {
+      for (int t = 0; t + 1 < steps; ++t) {               // the last step publishes nothing
+        const uint32_t par = (uint32_t)t & 1u;
+        mbar_wait(bar_done, par);                         // this CTA's epilogue warps stored this half of h_t
+        DJ_TR(t, 4 * hf + 0);
+        if (lane < C) mbar_arrive_remote(bar_pub, (uint32_t)lane);   // release.cluster, cumulative
+        __syncwarp();
+        mbar_wait_cluster(bar_pub, par);                  // every CTA of the cluster has published
+        DJ_TR(t, 4 * hf + 1);
+        if (elect_one()) {
+          mbar_expect_tx(bar_h, HB * U * 2);
+          if (NS == 1 || my_hh == hf)
+            tma_load_3d_mc(sbase + SM::H_OFF + my_ka * (BS * 128) + my_hh * (RH * 128), &tmH, bar_h, my_ka * 64,
+                           (t + 1) * map.step1 + my_hh * map.off1, tile * map.base2 + my_hh * map.off2,
+                           (uint16_t)((1u << C) - 1u));
+        }
+        __syncwarp();
+        if (t == 0) mbar_wait(bar_a, 0);
+        mbar_wait(bar_h, par);                            // all C slices of this half landed
+        DJ_TR(t, 4 * hf + 2);
         tc_fence_after();
         if (elect_one()) {
-          constexpr uint32_t idesc = make_idesc(128, BS, 0, 0);
+          constexpr uint32_t idesc = make_idesc(128, HB, 0, 0);
           const uint64_t adesc0 = make_smem_desc(sbase + SM::A_OFF, 16, 1024);
-          const uint64_t bdesc0 = make_smem_desc(sbase + SM::H_OFF, 16, 1024);
+          const uint64_t bdesc0 = make_smem_desc(sbase + SM::H_OFF + hf * (HB * 128), 16, 1024);
 #pragma unroll
           for (int ka = 0; ka < KA; ++ka)
 #pragma unroll
             for (int k = 0; k < 4; ++k)   // descriptor start addresses are in 16-byte units
-              umma_bf16(tmem_base, adesc0 + (uint64_t)((ka * 16384 + k * 32) >> 4),
+              umma_bf16(tmem_base + (uint32_t)(hf * HB), adesc0 + (uint64_t)((ka * 16384 + k * 32) >> 4),
                         bdesc0 + (uint64_t)((ka * (BS * 128) + k * 32) >> 4), idesc, (ka | k) != 0);
           umma_commit(bar_acc);
-          DJ_TR(t, 1);
         }
         __syncwarp();
+        DJ_TR(t, 4 * hf + 3);
       }
-      cl_arrive();
-      cl_wait();     // every CTA of the cluster has published its slice of h_t (and fenced it for the async proxy)
-      DJ_TR(t, 2);
-      if (t + 1 < steps && elect_one()) {
-        mbar_expect_tx(bar_h, SM::H_BYTES);
-        const int ka = rank >> 1, hh = rank & 1;
-        tma_load_3d_mc(sbase + SM::H_OFF + ka * (BS * 128) + hh * (RH * 128), &tmH, bar_h, ka * 64,
-                       (t + 1) * map.step1 + hh * map.off1, tile * map.base2 + hh * map.off2,
-                       (uint16_t)((1u << C) - 1u));
-        DJ_TR(t, 3);
-      }
-      __syncwarp();
     }
   } else {
     // ================= epilogue warps =================
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int w2 = (warp - 1) >> 2;         // which 8 of a chunk's 16 sequences
     const int up = lane >> 2;               // unit inside the warp (0..7)
     const int g = lane & 3;                 // gate held before the transpose / sequence slot after it
     const uint32_t col = 32 * rank + 8 * q + up;          // global hidden unit
     const uint32_t zc = 128 * rank + 32 * q + lane;       // gate-interleaved column this lane reads
-    float cst[NCH][4];
-    uint32_t rowb[NCH];                     // row of each chunk's first sequence at step 0
+    float cst[NCH][2];
+    uint32_t rowb[NCH];                     // row of this warp's first sequence of each chunk at step 0
 #pragma unroll
     for (int i = 0; i < NCH; ++i) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) cst[i][j] = 0.f;
-      rowb[i] = (uint32_t)tc_row0(map, tile * BS + i * 16);   // a 16-chunk never straddles a batch element
+      cst[i][0] = cst[i][1] = 0.f;
+      // a 16-chunk never straddles a batch element
+      rowb[i] = (uint32_t)tc_row0(map, tile * BS + i * 16) + (uint32_t)(8 * w2) * SSTR;
     }
     // x.W pre-activations are prefetched NB chunks ahead into registers (NB divides NCH, so after
     // unrolling every buffer index is static)
     static_assert(NCH % NB == 0, "prefetch ring must divide the chunk count");
-    float zreg[NB][16];
+    float zreg[NB][8];
     auto load_z = [&](int ci, uint32_t t) {
       const float* zp = Z + (size_t)(rowb[ci] + t * TSTR) * (4 * U) + zc;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) zreg[ci % NB][j] = zp[(size_t)j * SSTR * (4 * U)];
+      for (int j = 0; j < 8; ++j) zreg[ci % NB][j] = zp[(size_t)j * SSTR * (4 * U)];
     };
 #pragma unroll
     for (int ci = 0; ci < NB; ++ci) load_z(ci, 0);
-    uint32_t acc_phase = 0;
+    const bool tr = (warp == 1 && lane == 0);
     for (int t = 0; t < steps; ++t) {
-      if (t > 0) {
-        mbar_wait(bar_acc, acc_phase);
-        acc_phase ^= 1;
-        tc_fence_after();
-      }
-      if (warp == 1 && lane == 0) DJ_TR(t, 8);
-      if (t + 1 < steps && lane < 16) {   // warm L2 with the next step's x.W rows (this warp's 128-byte segments)
-#pragma unroll
-        for (int ci = 0; ci < NCH; ++ci)
-          asm volatile("prefetch.global.L2 [%0];\n" ::"l"(Z + (size_t)(rowb[ci] + lane * SSTR + (t + 1) * TSTR) * (4 * U) +
-                                                              128 * rank + 32 * q));
-      }
-      long long trs[4] = {0, 0, 0, 0};
       const bool not_last = (t + 1 < steps);
+      const uint32_t par = (uint32_t)(t + 1) & 1u;        // accumulators of step t were produced in issuer round t-1
 #pragma unroll
-      for (int ci = 0; ci < NCH; ++ci) {
-        float v[16];
-        const long long c0 = DJ_CLK();
-        long long c1 = c0;
+      for (int hf = 0; hf < NS; ++hf) {
         if (t > 0) {
-          uint32_t acc[16];
-          tmem_ld16(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(ci * 16), acc);
-          c1 = DJ_CLK();
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]) + zreg[ci % NB][j];
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = zreg[ci % NB][j];
+          mbar_wait(bar_acc0 + 8 * hf, par);
+          tc_fence_after();
         }
-#ifdef DJ_TRACE
-        asm volatile("" ::"f"(v[0]), "f"(v[5]), "f"(v[10]), "f"(v[15]) : "memory");
+        if (tr) DJ_TR(t, 8 + 4 * hf);
+        if (not_last && lane < 8) {   // warm L2 with the next step's x.W rows (this warp's 128-byte segments)
+#pragma unroll
+          for (int ci = hf * NCHH; ci < (hf + 1) * NCHH; ++ci)
+            asm volatile("prefetch.global.L2 [%0];\n" ::"l"(Z + (size_t)(rowb[ci] + lane * SSTR + (t + 1) * TSTR) * (4 * U) +
+                                                                128 * rank + 32 * q));
+        }
+#pragma unroll
+        for (int ci = hf * NCHH; ci < (hf + 1) * NCHH; ++ci) {
+          float v[8];
+          if (t > 0) {
+            uint32_t acc[8];
+            tmem_ld8(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(ci * 16 + 8 * w2), acc);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(acc[j]) + zreg[ci % NB][j];
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = zreg[ci % NB][j];
+          }
+          // refill the buffer just consumed: NB chunks ahead, wrapping into the next step
+          if (ci + NB < NCH) load_z(ci + NB, t);
+          else if (not_last) load_z(ci + NB - NCH, t + 1);
+          // this lane's cell after the transpose: sequence 16*ci + 8*w2 + 4*blk + g, unit `col`
+          const uint32_t row_c = rowb[ci] + (uint32_t)g * SSTR + (uint32_t)t * TSTR;
+          float* const zg = Z + (size_t)row_c * (4 * U) + 4 * col;
+          const size_t o1 = (size_t)row_c * U + col;
+          float* const hp = Hout + o1;
+          float* const cp = Cout + o1;                       // only dereferenced when Cout != nullptr
+          __nv_bfloat16* const hb = Hprev + o1;
+#pragma unroll
+          for (int blk = 0; blk < 2; ++blk) {
+            // 4x4 transpose across the 4 lanes of a unit: lane g ends with i,f,g,o of sequence 4*blk+g
+            const float a0 = v[4 * blk], a1 = v[4 * blk + 1], a2 = v[4 * blk + 2], a3 = v[4 * blk + 3];
+            const bool odd = g & 1, hi = g & 2;
+            const float x1 = __shfl_xor_sync(0xffffffffu, odd ? a0 : a1, 1);
+            const float x2 = __shfl_xor_sync(0xffffffffu, odd ? a2 : a3, 1);
+            const float b0 = odd ? x1 : a0, b1 = odd ? a1 : x1, b2 = odd ? x2 : a2, b3 = odd ? a3 : x2;
+            const float y0 = __shfl_xor_sync(0xffffffffu, hi ? b0 : b2, 2);
+            const float y1 = __shfl_xor_sync(0xffffffffu, hi ? b1 : b3, 2);
+            const float zi = hi ? y0 : b0, zf = hi ? y1 : b1, zg_ = hi ? b2 : y0, zo = hi ? b3 : y1;
+
+            const float gi = gate_act_fast<HARD>(zi), gf = gate_act_fast<HARD>(zf);
+            const float gg = fast_tanh(zg_), go = gate_act_fast<HARD>(zo);
+            const float cn = fmaf(gf, cst[ci][blk], gi * gg);
+            const float hn = go * fast_tanh(cn);
+            cst[ci][blk] = cn;
+
+            constexpr size_t RO = (size_t)4 * SSTR;          // rows between consecutive blocks
+            // h_t (bf16) at the NEXT step's row: the A operand of dU = H_{t-1}^T.dZ
+            if (not_last) hb[(blk * RO + TSTR) * U] = __float2bfloat16_rn(hn);
+            if (t == 0) hb[blk * RO * U] = __float2bfloat16_rn(0.f);
+#ifndef DJ_EXP
+#define DJ_EXP 0   // timing experiments only: bit0/1/2 drop the gate / h / c stores
 #endif
-        const long long c2 = DJ_CLK();
-        // refill the buffer just consumed: NB chunks ahead, wrapping into the next step (those loads
-        // then overlap the fence + cluster barrier + TMA + MMA of the step boundary)
-        if (ci + NB < NCH) load_z(ci + NB, t);
-        else if (not_last) load_z(ci + NB - NCH, t + 1);
-        const long long c3 = DJ_CLK();
-        // this lane's cell after the transpose: sequence 16*ci + 4*blk + g, unit `col`
-        const uint32_t row_c = rowb[ci] + (uint32_t)g * SSTR + (uint32_t)t * TSTR;
-        float* const zg = Z + (size_t)row_c * (4 * U) + 4 * col;
-        const size_t o1 = (size_t)row_c * U + col;
-        float* const hp = Hout + o1;
-        float* const cp = Cout + o1;                       // only dereferenced when Cout != nullptr
-        __nv_bfloat16* const hb = Hprev + o1;
-#pragma unroll
-        for (int blk = 0; blk < 4; ++blk) {
-          // 4x4 transpose across the 4 lanes of a unit: lane g ends with i,f,g,o of sequence 4*blk+g
-          const float a0 = v[4 * blk], a1 = v[4 * blk + 1], a2 = v[4 * blk + 2], a3 = v[4 * blk + 3];
-          const bool odd = g & 1, hi = g & 2;
-          const float x1 = __shfl_xor_sync(0xffffffffu, odd ? a0 : a1, 1);
-          const float x2 = __shfl_xor_sync(0xffffffffu, odd ? a2 : a3, 1);
-          const float b0 = odd ? x1 : a0, b1 = odd ? a1 : x1, b2 = odd ? x2 : a2, b3 = odd ? a3 : x2;
-          const float y0 = __shfl_xor_sync(0xffffffffu, hi ? b0 : b2, 2);
-          const float y1 = __shfl_xor_sync(0xffffffffu, hi ? b1 : b3, 2);
-          const float zi = hi ? y0 : b0, zf = hi ? y1 : b1, zg_ = hi ? b2 : y0, zo = hi ? b3 : y1;
-
-          const float gi = gate_act_fast<HARD>(zi), gf = gate_act_fast<HARD>(zf);
-          const float gg = fast_tanh(zg_), go = gate_act_fast<HARD>(zo);
-          const float cn = fmaf(gf, cst[ci][blk], gi * gg);
-          const float hn = go * fast_tanh(cn);
-          cst[ci][blk] = cn;
-
-          constexpr size_t RO = (size_t)4 * SSTR;          // rows between consecutive blocks
-          // h_t (bf16) at the NEXT step's row: the A operand of dU = H_{t-1}^T.dZ
-          if (not_last) hb[(blk * RO + TSTR) * U] = __float2bfloat16_rn(hn);
-          if (t == 0) hb[blk * RO * U] = __float2bfloat16_rn(0.f);
-          *reinterpret_cast<float4*>(zg + blk * RO * (4 * U)) = make_float4(gi, gf, gg, go);
-          hp[blk * RO * U] = hn;
-          if (Cout != nullptr) cp[blk * RO * U] = cn;
+            if (!(DJ_EXP & 1)) *reinterpret_cast<float4*>(zg + blk * RO * (4 * U)) = make_float4(gi, gf, gg, go);
+            if (!(DJ_EXP & 2)) hp[blk * RO * U] = hn;
+            if (!(DJ_EXP & 4) && Cout != nullptr) cp[blk * RO * U] = cn;
+          }
         }
-        const long long c4 = DJ_CLK();
-        trs[0] += c1 - c0; trs[1] += c2 - c1; trs[2] += c3 - c2; trs[3] += c4 - c3;
+        if (tr) DJ_TR(t, 9 + 4 * hf);
+        if (not_last) {
+          tc_fence_before();
+          fence_proxy_async_all();   // generic-proxy global stores of h_t -> later async-proxy (TMA) reads
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_done0 + 8 * hf);   // release.cta: hands this warp's stores to the issuer
+        }
+        if (tr) DJ_TR(t, 10 + 4 * hf);
       }
-      if (warp == 1 && lane == 0) {
-        DJ_TR(t, 9);
-        DJ_TRV(t, 12, trs[0]); DJ_TRV(t, 13, trs[1]); DJ_TRV(t, 14, trs[2]); DJ_TRV(t, 15, trs[3]);
-      }
-      tc_fence_before();
-      fence_proxy_async_all();   // generic-proxy global stores of h_t -> visible to the TMA (async proxy) reads
-      if (warp == 1 && lane == 0) DJ_TR(t, 10);
-      cl_arrive();
-      cl_wait();
-      if (warp == 1 && lane == 0) DJ_TR(t, 11);
     }
   }
   tc_fence_before();
@@ -313,7 +343,7 @@ scan_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
   if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-template <int U, int BS, bool TIME, bool HARD, int NB>
+template <int U, int BS, bool TIME, bool HARD, int NB, int NS>
 int launch_tc_fwd_inst(const void* Ut_bf, float* Z, float* h_out, float* c_out, void* hprev, int S, int steps,
                        const TcMap& map_in, cudaStream_t st) {
   constexpr int C = U / 32;
@@ -339,7 +369,7 @@ int launch_tc_fwd_inst(const void* Ut_bf, float* Z, float* h_out, float* c_out, 
     map.step1 = 1; map.off1 = 0; map.base2 = BS; map.off2 = RH;
     map.seq_stride = map.outer_stride;
   }
-  auto kernel = scan_tc_fwd_kernel<U, BS, TIME, HARD, NB>;
+  auto kernel = scan_tc_fwd_kernel<U, BS, TIME, HARD, NB, NS>;
   DJ_CUDA(cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
   if (C > 8) DJ_CUDA(cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   cudaLaunchConfig_t cfg{};
@@ -364,24 +394,37 @@ inline int fwd_prefetch_depth(int nch, int dflt) {
     env = e ? atoi(e) : 0;
   }
   const int nb = env > 0 ? env : dflt;
-  return (nb >= 1 && nb <= 3 && nch % nb == 0) ? nb : dflt;
+  return (nb >= 1 && nb <= 2 && nch % nb == 0) ? nb : dflt;
+}
+
+// DJ_FWD_NS=1 forces the unsplit tile (experiments)
+inline bool fwd_split_enabled() {
+  static int env = -1;
+  if (env < 0) {
+    const char* e = getenv("DJ_FWD_NS");
+    env = (e && atoi(e) == 1) ? 0 : 1;
+  }
+  return env != 0;
 }
 
 template <int U, int BS, bool TIME>
 int launch_tc_fwd(const void* Ut_bf, float* Z, float* h_out, float* c_out, void* hprev, int S, int steps,
                   const TcMap& map, int /*axis_time*/, int hard, cudaStream_t st) {
   constexpr int NCH = BS / 16;
-  constexpr int NB_DEF = 1;
+  constexpr bool CAN_SPLIT = (NCH % 2 == 0);
+  constexpr int NB_DEF = (NCH % 2 == 0) ? 2 : 1;
   const int nb = fwd_prefetch_depth(NCH, NB_DEF);
-#define DJ_FWD_CASE(NBV)                                                                                        \
-  if constexpr (NCH % NBV == 0) {                                                                               \
-    if (nb == NBV)                                                                                              \
-      return hard ? launch_tc_fwd_inst<U, BS, TIME, true, NBV>(Ut_bf, Z, h_out, c_out, hprev, S, steps, map, st) \
-                  : launch_tc_fwd_inst<U, BS, TIME, false, NBV>(Ut_bf, Z, h_out, c_out, hprev, S, steps, map, st); \
+  const bool split = CAN_SPLIT && fwd_split_enabled();
+#define DJ_FWD_CASE(NBV, NSV)                                                                                       \
+  if constexpr (NCH % NBV == 0 && (NSV == 1 || CAN_SPLIT)) {                                                        \
+    if (nb == NBV && split == (NSV == 2))                                                                           \
+      return hard ? launch_tc_fwd_inst<U, BS, TIME, true, NBV, NSV>(Ut_bf, Z, h_out, c_out, hprev, S, steps, map, st) \
+                  : launch_tc_fwd_inst<U, BS, TIME, false, NBV, NSV>(Ut_bf, Z, h_out, c_out, hprev, S, steps, map, st); \
   }
-  DJ_FWD_CASE(1)
-  DJ_FWD_CASE(2)
-  DJ_FWD_CASE(3)
+  DJ_FWD_CASE(1, 1)
+  DJ_FWD_CASE(1, 2)
+  DJ_FWD_CASE(2, 1)
+  DJ_FWD_CASE(2, 2)
 #undef DJ_FWD_CASE
   DJ_CHECK_ARG(false, "dj_lstm_scan_tc_fwd: no kernel instance for prefetch depth %d", nb);
   return -1;
@@ -409,13 +452,6 @@ struct TcBwdSmem {
 
 constexpr int TCB_THREADS = 32 * 9;   // 1 issuer warp + 8 epilogue warps
 
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t v[8]) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
-               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-               : "r"(taddr)
-               : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
 
 template <int U, int BS, int UPC, bool AXIS_TIME>
 __global__ void __launch_bounds__(TCB_THREADS, (U == 128 && BS <= 32) ? 2 : 1)

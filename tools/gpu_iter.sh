@@ -2,9 +2,8 @@
 # one development iteration on the GPU: kernel parity tests, scan timelines, short bench
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_model.py -x -q -m gpu --timeout 600 2>&1 | tail -4
-for nb in 1 2 3; do echo "== DJ_FWD_NB=$nb"; DJ_FWD_NB=$nb python tools/scan_trace.py 64 2>&1 | grep -E "fwd"; done
-echo "== bwd"; python tools/scan_trace.py 64 2>&1 | grep -E "bwd"
-echo "== fence.proxy.async.global"; DJ_TRACE_LIB=libdeepj_trace2.so python tools/scan_trace.py 64 2>&1 | grep -E "B=64|STEP"
+python tools/scan_trace.py 64 2>&1 | grep fwd
+for v in "DJ_FWD_NS=1" "DJ_FWD_NB=1" "DJ_FWD_NB=2"; do echo "== $v"; env $v python tools/scan_probe.py 64 fwd; done
 python tools/scan_probe.py 64 all
 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-generation 2>/dev/null | python -c "
 import json,sys; d=json.loads(sys.stdin.read()); print('bench', d['value'], d['ms_per_step'], 'e2e', d['e2e']['value'], 'loss', d['loss'], d['roofline']['avg_launch_ms'])"

@@ -31,33 +31,15 @@ assert lib.dj_debug_trace_set(P(trace)) == 0
 
 
 def report(name, steps, reverse):
+    """Median of every stamp relative to stamp 8 (first accumulator ready) of the same step, and the step period."""
     tr = trace.cpu().numpy().reshape(2, 512, 16)
     for slot in range(2):
         a = tr[slot, :steps].astype(np.float64)
-        order = range(steps - 2, 1, -1) if reverse else range(2, steps - 1)
-        rows = []
-        prev = None
-        for t in order:
-            if prev is not None:
-                # one step = from accumulator-ready of step `prev` to accumulator-ready of step t
-                e8p, e9, e10, e11 = a[prev, 8], a[prev, 9], a[prev, 10], a[prev, 11]
-                w2, w3 = a[prev, 2], a[prev, 3]
-                w0, w1, e8 = a[t, 0], a[t, 1], a[t, 8]
-                rows.append([e9 - e8p, e10 - e9, e11 - e10, w2 - e10, w3 - w2, w0 - w3, w1 - w0, e8 - w1, e8 - e8p])
-            prev = t
-        if not reverse:
-            ex = a[4:steps - 4, 12:16]
-            print(f"   fwd epilogue split (sum over chunks): tmem_ld {np.median(ex[:, 0]):.0f}  z landed {np.median(ex[:, 1]):.0f}"
-                  f"  load issue {np.median(ex[:, 2]):.0f}  math+stores {np.median(ex[:, 3]):.0f}")
-        else:
-            sel = a[4:steps - 4]
-            print(f"   bwd epilogue split: tmem_ld {np.median(sel[:, 12] - sel[:, 8]):.0f}  math+stores {np.median(sel[:, 9] - sel[:, 12]):.0f}"
-                  f"  fences {np.median(sel[:, 13] - sel[:, 9]):.0f}  arrive {np.median(sel[:, 10] - sel[:, 13]):.0f}"
-                  f"  issue_loads+cl_wait {np.median(sel[:, 11] - sel[:, 10]):.0f}")
-        r = np.array(rows[4:-4])
-        lab = ["epilogue", "fence", "cl_barrier(epi)", "cl_barrier(issuer, from fence)", "tma issue", "tma flight",
-               "mma issue", "mma->acc ready", "STEP"]
-        print(f"{name} slot {slot}: " + "  ".join(f"{l} {m:.0f}" for l, m in zip(lab, np.median(r, axis=0))) + " [cycles]")
+        sel = a[6:steps - 6]
+        nxt = a[5:steps - 7] if reverse else a[7:steps - 5]
+        period = np.median(nxt[:, 8] - sel[:, 8])
+        rel = {k: np.median(sel[:, k] - sel[:, 8]) for k in range(16) if k != 8 and np.all(sel[:, k] != 0)}
+        print(f"{name} slot {slot}: STEP {period:.0f} | " + "  ".join(f"k{k}:{v:+.0f}" for k, v in sorted(rel.items(), key=lambda kv: kv[1])))
 
 
 AXES = [a for a in (("time", 256), ("note", 128)) if len(sys.argv) < 3 or sys.argv[2] == a[0]]
