@@ -39,6 +39,10 @@ struct GenSmem {
                                                  // parity: a fast peer may already push h_n while this CTA still reads h_{n-1}
   float c0[MAXG][32], c1[MAXG][32];              // cell states of the 32 local units
   float prev[MAXG][4];                           // chosen_{n-1} (play, replay, volume)
+  float sp1[MAXG][UN];                           // tanh(Dense(style)) added to h0 before layer 1 (constant over notes)
+  float wh[3][UN];                               // head weights: play, replay, volume
+  float bh[4];
+  double temp[MAXG];
   float head[3];
   int played_any[MAXG];
   double margin[MAXG];
@@ -57,7 +61,6 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NTHR, 1) gen_sample
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   const int tid = threadIdx.x, c = tid & (CW - 1), kq = tid >> 7;
-  const int col = rank * CW + c;                       // global gate-interleaved column
   const int g_base = (blockIdx.x / CL) * gcount;
 
   for (int i = tid; i < UN * CW; i += NTHR) {          // resident weight slices
@@ -74,8 +77,25 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NTHR, 1) gen_sample
     S.margin[tid] = 1e300;
   }
   if (tid == 0) S.cursor = (stream_mode == 0 && ucursor != nullptr) ? *ucursor : 0;
-  const float w0c0 = W0c[col], w0c1 = W0c[G4 + col], w0c2 = W0c[2 * G4 + col];
-  const float bias1 = b1[col];
+  // everything the per-note critical path would otherwise fetch from global memory
+  for (int i = tid; i < gcount * UN; i += NTHR) S.sp1[i / UN][i % UN] = sp1[(int64_t)(g_base + i / UN) * UN + i % UN];
+  for (int i = tid; i < UN; i += NTHR) { S.wh[0][i] = Wn[i * 2]; S.wh[1][i] = Wn[i * 2 + 1]; S.wh[2][i] = Wv[i]; }
+  if (tid == 0) { S.bh[0] = bn[0]; S.bh[1] = bn[1]; S.bh[2] = bv[0]; }
+  if (tid < gcount) S.temp[tid] = temperature[g_base + tid];
+  float w0c[3][4], bias1[4];                            // tid < 32: the four gate columns of local unit `tid`
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int gc = rank * CW + 4 * (tid & 31) + q;
+    w0c[0][q] = W0c[gc]; w0c[1][q] = W0c[G4 + gc]; w0c[2][q] = W0c[2 * G4 + gc];
+    bias1[q] = b1[gc];
+  }
+  // x.W0 pre-activations of the next (sequence, note) are fetched one unit of work ahead
+  auto load_zpre = [&](int gl, int n) {
+    return (tid < 32 && n < N_) ? *reinterpret_cast<const float4*>(zpre + ((int64_t)(g_base + gl) * N_ + n) * G4 +
+                                                                     rank * CW + 4 * tid)
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  float4 zp_next = load_zpre(0, 0);
   GenSmem* peer[CL];
 #pragma unroll
   for (int r = 0; r < CL; ++r) peer[r] = cluster.map_shared_rank(&S, r);
@@ -97,20 +117,26 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NTHR, 1) gen_sample
 
   for (int n = 0; n < N_; ++n) {
     const int cur = n & 1, nxt = cur ^ 1;
+    // the first uniform this note is certain to consume (the rest of its cache line is then in L1)
+    double upre0 = 0.0;
+    if (rank == 0 && tid == 0)
+      upre0 = (stream_mode == 0) ? uniforms[S.cursor] : uniforms[((int64_t)g_base * N_ + n) * 2];
     // ---- note layer 0 for every sequence of the group: z = zpre + chosen_{n-1}.W0[Ut:Ut+3] + h0.U0
     for (int gl = 0; gl < gcount; ++gl) {
+      const float4 zp4 = zp_next;
+      zp_next = (gl + 1 < gcount) ? load_zpre(gl + 1, n) : load_zpre(0, n + 1);
       S.part[kq][c] = matvec(S.U0, S.h0[cur][gl]);
       __syncthreads();
       if (tid < 32) {   // one thread per local hidden unit: its four gate columns are adjacent
-        const int g = g_base + gl;
+        const float zp[4] = {zp4.x, zp4.y, zp4.z, zp4.w};
         float z[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const int cc = 4 * tid + q, gc = rank * CW + cc;
-          float acc = zpre[((int64_t)g * N_ + n) * G4 + gc];
-          acc = fmaf(S.prev[gl][0], W0c[gc], acc);
-          acc = fmaf(S.prev[gl][1], W0c[G4 + gc], acc);
-          acc = fmaf(S.prev[gl][2], W0c[2 * G4 + gc], acc);
+          const int cc = 4 * tid + q;
+          float acc = zp[q];
+          acc = fmaf(S.prev[gl][0], w0c[0][q], acc);
+          acc = fmaf(S.prev[gl][1], w0c[1][q], acc);
+          acc = fmaf(S.prev[gl][2], w0c[2][q], acc);
           z[q] = acc + ((S.part[0][cc] + S.part[1][cc]) + (S.part[2][cc] + S.part[3][cc]));
         }
         const float gi = dj_gate_act(z[0], hard), gf = dj_gate_act(z[1], hard);
@@ -128,15 +154,14 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NTHR, 1) gen_sample
     cluster.sync();
     // ---- note layer 1
     for (int gl = 0; gl < gcount; ++gl) {
-      const int g = g_base + gl;
       // x1 = h0 + sp1 (built on the fly from the all-gathered h0)
       float a = 0.f;
       {
         float a0 = 0.f, a1 = 0.f;
 #pragma unroll 8
         for (int k = 0; k < UN / KQ; k += 2) {
-          a0 = fmaf(S.h0[nxt][gl][k0 + k] + sp1[(int64_t)g * UN + k0 + k], S.W1[(k0 + k) * CW + c], a0);
-          a1 = fmaf(S.h0[nxt][gl][k0 + k + 1] + sp1[(int64_t)g * UN + k0 + k + 1], S.W1[(k0 + k + 1) * CW + c], a1);
+          a0 = fmaf(S.h0[nxt][gl][k0 + k] + S.sp1[gl][k0 + k], S.W1[(k0 + k) * CW + c], a0);
+          a1 = fmaf(S.h0[nxt][gl][k0 + k + 1] + S.sp1[gl][k0 + k + 1], S.W1[(k0 + k + 1) * CW + c], a1);
         }
         a = a0 + a1;
       }
@@ -147,7 +172,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NTHR, 1) gen_sample
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int cc = 4 * tid + q;
-          z[q] = b1[rank * CW + cc] + ((S.part[0][cc] + S.part[1][cc]) + (S.part[2][cc] + S.part[3][cc]));
+          z[q] = bias1[q] + ((S.part[0][cc] + S.part[1][cc]) + (S.part[2][cc] + S.part[3][cc]));
         }
         const float gi = dj_gate_act(z[0], hard), gf = dj_gate_act(z[1], hard);
         const float gg = tanhf(z[2]), go = dj_gate_act(z[3], hard);
@@ -167,9 +192,9 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NTHR, 1) gen_sample
         if (tid < 96) {
           const int o = tid >> 5, lane = tid & 31;
           float s = 0.f;
-          for (int k = lane; k < UN; k += 32) s = fmaf(S.h1[nxt][gl][k], (o < 2) ? Wn[k * 2 + o] : Wv[k], s);
+          for (int k = lane; k < UN; k += 32) s = fmaf(S.h1[nxt][gl][k], S.wh[o][k], s);
           s = dj_warp_sum(s);
-          if (lane == 0) S.head[o] = s + ((o < 2) ? bn[o] : bv[0]);
+          if (lane == 0) S.head[o] = s + S.bh[o];
         }
         __syncthreads();
         if (tid == 0) {
@@ -179,7 +204,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NTHR, 1) gen_sample
             float* po = probs_out + ((int64_t)g * N_ + n) * 3;
             po[0] = p0; po[1] = p1; po[2] = vol;
           }
-          const double temp = temperature[g];
+          const double temp = S.temp[gl];
           if (temp != 1.0) {   // generate.py:81-91, float32 arithmetic like NumPy on a float32 array
             const float tf = (float)temp;
             const float xa = -logf(1.0f / p0 - 1.0f), xb = -logf(1.0f / p1 - 1.0f);
@@ -188,7 +213,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NTHR, 1) gen_sample
           }
           double u1, u2;
           const double* ui = uniforms + ((int64_t)g * N_ + n) * 2;
-          if (stream_mode == 0) u1 = uniforms[S.cursor++]; else u1 = ui[0];
+          if (stream_mode == 0) { u1 = (gl == 0) ? upre0 : uniforms[S.cursor]; S.cursor++; } else u1 = (gl == 0) ? upre0 : ui[0];
           float e0 = 0.f, e1 = 0.f, e2 = 0.f;
           double mg = fabs(u1 - (double)p0);
           if (u1 <= (double)p0) {   // generate.py:52

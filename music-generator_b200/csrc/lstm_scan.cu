@@ -213,6 +213,122 @@ scan_fwd_kernel(float* __restrict__ Z, float* __restrict__ Hout, float* __restri
 }
 
 // ---------------------------------------------------------------------------
+// forward, few sequences (generation: one window = 48 time-axis sequences).
+//   Same arithmetic and the same k-ordered FMA chain per accumulator as scan_fwd_kernel (so the
+//   results are bit-identical), but tiles of 16 sequences and ONE hidden unit per thread:
+//   thread (sg, ug) = sequences 4*sg..4*sg+3, unit ug, four gates -> 16 accumulators.  A 48-sequence
+//   window then runs on 3 clusters x 8 CTAs x 4 warps (one per scheduler) instead of 1 cluster x
+//   8 CTAs x 6 warps: a quarter of the FFMA2 chain per warp and three times the SMs.
+// ---------------------------------------------------------------------------
+constexpr int SBS = 16;   // sequences per tile of the small-tile forward scan
+
+template <int U, int C>
+__global__ void __launch_bounds__((SBS / 4) * UC, 1)
+scan_fwd_small_kernel(float* __restrict__ Z, float* __restrict__ Hout, float* __restrict__ Cout,
+                      __nv_bfloat16* __restrict__ Hbf, const float* __restrict__ Uw, int S, int steps,
+                      ScanMap map, int hard) {
+  static_assert(U / C == UC, "each CTA owns 32 hidden units");
+  constexpr int NT = (SBS / 4) * UC;
+  using SM = FwdSmem<U, SBS>;
+  extern __shared__ __align__(16) float smem[];
+  float* Us = smem;               // [U][32 units][4 gates]
+  float* hbuf = smem + SM::US;    // [2][SBS/4][U*4+4]
+
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int cid = blockIdx.x / C, ncl = gridDim.x / C;
+  const int tid = threadIdx.x, sg = tid >> 5, ug = tid & 31;
+  const int unit0 = rank * UC;
+  const int col = unit0 + ug;
+
+  for (int idx = tid; idx < SM::US; idx += NT)
+    Us[idx] = Uw[(size_t)(idx >> 7) * 4 * U + 4 * unit0 + (idx & 127)];
+  float* rbuf[C];
+#pragma unroll
+  for (int r = 0; r < C; ++r) rbuf[r] = cluster.map_shared_rank(hbuf, r);
+  cluster.sync();   // every CTA of the cluster is resident before any remote store
+
+  const int ntiles = (S + SBS - 1) / SBS;
+  for (int tile = cid; tile < ntiles; tile += ncl) {
+    for (int idx = tid; idx < SM::HBUF; idx += NT) hbuf[idx] = 0.f;   // h_{-1} = 0
+    float c[4];
+    bool ok[4];
+    int64_t row0[4];
+    float4 zn[4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      const int seq = tile * SBS + sg * 4 + s;
+      ok[s] = seq < S;
+      row0[s] = scan_row0(map, ok[s] ? seq : 0);
+      c[s] = 0.f;
+      zn[s] = ok[s] ? *reinterpret_cast<const float4*>(Z + row0[s] * (4 * U) + 4 * col) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+
+    for (int t = 0; t < steps; ++t) {
+      const int cur = t & 1, nxt = cur ^ 1;
+      uint64_t acc2[4][2];   // [seq][gate pair (i,f) / (g,o)]
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        acc2[s][0] = pack2(zn[s].x, zn[s].y);
+        acc2[s][1] = pack2(zn[s].z, zn[s].w);
+      }
+      if (t + 1 < steps) {   // register prefetch of the next step's pre-activations
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+          const int64_t r = row0[s] + (int64_t)(t + 1) * map.step_stride;
+          zn[s] = ok[s] ? *reinterpret_cast<const float4*>(Z + r * (4 * U) + 4 * col) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      const float* hb = hbuf + cur * SM::HBUF + sg * SM::HSTR;
+      const float* ua = Us + ug * 4;
+#pragma unroll 8
+      for (int k = 0; k < U; ++k) {
+        const float4 hv = *reinterpret_cast<const float4*>(hb + k * 4);
+        const ulonglong2 u0 = *reinterpret_cast<const ulonglong2*>(ua + k * (UC * 4));
+        const uint64_t hs[4] = {pack2(hv.x, hv.x), pack2(hv.y, hv.y), pack2(hv.z, hv.z), pack2(hv.w, hv.w)};
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+          acc2[s][0] = ffma2(hs[s], u0.x, acc2[s][0]);
+          acc2[s][1] = ffma2(hs[s], u0.y, acc2[s][1]);
+        }
+      }
+      float hnew[4];
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        float a0, a1, a2, a3;
+        unpack2(acc2[s][0], a0, a1);
+        unpack2(acc2[s][1], a2, a3);
+        const int64_t r = row0[s] + (int64_t)t * map.step_stride;
+        const float gi = dj_gate_act(a0, hard);
+        const float gf = dj_gate_act(a1, hard);
+        const float gg = tanhf(a2);
+        const float go = dj_gate_act(a3, hard);
+        const float cn = fmaf(gf, c[s], gi * gg);
+        const float hn = go * tanhf(cn);
+        c[s] = cn;
+        hnew[s] = hn;
+        if (ok[s]) {
+          *reinterpret_cast<float4*>(Z + r * (4 * U) + 4 * col) = make_float4(gi, gf, gg, go);
+          Hout[r * U + col] = hn;
+          if (Cout != nullptr) Cout[r * U + col] = cn;
+          if (Hbf != nullptr) {
+            if (t + 1 < steps) Hbf[(r + map.step_stride) * U + col] = __float2bfloat16_rn(hn);
+            if (t == 0) Hbf[r * U + col] = __float2bfloat16_rn(0.f);
+          }
+        }
+      }
+      // all-gather of h_t into every CTA's next buffer (DSMEM, 32 lanes x 16 B contiguous)
+#pragma unroll
+      for (int r = 0; r < C; ++r)
+        *reinterpret_cast<float4*>(rbuf[r] + nxt * SM::HBUF + sg * SM::HSTR + col * 4) =
+            make_float4(hnew[0], hnew[1], hnew[2], hnew[3]);
+      cluster.sync();
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
 // backward (reverse scan).  Per step:
 //   D  dh_rec = sum over the C source CTAs of the partial dz.U^T slots
 //   A  gate derivatives for this CTA's (sequence, unit) pairs -> dz (global + smem)
@@ -427,6 +543,10 @@ extern "C" int dj_lstm_scan_fwd(float* Z, float* h_out, float* c_out, void* h_pr
   cudaStream_t st = (cudaStream_t)stream;
   if (units == 256) {
     constexpr int C = 8, BS = 48;
+    // few sequences (a generation window is 48): 16-sequence tiles spread the step over three times the SMs
+    if ((S + SBS - 1) / SBS <= dj_num_sms() / C)
+      return launch_cluster(scan_fwd_small_kernel<256, C>, C, (SBS / 4) * UC, FwdSmem<256, SBS>::BYTES,
+                            pick_clusters(C, (S + SBS - 1) / SBS), st, args);
     return launch_cluster(scan_fwd_kernel<256, C, BS>, C, (BS / 4) * 16, FwdSmem<256, BS>::BYTES,
                           pick_clusters(C, (S + BS - 1) / BS), st, args);
   } else if (units == 128) {

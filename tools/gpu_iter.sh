@@ -1,9 +1,6 @@
 #!/bin/bash
-# one development iteration on the GPU: kernel parity tests, scan timelines, short bench
+# one development iteration on the GPU: full gpu test-suite, kernel probes, per-kernel timings
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_model.py -x -q -m gpu --timeout 600 2>&1 | tail -4
-python tools/scan_trace.py 64 2>&1 | grep fwd
-for v in "DJ_FWD_NS=1" "DJ_FWD_NB=1" "DJ_FWD_NB=2"; do echo "== $v"; env $v python tools/scan_probe.py 64 fwd; done
+timeout 1200 python -m pytest tests -x -q -m gpu --timeout 600 2>&1 | tail -4
 python tools/scan_probe.py 64 all
-python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-generation 2>/dev/null | python -c "
-import json,sys; d=json.loads(sys.stdin.read()); print('bench', d['value'], d['ms_per_step'], 'e2e', d['e2e']['value'], 'loss', d['loss'], d['roofline']['avg_launch_ms'])"
+python tools/quick_bench.py 64 2>&1 | grep -v "^fp32" | tail -75
