@@ -42,6 +42,46 @@ __device__ __forceinline__ void prefetch_l2(const void* p) {
 
 constexpr int UC = 32;   // hidden units owned by one CTA (=> 128 gate columns)
 
+// ---- DSMEM all-gather without a cluster barrier -----------------------------------------------
+// h_t goes to every CTA of the cluster as st.async stores that complete on the DESTINATION's
+// mbarrier (complete_tx bytes), so the consumer waits on a local mbarrier and nobody executes a
+// barrier.cluster (whose release is a gpu-scope membar that also drains the gate stores to HBM).
+__device__ __forceinline__ uint32_t sm_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t cta) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(addr), "r"(cta));
+  return r;
+}
+__device__ __forceinline__ void st_async_f4(uint32_t raddr, float a, float b, float c, float d, uint32_t rbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];\n" ::"r"(raddr),
+               "f"(a), "f"(b), "f"(c), "f"(d), "r"(rbar)
+               : "memory");
+}
+__device__ __forceinline__ void sbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void sbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  const long long t0 = clock64();
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (clock64() - t0 > 4000000000LL) {   // ~2 s: a protocol bug must not hang the GPU
+      printf("deepj lstm_scan: h all-gather wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+
 __device__ __forceinline__ void store_dz4(float* p, const float v[4]) {
   *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
 }
@@ -75,13 +115,15 @@ struct FwdSmem {
   static constexpr int HSTR = U * 4 + 4;            // floats per 4-sequence group (+4: bank skew)
   static constexpr int HBUF = (BS / 4) * HSTR;      // one h buffer
   static constexpr int US = U * UC * 4;             // resident U slice
-  static constexpr size_t BYTES = sizeof(float) * (size_t)(US + 2 * HBUF);
+  static constexpr size_t BYTES = sizeof(float) * (size_t)(US + 2 * HBUF) + 16;   // + two mbarriers
 };
 
 // ---------------------------------------------------------------------------
-// forward
+// forward, many sequences
 //   thread (sg, ug): sequences 4*sg..4*sg+3 of the tile, hidden units ug and
-//   ug+16 of this CTA's slice, all four gates -> 32 accumulators, c in registers.
+//   ug+16 of this CTA's slice, all four gates -> 32 accumulators, c in registers
+//   (16 FFMA2 per 3 shared-memory loads: the best FMA : load ratio).  BS = 32 gives
+//   4 warps, one per scheduler.
 // ---------------------------------------------------------------------------
 template <int U, int C, int BS>
 __global__ void __launch_bounds__((BS / 4) * 16, 1)
@@ -103,14 +145,21 @@ scan_fwd_kernel(float* __restrict__ Z, float* __restrict__ Hout, float* __restri
 
   for (int idx = tid; idx < SM::US; idx += NT)   // [k][32 units][4 gates] is a contiguous 512 B run per k
     Us[idx] = Uw[(size_t)(idx >> 7) * 4 * U + 4 * unit0 + (idx & 127)];
-  float* rbuf[C];
+  const uint32_t bar0 = sm_u32(hbuf + 2 * SM::HBUF);   // bar0 + 8*b: "buffer b holds the whole h of a step"
+  if (tid == 0) {
+    sbar_init(bar0, 1); sbar_init(bar0 + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  uint32_t rdst[C], rbar[C];
 #pragma unroll
-  for (int r = 0; r < C; ++r) rbuf[r] = cluster.map_shared_rank(hbuf, r);
-  cluster.sync();   // every CTA of the cluster is resident before any remote store
+  for (int r = 0; r < C; ++r) { rdst[r] = mapa_u32(sm_u32(hbuf), r); rbar[r] = mapa_u32(bar0, r); }
+  constexpr uint32_t STEP_BYTES = (uint32_t)C * NT * 32;   // every thread of the cluster sends 2 x 16 B to each CTA
+  uint32_t ph[2] = {0u, 0u};
+  cluster.sync();   // every CTA of the cluster is resident, its barriers initialised, before any remote store
 
   const int ntiles = (S + BS - 1) / BS;
   for (int tile = cid; tile < ntiles; tile += ncl) {
-    for (int idx = tid; idx < SM::HBUF; idx += NT) hbuf[idx] = 0.f;   // h_{-1} = 0
+    for (int idx = tid; idx < SM::HBUF; idx += NT) hbuf[idx] = 0.f;   // h_{-1} = 0 (buffer 0; nothing is in flight)
     float c[4][2];
     bool ok[4];
     int64_t row0[4];
@@ -132,6 +181,7 @@ scan_fwd_kernel(float* __restrict__ Z, float* __restrict__ Hout, float* __restri
 
     for (int t = 0; t < steps; ++t) {
       const int cur = t & 1, nxt = cur ^ 1;
+      if (tid == 0) sbar_expect_tx(bar0 + 8 * nxt, STEP_BYTES);   // h_t will arrive in buffer nxt
       uint64_t acc2[4][2][2];   // [seq][unit half][gate pair (i,f) / (g,o)]
 #pragma unroll
       for (int s = 0; s < 4; ++s)
@@ -150,6 +200,7 @@ scan_fwd_kernel(float* __restrict__ Z, float* __restrict__ Hout, float* __restri
                               : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
+      if (t > 0) { sbar_wait(bar0 + 8 * cur, ph[cur]); ph[cur] ^= 1u; }   // all of h_{t-1} has landed
       const float* hb = hbuf + cur * SM::HBUF + sg * SM::HSTR;
       const float* ua = Us + ug * 4;
 #pragma unroll 4
@@ -200,31 +251,34 @@ scan_fwd_kernel(float* __restrict__ Z, float* __restrict__ Hout, float* __restri
           }
         }
       }
-      // all-gather of h_t into every CTA's next buffer (DSMEM, 16 lanes x 16 B contiguous)
+      // all-gather of h_t into every CTA's next buffer (DSMEM, 16 lanes x 16 B contiguous).  Two buffers
+      // are enough without a barrier: a CTA that is already sending h_{t+1} into buffer `cur` has received
+      // every h_t, so every peer has finished reading h_{t-1} from it.
+      const uint32_t off = (uint32_t)(nxt * SM::HBUF + sg * SM::HSTR + (unit0 + ug) * 4) * 4u;
 #pragma unroll
       for (int r = 0; r < C; ++r) {
-        float* dst = rbuf[r] + nxt * SM::HBUF + sg * SM::HSTR + (unit0 + ug) * 4;
-        *reinterpret_cast<float4*>(dst) = make_float4(hnew[0][0], hnew[0][1], hnew[0][2], hnew[0][3]);
-        *reinterpret_cast<float4*>(dst + 64) = make_float4(hnew[1][0], hnew[1][1], hnew[1][2], hnew[1][3]);
+        st_async_f4(rdst[r] + off, hnew[0][0], hnew[0][1], hnew[0][2], hnew[0][3], rbar[r] + 8 * nxt);
+        st_async_f4(rdst[r] + off + 256, hnew[1][0], hnew[1][1], hnew[1][2], hnew[1][3], rbar[r] + 8 * nxt);
       }
-      cluster.sync();
     }
+    // drain the last step's (unused) h so that no store of this tile is in flight anywhere in the cluster
+    const int last = steps & 1;
+    sbar_wait(bar0 + 8 * last, ph[last]); ph[last] ^= 1u;
+    cluster.sync();
   }
 }
 
 // ---------------------------------------------------------------------------
-// forward, few sequences (generation: one window = 48 time-axis sequences).
-//   Same arithmetic and the same k-ordered FMA chain per accumulator as scan_fwd_kernel (so the
-//   results are bit-identical), but tiles of 16 sequences and ONE hidden unit per thread:
-//   thread (sg, ug) = sequences 4*sg..4*sg+3, unit ug, four gates -> 16 accumulators.  A 48-sequence
-//   window then runs on 3 clusters x 8 CTAs x 4 warps (one per scheduler) instead of 1 cluster x
-//   8 CTAs x 6 warps: a quarter of the FFMA2 chain per warp and three times the SMs.
+// forward, few sequences
+//   thread (sg, ug) = sequences 4*sg..4*sg+3 of the tile, hidden unit ug of this CTA's slice, four
+//   gates -> 16 accumulators (8 packed FFMA2 per k), c in registers.  Every accumulator is one FMA
+//   chain over k in order, exactly as in scan_fwd_kernel, so the result does not depend on which of
+//   the two kernels ran.  Used when all 16-sequence tiles fit one round of clusters: a generation
+//   window (48 sequences) runs on 3 clusters x 8 CTAs x 4 warps instead of one cluster.
 // ---------------------------------------------------------------------------
-constexpr int SBS = 16;   // sequences per tile of the small-tile forward scan
-
-template <int U, int C>
+template <int U, int C, int SBS>
 __global__ void __launch_bounds__((SBS / 4) * UC, 1)
-scan_fwd_small_kernel(float* __restrict__ Z, float* __restrict__ Hout, float* __restrict__ Cout,
+scan_fwd_u1_kernel(float* __restrict__ Z, float* __restrict__ Hout, float* __restrict__ Cout,
                       __nv_bfloat16* __restrict__ Hbf, const float* __restrict__ Uw, int S, int steps,
                       ScanMap map, int hard) {
   static_assert(U / C == UC, "each CTA owns 32 hidden units");
@@ -243,14 +297,21 @@ scan_fwd_small_kernel(float* __restrict__ Z, float* __restrict__ Hout, float* __
 
   for (int idx = tid; idx < SM::US; idx += NT)
     Us[idx] = Uw[(size_t)(idx >> 7) * 4 * U + 4 * unit0 + (idx & 127)];
-  float* rbuf[C];
+  const uint32_t bar0 = sm_u32(hbuf + 2 * SM::HBUF);   // bar0 + 8*b: "buffer b holds the whole h of a step"
+  if (tid == 0) {
+    sbar_init(bar0, 1); sbar_init(bar0 + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  uint32_t rdst[C], rbar[C];
 #pragma unroll
-  for (int r = 0; r < C; ++r) rbuf[r] = cluster.map_shared_rank(hbuf, r);
-  cluster.sync();   // every CTA of the cluster is resident before any remote store
+  for (int r = 0; r < C; ++r) { rdst[r] = mapa_u32(sm_u32(hbuf), r); rbar[r] = mapa_u32(bar0, r); }
+  constexpr uint32_t STEP_BYTES = (uint32_t)C * NT * 16;   // every thread of the cluster sends 16 B to each CTA
+  uint32_t ph[2] = {0u, 0u};
+  cluster.sync();   // every CTA of the cluster is resident, its barriers initialised, before any remote store
 
   const int ntiles = (S + SBS - 1) / SBS;
   for (int tile = cid; tile < ntiles; tile += ncl) {
-    for (int idx = tid; idx < SM::HBUF; idx += NT) hbuf[idx] = 0.f;   // h_{-1} = 0
+    for (int idx = tid; idx < SM::HBUF; idx += NT) hbuf[idx] = 0.f;   // h_{-1} = 0 (buffer 0; nothing is in flight)
     float c[4];
     bool ok[4];
     int64_t row0[4];
@@ -267,6 +328,7 @@ scan_fwd_small_kernel(float* __restrict__ Z, float* __restrict__ Hout, float* __
 
     for (int t = 0; t < steps; ++t) {
       const int cur = t & 1, nxt = cur ^ 1;
+      if (tid == 0) sbar_expect_tx(bar0 + 8 * nxt, STEP_BYTES);   // h_t will arrive in buffer nxt
       uint64_t acc2[4][2];   // [seq][gate pair (i,f) / (g,o)]
 #pragma unroll
       for (int s = 0; s < 4; ++s) {
@@ -280,6 +342,7 @@ scan_fwd_small_kernel(float* __restrict__ Z, float* __restrict__ Hout, float* __
           zn[s] = ok[s] ? *reinterpret_cast<const float4*>(Z + r * (4 * U) + 4 * col) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
+      if (t > 0) { sbar_wait(bar0 + 8 * cur, ph[cur]); ph[cur] ^= 1u; }   // all of h_{t-1} has landed
       const float* hb = hbuf + cur * SM::HBUF + sg * SM::HSTR;
       const float* ua = Us + ug * 4;
 #pragma unroll 8
@@ -318,13 +381,16 @@ scan_fwd_small_kernel(float* __restrict__ Z, float* __restrict__ Hout, float* __
           }
         }
       }
-      // all-gather of h_t into every CTA's next buffer (DSMEM, 32 lanes x 16 B contiguous)
+      // all-gather of h_t into every CTA's next buffer (DSMEM, 32 lanes x 16 B contiguous); see
+      // scan_fwd_kernel for why two buffers need no barrier
+      const uint32_t off = (uint32_t)(nxt * SM::HBUF + sg * SM::HSTR + col * 4) * 4u;
 #pragma unroll
       for (int r = 0; r < C; ++r)
-        *reinterpret_cast<float4*>(rbuf[r] + nxt * SM::HBUF + sg * SM::HSTR + col * 4) =
-            make_float4(hnew[0], hnew[1], hnew[2], hnew[3]);
-      cluster.sync();
+        st_async_f4(rdst[r] + off, hnew[0], hnew[1], hnew[2], hnew[3], rbar[r] + 8 * nxt);
     }
+    const int last = steps & 1;
+    sbar_wait(bar0 + 8 * last, ph[last]); ph[last] ^= 1u;
+    cluster.sync();
   }
 }
 
@@ -542,15 +608,20 @@ extern "C" int dj_lstm_scan_fwd(float* Z, float* h_out, float* c_out, void* h_pr
   void* args[] = {&Z, &h_out, &c_out, &hb, (void*)&Uw, &S, &steps, &map, &hard};
   cudaStream_t st = (cudaStream_t)stream;
   if (units == 256) {
-    constexpr int C = 8, BS = 48;
-    // few sequences (a generation window is 48): 16-sequence tiles spread the step over three times the SMs
-    if ((S + SBS - 1) / SBS <= dj_num_sms() / C)
-      return launch_cluster(scan_fwd_small_kernel<256, C>, C, (SBS / 4) * UC, FwdSmem<256, SBS>::BYTES,
-                            pick_clusters(C, (S + SBS - 1) / SBS), st, args);
+    constexpr int C = 8;
+    // few sequences (a generation window is 48): 16-sequence tiles spread the step over more clusters
+    if ((S + 15) / 16 <= dj_num_sms() / C)
+      return launch_cluster(scan_fwd_u1_kernel<256, C, 16>, C, 4 * UC, FwdSmem<256, 16>::BYTES,
+                            pick_clusters(C, (S + 15) / 16), st, args);
+    constexpr int BS = 32;
     return launch_cluster(scan_fwd_kernel<256, C, BS>, C, (BS / 4) * 16, FwdSmem<256, BS>::BYTES,
                           pick_clusters(C, (S + BS - 1) / BS), st, args);
   } else if (units == 128) {
-    constexpr int C = 4, BS = 64;
+    constexpr int C = 4;
+    if ((S + 15) / 16 <= dj_num_sms() / C)
+      return launch_cluster(scan_fwd_u1_kernel<128, C, 16>, C, 4 * UC, FwdSmem<128, 16>::BYTES,
+                            pick_clusters(C, (S + 15) / 16), st, args);
+    constexpr int BS = 32;
     return launch_cluster(scan_fwd_kernel<128, C, BS>, C, (BS / 4) * 16, FwdSmem<128, BS>::BYTES,
                           pick_clusters(C, (S + BS - 1) / BS), st, args);
   }

@@ -115,6 +115,40 @@ def test_wgrad_gemm_tcgen05(lib, shape):
     assert helpers.rel_err(Cd.cpu().numpy(), ref) < 5e-5
 
 
+@pytest.mark.parametrize("axis,B,T", [("time", 1, 12), ("time", 5, 7), ("time", 8, 6), ("note", 1, 5), ("note", 13, 40)])
+def test_lstm_scan_fp32_matches_recurrence(lib, axis, B, T):
+    """fp32 CUDA-core forward recurrence (both tilings: 16-sequence tiles / one unit per thread for few
+    sequences, 32-sequence tiles otherwise; ragged last tiles) against a float64 restatement of the
+    Keras LSTM step (gate order i,f,c,o, hard_sigmoid, zero initial state)."""
+    from music_generator_b200 import _lib
+    g = torch.Generator().manual_seed(11)
+    U = 256 if axis == "time" else 128
+    M = B * T * 48
+    Z0 = torch.randn(M, 4 * U, generator=g)            # gate-interleaved columns: col = 4*unit + gate
+    Uw = torch.randn(U, 4 * U, generator=g) * 0.06
+    if axis == "time":
+        S, steps, m = B * 48, T, (48, T * 48, 1, 48)
+        rows = torch.arange(M).view(B, T, 48).permute(0, 2, 1).reshape(S, steps)      # [seq, step] -> row
+    else:
+        S, steps, m = B * T, 48, (1, 48, 0, 1)
+        rows = torch.arange(M).view(S, steps)
+    Zd, Ud = Z0.cuda(), Uw.cuda()
+    h, c = torch.empty(M, U, device="cuda"), torch.empty(M, U, device="cuda")
+    _lib.check(lib.dj_lstm_scan_fwd(P(Zd), P(h), P(c), None, P(Ud), S, steps, U, *m, 1, None))
+    torch.cuda.synchronize()
+    Z64, U64 = Z0.double(), Uw.double()
+    hs, cs = torch.zeros(S, U, dtype=torch.float64), torch.zeros(S, U, dtype=torch.float64)
+    href, cref = torch.zeros(M, U, dtype=torch.float64), torch.zeros(M, U, dtype=torch.float64)
+    for t in range(steps):
+        z = (Z64[rows[:, t]] + hs @ U64).view(S, U, 4)
+        i, f, o = [(0.2 * z[..., k] + 0.5).clamp(0, 1) for k in (0, 1, 3)]
+        cs = f * cs + i * torch.tanh(z[..., 2])
+        hs = o * torch.tanh(cs)
+        href[rows[:, t]], cref[rows[:, t]] = hs, cs
+    assert float((h.cpu().double() - href).abs().max()) < 2e-5
+    assert float((c.cpu().double() - cref).abs().max()) < 2e-5
+
+
 @pytest.mark.parametrize("axis,B,T", [("time", 3, 8), ("note", 2, 32), ("time", 20, 4), ("note", 40, 128),
                                       ("note256", 2, 32)])
 def test_lstm_scan_tcgen05_matches_fp32_scan(lib, axis, B, T):
