@@ -181,45 +181,56 @@ __global__ void __launch_bounds__(256) frontend_fwd_kernel(
 // ---------------------------------------------------------------------------
 // A operand of LSTM layers 1.. : drop(h_prev) (+ shifted chosen) + drop(style)
 // ---------------------------------------------------------------------------
+// One warp per row (grid-stride over rows): the row's (b, t, n) split and base pointers are computed once
+// with 32-bit arithmetic, then each lane converts 8 consecutive features per trip (two 16-byte loads of h,
+// one 16-byte bf16 store).
 template <typename TA>
 __global__ void __launch_bounds__(256) layer_input_kernel(
     const float* __restrict__ h_prev, int Uprev, int64_t h_row0, int64_t h_b_rows, dj_dropout d_h,
     const float* __restrict__ sp, int F, dj_dropout d_sp, const float* __restrict__ chosen_in,
     int64_t chosen_bstride, dj_dropout d_chosen, int B, int T, TA* __restrict__ A, int ldA) {
   const int ld4 = (F + 3) & ~3;
-  const int g_per_row = ldA / 4;
-  const int64_t total = (int64_t)B * T * N_ * g_per_row;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t row = i / g_per_row;
-    const int f4 = (int)(i % g_per_row) * 4;
-    const int n = (int)(row % N_);
-    const int64_t bt = row / N_;
-    const int b = (int)(bt / T), t = (int)(bt % T);
-    float v[4] = {0.f, 0.f, 0.f, 0.f};
-    if (f4 < Uprev) {
-      const int64_t hrow = h_row0 + (int64_t)b * h_b_rows + (int64_t)t * N_ + n;
-      const float4 hv = *reinterpret_cast<const float4*>(h_prev + hrow * Uprev + f4);
-      float m[4];
-      dj_dropmul4(d_h, (uint32_t)row * Uprev + f4, m);
-      v[0] = hv.x * m[0]; v[1] = hv.y * m[1]; v[2] = hv.z * m[2]; v[3] = hv.w * m[3];
-    } else if (f4 < F && chosen_in != nullptr && n > 0) {
-      // shift_chosen (model.py:101): previous NOTE of the same timestep, 3 channels
-      const float* cr = chosen_in + (int64_t)b * chosen_bstride + ((int64_t)t * N_ + (n - 1)) * NU_;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rows = (uint32_t)B * (uint32_t)T * N_;
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < rows; row += nwarps) {
+    const uint32_t n = row % N_, bt = row / N_;
+    const uint32_t b = bt / (uint32_t)T, t = bt - b * (uint32_t)T;
+    const float* hrow = h_prev + (h_row0 + (int64_t)b * h_b_rows + (int64_t)t * N_ + n) * Uprev;
+    const float* sprow = sp + (int64_t)bt * F;
+    // shift_chosen (model.py:101): previous NOTE of the same timestep, 3 channels
+    const float* cr = (chosen_in != nullptr && n > 0)
+                          ? chosen_in + (int64_t)b * chosen_bstride + ((int64_t)t * N_ + (n - 1)) * NU_ : nullptr;
+    for (int f8 = lane * 8; f8 < ldA; f8 += 256) {
+      float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int c = f4 + j - Uprev;
-        if (c < NU_) v[j] = cr[c] * dj_dropmul(d_chosen, (uint32_t)(row - 1) * 4u + c);
+      for (int hh = 0; hh < 2; ++hh) {
+        const int f4 = f8 + 4 * hh;
+        float* vv = v + 4 * hh;
+        if (f4 < Uprev) {
+          const float4 hv = *reinterpret_cast<const float4*>(hrow + f4);
+          float m[4];
+          dj_dropmul4(d_h, row * (uint32_t)Uprev + f4, m);
+          vv[0] = hv.x * m[0]; vv[1] = hv.y * m[1]; vv[2] = hv.z * m[2]; vv[3] = hv.w * m[3];
+        } else if (f4 < F && cr != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int c = f4 + j - Uprev;
+            if (c < NU_) vv[j] = cr[c] * dj_dropmul(d_chosen, (row - 1) * 4u + c);
+          }
+        }
+        if (f4 < F) {
+          float m[4];
+          dj_dropmul4(d_sp, row * (uint32_t)ld4 + f4, m);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (f4 + j < F) vv[j] = fmaf(sprow[f4 + j], m[j], vv[j]);
+        }
       }
+      TA* out = A + (int64_t)row * ldA + f8;
+      store4(out, v);
+      store4(out + 4, v + 4);
     }
-    if (f4 < F) {
-      float m[4];
-      dj_dropmul4(d_sp, (uint32_t)row * ld4 + f4, m);
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (f4 + j < F) v[j] = fmaf(sp[bt * F + f4 + j], m[j], v[j]);
-    }
-    store4(A + row * ldA + f4, v);
   }
 }
 
@@ -349,7 +360,7 @@ extern "C" int dj_layer_input(const float* h_prev, int Uprev, int64_t h_row0, in
   DJ_CHECK_ARG(F == Uprev || (chosen_in && F == Uprev + NU_), "dj_layer_input: F must be Uprev or Uprev+3 with chosen");
   DJ_CHECK_ARG(ldA >= ((F + 3) & ~3) && ldA % 8 == 0, "dj_layer_input: ldA %d too small or not a multiple of 8", ldA);
   DJ_CHECK_ARG((int64_t)B * T * N_ * ((F + 3) & ~3) < (int64_t)4294967296LL, "dj_layer_input: batch too large");
-  const int64_t total = (int64_t)B * T * N_ * (ldA / 4);
+  const int64_t total = (int64_t)B * T * N_ * 32;   // one warp per row
   const int grid = grid_for(total, 256, dj_num_sms() * 16);
   cudaStream_t st = (cudaStream_t)stream;
   if (a_dtype == DJ_F32)

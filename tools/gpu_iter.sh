@@ -1,5 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -x -q -m gpu --timeout 600 2>&1 | tail -4
-python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "
-import json,sys; d=json.loads(sys.stdin.read()); print('bench', d['value'], d['ms_per_step'], 'e2e', d['e2e']['value'], 'loss', d['loss'], d['roofline']['avg_launch_ms'], d['generation'])"
+timeout 900 python -m pytest tests -x -q -m gpu --timeout 600 2>&1 | tail -3
+python tools/quick_bench.py 64 2>&1 | grep -A12 "^bf16"
+python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-generation 2>/dev/null | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print('bench', d['value'], d['ms_per_step'], 'e2e', d['e2e']['value'], 'loss', d['loss'], d['roofline']['avg_launch_ms'])"
