@@ -217,14 +217,16 @@ def _run_ours(args):
     peak, how = peaks()
     dom_ms = dom[1] / max(dom[0], 1)
     achieved = alg_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else None
-    kname = "scan_tc_bwd_kernel<512,16,32>" if scaled else "scan_tc_bwd_kernel<256,48,64>"
+    kname = "scan_tc_bwd_kernel<512,16,32,time>" if scaled else "scan_tc_bwd_kernel<256,48,64,time>"
     roofline = {"kernel": kname + " (dj_lstm_scan_tc_bwd, time-axis layer 1 reverse scan)", "bound": "hbm",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                 # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape from the ncu --set full
-                # capture summarised in profiles/r01_scan_tc_bwd_time.md (2.417 GB + 0.785 GB per launch)
-                "traffic": 3.202e9 if (B == 64 and not scaled) else None, "peak_source": how, "avg_launch_ms": dom_ms, "launches_timed": dom[0],
+                # capture summarised in profiles/r01_scan_tc_bwd_time.md (2.418 GB + 0.786 GB per launch)
+                "traffic": 3.204e9 if (B == 64 and not scaled) else None, "peak_source": how, "avg_launch_ms": dom_ms, "launches_timed": dom[0],
                 "algorithmic_bytes_per_launch": alg_bytes,
-                "note": "sequential recurrence: bound by the per-step barrier/TMA/MMA latency chain, see DESIGN.md"}
+                "note": "sequential recurrence: bound by the per-step publish/TMA/MMA latency chain, not by HBM; timed inside the "
+                        "step, where it shares the GPU with the weight-gradient GEMMs of the second stream (alone: 1.28 ms), "
+                        "see DESIGN.md section 4"}
 
     # ---------------- generation probe (configs[1])
     gen = None
