@@ -103,8 +103,6 @@ template <bool HARD> __device__ __forceinline__ float gate_act_fast(float x) {
 __device__ __forceinline__ int64_t tc_row0(const TcMap& m, int seq) {
   return (int64_t)(seq / m.seq_inner) * m.outer_stride + (int64_t)(seq % m.seq_inner) * m.inner_stride;
 }
-__device__ __forceinline__ void cl_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory"); }
-__device__ __forceinline__ void cl_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory"); }
 // Forward recurrence.  h_t leaves the epilogue as bf16 into `hprev` (global, the row of
 // step t+1); after ONE cluster barrier per step every CTA TMA-loads 1/C of the tile's
 // rows back from L2 and multicasts them into all C CTAs' B-operand tiles.  (A variant
@@ -447,13 +445,24 @@ struct TcBwdSmem {
   static constexpr int A_BYTES = UPC * 4 * U * 2;
   static constexpr int B_BYTES = BS * 4 * U * 2;
   static constexpr int A_OFF = 0, B_OFF = A_BYTES, BAR_OFF = A_BYTES + B_BYTES;
-  static constexpr int TOTAL = BAR_OFF + 64 + 1024;
+  static constexpr int TOTAL = BAR_OFF + 128 + 1024;
 };
 
-constexpr int TCB_THREADS = 32 * 9;   // 1 issuer warp + 8 epilogue warps
+constexpr int TCB_THREADS = 32 * 10;   // warps 0 and 9: issuers of the two half-tiles; warps 1..8: epilogue
 
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t v[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
+               : "r"(taddr)
+               : "memory");
+}
 
-template <int U, int BS, int UPC, bool AXIS_TIME>
+// NS = 2 software-pipelines the tile as two half-tiles (HB = BS/2 sequences, MMA N = HB) that alternate through
+// the same epilogue warps: while they compute the gate derivatives of half B, half A's publish -> all-gather ->
+// 64-MMA chain is in flight.  Hand-offs are mbarriers as in the forward scan (epilogue --done--> issuer, the issuer
+// does the one gpu-scope release of the CTA and a remote arrive on pub[hf] of every CTA), so the epilogue warps
+// execute neither a gpu-scope membar nor a cluster barrier.
+template <int U, int BS, int UPC, bool AXIS_TIME, int NS>
 __global__ void __launch_bounds__(TCB_THREADS, (U == 128 && BS <= 32) ? 2 : 1)
 scan_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmZ,
                    const float* __restrict__ G, const float* __restrict__ Cst, const float* __restrict__ dY,
@@ -464,17 +473,23 @@ scan_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
   constexpr int ATOM = UPC * 128;       // bytes of one resident K atom of U (UPC rows x 128 B)
   static_assert(UPC == 64 || UPC == 32, "units per CTA");
   constexpr int KPC = KA / C;           // atoms each CTA multicasts per step
-  constexpr int WC = BS / 2;            // accumulator columns (sequences) per epilogue warp
-  constexpr int CPL = BS / 4;           // cells per lane
+  constexpr int HB = BS / NS;           // sequences per half-tile
+  constexpr int WC = HB / 2;            // accumulator columns (sequences) per epilogue warp and half
+  constexpr int CPL = HB / 4;           // cells per lane and half
+  constexpr int HALF_BYTES = KA * HB * 128;   // one half of the B operand: [KA atoms][HB rows][128 B]
   constexpr uint32_t TMEM_COLS = BS <= 32 ? 32 : BS <= 64 ? 64 : BS <= 128 ? 128 : 256;
-  static_assert(WC % 8 == 0, "warp column range is loaded in 8-column pieces");
+  static_assert(NS == 1 || NS == 2, "one tile or two half-tiles");
+  static_assert(HB % 8 == 0 && WC % 4 == 0, "half-tiles are whole 8-row swizzle groups; columns load in 4-column pieces");
   using SM = TcBwdSmem<U, BS, UPC>;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const uint32_t sbase = smem_u32(smem);
-  const uint32_t bar_a = sbase + SM::BAR_OFF, bar_z = bar_a + 8, bar_acc = bar_a + 16;
-  uint32_t* tmem_slot = (uint32_t*)(smem + SM::BAR_OFF + 24);
+  // barriers: a | z[2] | acc[2] | done[2] | pub[2] | tmem slot
+  constexpr uint32_t BAR_Z = SM::BAR_OFF + 8, BAR_ACC = SM::BAR_OFF + 24, BAR_DONE = SM::BAR_OFF + 40,
+                     BAR_PUB = SM::BAR_OFF + 56;
+  const uint32_t bar_a = sbase + SM::BAR_OFF;
+  uint32_t* tmem_slot = (uint32_t*)(smem + SM::BAR_OFF + 72);
 
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
@@ -484,7 +499,12 @@ scan_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
   if (warp == 0) {
     if (lane == 0) {
       prefetch_tmap(&tmU); prefetch_tmap(&tmZ);
-      mbar_init(bar_a, 1); mbar_init(bar_z, 1); mbar_init(bar_acc, 1);
+      mbar_init(bar_a, 1);
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        mbar_init(sbase + BAR_Z + 8 * hf, 1); mbar_init(sbase + BAR_ACC + 8 * hf, 1);
+        mbar_init(sbase + BAR_DONE + 8 * hf, 8); mbar_init(sbase + BAR_PUB + 8 * hf, C);
+      }
       fence_barrier_init();
     }
     __syncwarp();
@@ -496,144 +516,156 @@ scan_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
   const uint32_t tmem_base = *tmem_slot;
   cluster.sync();
 
-  if (warp == 0) {
-    // ================= TMA + MMA issuer: dh_t = U . dz_{t+1}^T =================
+  if (warp == 0 || warp == 9) {
+    // ================= issuer + publisher of half-tile hf: dh_t = U . dz_{t+1}^T =================
     // the whole warp walks the loop converged; single-thread work sits under elect_one()
-    if (elect_one()) {   // resident A operand: rows [UPC*rank, +UPC) of U, all 4U columns
+    const int hf = (warp == 0) ? 0 : 1;
+    if (warp == 0 && elect_one()) {   // resident A operand: rows [UPC*rank, +UPC) of U, all 4U columns
       mbar_expect_tx(bar_a, SM::A_BYTES);
       for (int ja = 0; ja < KA; ++ja)
         tma_load_2d(sbase + SM::A_OFF + ja * ATOM, &tmU, bar_a, ja * 64, UPC * rank);
     }
     __syncwarp();
-    uint32_t z_phase = 0;
-    for (int t = steps - 1; t >= 0; --t) {
-      if (t != steps - 1) {
-        if (t == steps - 2) mbar_wait(bar_a, 0);
-        mbar_wait(bar_z, z_phase);
-        DJ_TR(t, 0);
-        z_phase ^= 1;
+    const uint32_t bar_z = sbase + BAR_Z + 8 * hf, bar_acc = sbase + BAR_ACC + 8 * hf,
+                   bar_done = sbase + BAR_DONE + 8 * hf, bar_pub = sbase + BAR_PUB + 8 * hf;
+    const uint32_t b_half = sbase + SM::B_OFF + hf * HALF_BYTES;
+    // TMA coordinates of this half-tile: rows (time axis: within the batch element) / sequences (note axis)
+    const int c_row0 = AXIS_TIME ? (tile % map.off2) * BS + hf * HB : tile * BS + hf * HB;
+    const int c_outer = AXIS_TIME ? tile / map.off2 : 0;
+    if (hf < NS) {
+      uint32_t par = 0;
+      for (int t = steps - 1; t > 0; --t, par ^= 1u) {   // round: dz_t in, dh of step t-1 out
+        mbar_wait(bar_done, par);                         // this CTA's epilogue warps stored their dz_t
+        DJ_TR(t, 4 * hf + 0);
+        if (lane < C) mbar_arrive_remote(bar_pub, (uint32_t)lane);   // release.cluster, cumulative
+        __syncwarp();
+        mbar_wait_cluster(bar_pub, par);                  // every CTA of the cluster has published
+        DJ_TR(t, 4 * hf + 1);
+        if (elect_one()) {
+          mbar_expect_tx(bar_z, HALF_BYTES);
+          // one 4-D box {64 columns, HB rows, KPC atoms, 1}: lands as KPC consecutive [HB x 128 B] swizzled atoms
+          tma_load_4d_mc(b_half + rank * KPC * (HB * 128), &tmZ, bar_z, 0, AXIS_TIME ? t * 48 + c_row0 : c_row0,
+                         rank * KPC, AXIS_TIME ? c_outer : t, (uint16_t)((1u << C) - 1u));
+        }
+        __syncwarp();
+        if (t == steps - 1) mbar_wait(bar_a, 0);
+        mbar_wait(bar_z, par);
+        DJ_TR(t, 4 * hf + 2);
         tc_fence_after();
         if (elect_one()) {
-          constexpr uint32_t idesc = make_idesc(64, BS, 0, 0);
+          constexpr uint32_t idesc = make_idesc(64, HB, 0, 0);
           const uint64_t adesc0 = make_smem_desc(sbase + SM::A_OFF, 16, 1024);
-          const uint64_t bdesc0 = make_smem_desc(sbase + SM::B_OFF, 16, 1024);
+          const uint64_t bdesc0 = make_smem_desc(b_half, 16, 1024);
 #pragma unroll
           for (int ja = 0; ja < KA; ++ja)
 #pragma unroll
             for (int k = 0; k < 4; ++k)   // descriptor start addresses are in 16-byte units
-              umma_bf16(tmem_base, adesc0 + (uint64_t)((ja * ATOM + k * 32) >> 4),
-                        bdesc0 + (uint64_t)((ja * (BS * 128) + k * 32) >> 4), idesc, (ja | k) != 0);
+              umma_bf16(tmem_base + (uint32_t)(hf * HB), adesc0 + (uint64_t)((ja * ATOM + k * 32) >> 4),
+                        bdesc0 + (uint64_t)((ja * (HB * 128) + k * 32) >> 4), idesc, (ja | k) != 0);
           umma_commit(bar_acc);
-          DJ_TR(t, 1);
         }
         __syncwarp();
+        DJ_TR(t, 4 * hf + 3);
       }
-      cl_arrive();
-      cl_wait();
-      DJ_TR(t, 2);
-      // all-gather dz_t: this CTA multicasts KPC of the KA column atoms.  The writers fenced their
-      // generic-proxy stores (fence.proxy.async) before arriving on the cluster barrier.
-      if (t > 0 && elect_one()) {
-        mbar_expect_tx(bar_z, SM::B_BYTES);
-        // one 4-D box {64 columns, BS rows, KPC atoms, 1}: lands as KPC consecutive [BS x 128 B] swizzled atoms.
-        // map.step1/off1: row coordinate = t*step1 + (tile % off2)*off1; map.base2: outer coordinate per tile group
-        tma_load_4d_mc(sbase + SM::B_OFF + rank * KPC * (BS * 128), &tmZ, bar_z, 0,
-                       AXIS_TIME ? t * 48 + (tile % map.off2) * BS : tile * BS, rank * KPC,
-                       AXIS_TIME ? tile / map.off2 : t, (uint16_t)((1u << C) - 1u));
-        DJ_TR(t, 3);
-      }
-      __syncwarp();
     }
   } else {
     // ================= epilogue: gate derivatives =================
     // TMEM quarter q holds units 16q..16q+15 in its lanes 0..15 (M = 64 layout); the two warps of a
-    // quarter split the tile's sequences, and lanes 16..31 take half of their warp's sequences by shuffle.
+    // quarter split a half-tile's sequences, and lanes 16..31 take half of their warp's sequences by shuffle.
     const int q = warp & 3;
     const int w2 = (warp - 1) >> 2;
     const int sh = lane >> 4;
     const uint32_t col = UPC * rank + 16 * q + (lane & 15);       // global hidden unit
     const bool active = (16 * q < UPC);                            // UPC = 32: only TMEM quarters 0,1 hold real rows
     const uint32_t sstr = (uint32_t)map.seq_stride, tstr = (uint32_t)map.step_stride;
-    const uint32_t n0 = w2 * WC + sh * CPL;                        // first sequence (in the tile) of this lane
-    const uint32_t row00 = (uint32_t)tc_row0(map, tile * BS) + n0 * sstr;
+    const uint32_t row_tile = (uint32_t)tc_row0(map, tile * BS);
+    uint32_t row00[NS];                                            // row of this lane's first sequence of each half, step 0
+#pragma unroll
+    for (int hf = 0; hf < NS; ++hf) row00[hf] = row_tile + (uint32_t)(hf * HB + w2 * WC + sh * CPL) * sstr;
     float dbacc[4] = {0.f, 0.f, 0.f, 0.f};
-    float dcn[CPL], ct[CPL], cpv[CPL], dyv[CPL];
-    float4 gv[CPL];
+    float dcn[NS][CPL], ct[NS][CPL], cpv[NS][CPL], dyv[NS][CPL];
+    float4 gv[NS][CPL];
     // Pure loads only: anything computed on a just-loaded value would serialise the loads (each use
     // waits for its own DRAM round trip).  Masks and the t==0 special case are applied at use time.
-    auto issue_loads = [&](int t) {       // everything of step t that does not depend on the recurrence
+    auto issue_loads = [&](int hf, int t) {   // everything of (half hf, step t) that does not depend on the recurrence
       const uint32_t tp = (t > 0) ? (uint32_t)(t - 1) : 0u;      // clamped: row of c_{t-1} (ignored at t == 0)
       if (!active) return;
 #pragma unroll
       for (int j = 0; j < CPL; ++j) {
-        const uint32_t r = row00 + j * sstr + (uint32_t)t * tstr;
-        gv[j] = __ldg(reinterpret_cast<const float4*>(G + (size_t)r * (4 * U) + 4 * col));
-        cpv[j] = __ldg(Cst + (size_t)(row00 + j * sstr + tp * tstr) * U + col);
-        dyv[j] = __ldg(dY + (size_t)r * ldY + col);
+        const uint32_t r = row00[hf] + j * sstr + (uint32_t)t * tstr;
+        gv[hf][j] = __ldg(reinterpret_cast<const float4*>(G + (size_t)r * (4 * U) + 4 * col));
+        cpv[hf][j] = __ldg(Cst + (size_t)(row00[hf] + j * sstr + tp * tstr) * U + col);
+        dyv[hf][j] = __ldg(dY + (size_t)r * ldY + col);
       }
     };
 #pragma unroll
-    for (int j = 0; j < CPL; ++j) {
-      dcn[j] = 0.f;
-      ct[j] = active ? Cst[(size_t)(row00 + j * sstr + (uint32_t)(steps - 1) * tstr) * U + col] : 0.f;
-      gv[j] = make_float4(0.f, 0.f, 0.f, 0.f); cpv[j] = 0.f; dyv[j] = 0.f;
-    }
-    issue_loads(steps - 1);
-    uint32_t acc_phase = 0;
-    for (int t = steps - 1; t >= 0; --t) {
-      float dh[CPL];
-      if (t != steps - 1) {
-        mbar_wait(bar_acc, acc_phase);
-        acc_phase ^= 1;
-        tc_fence_after();
-        if (warp == 1 && lane == 0) DJ_TR(t, 8);
-        uint32_t acc[WC];
-#pragma unroll
-        for (int p8 = 0; p8 < WC / 8; ++p8)
-          tmem_ld8(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(w2 * WC + p8 * 8), acc + p8 * 8);
-        tmem_ld_wait();
-        if (warp == 1 && lane == 0) DJ_TR(t, 12);
-#pragma unroll
-        for (int j = 0; j < CPL; ++j) {
-          const float up = __shfl_sync(0xffffffffu, __uint_as_float(acc[CPL + j]), lane & 15);
-          dh[j] = sh ? up : __uint_as_float(acc[j]);
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < CPL; ++j) dh[j] = 0.f;
-      }
+    for (int hf = 0; hf < NS; ++hf) {
 #pragma unroll
       for (int j = 0; j < CPL; ++j) {
-        if (!active) break;
-        const uint32_t r = row00 + j * sstr + (uint32_t)t * tstr;
-        const float4 g4 = gv[j];
-        const float cprev = (t > 0) ? cpv[j] : 0.f;
-        const float dht = fmaf(dyv[j], dj_dropmul(d_y, r * U + col), dh[j]);
-        const float tc = fast_tanh(ct[j]);
-        const float d_o = dht * tc;
-        const float dc = fmaf(dht * g4.w, 1.f - tc * tc, dcn[j]);
-        dcn[j] = dc * g4.y;
-        const float dz0 = dc * g4.z * dj_gate_dact(g4.x, hard);
-        const float dz1 = dc * cprev * dj_gate_dact(g4.y, hard);
-        const float dz2 = dc * g4.x * (1.f - g4.z * g4.z);
-        const float dz3 = d_o * dj_gate_dact(g4.w, hard);
-        __nv_bfloat162 lo = __floats2bfloat162_rn(dz0, dz1), hi = __floats2bfloat162_rn(dz2, dz3);
-        uint2 pk;
-        pk.x = *reinterpret_cast<uint32_t*>(&lo);
-        pk.y = *reinterpret_cast<uint32_t*>(&hi);
-        *reinterpret_cast<uint2*>(dZ + (size_t)r * (4 * U) + 4 * col) = pk;
-        dbacc[0] += dz0; dbacc[1] += dz1; dbacc[2] += dz2; dbacc[3] += dz3;
-        ct[j] = cprev;                    // c_{t-1} is the cell state of the next (earlier) step
+        dcn[hf][j] = 0.f;
+        ct[hf][j] = active ? Cst[(size_t)(row00[hf] + j * sstr + (uint32_t)(steps - 1) * tstr) * U + col] : 0.f;
+        gv[hf][j] = make_float4(0.f, 0.f, 0.f, 0.f); cpv[hf][j] = 0.f; dyv[hf][j] = 0.f;
       }
-      if (warp == 1 && lane == 0) DJ_TR(t, 9);
-      tc_fence_before();
-      fence_proxy_async_all();            // dz_t (generic-proxy global stores) -> TMA (async proxy) reads
-      if (warp == 1 && lane == 0) DJ_TR(t, 13);
-      cl_arrive();                        // publish first: the other CTAs' chain only needs dz_t ...
-      if (warp == 1 && lane == 0) DJ_TR(t, 10);
-      if (t > 0) issue_loads(t - 1);      // ... these land during the barrier / TMA / MMA of the step boundary
-      cl_wait();
-      if (warp == 1 && lane == 0) DJ_TR(t, 11);
+      issue_loads(hf, steps - 1);
+    }
+    const bool tr = (warp == 1 && lane == 0);
+    uint32_t par = 0;
+    for (int t = steps - 1; t >= 0; --t) {
+#pragma unroll
+      for (int hf = 0; hf < NS; ++hf) {
+        float dh[CPL];
+        if (t != steps - 1) {
+          mbar_wait(sbase + BAR_ACC + 8 * hf, par ^ 1u);   // produced by issuer round t+1
+          tc_fence_after();
+          if (tr) DJ_TR(t, 8 + 3 * hf);
+          uint32_t acc[WC];
+#pragma unroll
+          for (int p4 = 0; p4 < WC / 4; ++p4)
+            tmem_ld4(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(hf * HB + w2 * WC + p4 * 4), acc + p4 * 4);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < CPL; ++j) {
+            const float up = __shfl_sync(0xffffffffu, __uint_as_float(acc[CPL + j]), lane & 15);
+            dh[j] = sh ? up : __uint_as_float(acc[j]);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < CPL; ++j) dh[j] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) {
+          if (!active) break;
+          const uint32_t r = row00[hf] + j * sstr + (uint32_t)t * tstr;
+          const float4 g4 = gv[hf][j];
+          const float cprev = (t > 0) ? cpv[hf][j] : 0.f;
+          const float dht = fmaf(dyv[hf][j], dj_dropmul(d_y, r * U + col), dh[j]);
+          const float tc = fast_tanh(ct[hf][j]);
+          const float d_o = dht * tc;
+          const float dc = fmaf(dht * g4.w, 1.f - tc * tc, dcn[hf][j]);
+          dcn[hf][j] = dc * g4.y;
+          const float dz0 = dc * g4.z * dj_gate_dact(g4.x, hard);
+          const float dz1 = dc * cprev * dj_gate_dact(g4.y, hard);
+          const float dz2 = dc * g4.x * (1.f - g4.z * g4.z);
+          const float dz3 = d_o * dj_gate_dact(g4.w, hard);
+          __nv_bfloat162 lo = __floats2bfloat162_rn(dz0, dz1), hi = __floats2bfloat162_rn(dz2, dz3);
+          uint2 pk;
+          pk.x = *reinterpret_cast<uint32_t*>(&lo);
+          pk.y = *reinterpret_cast<uint32_t*>(&hi);
+          *reinterpret_cast<uint2*>(dZ + (size_t)r * (4 * U) + 4 * col) = pk;
+          dbacc[0] += dz0; dbacc[1] += dz1; dbacc[2] += dz2; dbacc[3] += dz3;
+          ct[hf][j] = cprev;                // c_{t-1} is the cell state of the next (earlier) step
+        }
+        if (tr) DJ_TR(t, 9 + 3 * hf);
+        if (t > 0) {
+          tc_fence_before();
+          fence_proxy_async_all();          // dz_t (generic-proxy global stores) -> later TMA (async proxy) reads
+          __syncwarp();
+          if (lane == 0) mbar_arrive(sbase + BAR_DONE + 8 * hf);   // release.cta: hands this warp's stores to the issuer
+          issue_loads(hf, t - 1);           // land during this half's publish / TMA / MMA chain
+        }
+        if (tr) DJ_TR(t, 10 + 3 * hf);
+      }
+      par ^= 1u;
     }
     if (active) {
 #pragma unroll
@@ -645,10 +677,20 @@ scan_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
   if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-template <int U, int BS, int UPC, bool AXIS_TIME>
-int launch_tc_bwd(const void* Un_bf, const float* gates, const float* c, const float* dY, int64_t ldY, dj_dropout d_y,
-                  void* dZ, float* db, int S, int steps, const TcMap& map_in, int hard, cudaStream_t st) {
+inline bool bwd_split_enabled() {   // DJ_BWD_NS=1 forces the unsplit tile (experiments)
+  static int env = -1;
+  if (env < 0) {
+    const char* e = getenv("DJ_BWD_NS");
+    env = (e && atoi(e) == 1) ? 0 : 1;
+  }
+  return env != 0;
+}
+
+template <int U, int BS, int UPC, bool AXIS_TIME, int NS>
+int launch_tc_bwd_inst(const void* Un_bf, const float* gates, const float* c, const float* dY, int64_t ldY, dj_dropout d_y,
+                       void* dZ, float* db, int S, int steps, const TcMap& map_in, int hard, cudaStream_t st) {
   constexpr int C = U / UPC;
+  constexpr int HB = BS / NS;
   using SM = TcBwdSmem<U, BS, UPC>;
   DJ_CHECK_ARG(S % BS == 0, "dj_lstm_scan_tc_bwd: the number of sequences (%d) must be a multiple of %d", S, BS);
   TcMap map = map_in;
@@ -661,18 +703,18 @@ int launch_tc_bwd(const void* Un_bf, const float* gates, const float* c, const f
     static_assert(!AXIS_TIME || 48 % BS == 0, "time-axis tiles divide a batch element");
     const uint64_t rows_per_b = (uint64_t)map.outer_stride, B = (uint64_t)(S / 48);
     const uint64_t dims[4] = {64, rows_per_b, (uint64_t)KA, B}, str[3] = {(uint64_t)4 * U, 64, rows_per_b * 4 * U};
-    const uint32_t box[4] = {64, (uint32_t)BS, (uint32_t)KPC, 1};
+    const uint32_t box[4] = {64, (uint32_t)HB, (uint32_t)KPC, 1};
     if ((rc = make_map(&tmZ, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dZ, 4, dims, str, box))) return rc;
     map.step1 = 48; map.off1 = BS; map.base2 = 1; map.off2 = 48 / BS;
     map.seq_stride = map.inner_stride;
   } else {           // dZ viewed as [n][atom][seq][64] (strides: seq 48*4U, atom 64, n 4U)
     const uint64_t dims[4] = {64, (uint64_t)S, (uint64_t)KA, 48}, str[3] = {(uint64_t)48 * 4 * U, 64, (uint64_t)4 * U};
-    const uint32_t box[4] = {64, (uint32_t)BS, (uint32_t)KPC, 1};
+    const uint32_t box[4] = {64, (uint32_t)HB, (uint32_t)KPC, 1};
     if ((rc = make_map(&tmZ, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dZ, 4, dims, str, box))) return rc;
     map.step1 = 1; map.off1 = 0; map.base2 = BS; map.off2 = 1;
     map.seq_stride = map.outer_stride;
   }
-  auto kernel = scan_tc_bwd_kernel<U, BS, UPC, AXIS_TIME>;
+  auto kernel = scan_tc_bwd_kernel<U, BS, UPC, AXIS_TIME, NS>;
   DJ_CUDA(cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
   if (C > 8) DJ_CUDA(cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   cudaLaunchConfig_t cfg{};
@@ -688,6 +730,14 @@ int launch_tc_bwd(const void* Un_bf, const float* gates, const float* c, const f
   const uint32_t ldy32 = (uint32_t)ldY;
   DJ_CUDA(cudaLaunchKernelEx(&cfg, kernel, tmU, tmZ, gates, c, dY, ldy32, d_y, dzp, db, steps, map, hard));
   return 0;
+}
+
+template <int U, int BS, int UPC, bool AXIS_TIME>
+int launch_tc_bwd(const void* Un_bf, const float* gates, const float* c, const float* dY, int64_t ldY, dj_dropout d_y,
+                  void* dZ, float* db, int S, int steps, const TcMap& map, int hard, cudaStream_t st) {
+  if (bwd_split_enabled())
+    return launch_tc_bwd_inst<U, BS, UPC, AXIS_TIME, 2>(Un_bf, gates, c, dY, ldY, d_y, dZ, db, S, steps, map, hard, st);
+  return launch_tc_bwd_inst<U, BS, UPC, AXIS_TIME, 1>(Un_bf, gates, c, dY, ldY, d_y, dZ, db, S, steps, map, hard, st);
 }
 
 }  // namespace
