@@ -459,9 +459,10 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t v[4]) {
 
 // NS = 2 software-pipelines the tile as two half-tiles (HB = BS/2 sequences, MMA N = HB) that alternate through
 // the same epilogue warps: while they compute the gate derivatives of half B, half A's publish -> all-gather ->
-// 64-MMA chain is in flight.  Hand-offs are mbarriers as in the forward scan (epilogue --done--> issuer, the issuer
-// does the one gpu-scope release of the CTA and a remote arrive on pub[hf] of every CTA), so the epilogue warps
-// execute neither a gpu-scope membar nor a cluster barrier.
+// 64-MMA chain is in flight.  Hand-offs are mbarriers: epilogue --done[hf]--> issuer --TMA multicast of this CTA's own
+// dz columns--> bar_z[hf] of every CTA --MMA--> bar_acc[hf]; the MMA commit also multicasts to free[hf] of every CTA
+// ("my operand tile may be overwritten").  A CTA's dz is only ever read from memory by that CTA's own TMA, so the
+// chain contains no gpu-scope membar and no cluster barrier.
 template <int U, int BS, int UPC, bool AXIS_TIME, int NS>
 __global__ void __launch_bounds__(TCB_THREADS, (U == 128 && BS <= 32) ? 2 : 1)
 scan_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmZ,
@@ -485,9 +486,9 @@ scan_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const uint32_t sbase = smem_u32(smem);
-  // barriers: a | z[2] | acc[2] | done[2] | pub[2] | tmem slot
+  // barriers: a | z[2] | acc[2] | done[2] | free[2] | tmem slot
   constexpr uint32_t BAR_Z = SM::BAR_OFF + 8, BAR_ACC = SM::BAR_OFF + 24, BAR_DONE = SM::BAR_OFF + 40,
-                     BAR_PUB = SM::BAR_OFF + 56;
+                     BAR_FREE = SM::BAR_OFF + 56;
   const uint32_t bar_a = sbase + SM::BAR_OFF;
   uint32_t* tmem_slot = (uint32_t*)(smem + SM::BAR_OFF + 72);
 
@@ -503,7 +504,7 @@ scan_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
         mbar_init(sbase + BAR_Z + 8 * hf, 1); mbar_init(sbase + BAR_ACC + 8 * hf, 1);
-        mbar_init(sbase + BAR_DONE + 8 * hf, 8); mbar_init(sbase + BAR_PUB + 8 * hf, C);
+        mbar_init(sbase + BAR_DONE + 8 * hf, 8); mbar_init(sbase + BAR_FREE + 8 * hf, C);
       }
       fence_barrier_init();
     }
@@ -527,7 +528,7 @@ scan_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
     }
     __syncwarp();
     const uint32_t bar_z = sbase + BAR_Z + 8 * hf, bar_acc = sbase + BAR_ACC + 8 * hf,
-                   bar_done = sbase + BAR_DONE + 8 * hf, bar_pub = sbase + BAR_PUB + 8 * hf;
+                   bar_done = sbase + BAR_DONE + 8 * hf, bar_free = sbase + BAR_FREE + 8 * hf;
     const uint32_t b_half = sbase + SM::B_OFF + hf * HALF_BYTES;
     // TMA coordinates of this half-tile: rows (time axis: within the batch element) / sequences (note axis)
     const int c_row0 = AXIS_TIME ? (tile % map.off2) * BS + hf * HB : tile * BS + hf * HB;
@@ -535,11 +536,12 @@ scan_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
     if (hf < NS) {
       uint32_t par = 0;
       for (int t = steps - 1; t > 0; --t, par ^= 1u) {   // round: dz_t in, dh of step t-1 out
-        mbar_wait(bar_done, par);                         // this CTA's epilogue warps stored their dz_t
+        mbar_wait(bar_done, par);                         // this CTA's epilogue warps stored (and proxy-fenced) their dz_t
         DJ_TR(t, 4 * hf + 0);
-        if (lane < C) mbar_arrive_remote(bar_pub, (uint32_t)lane);   // release.cluster, cumulative
-        __syncwarp();
-        mbar_wait_cluster(bar_pub, par);                  // every CTA of the cluster has published
+        // Nobody else reads this CTA's dz_t from memory: THIS CTA's TMA multicasts it into every CTA's operand tile,
+        // so no gpu-scope release and no cluster-wide "published" round trip is needed -- only the guarantee that
+        // every peer's MMAs of the previous round have finished reading the tile we are about to overwrite.
+        if (t != steps - 1) mbar_wait_cluster(bar_free, par ^ 1u);
         DJ_TR(t, 4 * hf + 1);
         if (elect_one()) {
           mbar_expect_tx(bar_z, HALF_BYTES);
@@ -562,11 +564,14 @@ scan_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
             for (int k = 0; k < 4; ++k)   // descriptor start addresses are in 16-byte units
               umma_bf16(tmem_base + (uint32_t)(hf * HB), adesc0 + (uint64_t)((ja * ATOM + k * 32) >> 4),
                         bdesc0 + (uint64_t)((ja * (HB * 128) + k * 32) >> 4), idesc, (ja | k) != 0);
-          umma_commit(bar_acc);
+          umma_commit(bar_acc);                                   // -> this CTA's epilogue
+          umma_commit_mc(bar_free, (uint16_t)((1u << C) - 1u));   // -> every CTA: my operand tile may be rewritten
         }
         __syncwarp();
         DJ_TR(t, 4 * hf + 3);
       }
+      // drain the peers' last multicast arrives before this CTA can exit
+      if (steps > 1) mbar_wait_cluster(bar_free, par ^ 1u);
     }
   } else {
     // ================= epilogue: gate derivatives =================
