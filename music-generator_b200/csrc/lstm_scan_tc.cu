@@ -198,7 +198,9 @@ scan_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
         DJ_TR(t, 4 * hf + 0);
         if (lane < C) mbar_arrive_remote(bar_pub, (uint32_t)lane);   // release.cluster, cumulative
         __syncwarp();
-        mbar_wait_cluster(bar_pub, par);                  // every CTA of the cluster has published
+        // every CTA of the cluster has published.  The producers' release put h_t in L2 and the only consumer is the
+        // TMA below, which reads L2: a CTA-scope wait is enough (a cluster-scope acquire adds an L1 invalidate)
+        mbar_wait(bar_pub, par);
         DJ_TR(t, 4 * hf + 1);
         if (elect_one()) {
           mbar_expect_tx(bar_h, HB * U * 2);
@@ -541,7 +543,7 @@ scan_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
         // Nobody else reads this CTA's dz_t from memory: THIS CTA's TMA multicasts it into every CTA's operand tile,
         // so no gpu-scope release and no cluster-wide "published" round trip is needed -- only the guarantee that
         // every peer's MMAs of the previous round have finished reading the tile we are about to overwrite.
-        if (t != steps - 1) mbar_wait_cluster(bar_free, par ^ 1u);
+        if (t != steps - 1) mbar_wait(bar_free, par ^ 1u);   // (orders TMA writes after MMA reads: no data to acquire)
         DJ_TR(t, 4 * hf + 1);
         if (elect_one()) {
           mbar_expect_tx(bar_z, HALF_BYTES);
@@ -571,7 +573,7 @@ scan_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
         DJ_TR(t, 4 * hf + 3);
       }
       // drain the peers' last multicast arrives before this CTA can exit
-      if (steps > 1) mbar_wait_cluster(bar_free, par ^ 1u);
+      if (steps > 1) mbar_wait(bar_free, par ^ 1u);
     }
   } else {
     // ================= epilogue: gate derivatives =================
