@@ -125,11 +125,15 @@ __device__ __forceinline__ int64_t tc_row0(const TcMap& m, int seq) {
 //           one thread's fence publishes everybody's stores), then a remote arrive on pub[hf] of all C CTAs
 //   pub[hf] complete (count C) -> this CTA's multicast TMA of its slice of h_t -> bar_h[hf] -> MMA -> bar_acc[hf]
 // so the epilogue warps never execute a gpu-scope membar or a cluster barrier.
-template <int U, int BS, bool TIME, bool HARD, int NB, int NS>
+// ATM: the resident A operand (this CTA's 128 rows of U^T) lives in TENSOR MEMORY instead of shared memory
+// (tcgen05.mma with A from TMEM): the per-step MMAs then read only the small B operand from shared memory.  With A
+// in shared memory the 16 MMAs of a half-step are bound by re-reading the 64 KB of weights (~80 cycles per MMA
+// against a 24-cycle floor).  Needs 2 x (BS + U/2 rounded up) <= 512 TMEM columns for two CTAs per SM: U <= 256.
+template <int U, int BS, bool TIME, bool HARD, int NB, int NS, bool ATM>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 scan_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmH,
                    float* __restrict__ Z, float* __restrict__ Hout, float* __restrict__ Cout,
-                   __nv_bfloat16* __restrict__ Hprev, int steps, TcMap map) {
+                   __nv_bfloat16* __restrict__ Hprev, const uint32_t* __restrict__ Ut_words, int steps, TcMap map) {
   constexpr uint32_t SSTR = TIME ? 1u : 48u, TSTR = TIME ? 48u : 1u;
   constexpr int C = U / 32;            // cluster size
   constexpr int KA = U / 64;           // 64-wide K atoms
@@ -140,8 +144,11 @@ scan_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
   static_assert(NS == 1 || NS == 2, "one tile or two half-tiles");
   static_assert(NS == 1 || (NCH % 2 == 0), "half-tiles are whole 16-sequence chunks");
   static_assert(C == 2 * KA && RH % 8 == 0, "slices = K atoms x 2 row halves");
-  constexpr uint32_t TMEM_COLS = BS <= 32 ? 32 : BS <= 64 ? 64 : BS <= 128 ? 128 : 256;
-  static_assert(BS % 16 == 0 && BS <= 256, "tile shape");
+  constexpr uint32_t D_COLS = BS <= 32 ? 32 : BS <= 64 ? 64 : BS <= 128 ? 128 : 256;   // accumulators: columns [0, BS)
+  constexpr uint32_t A_COL0 = D_COLS;                                                   // A operand: columns [A_COL0, +U/2)
+  constexpr uint32_t NEED = ATM ? D_COLS + U / 2 : D_COLS;
+  constexpr uint32_t TMEM_COLS = NEED <= 32 ? 32 : NEED <= 64 ? 64 : NEED <= 128 ? 128 : NEED <= 256 ? 256 : 512;
+  static_assert(BS % 16 == 0 && BS <= 256 && (!ATM || TMEM_COLS <= 256), "tile shape / two CTAs share 512 TMEM columns");
   using SM = TcFwdSmem<U, BS>;
 
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -175,13 +182,31 @@ scan_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_p;
-  cluster.sync();   // peers' barriers are initialised before any multicast / remote arrive can target them
+  if (ATM && warp >= 1 && warp <= 4) {
+    // lane = one row of this CTA's slice of U^T (256 B .. 1 KB contiguous in global memory): 16 packed bf16 pairs
+    // per tcgen05.st, straight into the TMEM lanes of this warp's quarter
+    const uint32_t* src = Ut_words + (size_t)(128 * rank + 32 * (warp & 3) + lane) * (U / 2);
+#pragma unroll 1
+    for (int c = 0; c < U / 2; c += 16) {
+      uint32_t w[16];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint4 q4 = *reinterpret_cast<const uint4*>(src + c + 4 * j);
+        w[4 * j] = q4.x; w[4 * j + 1] = q4.y; w[4 * j + 2] = q4.z; w[4 * j + 3] = q4.w;
+      }
+      tmem_st16(tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + A_COL0 + (uint32_t)c, w);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+  }
+  cluster.sync();   // peers' barriers are initialised before any multicast / remote arrive can target them (and A is in TMEM)
+  tc_fence_after();
 
   if (warp == 0 || warp == 1 + TC_EPI_WARPS) {
     // ================= issuer + publisher of half-tile hf =================
     // the whole warp walks the loop converged; single-thread work sits under elect_one()
     const int hf = (warp == 0) ? 0 : 1;
-    if (warp == 0 && elect_one()) {   // resident A operand: rows [128*rank, +128) of U^T
+    if (!ATM && warp == 0 && elect_one()) {   // resident A operand in shared memory: rows [128*rank, +128) of U^T
       mbar_expect_tx(bar_a, SM::A_BYTES);
 #pragma unroll
       for (int ka = 0; ka < KA; ++ka)
@@ -210,7 +235,7 @@ scan_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
                            (uint16_t)((1u << C) - 1u));
         }
         __syncwarp();
-        if (t == 0) mbar_wait(bar_a, 0);
+        if (!ATM && t == 0) mbar_wait(bar_a, 0);
         mbar_wait(bar_h, par);                            // all C slices of this half landed
         DJ_TR(t, 4 * hf + 2);
         tc_fence_after();
@@ -221,9 +246,15 @@ scan_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
 #pragma unroll
           for (int ka = 0; ka < KA; ++ka)
 #pragma unroll
-            for (int k = 0; k < 4; ++k)   // descriptor start addresses are in 16-byte units
-              umma_bf16(tmem_base + (uint32_t)(hf * HB), adesc0 + (uint64_t)((ka * 16384 + k * 32) >> 4),
-                        bdesc0 + (uint64_t)((ka * (BS * 128) + k * 32) >> 4), idesc, (ka | k) != 0);
+            for (int k = 0; k < 4; ++k) {   // descriptor start addresses are in 16-byte units
+              const uint64_t bdesc = bdesc0 + (uint64_t)((ka * (BS * 128) + k * 32) >> 4);
+              if constexpr (ATM)
+                umma_bf16_ts(tmem_base + (uint32_t)(hf * HB), tmem_base + A_COL0 + (uint32_t)(ka * 32 + k * 8), bdesc,
+                             idesc, (ka | k) != 0);
+              else
+                umma_bf16(tmem_base + (uint32_t)(hf * HB), adesc0 + (uint64_t)((ka * 16384 + k * 32) >> 4), bdesc,
+                          idesc, (ka | k) != 0);
+            }
           umma_commit(bar_acc);
         }
         __syncwarp();
@@ -343,6 +374,15 @@ scan_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
   if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+inline bool fwd_atm_enabled() {   // DJ_FWD_ATM=0 keeps the A operand in shared memory (experiments)
+  static int env = -1;
+  if (env < 0) {
+    const char* e = getenv("DJ_FWD_ATM");
+    env = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return env != 0;
+}
+
 template <int U, int BS, bool TIME, bool HARD, int NB, int NS>
 int launch_tc_fwd_inst(const void* Ut_bf, float* Z, float* h_out, float* c_out, void* hprev, int S, int steps,
                        const TcMap& map_in, cudaStream_t st) {
@@ -369,7 +409,12 @@ int launch_tc_fwd_inst(const void* Ut_bf, float* Z, float* h_out, float* c_out, 
     map.step1 = 1; map.off1 = 0; map.base2 = BS; map.off2 = RH;
     map.seq_stride = map.outer_stride;
   }
-  auto kernel = scan_tc_fwd_kernel<U, BS, TIME, HARD, NB, NS>;
+  constexpr bool CAN_ATM = (U <= 256);
+  const bool atm = CAN_ATM && fwd_atm_enabled();
+  auto kernel = scan_tc_fwd_kernel<U, BS, TIME, HARD, NB, NS, false>;
+  if constexpr (CAN_ATM) {
+    if (atm) kernel = scan_tc_fwd_kernel<U, BS, TIME, HARD, NB, NS, true>;
+  }
   DJ_CUDA(cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
   if (C > 8) DJ_CUDA(cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   cudaLaunchConfig_t cfg{};
@@ -382,7 +427,8 @@ int launch_tc_fwd_inst(const void* Ut_bf, float* Z, float* h_out, float* c_out, 
   at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
   __nv_bfloat16* hp = (__nv_bfloat16*)hprev;
-  DJ_CUDA(cudaLaunchKernelEx(&cfg, kernel, tmU, tmH, Z, h_out, c_out, hp, steps, map));
+  const uint32_t* utw = (const uint32_t*)Ut_bf;
+  DJ_CUDA(cudaLaunchKernelEx(&cfg, kernel, tmU, tmH, Z, h_out, c_out, hp, utw, steps, map));
   return 0;
 }
 
