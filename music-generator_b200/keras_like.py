@@ -62,9 +62,20 @@ class _Base:
         eng = self.engine
 
         class _Style:
+            """The shared `Dense(STYLE_UNITS, name='style')` layer (model.py:141): weights, and a call that
+            embeds style vectors on the device (what visualize.py:16-23 does through a TF session)."""
+
             def get_weights(self_inner):
                 p = eng.get_params()
                 return [p["style.W"], p["style.b"]]
+
+            def __call__(self_inner, style_vectors):
+                sv = np.ascontiguousarray(style_vectors, dtype=np.float32)
+                n, ns = sv.shape
+                ws = eng.workspace(n, 1, False, False)
+                eng._style(ws, _dev(eng, sv), ns, 0, n, 1)     # dj_style_fwd: emb = style.W + b (linear)
+                torch.cuda.synchronize()
+                return ws.emb[:n].cpu().numpy().copy()
         return _Style()
 
 

@@ -35,7 +35,9 @@ def test_engine_init_matches_oracle_init():
     assert e.num_params == 1269476
 
 
-@pytest.mark.parametrize("BT", [(2, 4), (3, 16), (2, 128)])
+# (1, 1): one sequence, one timestep (the note_model shape of generation); (5, 3) / (7, 2): ragged last tiles of
+# both fp32 scan tilings (240 / 336 time-axis sequences: 16- and 32-sequence tiles do not divide them evenly)
+@pytest.mark.parametrize("BT", [(1, 1), (2, 4), (5, 3), (7, 2), (3, 16), (2, 128)])
 def test_forward_fp32_matches_oracle(BT):
     B, T = BT
     e = make_engine("fp32")
@@ -173,6 +175,18 @@ def test_keras_like_predict_api():
     out = models[0].predict([notes, chosen, beat, style])
     oref = O.model_forward(p64, CFG, *[t.double() for t in cpu[:4]])
     assert np.abs(out - oref.numpy()).max() < 2e-5
+
+
+def test_style_layer_embeds_identity_like_visualize():
+    """visualize.py:13-23: the `style` Dense layer applied to all one-hot styles (linear: W + b per row)."""
+    import model as M
+    import visualize
+    models = M.build_models(precision="fp32")
+    layer = models[0].get_layer('style')
+    W, b = layer.get_weights()
+    emb = layer(np.identity(23))
+    assert emb.shape == (23, 64) and np.abs(emb - (W + b[None, :])).max() < 1e-6
+    assert visualize.style_labels().shape == (24, 2)
 
 
 def test_generation_lockstep_bit_exact():

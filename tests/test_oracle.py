@@ -164,3 +164,13 @@ def test_fp32_oracle_close_to_fp64():
     b32 = [t.float() for t in b64]
     a = O.model_forward(p64, CFG, *b64[:4]); b = O.model_forward(p32, CFG, *b32[:4])
     assert helpers.rel_err(b.numpy(), a.numpy()) < 1e-5
+
+
+def test_visualize_labels_table_matches_reference_layout():
+    """visualize.py:27-40: header + one (genre, artist path) row per style, genre-major."""
+    import visualize
+    import constants
+    t = visualize.style_labels()
+    assert t.shape == (1 + constants.NUM_STYLES, 2) and list(t[0]) == ['Genre', 'Artist']
+    assert t[1][0] == constants.genre[0] and t[1][1] == constants.styles[0][0]
+    assert t[-1][1] == constants.styles[-1][-1]
