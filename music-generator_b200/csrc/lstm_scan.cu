@@ -569,12 +569,46 @@ scan_bwd_kernel(const float* __restrict__ G, const float* __restrict__ Cst, cons
   }
 }
 
+// Clusters of C CTAs that can be resident at once.  This is NOT num_sms / C: a cluster lives inside one GPC, and on
+// B200 only 15 clusters of 8 one-CTA-per-SM blocks fit (ncu launch__cluster_max_active), so a grid of 16 such
+// clusters runs as two waves.  Asked from the driver with the real launch configuration.
 template <typename K>
-int launch_cluster(K kernel, int C, int nthreads, size_t smem, int nclusters, cudaStream_t st, void** args) {
+int max_active_clusters(K kernel, int C, int nthreads, size_t smem) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(C);
+  cfg.blockDim = dim3(nthreads);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, (const void*)kernel, &cfg) != cudaSuccess || n < 1) {
+    cudaGetLastError();
+    n = dj_num_sms() / C > 1 ? dj_num_sms() / C - 1 : 1;
+  }
+  return n;
+}
+
+template <typename K>
+int prepare_cluster_kernel(K kernel, int C, size_t smem) {
   DJ_CUDA(cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (C > 8) DJ_CUDA(cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  return 0;
+}
+
+// Persistent clusters: `ntiles` tiles are walked by as many clusters as can be resident, balanced so that every
+// cluster does the same number of rounds.
+template <typename K>
+int launch_cluster(K kernel, int C, int nthreads, size_t smem, int ntiles, cudaStream_t st, void** args) {
+  int rc = prepare_cluster_kernel(kernel, C, smem);
+  if (rc) return rc;
+  int ncl = max_active_clusters(kernel, C, nthreads, smem);
+  if (ncl > ntiles) ncl = ntiles;
+  const int rounds = (ntiles + ncl - 1) / ncl;
+  ncl = (ntiles + rounds - 1) / rounds;
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(nclusters * C);
+  cfg.gridDim = dim3(ncl * C);
   cfg.blockDim = dim3(nthreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
@@ -584,16 +618,6 @@ int launch_cluster(K kernel, int C, int nthreads, size_t smem, int nclusters, cu
   cfg.attrs = at; cfg.numAttrs = 1;
   DJ_CUDA(cudaLaunchKernelExC(&cfg, (const void*)kernel, args));
   return 0;
-}
-
-int pick_clusters(int C, int ntiles) {
-  int ncl = dj_num_sms() / C;
-  if (ncl < 1) ncl = 1;
-  if (ncl > ntiles) ncl = ntiles;
-  // balance: same number of rounds with fewer idle clusters
-  const int rounds = (ntiles + ncl - 1) / ncl;
-  ncl = (ntiles + rounds - 1) / rounds;
-  return ncl;
 }
 
 }  // namespace
@@ -610,20 +634,20 @@ extern "C" int dj_lstm_scan_fwd(float* Z, float* h_out, float* c_out, void* h_pr
   if (units == 256) {
     constexpr int C = 8;
     // few sequences (a generation window is 48): 16-sequence tiles spread the step over more clusters
-    if ((S + 15) / 16 <= dj_num_sms() / C)
-      return launch_cluster(scan_fwd_u1_kernel<256, C, 16>, C, 4 * UC, FwdSmem<256, 16>::BYTES,
-                            pick_clusters(C, (S + 15) / 16), st, args);
+    if (prepare_cluster_kernel(scan_fwd_u1_kernel<256, C, 16>, C, FwdSmem<256, 16>::BYTES) == 0 &&
+        (S + 15) / 16 <= max_active_clusters(scan_fwd_u1_kernel<256, C, 16>, C, 4 * UC, FwdSmem<256, 16>::BYTES))
+      return launch_cluster(scan_fwd_u1_kernel<256, C, 16>, C, 4 * UC, FwdSmem<256, 16>::BYTES, (S + 15) / 16, st, args);
     constexpr int BS = 32;
-    return launch_cluster(scan_fwd_kernel<256, C, BS>, C, (BS / 4) * 16, FwdSmem<256, BS>::BYTES,
-                          pick_clusters(C, (S + BS - 1) / BS), st, args);
+    return launch_cluster(scan_fwd_kernel<256, C, BS>, C, (BS / 4) * 16, FwdSmem<256, BS>::BYTES, (S + BS - 1) / BS, st,
+                          args);
   } else if (units == 128) {
     constexpr int C = 4;
-    if ((S + 15) / 16 <= dj_num_sms() / C)
-      return launch_cluster(scan_fwd_u1_kernel<128, C, 16>, C, 4 * UC, FwdSmem<128, 16>::BYTES,
-                            pick_clusters(C, (S + 15) / 16), st, args);
+    if (prepare_cluster_kernel(scan_fwd_u1_kernel<128, C, 16>, C, FwdSmem<128, 16>::BYTES) == 0 &&
+        (S + 15) / 16 <= max_active_clusters(scan_fwd_u1_kernel<128, C, 16>, C, 4 * UC, FwdSmem<128, 16>::BYTES))
+      return launch_cluster(scan_fwd_u1_kernel<128, C, 16>, C, 4 * UC, FwdSmem<128, 16>::BYTES, (S + 15) / 16, st, args);
     constexpr int BS = 32;
-    return launch_cluster(scan_fwd_kernel<128, C, BS>, C, (BS / 4) * 16, FwdSmem<128, BS>::BYTES,
-                          pick_clusters(C, (S + BS - 1) / BS), st, args);
+    return launch_cluster(scan_fwd_kernel<128, C, BS>, C, (BS / 4) * 16, FwdSmem<128, BS>::BYTES, (S + BS - 1) / BS, st,
+                          args);
   }
   DJ_CHECK_ARG(false, "dj_lstm_scan_fwd: units=%d unsupported (128 or 256; U must fit cluster shared memory in fp32)", units);
   return -1;
@@ -641,13 +665,13 @@ extern "C" int dj_lstm_scan_bwd(const float* gates, const float* c, const float*
   cudaStream_t st = (cudaStream_t)stream;
   if (units == 256) {
     constexpr int C = 8, BS = 48;
-    const int ncl = pick_clusters(C, (S + BS - 1) / BS);
+    const int ncl = (S + BS - 1) / BS;   // tiles; launch_cluster picks the resident cluster count
     if (dz_dtype == DJ_F32)
       return launch_cluster(scan_bwd_kernel<256, C, BS, float>, C, (BS / 4) * 16, BwdSmem<256, C, BS>::BYTES, ncl, st, args);
     return launch_cluster(scan_bwd_kernel<256, C, BS, __nv_bfloat16>, C, (BS / 4) * 16, BwdSmem<256, C, BS>::BYTES, ncl, st, args);
   } else if (units == 128) {
     constexpr int C = 4, BS = 64;
-    const int ncl = pick_clusters(C, (S + BS - 1) / BS);
+    const int ncl = (S + BS - 1) / BS;   // tiles; launch_cluster picks the resident cluster count
     if (dz_dtype == DJ_F32)
       return launch_cluster(scan_bwd_kernel<128, C, BS, float>, C, (BS / 4) * 16, BwdSmem<128, C, BS>::BYTES, ncl, st, args);
     return launch_cluster(scan_bwd_kernel<128, C, BS, __nv_bfloat16>, C, (BS / 4) * 16, BwdSmem<128, C, BS>::BYTES, ncl, st, args);
