@@ -426,6 +426,11 @@ int launch_tc_fwd_inst(const void* Ut_bf, float* Z, float* h_out, float* c_out, 
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
+  if (getenv("DJ_DEBUG_OCC")) {   // how many clusters the driver can keep resident vs how many tiles there are
+    int n = 0;
+    cudaOccupancyMaxActiveClusters(&n, (const void*)kernel, &cfg);
+    fprintf(stderr, "scan_tc_fwd<%d,%d>: %d clusters of %d launched, %d can be resident\n", U, BS, S / BS, C, n);
+  }
   __nv_bfloat16* hp = (__nv_bfloat16*)hprev;
   const uint32_t* utw = (const uint32_t*)Ut_bf;
   DJ_CUDA(cudaLaunchKernelEx(&cfg, kernel, tmU, tmH, Z, h_out, c_out, hp, utw, steps, map));
@@ -779,6 +784,11 @@ int launch_tc_bwd_inst(const void* Un_bf, const float* gates, const float* c, co
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
+  if (getenv("DJ_DEBUG_OCC")) {
+    int n = 0;
+    cudaOccupancyMaxActiveClusters(&n, (const void*)kernel, &cfg);
+    fprintf(stderr, "scan_tc_bwd<%d,%d>: %d clusters of %d launched, %d can be resident\n", U, BS, S / BS, C, n);
+  }
   __nv_bfloat16* dzp = (__nv_bfloat16*)dZ;
   const uint32_t ldy32 = (uint32_t)ldY;
   DJ_CUDA(cudaLaunchKernelEx(&cfg, kernel, tmU, tmZ, gates, c, dY, ldy32, d_y, dzp, db, steps, map, hard));

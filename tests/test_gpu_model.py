@@ -147,6 +147,24 @@ def test_train_step_bf16_within_1e3():
     _train_compare("bf16", 2, 128, 1e-3, 3e-2)
 
 
+def test_training_trajectory_bf16_tracks_fp32():
+    """Twelve Nadam steps on the same batches, dropout on with the same seeds: the tensor-core path (bf16 gate-GEMM
+    and recurrence operands) must follow the fp32 path's loss curve, and both must actually learn."""
+    B, T = 4, 32                                   # 192 time-axis / 128 note-axis sequences: whole tensor-core tiles
+    losses = {}
+    for prec in ("fp32", "bf16"):
+        e = make_engine(prec)
+        _, dev = batch_dev(B, T)
+        out = []
+        for step in range(12):
+            out.append(float(e.train_step(*dev, seed=100 + step).item()))
+        losses[prec] = np.array(out)
+    f, b = losses["fp32"], losses["bf16"]
+    assert np.all(np.isfinite(f)) and np.all(np.isfinite(b))
+    assert f[-1] < 0.8 * f[0] and b[-1] < 0.8 * b[0], (f, b)          # same batch every step: the loss must fall
+    assert np.max(np.abs(b - f) / f) < 1e-2, (f, b)
+
+
 def test_train_step_bf16_odd_shape_uses_fp32_scans():
     """Batch shapes that are not whole tensor-core tiles (B*T % 64 != 0) run the CUDA-core scans
     with the tcgen05 GEMMs; same tolerance."""
