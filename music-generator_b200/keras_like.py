@@ -102,25 +102,63 @@ class TrainModel(_Base):
 
     def fit(self, x, y, epochs: int = 1, callbacks: Optional[list] = None, batch_size: int = 16,
             shuffle: bool = True, seed: int = 0, verbose: int = 1, allreduce=None, world: int = 1) -> History:
-        """Keras-style epoch loop: shuffled mini-batches (the last one may be
-        short; the pitch_bins scramble is scoped to each batch like in Keras)."""
+        """Keras-style epoch loop: shuffled mini-batches (the last one may be short; the pitch_bins scramble is
+        scoped to each batch like in Keras).
+
+        Input pipeline: batch i+1 is gathered into pinned host memory and copied to the device on a copy stream
+        while batch i trains; the loss is accumulated on the device and read back once per epoch, so there is no
+        host synchronisation inside an epoch (the callbacks only need the epoch loss, train.py:22-26)."""
+        e = self.engine
         hist = History()
         y0 = y[0] if isinstance(y, (list, tuple)) else y
-        n = len(x[0])
+        arrays = [np.asarray(a) for a in x] + [np.asarray(y0)]
+        n = len(arrays[0])
         rs = np.random.RandomState(seed)
         callbacks = callbacks or []
         for cb in callbacks:
             cb.set_model(self)
+        bsz = min(batch_size, n)
+        pinned = [[torch.empty((bsz,) + a.shape[1:], dtype=torch.float32).pin_memory() for a in arrays] for _ in range(2)]
+        devb = [[torch.empty((bsz,) + a.shape[1:], dtype=torch.float32, device=e.dev) for a in arrays] for _ in range(2)]
+        copy_stream = torch.cuda.Stream(device=e.dev)
+        copied = [None, None]          # event: H2D of this slot finished (the pinned buffers may be rewritten)
+        consumed = [None, None]        # event: the train step that read this slot's device buffers finished
+
+        def stage(slot, idx):
+            if copied[slot] is not None:
+                copied[slot].synchronize()
+            b = len(idx)
+            for k, a in enumerate(arrays):
+                pinned[slot][k].numpy()[:b] = a[idx]
+            with torch.cuda.stream(copy_stream):
+                if consumed[slot] is not None:
+                    copy_stream.wait_event(consumed[slot])
+                for k in range(len(arrays)):
+                    devb[slot][k][:b].copy_(pinned[slot][k][:b], non_blocking=True)
+                copied[slot] = torch.cuda.Event()
+                copied[slot].record(copy_stream)
+            return b
+
         step = 0
+        main = torch.cuda.current_stream(e.dev)
         for ep in range(epochs):
             order = rs.permutation(n) if shuffle else np.arange(n)
-            tot, cnt = 0.0, 0
-            for s in range(0, n, batch_size):
-                idx = order[s:s + batch_size]
-                loss = self.train_on_batch([a[idx] for a in x], y0[idx], seed=seed * 1000003 + step,
-                                           allreduce=allreduce, world=world)
-                tot += loss * len(idx); cnt += len(idx); step += 1
-            logs = {"loss": tot / max(cnt, 1)}
+            starts = list(range(0, n, batch_size))
+            tot = torch.zeros((), dtype=torch.float64, device=e.dev)
+            nb = stage(0, order[starts[0]:starts[0] + batch_size])
+            for bi, s0 in enumerate(starts):
+                slot, b = bi & 1, nb
+                main.wait_event(copied[slot])
+                if bi + 1 < len(starts):
+                    s1 = starts[bi + 1]
+                    nb = stage(slot ^ 1, order[s1:s1 + batch_size])
+                d = [t[:b] for t in devb[slot]]
+                loss = e.train_step(d[0], d[1], d[2], d[3], d[4], seed * 1000003 + step, allreduce, world)
+                tot += loss.double().reshape(()) * b
+                consumed[slot] = torch.cuda.Event()
+                consumed[slot].record(main)
+                step += 1
+            logs = {"loss": float(tot.item()) / max(n, 1)}
             hist.history["loss"].append(logs["loss"])
             if verbose:
                 print(f"Epoch {ep + 1}/{epochs} - loss: {logs['loss']:.4f}")

@@ -195,6 +195,32 @@ def test_keras_like_predict_api():
     assert np.abs(out - oref.numpy()).max() < 2e-5
 
 
+def test_fit_pipeline_equals_per_batch_training():
+    """fit() (pinned staging, async H2D on a copy stream, loss read back once per epoch) must train exactly like a
+    loop of train_on_batch over the same shuffled mini-batches, including the short last batch."""
+    import model as M
+    cpu, _ = batch_dev(7, 8)                          # 7 sequences, batch 3 -> batches of 3, 3, 1
+    xs = [t.numpy() for t in cpu[:4]]
+    ys = cpu[4].numpy()
+    a = M.build_models(time_steps=8, precision="fp32")[0]
+    h = a.fit(xs, [ys], epochs=2, batch_size=3, seed=5, verbose=0)
+    b = M.build_models(time_steps=8, precision="fp32")[0]
+    rs = np.random.RandomState(5)
+    ref, step = [], 0
+    for ep in range(2):
+        order = rs.permutation(7)
+        tot = 0.0
+        for s0 in range(0, 7, 3):
+            idx = order[s0:s0 + 3]
+            tot += b.train_on_batch([x[idx] for x in xs], ys[idx], seed=5 * 1000003 + step) * len(idx)
+            step += 1
+        ref.append(tot / 7)
+    assert np.allclose(h.history["loss"], ref, rtol=1e-6, atol=0), (h.history["loss"], ref)
+    pa, pb = a.engine.get_params(), b.engine.get_params()
+    # (not bit-equal: the weight-gradient reductions use fp32 atomics, whose order varies from run to run)
+    assert all(np.allclose(pa[k], pb[k], rtol=1e-4, atol=1e-6) for k in pa)
+
+
 def test_style_layer_embeds_identity_like_visualize():
     """visualize.py:13-23: the `style` Dense layer applied to all one-hot styles (linear: W + b per row)."""
     import model as M
