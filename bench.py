@@ -283,10 +283,13 @@ def _run_ours(args):
         u = np.random.RandomState(42).random_sample(2 * 48 * gsteps)
         generate_events(ge, [sty], 4, u)
         torch.cuda.synchronize()
-        t0 = time.time()
-        generate_events(ge, [sty], gsteps, u)
-        torch.cuda.synchronize()
-        gen = {"timesteps_per_s": gsteps / (time.time() - t0), "sequences": 1, "timesteps": gsteps,
+        rates = []
+        for _ in range(3):                       # the one-sequence loop is launch-heavy: median of three runs
+            t0 = time.time()
+            generate_events(ge, [sty], gsteps, u)
+            torch.cuda.synchronize()
+            rates.append(gsteps / (time.time() - t0))
+        gen = {"timesteps_per_s": sorted(rates)[1], "sequences": 1, "timesteps": gsteps, "runs": [round(r, 1) for r in rates],
                "workload": "generate.py path, 1 style-mixed sequence, full 128-step window recompute per timestep"}
         # configs[3] per-GPU share: 128 independent sequences (4 predict-chunks of 32), indexed uniform stream
         Gb, bsteps = 128, 4
