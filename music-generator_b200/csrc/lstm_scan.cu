@@ -21,6 +21,19 @@
 
 namespace cg = cooperative_groups;
 
+#ifdef DJ_TRACE
+// debug build only (tools/scan_trace.py fp32): clock64() stamps of thread 0 of block 0
+__device__ long long* g_dj_ftrace = nullptr;
+extern "C" int dj_debug_ftrace_set(void* buf) { return (int)cudaMemcpyToSymbol(g_dj_ftrace, &buf, sizeof(buf)); }
+#define DJ_FTR(t, k)                                                                   \
+  do {                                                                                 \
+    if (g_dj_ftrace != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && (t) < 512)    \
+      g_dj_ftrace[(t) * 8 + (k)] = clock64();                                          \
+  } while (0)
+#else
+#define DJ_FTR(t, k) do {} while (0)
+#endif
+
 namespace {
 
 struct ScanMap {
@@ -200,7 +213,9 @@ scan_fwd_kernel(float* __restrict__ Z, float* __restrict__ Hout, float* __restri
                               : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
+      DJ_FTR(t, 0);
       if (t > 0) { sbar_wait(bar0 + 8 * cur, ph[cur]); ph[cur] ^= 1u; }   // all of h_{t-1} has landed
+      DJ_FTR(t, 1);
       const float* hb = hbuf + cur * SM::HBUF + sg * SM::HSTR;
       const float* ua = Us + ug * 4;
 #pragma unroll 4
@@ -217,6 +232,7 @@ scan_fwd_kernel(float* __restrict__ Z, float* __restrict__ Hout, float* __restri
           acc2[s][1][1] = ffma2(hs[s], u1.y, acc2[s][1][1]);
         }
       }
+      DJ_FTR(t, 2);
       float acc[4][2][4];
 #pragma unroll
       for (int s = 0; s < 4; ++s)
@@ -254,6 +270,7 @@ scan_fwd_kernel(float* __restrict__ Z, float* __restrict__ Hout, float* __restri
       // all-gather of h_t into every CTA's next buffer (DSMEM, 16 lanes x 16 B contiguous).  Two buffers
       // are enough without a barrier: a CTA that is already sending h_{t+1} into buffer `cur` has received
       // every h_t, so every peer has finished reading h_{t-1} from it.
+      DJ_FTR(t, 3);
       const uint32_t off = (uint32_t)(nxt * SM::HBUF + sg * SM::HSTR + (unit0 + ug) * 4) * 4u;
 #pragma unroll
       for (int r = 0; r < C; ++r) {
@@ -342,7 +359,9 @@ scan_fwd_u1_kernel(float* __restrict__ Z, float* __restrict__ Hout, float* __res
           zn[s] = ok[s] ? *reinterpret_cast<const float4*>(Z + r * (4 * U) + 4 * col) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
+      DJ_FTR(t, 0);
       if (t > 0) { sbar_wait(bar0 + 8 * cur, ph[cur]); ph[cur] ^= 1u; }   // all of h_{t-1} has landed
+      DJ_FTR(t, 1);
       const float* hb = hbuf + cur * SM::HBUF + sg * SM::HSTR;
       const float* ua = Us + ug * 4;
 #pragma unroll 8
@@ -356,6 +375,7 @@ scan_fwd_u1_kernel(float* __restrict__ Z, float* __restrict__ Hout, float* __res
           acc2[s][1] = ffma2(hs[s], u0.y, acc2[s][1]);
         }
       }
+      DJ_FTR(t, 2);
       float hnew[4];
 #pragma unroll
       for (int s = 0; s < 4; ++s) {
@@ -383,6 +403,7 @@ scan_fwd_u1_kernel(float* __restrict__ Z, float* __restrict__ Hout, float* __res
       }
       // all-gather of h_t into every CTA's next buffer (DSMEM, 32 lanes x 16 B contiguous); see
       // scan_fwd_kernel for why two buffers need no barrier
+      DJ_FTR(t, 3);
       const uint32_t off = (uint32_t)(nxt * SM::HBUF + sg * SM::HSTR + col * 4) * 4u;
 #pragma unroll
       for (int r = 0; r < C; ++r)
