@@ -68,7 +68,7 @@ def test_forward_matches_golden_fixture():
     assert np.abs(got - z["predict_probs"]).max() < 2e-5
 
 
-def _train_compare(precision, B, T, tol_loss, tol_grad, CFG=CFG, **cfg_kw):
+def _train_compare(precision, B, T, tol_loss, tol_grad, CFG=CFG, tol_prob=None, **cfg_kw):
     e = make_engine(precision, **cfg_kw)
     p64 = helpers.to_oracle_params(e.get_params())
     b = O.synthetic_batch(CFG, B, T, 1234, torch.float32)
@@ -84,7 +84,8 @@ def _train_compare(precision, B, T, tol_loss, tol_grad, CFG=CFG, **cfg_kw):
     rloss, rprobs, rgrads = O.loss_and_grads(p64, CFG, *[t.double() for t in cpu], masks)
     assert abs(loss - float(rloss)) / float(rloss) < tol_loss, (loss, float(rloss))
     got = ws.probs.cpu().numpy().reshape(B, T, 48, 3)
-    assert np.abs(got - rprobs.numpy()).max() < max(tol_loss, 2e-5) * 2
+    perr = np.abs(got - rprobs.numpy())
+    assert perr.max() < (tol_prob if tol_prob is not None else max(tol_loss, 2e-5) * 2), (perr.max(), perr.mean())
     worst = {}
     ggpu = e.get_grads()
     for k, g in rgrads.items():
@@ -163,6 +164,15 @@ def test_training_trajectory_bf16_tracks_fp32():
     assert np.all(np.isfinite(f)) and np.all(np.isfinite(b))
     assert f[-1] < 0.8 * f[0] and b[-1] < 0.8 * b[0], (f, b)          # same batch every step: the loss must fall
     assert np.max(np.abs(b - f) / f) < 1e-2, (f, b)
+
+
+def test_train_step_bf16_single_timestep_and_many_tiles():
+    """Edge shapes of the tensor-core scans: a one-step time axis (T = 1: no recurrent MMA at all, B*T = 64 keeps the
+    tensor-core path) and a batch whose time-axis tiles exceed one wave of clusters (B = 36 at T = 16)."""
+    _train_compare("bf16", 64, 1, 1e-3, 3e-2)
+    # 82 944 outputs with dropout on: the worst single element (the unbounded linear volume head) of the bf16 path
+    # reaches 2e-3 absolute; the loss stays within 1e-3 relative
+    _train_compare("bf16", 36, 16, 1e-3, 3e-2, tol_prob=4e-3)
 
 
 def test_train_step_bf16_odd_shape_uses_fp32_scans():
