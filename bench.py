@@ -5,7 +5,8 @@
 
 Workload (BASELINE.json configs[2], "DeepJ training, batch 64 synthetic
 sequences, data-parallel with NCCL gradient allreduce"): one step = forward +
-primary_loss + backward + gradient all-reduce + Nadam on 64 synthetic
+primary_loss + backward + gradient exchange + Nadam (one fused kernel over NVLink
+peer memory; DJ_PEER_NADAM=0 = NCCL all-reduce + Nadam kernel) on 64 synthetic
 [128,48,3] windows PER GPU (weak scaling), default constants.py model, dropout
 on, bf16 gate-GEMM operands / fp32 everything else.  A short generation probe
 (configs[1], 1 style-mixed sequence) is reported under "generation".
@@ -181,7 +182,8 @@ def _run_ours(args):
     x, y = dataset.synthetic_all(B, T, seed=1234 + rank)
     host = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in (x[0], x[1], x[2], x[3], y[0])]
     dev = [h.cuda(non_blocking=True) for h in host]
-    allreduce = parallel.allreduce_flat if world > 1 else None
+    # gradient exchange: NCCL all-reduce + Nadam kernel, or (DJ_PEER_NADAM=1) one fused kernel over peer memory
+    allreduce, peer = parallel.make_step_exchange(eng, world)
 
     def barrier():
         if world > 1:
@@ -249,6 +251,11 @@ def _run_ours(args):
     sampler.stop_flag = True
     sampler.join(timeout=2)
     e2e = world * B * K / (ms_e2e * 1e-3)
+    exchange = "NCCL all-reduce of the flat gradient + Nadam kernel"
+    if peer is not None:
+        exchange = "fused reduce-scatter + Nadam + all-gather kernel over peer memory (CUDA IPC)"
+        peer.raise_if_timed_out()
+        peer.close(eng)          # collective: every rank, before the non-zero ranks leave
 
     if rank != 0:
         if world > 1:
@@ -322,6 +329,8 @@ def _run_ours(args):
                     "ms_per_step": ms_e2e / K},
             "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roofline, "cpu_baseline": cpu,
             "generation": gen, "loss": lossv}
+    if world > 1:
+        line["config"]["exchange"] = exchange
     if world > 1:
         dist.destroy_process_group()
     return line

@@ -187,6 +187,32 @@ int dj_nadam_step(float* p, const float* g, float* m, float* v, int64_t n, float
                   float beta1, float beta2, float eps, float mu_t, float mu_t1, float m_sched_new,
                   float m_sched_next, float bias2, void* stream);
 
+/* ---- data-parallel step: gradient exchange fused with Nadam over peer memory ----
+ * The reference trains on one device (train.py:29 model.fit); SURVEY.md 8e adds
+ * data parallelism with one process per GPU.  Instead of an all-reduce followed by
+ * dj_nadam_step, every rank launches ONE kernel that waits for all local gradients,
+ * reduces its 1/world slice of the flat gradient with loads from every rank's
+ * buffer (fixed rank order), applies Nadam to that slice (the moments of a slice
+ * live on its owner only) and stores the new weights into every rank's parameter
+ * buffer, then waits until all ranks are done.
+ *   dj_peer_alloc   cudaMalloc'd, zeroed buffer + its 64-byte CUDA IPC handle
+ *   dj_peer_open    map another rank's buffer (same node, peer access over NVLink)
+ *   dj_peer_flag_words  size, in uint32 words, of the per-rank flag block (zeroed)
+ *   peer_params / peer_grads / peer_flags: host arrays [world] of the ranks' buffers
+ *   in THIS process' address space (entry `rank` is the local one); n floats, n%4==0;
+ *   epoch = 1, 2, 3, ... the same on every rank.  Waits are bounded (20 s): on a
+ *   timeout word [dj_peer_flag_words()-1] of the local flag block is set to 1. */
+int64_t dj_peer_flag_words(void);
+int dj_peer_alloc(int64_t bytes, void** ptr, unsigned char* handle64);
+int dj_peer_open(const unsigned char* handle64, void** ptr);
+int dj_peer_close(void* ptr);
+int dj_peer_free(void* ptr);
+int dj_nadam_allreduce_peer(float* const* peer_params, const float* const* peer_grads,
+                            uint32_t* const* peer_flags, int rank, int world, float* m, float* v,
+                            int64_t n, uint32_t epoch, float gscale, float lr, float beta1, float beta2,
+                            float eps, float mu_t, float mu_t1, float m_sched_new, float m_sched_next,
+                            float bias2, void* stream);
+
 /* ---- generation (generate.py:47-79,98-121) -----------------------------------
  * Persistent note-by-note sampler: for each of `G` sequences walks the 48 notes
  * carrying the note-axis LSTM state, applies the temperature transform, draws

@@ -55,6 +55,13 @@ SIGNATURES = {
     "dj_colsum": (_i, [_p, _i64, _i64, _i, _p, _i, _p]),
     "dj_conv_bwd": (_i, [_p, _i64, _i, _i, _p, _p, Dropout, Dropout, _p, _i64, _p, _p, _p]),
     "dj_nadam_step": (_i, [_p, _p, _p, _p, _i64, _f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _p]),
+    "dj_peer_flag_words": (_i64, []),
+    "dj_peer_alloc": (_i, [_i64, C.POINTER(_p), C.c_char_p]),
+    "dj_peer_open": (_i, [C.c_char_p, C.POINTER(_p)]),
+    "dj_peer_close": (_i, [_p]),
+    "dj_peer_free": (_i, [_p]),
+    "dj_nadam_allreduce_peer": (_i, [C.POINTER(_p), C.POINTER(_p), C.POINTER(_p), _i, _i, _p, _p, _i64, C.c_uint32,
+                                     _f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _p]),
     "dj_gen_sample": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p, _p, _i, _p, _p, _d,
                            _i, _p, _p, _p, _p]),
 }

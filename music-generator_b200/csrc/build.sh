@@ -4,7 +4,7 @@ set -e
 cd "$(dirname "$0")"
 OUT=${DJ_OUT:-../libdeepj_sm100.so}
 BLD=${DJ_BUILD_DIR:-../build}
-SRCS="api.cu frontend.cu gemm_simt.cu gemm_tc.cu lstm_scan.cu lstm_scan_tc.cu head_bwd.cu generate.cu"
+SRCS="api.cu frontend.cu gemm_simt.cu gemm_tc.cu lstm_scan.cu lstm_scan_tc.cu head_bwd.cu generate.cu peer_nadam.cu"
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC --expt-relaxed-constexpr"
 mkdir -p $BLD
 pids=()

@@ -33,6 +33,25 @@ static inline int dj_num_sms() {
   return n;
 }
 
+// ---- keras.optimizers.Nadam.get_updates (model.py:152), one element ------------
+// Shared by dj_nadam_step and dj_nadam_allreduce_peer; the roundings are spelled out so both kernels produce the
+// same bits whatever the compiler would contract.
+#ifdef __CUDACC__
+__device__ __forceinline__ float dj_nadam_one(float p, float gi, float& m, float& v, float lr, float beta1,
+                                              float beta2, float eps, float mu_t, float mu_t1, float inv_1m_ms_new,
+                                              float inv_1m_ms_next, float inv_bias2) {
+  const float g_prime = __fmul_rn(gi, inv_1m_ms_new);
+  const float mt = __fmaf_rn(beta1, m, __fmul_rn(1.f - beta1, gi));
+  const float m_prime = __fmul_rn(mt, inv_1m_ms_next);
+  const float vt = __fmaf_rn(beta2, v, __fmul_rn(__fmul_rn(1.f - beta2, gi), gi));
+  const float v_prime = __fmul_rn(vt, inv_bias2);
+  const float m_bar = __fmaf_rn(mu_t1, m_prime, __fmul_rn(1.f - mu_t, g_prime));
+  m = mt;
+  v = vt;
+  return __fsub_rn(p, __fdiv_rn(__fmul_rn(lr, m_bar), __fadd_rn(__fsqrt_rn(v_prime), eps)));
+}
+#endif
+
 // ---- counter-based dropout masks --------------------------------------------
 // A mask bit is a pure function of (seed, site, element index), so the backward
 // kernels regenerate it instead of reading a stored mask.  Two lowbias32 rounds

@@ -235,16 +235,11 @@ __global__ void __launch_bounds__(256) nadam_kernel(float* __restrict__ p, const
                                                     float mu_t, float mu_t1, float inv_1m_ms_new,
                                                     float inv_1m_ms_next, float inv_bias2) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const float gi = g[i] * gscale;
-    const float g_prime = gi * inv_1m_ms_new;
-    const float mt = beta1 * m[i] + (1.f - beta1) * gi;
-    const float m_prime = mt * inv_1m_ms_next;
-    const float vt = beta2 * v[i] + (1.f - beta2) * gi * gi;
-    const float v_prime = vt * inv_bias2;
-    const float m_bar = (1.f - mu_t) * g_prime + mu_t1 * m_prime;
-    p[i] = p[i] - lr * m_bar / (sqrtf(v_prime) + eps);
-    m[i] = mt;
-    v[i] = vt;
+    float mi = m[i], vi = v[i];
+    p[i] = dj_nadam_one(p[i], __fmul_rn(g[i], gscale), mi, vi, lr, beta1, beta2, eps, mu_t, mu_t1, inv_1m_ms_new,
+                        inv_1m_ms_next, inv_bias2);
+    m[i] = mi;
+    v[i] = vi;
   }
 }
 

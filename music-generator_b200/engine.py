@@ -112,12 +112,24 @@ class Engine:
         self.overlap = os.environ.get("DJ_NO_OVERLAP", "") == ""
         self._hi = None
         self._tag = ""
+        self.peer = None      # parallel.PeerNadam: fused gradient exchange + Nadam over peer memory
 
     # ------------------------------------------------------------------ params
     def _view(self, flat, k):
         shp = self.shapes[k]
         n = int(np.prod(shp))
         return flat[self.offsets[k]:self.offsets[k] + n].view(*shp)
+
+    def rebind_flat(self, flat: torch.Tensor, gflat: torch.Tensor) -> None:
+        """Move the flat parameter / gradient buffers into caller-provided device memory (parallel.PeerNadam puts
+        them into an allocation the other ranks can map); the current weights are carried over."""
+        assert flat.numel() == self.flat_size and gflat.numel() == self.flat_size
+        flat.copy_(self.flat)
+        gflat.zero_()
+        self.flat, self.gflat = flat, gflat
+        self.params = {k: self._view(self.flat, k) for k in self.shapes}
+        self.grads = {k: self._view(self.gflat, k) for k in self.shapes}
+        self._version += 1
 
     # The LSTM tensors live on the device in GATE-INTERLEAVED column order
     # (col = 4*unit + gate) so a cell's four gates are one 16-byte vector; the
@@ -462,25 +474,34 @@ class Engine:
         return ws.loss
 
     # ------------------------------------------------------------- optimizer
-    def nadam_step(self, gscale: float = 1.0):
-        """keras.optimizers.Nadam.get_updates on the flat buffers (model.py:152)."""
+    def _nadam_scalars(self):
+        """Advance the Nadam schedule by one iteration; returns the scalar arguments of the update kernels
+        (lr, beta_1, beta_2, eps, mu_t, mu_t1, m_schedule_new, m_schedule_next, 1-beta_2^t)."""
         o = self.nadam
         t = self.iterations + 1
         mu_t = o["beta_1"] * (1.0 - 0.5 * (0.96 ** (t * o["schedule_decay"])))
         mu_t1 = o["beta_1"] * (1.0 - 0.5 * (0.96 ** ((t + 1) * o["schedule_decay"])))
         ms_new = self.m_schedule * mu_t
         ms_next = self.m_schedule * mu_t * mu_t1
-        self._call("dj_nadam_step", _ptr(self.flat), _ptr(self.gflat), _ptr(self.m), _ptr(self.v), self.flat_size,
-                   gscale, o["lr"], o["beta_1"], o["beta_2"], o["eps"], mu_t, mu_t1, ms_new, ms_next,
-                   1.0 - o["beta_2"] ** t, _stream())
         self.iterations, self.m_schedule = t, ms_new
         self._version += 1
+        return (o["lr"], o["beta_1"], o["beta_2"], o["eps"], mu_t, mu_t1, ms_new, ms_next, 1.0 - o["beta_2"] ** t)
+
+    def nadam_step(self, gscale: float = 1.0):
+        """keras.optimizers.Nadam.get_updates on the flat buffers (model.py:152)."""
+        sc = self._nadam_scalars()
+        self._call("dj_nadam_step", _ptr(self.flat), _ptr(self.gflat), _ptr(self.m), _ptr(self.v), self.flat_size,
+                   gscale, *sc, _stream())
 
     def train_step(self, notes, chosen, beat, style, target, seed: int, allreduce=None, world: int = 1):
-        """One `fit` batch: forward + primary_loss + backward (+ gradient
-        all-reduce) + Nadam.  Returns the device scalar loss (no sync)."""
+        """One `fit` batch: forward + primary_loss + backward + gradient exchange + Nadam.  The exchange is either
+        `allreduce` (NCCL sum of the flat gradient) followed by the Nadam kernel, or -- when a parallel.PeerNadam is
+        attached -- one kernel that does both over peer memory.  Returns the device scalar loss (no sync)."""
         self.forward(notes, chosen, beat, style, target=target, train=True, seed=seed)
         loss = self.backward()
+        if self.peer is not None:
+            self.peer.step(self, self._nadam_scalars(), _stream())
+            return loss
         if allreduce is not None:
             allreduce(self.gflat)
         self.nadam_step(1.0 / world)

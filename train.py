@@ -60,7 +60,7 @@ def train(models, epochs=1000, num_seqs=256):
         idx = parallel.shard_indices(len(train_data[0]), rank, world)
         train_data = [a[idx] for a in train_data]
         train_labels = [a[idx] for a in train_labels]
-        allreduce = parallel.allreduce_flat
+        allreduce, _peer = parallel.make_step_exchange(models[0].engine, world)
     cbs = [ModelCheckpoint(MODEL_FILE), EarlyStopping(patience=5)] if rank == 0 else []
     print('Training')
     models[0].fit(train_data, train_labels, epochs=epochs, callbacks=cbs, batch_size=BATCH_SIZE,
