@@ -15,6 +15,7 @@ BENCH="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-generation"
 $BENCH > gpurun_out/plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -s 160 -c 110 --csv --log-file gpurun_out/launches.csv $BENCH > gpurun_out/ncu_launches.log 2>&1
 echo "ncu launches rc=$?"
+[ -n "$SKIP_FULL" ] && exit 0
 $BENCH > gpurun_out/plain.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:scan_tc_bwd_kernel -s 14 -c 1 -o gpurun_out/prof_scan_tc_bwd_time $BENCH > gpurun_out/ncu_full1.log 2>&1
 echo "ncu bwd rc=$?"
