@@ -77,3 +77,16 @@ def test_reference_arm_prints_one_line_from_rank0_only():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["n_gpus"] == 2
+
+
+def test_step_exchange_selection_without_gpus(monkeypatch):
+    """World 1 needs no exchange; on a host without CUDA a multi-rank job gets the all-reduce (the fused
+    peer-memory kernel is a GPU path and is never substituted by host code)."""
+    sys.path.insert(0, ROOT)
+    import music_generator_b200  # noqa: F401
+    from music_generator_b200 import parallel
+    assert parallel.make_step_exchange(None, 1) == (None, None)
+    if not torch.cuda.is_available():
+        assert parallel.make_step_exchange(None, 2) == (parallel.allreduce_flat, None)
+    monkeypatch.setenv("DJ_PEER_NADAM", "0")
+    assert parallel.make_step_exchange(None, 4) == (parallel.allreduce_flat, None)
