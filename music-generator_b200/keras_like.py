@@ -158,7 +158,14 @@ class TrainModel(_Base):
                 consumed[slot] = torch.cuda.Event()
                 consumed[slot].record(main)
                 step += 1
-            logs = {"loss": float(tot.item()) / max(n, 1)}
+            if world > 1:
+                # every rank must see the same epoch loss, or rank-local callbacks (early stopping) would make the
+                # ranks leave the epoch loop at different times and the next gradient exchange would wait forever
+                from . import parallel
+                tot_n = parallel.sum_over_ranks(torch.stack([tot, torch.full_like(tot, float(n))]))
+                logs = {"loss": float(tot_n[0].item()) / max(float(tot_n[1].item()), 1.0)}
+            else:
+                logs = {"loss": float(tot.item()) / max(n, 1)}
             hist.history["loss"].append(logs["loss"])
             if verbose:
                 print(f"Epoch {ep + 1}/{epochs} - loss: {logs['loss']:.4f}")

@@ -45,6 +45,13 @@ def allreduce_flat(flat: torch.Tensor) -> torch.Tensor:
     return flat
 
 
+def sum_over_ranks(t: torch.Tensor) -> torch.Tensor:
+    """Sum a small tensor over ranks in place (epoch statistics)."""
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t
+
+
 def max_over_ranks(value: float, device) -> float:
     if not (dist.is_initialized() and dist.get_world_size() > 1):
         return value

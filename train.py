@@ -1,7 +1,9 @@
 """Drop-in for the reference's train.py: `python train.py` builds or loads the
 model and calls `models[0].fit(...)` with best-loss checkpointing and early
 stopping (train.py:18-29).  Under torchrun it trains data-parallel: one process
-per GPU, gradients summed with one NCCL all-reduce of the flat buffer."""
+per GPU, each on its shard of the sequences; the gradient exchange and the Nadam
+update are one kernel over NVLink peer memory (parallel.make_step_exchange), the
+epoch loss the callbacks see is the mean over all ranks."""
 import argparse
 import os
 
@@ -55,16 +57,25 @@ def train(models, epochs=1000, num_seqs=256):
         train_data, train_labels = synthetic_all(num_seqs, SEQ_LEN)
     from music_generator_b200 import parallel
     rank, world, _ = parallel.init_distributed()
-    allreduce = None
+    allreduce, peer = None, None
     if world > 1:
-        idx = parallel.shard_indices(len(train_data[0]), rank, world)
+        # equal shards (the remainder of n / world is dropped): every rank must run the same number of steps
+        n = len(train_data[0])
+        idx = parallel.shard_indices(n, rank, world)[:n // world]
         train_data = [a[idx] for a in train_data]
         train_labels = [a[idx] for a in train_labels]
-        allreduce, _peer = parallel.make_step_exchange(models[0].engine, world)
-    cbs = [ModelCheckpoint(MODEL_FILE), EarlyStopping(patience=5)] if rank == 0 else []
+        allreduce, peer = parallel.make_step_exchange(models[0].engine, world)
+    # every rank stops on the same (global) epoch loss; only rank 0 writes the checkpoint
+    cbs = ([ModelCheckpoint(MODEL_FILE)] if rank == 0 else []) + [EarlyStopping(patience=5)]
     print('Training')
     models[0].fit(train_data, train_labels, epochs=epochs, callbacks=cbs, batch_size=BATCH_SIZE,
                   allreduce=allreduce, world=world, verbose=1 if rank == 0 else 0)
+    if peer is not None:
+        peer.raise_if_timed_out()
+        peer.close(models[0].engine)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
 
 
 def main():
@@ -72,6 +83,8 @@ def main():
     ap.add_argument('--epochs', type=int, default=1000)
     ap.add_argument('--num-seqs', type=int, default=256)
     args = ap.parse_args()
+    from music_generator_b200 import parallel
+    parallel.init_distributed()          # under torchrun: selects this rank's GPU before the model is built
     models = build_or_load()
     train(models, args.epochs, args.num_seqs)
 
