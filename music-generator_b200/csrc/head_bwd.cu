@@ -172,23 +172,33 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ X
   }
 }
 
-// conv weight gradient: recompute tanh(conv), form dpre, accumulate x^T.dpre per block
-__global__ void __launch_bounds__(256) conv_bwd_kernel(
+// conv weight gradient: recompute tanh(conv), form dpre, accumulate x^T.dpre per block.
+// Register tiles of 4 output channels keep the shared-memory loads per FMA low (the kernel is FMA work fed from
+// shared memory): a thread is (og = 4 adjacent channels, r = one of 16 groups).
+//   recompute: r = 3 adjacent notes          -> per tap 1 LDS.128 of weights + <= 3 LDS of x for 12 FMAs
+//   x^T.dpre : r = (q: 18 of the 72 taps, ng: 12 of the 48 notes) -> per note 1 LDS.128 of dpre + 18 LDS of x for 72 FMAs
+// The 72 partial sums per thread live in registers over all (b,t) of the block; at the end the four note groups are
+// folded in shared memory so that a block issues one atomic per weight.
+__global__ void __launch_bounds__(256, 2) conv_bwd_kernel(
     const float* __restrict__ notes_in, int64_t notes_bstride, int B, int T, const float* __restrict__ Wc,
     const float* __restrict__ bc, dj_dropout d_notes, dj_dropout d_conv, const float* __restrict__ dA0,
     int64_t ldA, float* __restrict__ dWc, float* __restrict__ dbc) {
-  __shared__ float Wc_s[CK_ * NU_ * OU_];
+  constexpr int KC = CK_ * NU_;          // 72 (tap, channel-in) pairs
+  constexpr int KPT = KC / 4;            // 18 of them per q
+  constexpr int NPT = N_ / 4;            // 12 notes per ng
+  static_assert(OU_ == 64 && N_ == 48 && KC == 72, "conv_bwd_kernel tiling");
+  __shared__ __align__(16) float Wc_s[KC * OU_];     // reused as the fold buffer at the end
   __shared__ float bc_s[OU_];
   __shared__ float xs[(N_ + CK_ - 1) * NU_];
-  __shared__ float dpre[N_][OU_];
-  const int tid = threadIdx.x, BT = B * T, o = tid % OU_, q = tid / OU_;
-  for (int i = tid; i < CK_ * NU_ * OU_; i += 256) Wc_s[i] = Wc[i];
+  __shared__ __align__(16) float dpre[N_][OU_];
+  const int tid = threadIdx.x, BT = B * T;
+  const int og = tid & 15, r = tid >> 4, q = r & 3, ng = r >> 2;
+  for (int i = tid; i < KC * OU_; i += 256) Wc_s[i] = Wc[i];
   if (tid < OU_) bc_s[tid] = bc[tid];
   for (int i = tid; i < (N_ + CK_ - 1) * NU_; i += 256) xs[i] = 0.f;
-  constexpr int KPT = CK_ * NU_ / 4;   // 18 (k,c) pairs per thread
-  float gw[KPT], gb = 0.f;
+  float gw[KPT][4], gb[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-  for (int i = 0; i < KPT; ++i) gw[i] = 0.f;
+  for (int i = 0; i < KPT; ++i) gw[i][0] = gw[i][1] = gw[i][2] = gw[i][3] = 0.f;
   __syncthreads();
   for (int bt = blockIdx.x; bt < BT; bt += gridDim.x) {
     const int b = bt / T, t = bt % T;
@@ -199,34 +209,89 @@ __global__ void __launch_bounds__(256) conv_bwd_kernel(
     }
     __syncthreads();
     {
-      float acc[12];
+      // notes 3r .. 3r+2, channels 4og .. 4og+3; same summation order per output as the forward kernel
+      float acc[3][4];
 #pragma unroll
-      for (int j = 0; j < 12; ++j) acc[j] = bc_s[o];
-      for (int kc = 0; kc < CK_ * NU_; ++kc) {
-        const float w = Wc_s[kc * OU_ + o];
+      for (int j = 0; j < 3; ++j)
 #pragma unroll
-        for (int j = 0; j < 12; ++j) acc[j] = fmaf(xs[(q * 12 + j) * NU_ + kc], w, acc[j]);
+        for (int c = 0; c < 4; ++c) acc[j][c] = bc_s[4 * og + c];
+      const float* xw = xs + 3 * r * NU_;
+      // upstream gradient of these 12 outputs: issued before the FMA loop so the loads are in flight under it
+      float up[3][4];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const int64_t row = (int64_t)bt * N_ + 3 * r + j;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) up[j][c] = dA0[row * ldA + 14 + 4 * og + c];
+      }
+#pragma unroll 8
+      for (int kc = 0; kc < KC; ++kc) {
+        const float4 w = *reinterpret_cast<const float4*>(Wc_s + kc * OU_ + 4 * og);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const float x = xw[j * NU_ + kc];
+          acc[j][0] = fmaf(x, w.x, acc[j][0]);
+          acc[j][1] = fmaf(x, w.y, acc[j][1]);
+          acc[j][2] = fmaf(x, w.z, acc[j][2]);
+          acc[j][3] = fmaf(x, w.w, acc[j][3]);
+        }
       }
 #pragma unroll
-      for (int j = 0; j < 12; ++j) {
-        const int n = q * 12 + j;
+      for (int j = 0; j < 3; ++j) {
+        const int n = 3 * r + j;
         const int64_t row = (int64_t)bt * N_ + n;
-        const float a = tanhf(acc[j]);
-        dpre[n][o] = dA0[row * ldA + 14 + o] * dj_dropmul(d_conv, (uint32_t)(row * OU_ + o)) * (1.f - a * a);
+        float4 d;
+        float* dv = reinterpret_cast<float*>(&d);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int o = 4 * og + c;
+          const float a = tanhf(acc[j][c]);
+          dv[c] = up[j][c] * dj_dropmul(d_conv, (uint32_t)(row * OU_ + o)) * (1.f - a * a);
+        }
+        *reinterpret_cast<float4*>(&dpre[n][4 * og]) = d;
       }
     }
     __syncthreads();
-    for (int n = 0; n < N_; ++n) {
-      const float d = dpre[n][o];
-      if (q == 0) gb += d;
+#pragma unroll 2
+    for (int nn = 0; nn < NPT; ++nn) {
+      const int n = ng * NPT + nn;
+      const float4 d = *reinterpret_cast<const float4*>(&dpre[n][4 * og]);
+      if (q == 0) { gb[0] += d.x; gb[1] += d.y; gb[2] += d.z; gb[3] += d.w; }
+      const float* xr = xs + n * NU_ + q * KPT;
 #pragma unroll
-      for (int i = 0; i < KPT; ++i) gw[i] = fmaf(xs[n * NU_ + q * KPT + i], d, gw[i]);
+      for (int i = 0; i < KPT; ++i) {
+        const float x = xr[i];
+        gw[i][0] = fmaf(x, d.x, gw[i][0]);
+        gw[i][1] = fmaf(x, d.y, gw[i][1]);
+        gw[i][2] = fmaf(x, d.z, gw[i][2]);
+        gw[i][3] = fmaf(x, d.w, gw[i][3]);
+      }
     }
     __syncthreads();
   }
+  // fold the four note groups (one after the other: within a round every (tap, channel) has one owner)
+  float* red = Wc_s;
+  for (int i = tid; i < KC * OU_; i += 256) red[i] = 0.f;
+  if (tid < OU_) bc_s[tid] = 0.f;
+  __syncthreads();
+  for (int g = 0; g < 4; ++g) {
+    if (ng == g) {
 #pragma unroll
-  for (int i = 0; i < KPT; ++i) atomicAdd(dWc + (q * KPT + i) * OU_ + o, gw[i]);
-  if (q == 0) atomicAdd(dbc + o, gb);
+      for (int i = 0; i < KPT; ++i) {
+        float4* p = reinterpret_cast<float4*>(red + (q * KPT + i) * OU_ + 4 * og);
+        float4 v = *p;
+        v.x += gw[i][0]; v.y += gw[i][1]; v.z += gw[i][2]; v.w += gw[i][3];
+        *p = v;
+      }
+      if (q == 0) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) bc_s[4 * og + c] += gb[c];
+      }
+    }
+    __syncthreads();
+  }
+  for (int i = tid; i < KC * OU_; i += 256) atomicAdd(dWc + i, red[i]);
+  if (tid < OU_) atomicAdd(dbc + tid, bc_s[tid]);
 }
 
 __global__ void __launch_bounds__(256) nadam_kernel(float* __restrict__ p, const float* __restrict__ g,
@@ -297,7 +362,7 @@ extern "C" int dj_conv_bwd(const float* notes_in, int64_t notes_bstride, int B, 
                            float* dWc, float* dbc, void* stream) {
   DJ_CHECK_ARG(notes_in && Wc && bc && dA0 && dWc && dbc, "dj_conv_bwd: NULL pointer");
   DJ_CHECK_ARG(B > 0 && T > 0 && ldA >= DJ_FEAT0, "dj_conv_bwd: bad sizes");
-  int grid = dj_num_sms() * 4;   // 31 KB smem, 256 threads: 4 resident blocks hide the per-(b,t) barriers
+  int grid = dj_num_sms() * 2;   // 31 KB smem, 256 threads x <=128 registers: 2 resident blocks overlap the barriers
   if (grid > B * T) grid = B * T;
   conv_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(notes_in, notes_bstride, B, T, Wc, bc, d_notes, d_conv,
                                                           dA0, ldA, dWc, dbc);
