@@ -39,70 +39,105 @@ __global__ void __launch_bounds__(256) head_loss_kernel(
 #pragma unroll
   for (int i = 0; i < V; ++i) g0[i] = g1[i] = g2[i] = 0.f;
 
-  // RB rows per warp iteration: all their loads are issued before any is used (memory-level parallelism)
-  constexpr int RB = 4;
+  // RB rows per warp iteration.  All their loads are issued before any is used; the 3 dot products of the RB rows
+  // are reduced with one butterfly that leaves row r's sums in lane group r (G = 32/RB lanes), so the scalar part
+  // (sigmoids, logs, loss derivatives) is computed G times per row instead of 32 times, and the reduction costs
+  // ~3.4 shuffles per row instead of 15.
+  constexpr int RB = (V <= 4) ? 8 : 4;
+  constexpr int G = 32 / RB;
+  const unsigned FULL = 0xffffffffu;
+  const int grp = lane / G;
   for (int64_t row0 = ((int64_t)blockIdx.x * 8 + warp) * RB; row0 < M; row0 += (int64_t)gridDim.x * 8 * RB) {
-    float4 hv[RB][V / 4];
-    float yv[RB][3];
+    float x[RB][V];
+    const int64_t myrow = row0 + grp;                      // the row whose scalars this lane owns
+    const bool myvalid = myrow < M;
+    float y0 = 0.f, y1 = 0.f, y2 = 0.f;
 #pragma unroll
     for (int rb = 0; rb < RB; ++rb) {
       const int64_t row = (row0 + rb < M) ? row0 + rb : M - 1;
 #pragma unroll
-      for (int i4 = 0; i4 < V; i4 += 4)
-        hv[rb][i4 / 4] = __ldg(reinterpret_cast<const float4*>(h + row * UNITS + lane * V + i4));
-      if (y != nullptr) { yv[rb][0] = __ldg(y + row * 3); yv[rb][1] = __ldg(y + row * 3 + 1); yv[rb][2] = __ldg(y + row * 3 + 2); }
+      for (int i4 = 0; i4 < V; i4 += 4) {
+        const float4 hv = __ldg(reinterpret_cast<const float4*>(h + row * UNITS + lane * V + i4));
+        x[rb][i4] = hv.x; x[rb][i4 + 1] = hv.y; x[rb][i4 + 2] = hv.z; x[rb][i4 + 3] = hv.w;
+      }
     }
+    if (y != nullptr && myvalid) { y0 = __ldg(y + myrow * 3); y1 = __ldg(y + myrow * 3 + 1); y2 = __ldg(y + myrow * 3 + 2); }
+    float s[RB][3];
 #pragma unroll
     for (int rb = 0; rb < RB; ++rb) {
-      const int64_t row = row0 + rb;
-      if (row >= M) break;
-      float x[V];
+      const int64_t row = (row0 + rb < M) ? row0 + rb : M - 1;
 #pragma unroll
       for (int i4 = 0; i4 < V; i4 += 4) {
-        const int u = lane * V + i4;
         float m[4];
-        dj_dropmul4(d_h, (uint32_t)(row * UNITS + u), m);
-        x[i4] = hv[rb][i4 / 4].x * m[0]; x[i4 + 1] = hv[rb][i4 / 4].y * m[1];
-        x[i4 + 2] = hv[rb][i4 / 4].z * m[2]; x[i4 + 3] = hv[rb][i4 / 4].w * m[3];
+        dj_dropmul4(d_h, (uint32_t)(row * UNITS + lane * V + i4), m);
+        x[rb][i4] *= m[0]; x[rb][i4 + 1] *= m[1]; x[rb][i4 + 2] *= m[2]; x[rb][i4 + 3] *= m[3];
       }
       float s0 = 0.f, s1 = 0.f, s2 = 0.f;
 #pragma unroll
       for (int i = 0; i < V; ++i) {
-        s0 = fmaf(x[i], wn0[i], s0); s1 = fmaf(x[i], wn1[i], s1); s2 = fmaf(x[i], wv[i], s2);
+        s0 = fmaf(x[rb][i], wn0[i], s0); s1 = fmaf(x[rb][i], wn1[i], s1); s2 = fmaf(x[rb][i], wv[i], s2);
       }
-      s0 = dj_warp_sum(s0) + b0; s1 = dj_warp_sum(s1) + b1; s2 = dj_warp_sum(s2) + b2;
-      const float p0 = dj_sigmoid(s0), p1 = dj_sigmoid(s1), vol = s2;
-      if (lane == 0) { probs[row * 3] = p0; probs[row * 3 + 1] = p1; probs[row * 3 + 2] = vol; }
-      if (y != nullptr) {
-        const float y0 = yv[rb][0], y1 = yv[rb][1], y2 = yv[rb][2];
+      s[rb][0] = s0; s[rb][1] = s1; s[rb][2] = s2;
+    }
+    // butterfly: each step halves the rows a lane carries (upper lanes keep the upper half)
+#pragma unroll
+    for (int half = RB / 2, off = 16; half >= 1; half >>= 1, off >>= 1) {
+      const bool upper = (lane & off) != 0;
+#pragma unroll
+      for (int j = 0; j < half; ++j)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const float keep = upper ? s[j + half][k] : s[j][k];
+          const float send = upper ? s[j][k] : s[j + half][k];
+          s[j][k] = keep + __shfl_xor_sync(FULL, send, off);
+        }
+    }
+#pragma unroll
+    for (int off = G / 2; off >= 1; off >>= 1)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) s[0][k] += __shfl_xor_sync(FULL, s[0][k], off);
+    // scalars of row `myrow` (identical in the G lanes of the group)
+    const float p0 = dj_sigmoid(s[0][0] + b0), p1 = dj_sigmoid(s[0][1] + b1), vol = s[0][2] + b2;
+    if (myvalid && (lane % G) == 0) { probs[myrow * 3] = p0; probs[myrow * 3 + 1] = p1; probs[myrow * 3 + 2] = vol; }
+    if (y != nullptr) {
+      float da0 = 0.f, da1 = 0.f, da2 = 0.f;
+      if (myvalid) {
         float dl0, dlq;
         const float l0 = bce_term(y0, p0, dl0);
         const float q = y0 * p1 + (1.f - y0) * y1;
         const float l1 = bce_term(y1, q, dlq);
         const float d = y2 - (y0 * vol + (1.f - y0) * y2);
-        const float da0 = dl0 * p0 * (1.f - p0) * inv_M;
-        const float da1 = dlq * y0 * p1 * (1.f - p1) * inv_M;
-        const float da2 = -2.f * d * y0 * inv_M;
-        if (lane == 0) { lsum += l0 + l1 + d * d; gb0 += da0; gb1 += da1; gb2 += da2; }
+        da0 = dl0 * p0 * (1.f - p0) * inv_M;
+        da1 = dlq * y0 * p1 * (1.f - p1) * inv_M;
+        da2 = -2.f * d * y0 * inv_M;
+        if ((lane % G) == 0) { lsum += l0 + l1 + d * d; gb0 += da0; gb1 += da1; gb2 += da2; }
+      }
+#pragma unroll
+      for (int rb = 0; rb < RB; ++rb) {
+        const float a0 = __shfl_sync(FULL, da0, rb * G), a1 = __shfl_sync(FULL, da1, rb * G),
+                    a2 = __shfl_sync(FULL, da2, rb * G);
+        if (row0 + rb >= M) break;                       // warp-uniform; a* of invalid rows are zero anyway
 #pragma unroll
         for (int i = 0; i < V; ++i) {
-          g0[i] = fmaf(x[i], da0, g0[i]); g1[i] = fmaf(x[i], da1, g1[i]); g2[i] = fmaf(x[i], da2, g2[i]);
+          g0[i] = fmaf(x[rb][i], a0, g0[i]); g1[i] = fmaf(x[rb][i], a1, g1[i]); g2[i] = fmaf(x[rb][i], a2, g2[i]);
         }
         if (dX != nullptr) {
 #pragma unroll
           for (int i4 = 0; i4 < V; i4 += 4) {
             float4 o;
-            o.x = da0 * wn0[i4] + da1 * wn1[i4] + da2 * wv[i4];
-            o.y = da0 * wn0[i4 + 1] + da1 * wn1[i4 + 1] + da2 * wv[i4 + 1];
-            o.z = da0 * wn0[i4 + 2] + da1 * wn1[i4 + 2] + da2 * wv[i4 + 2];
-            o.w = da0 * wn0[i4 + 3] + da1 * wn1[i4 + 3] + da2 * wv[i4 + 3];
-            *reinterpret_cast<float4*>(dX + row * UNITS + lane * V + i4) = o;
+            o.x = a0 * wn0[i4] + a1 * wn1[i4] + a2 * wv[i4];
+            o.y = a0 * wn0[i4 + 1] + a1 * wn1[i4 + 1] + a2 * wv[i4 + 1];
+            o.z = a0 * wn0[i4 + 2] + a1 * wn1[i4 + 2] + a2 * wv[i4 + 2];
+            o.w = a0 * wn0[i4 + 3] + a1 * wn1[i4 + 3] + a2 * wv[i4 + 3];
+            *reinterpret_cast<float4*>(dX + (row0 + rb) * UNITS + lane * V + i4) = o;
           }
         }
       }
     }
   }
   if (y == nullptr || partials == nullptr) return;
+  // the loss and bias-gradient terms were accumulated by the leader lane of each row group
+  lsum = dj_warp_sum(lsum); gb0 = dj_warp_sum(gb0); gb1 = dj_warp_sum(gb1); gb2 = dj_warp_sum(gb2);
 #pragma unroll
   for (int i = 0; i < V; ++i) {
     const int u = lane * V + i;
