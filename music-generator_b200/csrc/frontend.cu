@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(256) frontend_fwd_kernel(
     int64_t beat_bstride, int B, int T, const float* __restrict__ Wc, const float* __restrict__ bc,
     const float* __restrict__ sp0, dj_dropout d_notes, dj_dropout d_beat, dj_dropout d_conv,
     dj_dropout d_sp, TA* __restrict__ A0, int ldA) {
-  __shared__ float Wc_s[CK_ * NU_ * OU_];
+  __shared__ __align__(16) float Wc_s[CK_ * NU_ * OU_];
   __shared__ float bc_s[OU_];
   __shared__ float xs[(N_ + CK_ - 1) * NU_];
   __shared__ __align__(16) float tile[N_][F0P_];
@@ -127,21 +127,35 @@ __global__ void __launch_bounds__(256) frontend_fwd_kernel(
       bins_s[n] = s;
     }
     __syncthreads();
-    {  // octave convolution: thread = (out channel, group of 12 notes)
-      const int o = tid % OU_, ng = tid / OU_;
-      float acc[12];
+    {  // octave convolution: thread = (4 adjacent out channels, 3 adjacent notes): per tap one LDS.128 of weights
+       // and three of x feed 12 FMAs; every output sums bias + taps in ascending (k, c) order
+      const int og = tid & 15, r = tid >> 4;
+      float acc[3][4];
 #pragma unroll
-      for (int j = 0; j < 12; ++j) acc[j] = bc_s[o];
+      for (int j = 0; j < 3; ++j)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[j][c] = bc_s[4 * og + c];
+      const float* xw = xs + 3 * r * NU_;
+#pragma unroll 8
       for (int kc = 0; kc < CK_ * NU_; ++kc) {
-        const float w = Wc_s[kc * OU_ + o];
-        const int k = kc / NU_, c = kc % NU_;
+        const float4 w = *reinterpret_cast<const float4*>(Wc_s + kc * OU_ + 4 * og);
 #pragma unroll
-        for (int j = 0; j < 12; ++j) acc[j] = fmaf(xs[(ng * 12 + j + k) * NU_ + c], w, acc[j]);
+        for (int j = 0; j < 3; ++j) {
+          const float x = xw[j * NU_ + kc];
+          acc[j][0] = fmaf(x, w.x, acc[j][0]);
+          acc[j][1] = fmaf(x, w.y, acc[j][1]);
+          acc[j][2] = fmaf(x, w.z, acc[j][2]);
+          acc[j][3] = fmaf(x, w.w, acc[j][3]);
+        }
       }
 #pragma unroll
-      for (int j = 0; j < 12; ++j) {
-        const int n = ng * 12 + j;
-        tile[n][14 + o] = tanhf(acc[j]) * dj_dropmul(d_conv, (uint32_t)(bt * N_ + n) * OU_ + o);
+      for (int j = 0; j < 3; ++j) {
+        const int n = 3 * r + j;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int o = 4 * og + c;
+          tile[n][14 + o] = tanhf(acc[j][c]) * dj_dropmul(d_conv, (uint32_t)(bt * N_ + n) * OU_ + o);
+        }
       }
     }
     for (int i = tid; i < N_ * 32; i += 256) {   // the 30 non-conv features + 2 pad columns
