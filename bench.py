@@ -117,6 +117,16 @@ def cpu_oracle_rate(steps, warmup, B):
     return B * len(times) / sum(times), torch.get_num_threads()
 
 
+def workload_config(scaled: bool, B: int, T: int, world: int) -> dict:
+    """`config` of the JSON line: the same for our arm and for the reference arm."""
+    return {"workload": ("Scaled biaxial LSTM (BASELINE configs[4]): 512/256 units, 512-step windows, "
+                         "synthetic batch per GPU, fwd+loss+bwd+gradient exchange+Nadam, dropout on") if scaled else
+                        ("DeepJ training (BASELINE configs[2]): default constants.py model, "
+                         "batch 64 synthetic sequences per GPU, fwd+loss+bwd+gradient exchange+Nadam, dropout on"),
+            "batch_per_gpu": B, "global_batch": B * world, "seq_len": T, "parallelism": f"dp{world}",
+            "l2": "per-step working set (>5 GB of activations) exceeds the 126 MB L2; no explicit flush"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -129,8 +139,9 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
             "steps": steps, "warmup": warm, "ms_per_step": 1e3 * REF_SAMPLE_B / rate, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "DeepJ training, default constants.py model, synthetic piano-roll batch",
-                       "batch_per_step": REF_SAMPLE_B, "seq_len": 128},
+            # same workload as our arm; every CPU step is a bounded sample of it (REF_SAMPLE_B of the 64 sequences)
+            "config": dict({k: v for k, v in workload_config(False, BATCH, 128, 1).items() if k != "l2"},
+                           sample_sequences_per_step=REF_SAMPLE_B),
             "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -319,12 +330,7 @@ def _run_ours(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16 gate-GEMM operands, f32 accumulate/recurrence", "data": "synthetic",
-            "config": {"workload": ("Scaled biaxial LSTM (BASELINE configs[4]): 512/256 units, 512-step windows, "
-                                    "synthetic batch per GPU, fwd+loss+bwd+allreduce+Nadam, dropout on") if scaled else
-                                   ("DeepJ training (BASELINE configs[2]): default constants.py model, "
-                                    "batch 64 synthetic sequences per GPU, fwd+loss+bwd+allreduce+Nadam, dropout on"),
-                       "batch_per_gpu": B, "global_batch": B * world, "seq_len": T, "parallelism": f"dp{world}",
-                       "l2": "per-step working set (>5 GB of activations) exceeds the 126 MB L2; no explicit flush"},
+            "config": workload_config(scaled, B, T, world),
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / K},
             "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roofline, "cpu_baseline": cpu,
