@@ -33,6 +33,25 @@ static inline int dj_num_sms() {
   return n;
 }
 
+#ifdef __CUDACC__
+// Blackwell packed fp32 FMA (two independent IEEE fp32 FMAs per issue slot, SASS
+// FFMA2): the recurrent h.U product is CUDA-core work (fp32 recurrence, see
+// DESIGN.md) and plain 3-register FFMA issues at half rate on sm_100.
+__device__ __forceinline__ uint64_t pack2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+#endif
+
 // ---- keras.optimizers.Nadam.get_updates (model.py:152), one element ------------
 // Shared by dj_nadam_step and dj_nadam_allreduce_peer; the roundings are spelled out so both kernels produce the
 // same bits whatever the compiler would contract.

@@ -130,23 +130,30 @@ __global__ void __launch_bounds__(256) frontend_fwd_kernel(
     {  // octave convolution: thread = (4 adjacent out channels, 3 adjacent notes): per tap one LDS.128 of weights
        // and three of x feed 12 FMAs; every output sums bias + taps in ascending (k, c) order
       const int og = tid & 15, r = tid >> 4;
-      float acc[3][4];
+      // packed fp32 FMAs (FFMA2): one instruction updates two adjacent channels; each lane is an IEEE fma
+      uint64_t acc2[3][2];
 #pragma unroll
-      for (int j = 0; j < 3; ++j)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) acc[j][c] = bc_s[4 * og + c];
+      for (int j = 0; j < 3; ++j) {
+        acc2[j][0] = pack2(bc_s[4 * og], bc_s[4 * og + 1]);
+        acc2[j][1] = pack2(bc_s[4 * og + 2], bc_s[4 * og + 3]);
+      }
       const float* xw = xs + 3 * r * NU_;
 #pragma unroll 8
       for (int kc = 0; kc < CK_ * NU_; ++kc) {
-        const float4 w = *reinterpret_cast<const float4*>(Wc_s + kc * OU_ + 4 * og);
+        const ulonglong2 w = *reinterpret_cast<const ulonglong2*>(Wc_s + kc * OU_ + 4 * og);
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
           const float x = xw[j * NU_ + kc];
-          acc[j][0] = fmaf(x, w.x, acc[j][0]);
-          acc[j][1] = fmaf(x, w.y, acc[j][1]);
-          acc[j][2] = fmaf(x, w.z, acc[j][2]);
-          acc[j][3] = fmaf(x, w.w, acc[j][3]);
+          const uint64_t xx = pack2(x, x);
+          acc2[j][0] = ffma2(xx, w.x, acc2[j][0]);
+          acc2[j][1] = ffma2(xx, w.y, acc2[j][1]);
         }
+      }
+      float acc[3][4];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        unpack2(acc2[j][0], acc[j][0], acc[j][1]);
+        unpack2(acc2[j][1], acc[j][2], acc[j][3]);
       }
 #pragma unroll
       for (int j = 0; j < 3; ++j) {

@@ -231,9 +231,11 @@ __global__ void __launch_bounds__(256, 2) conv_bwd_kernel(
   for (int i = tid; i < KC * OU_; i += 256) Wc_s[i] = Wc[i];
   if (tid < OU_) bc_s[tid] = bc[tid];
   for (int i = tid; i < (N_ + CK_ - 1) * NU_; i += 256) xs[i] = 0.f;
-  float gw[KPT][4], gb[4] = {0.f, 0.f, 0.f, 0.f};
+  // packed fp32 FMAs (FFMA2): one instruction updates two adjacent channels; each lane is an IEEE fma
+  uint64_t gw2[KPT][2];
+  float gb[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-  for (int i = 0; i < KPT; ++i) gw[i][0] = gw[i][1] = gw[i][2] = gw[i][3] = 0.f;
+  for (int i = 0; i < KPT; ++i) gw2[i][0] = gw2[i][1] = pack2(0.f, 0.f);
   __syncthreads();
   for (int bt = blockIdx.x; bt < BT; bt += gridDim.x) {
     const int b = bt / T, t = bt % T;
@@ -245,11 +247,12 @@ __global__ void __launch_bounds__(256, 2) conv_bwd_kernel(
     __syncthreads();
     {
       // notes 3r .. 3r+2, channels 4og .. 4og+3; same summation order per output as the forward kernel
-      float acc[3][4];
+      uint64_t acc2[3][2];
 #pragma unroll
-      for (int j = 0; j < 3; ++j)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) acc[j][c] = bc_s[4 * og + c];
+      for (int j = 0; j < 3; ++j) {
+        acc2[j][0] = pack2(bc_s[4 * og], bc_s[4 * og + 1]);
+        acc2[j][1] = pack2(bc_s[4 * og + 2], bc_s[4 * og + 3]);
+      }
       const float* xw = xs + 3 * r * NU_;
       // upstream gradient of these 12 outputs: issued before the FMA loop so the loads are in flight under it
       float up[3][4];
@@ -261,15 +264,20 @@ __global__ void __launch_bounds__(256, 2) conv_bwd_kernel(
       }
 #pragma unroll 8
       for (int kc = 0; kc < KC; ++kc) {
-        const float4 w = *reinterpret_cast<const float4*>(Wc_s + kc * OU_ + 4 * og);
+        const ulonglong2 w = *reinterpret_cast<const ulonglong2*>(Wc_s + kc * OU_ + 4 * og);
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
           const float x = xw[j * NU_ + kc];
-          acc[j][0] = fmaf(x, w.x, acc[j][0]);
-          acc[j][1] = fmaf(x, w.y, acc[j][1]);
-          acc[j][2] = fmaf(x, w.z, acc[j][2]);
-          acc[j][3] = fmaf(x, w.w, acc[j][3]);
+          const uint64_t xx = pack2(x, x);
+          acc2[j][0] = ffma2(xx, w.x, acc2[j][0]);
+          acc2[j][1] = ffma2(xx, w.y, acc2[j][1]);
         }
+      }
+      float acc[3][4];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        unpack2(acc2[j][0], acc[j][0], acc[j][1]);
+        unpack2(acc2[j][1], acc[j][2], acc[j][3]);
       }
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
@@ -290,16 +298,19 @@ __global__ void __launch_bounds__(256, 2) conv_bwd_kernel(
 #pragma unroll 2
     for (int nn = 0; nn < NPT; ++nn) {
       const int n = ng * NPT + nn;
-      const float4 d = *reinterpret_cast<const float4*>(&dpre[n][4 * og]);
-      if (q == 0) { gb[0] += d.x; gb[1] += d.y; gb[2] += d.z; gb[3] += d.w; }
+      const ulonglong2 d2 = *reinterpret_cast<const ulonglong2*>(&dpre[n][4 * og]);
+      if (q == 0) {
+        float dx, dy, dz, dw;
+        unpack2(d2.x, dx, dy); unpack2(d2.y, dz, dw);
+        gb[0] += dx; gb[1] += dy; gb[2] += dz; gb[3] += dw;
+      }
       const float* xr = xs + n * NU_ + q * KPT;
 #pragma unroll
       for (int i = 0; i < KPT; ++i) {
         const float x = xr[i];
-        gw[i][0] = fmaf(x, d.x, gw[i][0]);
-        gw[i][1] = fmaf(x, d.y, gw[i][1]);
-        gw[i][2] = fmaf(x, d.z, gw[i][2]);
-        gw[i][3] = fmaf(x, d.w, gw[i][3]);
+        const uint64_t xx = pack2(x, x);
+        gw2[i][0] = ffma2(xx, d2.x, gw2[i][0]);
+        gw2[i][1] = ffma2(xx, d2.y, gw2[i][1]);
       }
     }
     __syncthreads();
@@ -315,7 +326,9 @@ __global__ void __launch_bounds__(256, 2) conv_bwd_kernel(
       for (int i = 0; i < KPT; ++i) {
         float4* p = reinterpret_cast<float4*>(red + (q * KPT + i) * OU_ + 4 * og);
         float4 v = *p;
-        v.x += gw[i][0]; v.y += gw[i][1]; v.z += gw[i][2]; v.w += gw[i][3];
+        float g0, g1, g2, g3;
+        unpack2(gw2[i][0], g0, g1); unpack2(gw2[i][1], g2, g3);
+        v.x += g0; v.y += g1; v.z += g2; v.w += g3;
         *p = v;
       }
       if (q == 0) {
