@@ -39,7 +39,10 @@ def _worker(rank, world, port, out_dir):
     parallel.allreduce_flat(flat)
     flat /= world
     lmax = parallel.max_over_ranks(float(loss), "cpu")
-    torch.save({"flat": flat, "loss": float(loss), "lmax": lmax, "idx": idx}, os.path.join(out_dir, f"r{rank}.pt"))
+    # epoch statistics as TrainModel.fit forms them: [sum of per-sequence losses, sequences] summed over ranks
+    tot_n = parallel.sum_over_ranks(torch.tensor([float(loss) * len(idx), float(len(idx))], dtype=torch.float64))
+    torch.save({"flat": flat, "loss": float(loss), "lmax": lmax, "idx": idx, "epoch_loss": float(tot_n[0] / tot_n[1])},
+               os.path.join(out_dir, f"r{rank}.pt"))
     torch.distributed.destroy_process_group()
 
 
@@ -50,6 +53,9 @@ def test_dp_allreduce_equals_mean_of_shard_gradients(tmp_path):
     assert torch.equal(res[0]["flat"], res[1]["flat"])                      # every rank holds the same average
     assert sorted(np.concatenate([r["idx"] for r in res]).tolist()) == [0, 1, 2, 3]
     assert res[0]["lmax"] == res[1]["lmax"] == max(r["loss"] for r in res)
+    # every rank reports the same epoch loss = the mean over all sequences of all ranks (early stopping stays in step)
+    assert res[0]["epoch_loss"] == res[1]["epoch_loss"]
+    assert abs(res[0]["epoch_loss"] - np.mean([r["loss"] for r in res])) < 1e-12
     # single-process check: average of the two shard gradients (pitch_bins is scoped to the LOCAL batch)
     sys.path.insert(0, ROOT)
     from oracle import deepj_oracle as O
@@ -90,3 +96,16 @@ def test_step_exchange_selection_without_gpus(monkeypatch):
         assert parallel.make_step_exchange(None, 2) == (parallel.allreduce_flat, None)
     monkeypatch.setenv("DJ_PEER_NADAM", "0")
     assert parallel.make_step_exchange(None, 4) == (parallel.allreduce_flat, None)
+
+
+def test_training_shards_are_equal_and_disjoint():
+    """train.py gives every rank n // world sequences (the remainder is dropped) so that all ranks run the same
+    number of steps per epoch."""
+    sys.path.insert(0, ROOT)
+    import music_generator_b200  # noqa: F401
+    from music_generator_b200 import parallel
+    for n, world in ((41, 2), (256, 8), (7, 4), (64, 1)):
+        shards = [parallel.shard_indices(n, r, world)[:n // world] for r in range(world)]
+        assert all(len(s) == n // world for s in shards)
+        allidx = np.concatenate(shards)
+        assert len(set(allidx.tolist())) == len(allidx) and allidx.max(initial=-1) < n
