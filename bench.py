@@ -100,7 +100,7 @@ class ClockSampler(threading.Thread):
 
 def cpu_oracle_rate(steps, warmup, B):
     """Times the CPU oracle's train step (forward + loss + autograd backward +
-    Nadam) on `B` sequences per step; returns (seqs/s, threads)."""
+    Nadam) on `B` sequences per step; returns (seqs/s of the median step, threads)."""
     from oracle import deepj_oracle as O
     cfg = O.Config()
     p = O.init_params(cfg, 0)
@@ -114,7 +114,8 @@ def cpu_oracle_rate(steps, warmup, B):
         p = O.nadam_step(p, grads, st)
         if i >= warmup:
             times.append(time.time() - t0)
-    return B * len(times) / sum(times), torch.get_num_threads()
+    times.sort()
+    return B / times[len(times) // 2], torch.get_num_threads()      # median step
 
 
 def workload_config(scaled: bool, B: int, T: int, world: int) -> dict:
@@ -323,9 +324,9 @@ def _run_ours(args):
     # ---------------- CPU baseline on this box's host cores (bounded sample)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        rate, threads = cpu_oracle_rate(2, 1, REF_SAMPLE_B)
+        rate, threads = cpu_oracle_rate(5, 1, REF_SAMPLE_B)
         cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"2 steps of {REF_SAMPLE_B} sequences after 1 warm-up, fp32 torch-CPU oracle of model.py"}
+               "sample": f"median of 5 steps of {REF_SAMPLE_B} sequences after 1 warm-up, fp32 torch-CPU oracle of model.py"}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
