@@ -50,6 +50,24 @@ def test_version_and_error_convention(lib):
     assert rc < 0
 
 
+def test_peer_exchange_rejects_bad_arguments_before_any_launch(lib):
+    """dj_nadam_allreduce_peer validates on the host: rank / world range, vector width, epoch numbering."""
+    C = ctypes
+    assert lib.dj_peer_flag_words() >= 2 * 16 + 2
+    one = (C.c_void_p * 1)(C.c_void_p(16))
+    sc = [C.c_float(v) for v in (1.0, 0.002, 0.9, 0.999, 1e-8, 0.9, 0.9, 0.5, 0.25, 0.001)]
+
+    def call(rank, world, n, epoch, arr=one):
+        return lib.dj_nadam_allreduce_peer(arr, arr, arr, rank, world, C.c_void_p(16), C.c_void_p(16), n, epoch,
+                                           *sc, None)
+    assert call(0, 17, 64, 1) < 0 and b"at most 16" in lib.dj_last_error()
+    assert call(2, 2, 64, 1) < 0
+    assert call(0, 1, 66, 1) < 0 and b"multiple of 4" in lib.dj_last_error()
+    assert call(0, 1, 64, 0) < 0 and b"epoch" in lib.dj_last_error()
+    assert lib.dj_nadam_allreduce_peer(None, one, one, 0, 1, C.c_void_p(16), C.c_void_p(16), 64, 1, *sc, None) < 0
+    assert lib.dj_peer_open(None, None) < 0 and lib.dj_peer_close(None) < 0 and lib.dj_peer_free(None) < 0
+
+
 def test_dropout_key_matches_numpy_twin(lib):
     from music_generator_b200 import _lib
     import helpers
