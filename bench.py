@@ -1,19 +1,23 @@
 """bench.py -- the driver's measurement contract for the DeepJ hot path.
 
-  python bench.py --gpus N --steps K --warmup W            (our arm; torchrun for N>1)
-  python bench.py --impl reference --gpus N --steps K --warmup W   (CPU reference arm)
+  python bench.py --gpus N --steps K --warmup W                     (our arm; torchrun for N>1)
+  python bench.py --impl reference --gpus N --steps K --warmup W    (CPU reference arm, rank 0 only)
 
-Workload (BASELINE.json configs[2], "DeepJ training, batch 64 synthetic
-sequences, data-parallel with NCCL gradient allreduce"): one step = forward +
-primary_loss + backward + gradient exchange + Nadam (one fused kernel over NVLink
-peer memory; DJ_PEER_NADAM=0 = NCCL all-reduce + Nadam kernel) on 64 synthetic
-[128,48,3] windows PER GPU (weak scaling), default constants.py model, dropout
-on, bf16 gate-GEMM operands / fp32 everything else.  A short generation probe
-(configs[1], 1 style-mixed sequence) is reported under "generation".
+Workloads (`--workload`, BASELINE.json configs):
+  train   (default, configs[2]) one step = forward + primary_loss + backward + gradient exchange + Nadam on 64
+          synthetic [128,48,3] windows PER GPU (`--scaling weak`, default) or 64 in total (`--scaling strong`),
+          default constants.py model, dropout on.  `--batch 16` is configs[0]/[1]'s batch size.
+  scaled  (configs[4]) the same step on the 2x-units / 4x-length model, 16 windows per GPU.
+  gen1    (configs[1]) autoregressive generation of ONE style-mixed sequence, 512 timesteps, reference uniform
+          stream; a "step" is one generated timestep.
+  gen1024 (configs[3]) 128 independent sequences PER GPU (1024 on 8), indexed uniform stream, no collective.
 
-The reference's Keras/TensorFlow path cannot run here (not installable, see
-DESIGN.md); `--impl reference` and `cpu_baseline` time the CPU oracle -- a
-restatement of model.py -- on the host cores.
+The default line also carries a `generation` object (gen1 + a 128-sequence probe + the CPU oracle in the
+reference's literal call structure) so that one driver run reports both halves of BASELINE's metric.
+
+The reference's Keras/TensorFlow path cannot run here (not installable); `--impl reference` and
+`cpu_baseline` time the CPU oracle -- a restatement of model.py / generate.py -- on the host cores
+(`kind: "port"`), with every host thread, whatever OMP_NUM_THREADS torchrun exported.
 """
 import argparse
 import json
@@ -29,9 +33,9 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC, UNIT = "train_seqs_per_sec", "seqs/s"
-BATCH = 64          # per GPU
-REF_SAMPLE_B = 2    # sequences per CPU step (bounded sample of the same workload)
+BATCH = 64          # sequences per GPU (weak scaling) / in total (strong scaling)
+REF_SAMPLE_B = 16   # sequences per CPU step: the reference's own batch size (constants.py:66)
+N_NOTES = 48
 
 
 def peaks():
@@ -40,6 +44,16 @@ def peaks():
         d = json.load(open(p))
         return float(d["hbm_gbs"]), "measured"
     return 6650.0, "fallback"
+
+
+def measured_traffic(kernel_key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full captures summarised under
+    profiles/ (profiles/traffic.json: kernel/shape key -> bytes, with the capture it came from), or None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None, None
+    ent = json.load(open(p)).get(kernel_key)
+    return (ent["dram_bytes_per_launch"], ent["source"]) if ent else (None, None)
 
 
 class ClockSampler(threading.Thread):
@@ -89,6 +103,11 @@ class ClockSampler(threading.Thread):
                 pass
             time.sleep(0.01 if self.nvml is not None else 0.2)
 
+    def finish(self):
+        self.stop_flag = True
+        self.join(timeout=2)
+        return self.summary()
+
     def summary(self):
         if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
@@ -98,11 +117,31 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.rows), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
-def cpu_oracle_rate(steps, warmup, B):
-    """Times the CPU oracle's train step (forward + loss + autograd backward +
-    Nadam) on `B` sequences per step; returns (seqs/s of the median step, threads)."""
+# ----------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle on the host cores
+# ----------------------------------------------------------------------------------------------------------------
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm is one process and takes every core the box has."""
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    torch.set_num_threads(n)
+    return torch.get_num_threads()
+
+
+def oracle_config(scaled):
     from oracle import deepj_oracle as O
-    cfg = O.Config()
+    return O.Config(time_axis_units=512, note_axis_units=256, seq_len=512) if scaled else O.Config()
+
+
+def cpu_train_rate(steps, warmup, B, scaled=False):
+    """CPU oracle train step (forward + loss + autograd backward + Nadam) on `B` sequences per step;
+    returns (seqs/s of the median step, threads)."""
+    from oracle import deepj_oracle as O
+    threads = use_all_host_threads()
+    cfg = oracle_config(scaled)
     p = O.init_params(cfg, 0)
     batch = O.synthetic_batch(cfg, B, cfg.seq_len, 1234)
     masks = O.random_masks(cfg, B, cfg.seq_len, 7)
@@ -115,36 +154,76 @@ def cpu_oracle_rate(steps, warmup, B):
         if i >= warmup:
             times.append(time.time() - t0)
     times.sort()
-    return B / times[len(times) // 2], torch.get_num_threads()      # median step
+    return B / times[len(times) // 2], threads
 
 
-def workload_config(scaled: bool, B: int, T: int, world: int) -> dict:
+def cpu_generation_rate(G, timesteps, warmup=1):
+    """CPU oracle generation in the reference's LITERAL call structure (generate.py:104-121: one full-window
+    time_model.predict and 48 full note_model.predict per timestep) for G sequences; returns (timesteps/s, threads)."""
+    from oracle import deepj_oracle as O
+    threads = use_all_host_threads()
+    cfg = O.Config()
+    p = O.init_params(cfg, 0)
+    styles = [np.mean([np.eye(23)[i] for i in (0, 5, 12)], axis=0)] if G == 1 else \
+        [np.eye(23)[i % 23] for i in range(G)]
+    u = np.random.RandomState(42).random_sample(2 * N_NOTES * (timesteps + warmup) * G)
+    O.generate(p, cfg, styles, warmup, u, mode="literal")
+    t0 = time.time()
+    O.generate(p, cfg, styles, timesteps, u, mode="literal")
+    return G * timesteps / (time.time() - t0), threads
+
+
+def workload_config(args, B, T, world):
     """`config` of the JSON line: the same for our arm and for the reference arm."""
-    return {"workload": ("Scaled biaxial LSTM (BASELINE configs[4]): 512/256 units, 512-step windows, "
-                         "synthetic batch per GPU, fwd+loss+bwd+gradient exchange+Nadam, dropout on") if scaled else
-                        ("DeepJ training (BASELINE configs[2]): default constants.py model, "
-                         "batch 64 synthetic sequences per GPU, fwd+loss+bwd+gradient exchange+Nadam, dropout on"),
-            "batch_per_gpu": B, "global_batch": B * world, "seq_len": T, "parallelism": f"dp{world}",
-            "l2": "per-step working set (>5 GB of activations) exceeds the 126 MB L2; no explicit flush"}
+    names = {
+        "train": "DeepJ training (BASELINE configs[2]): default constants.py model, synthetic sequences, "
+                 "fwd+loss+bwd+gradient exchange+Nadam, dropout on",
+        "scaled": "Scaled biaxial LSTM (BASELINE configs[4]): 512/256 units, 512-step windows, synthetic batch per GPU, "
+                  "fwd+loss+bwd+gradient exchange+Nadam, dropout on",
+        "gen1": "DeepJ generation (BASELINE configs[1]): 1 style-mixed sequence, 512 timesteps, reference uniform stream, "
+                "full 128-step window recompute per timestep",
+        "gen1024": "DeepJ batched generation (BASELINE configs[3]): 128 independent style-conditioned sequences per GPU "
+                   "(1024 on 8), indexed uniform stream, no collective",
+    }
+    cfg = {"workload": names[args.workload], "parallelism": f"dp{world}"}
+    if args.workload in ("train", "scaled"):
+        cfg.update(batch_per_gpu=B, global_batch=B * world, seq_len=T,
+                   l2="per-step working set (>5 GB of activations) exceeds the 126 MB L2; no explicit flush")
+    else:
+        cfg.update(sequences_per_gpu=B, sequences=B * world, window=128,
+                   l2="every timestep rewrites the 100+ MB window activations per 32 sequences; no explicit flush")
+    return cfg
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    world = args.gpus
     warm = min(args.warmup, 1)
-    steps = max(1, min(args.steps, 6))       # each CPU step is seconds; keep the arm within minutes
-    rate, threads = cpu_oracle_rate(steps, warm, REF_SAMPLE_B)
-    sample = (f"{steps} CPU steps of {REF_SAMPLE_B} sequences (forward+loss+backward+Nadam, fp32 torch-CPU oracle; "
-              f"Keras/TF reference not installable)")
-    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": steps, "warmup": warm, "ms_per_step": 1e3 * REF_SAMPLE_B / rate, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            # same workload as our arm; every CPU step is a bounded sample of it (REF_SAMPLE_B of the 64 sequences)
-            "config": dict({k: v for k, v in workload_config(False, BATCH, 128, 1).items() if k != "l2"},
-                           sample_sequences_per_step=REF_SAMPLE_B),
-            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
-            "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if args.workload in ("train", "scaled"):
+        scaled = args.workload == "scaled"
+        sample_b = 2 if scaled else REF_SAMPLE_B
+        steps = max(1, min(args.steps, 3 if scaled else 5))     # each CPU step is seconds; keep the arm within minutes
+        rate, threads = cpu_train_rate(steps, warm, sample_b, scaled)
+        B, T = (16, 512) if scaled else (BATCH if args.scaling == "weak" else BATCH // world, 128)
+        metric, unit, ms = "train_seqs_per_sec", "seqs/s", 1e3 * sample_b / rate
+        sample = (f"median of {steps} CPU steps of {sample_b} sequences each (forward+loss+autograd backward+Nadam, fp32 "
+                  f"torch-CPU oracle of model.py; Keras/TF reference not installable), {threads} threads")
+    else:
+        G = 1 if args.workload == "gen1" else 4
+        steps = max(2, min(args.steps, 8))
+        rate, threads = cpu_generation_rate(G, steps)
+        B, T = (1 if args.workload == "gen1" else 128), 128
+        metric, unit, ms = "generated_timesteps_per_sec", "timesteps/s", 1e3 * G / rate
+        sample = (f"{steps} timesteps of {G} sequence(s), fp32 torch-CPU oracle in the reference's literal call structure "
+                  f"(1 time_model.predict + 48 note_model.predict per timestep, generate.py:104-121), {threads} threads")
+    line = {"impl": "reference", "metric": metric, "value": rate, "unit": unit, "n_gpus": args.gpus,
+            "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, B, T, world),
+            "cpu_baseline": {"value": rate, "unit": unit, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": rate, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
@@ -166,44 +245,81 @@ class StdoutToStderr:
 
 def run_ours(args):
     with StdoutToStderr():
-        line = _run_ours(args)
+        line = _run_train(args) if args.workload in ("train", "scaled") else _run_generation(args)
     if line is not None:
         print(json.dumps(line), flush=True)
 
 
-def _run_ours(args):
+def _dist_helpers(world):
     import torch.distributed as dist
-    import music_generator_b200  # noqa: F401
-    from music_generator_b200.config import ModelConfig
-    from music_generator_b200.engine import Engine
-    from music_generator_b200.sampler import generate_events
-    import dataset
-
     from music_generator_b200 import parallel
-    rank, world, local = parallel.env_world()
-    torch.cuda.set_device(local)
-    parallel.init_distributed("nccl")
-    B, K, W = args.batch, args.steps, max(args.warmup, 3)
-    scaled = args.workload == "scaled"
-    T = 512 if scaled else 128
-    mcfg = ModelConfig(time_axis_units=512, note_axis_units=256, seq_len=512) if scaled else ModelConfig()
-    if scaled and args.batch == BATCH:
-        B = 16                                   # BASELINE configs[4]: 2x hidden units, 4x sequence length, B=16/GPU
-    eng = Engine(mcfg, precision="bf16")
-    eng.init_params(0)
-    x, y = dataset.synthetic_all(B, T, seed=1234 + rank)
-    host = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in (x[0], x[1], x[2], x[3], y[0])]
-    dev = [h.cuda(non_blocking=True) for h in host]
-    # gradient exchange: NCCL all-reduce + Nadam kernel, or (DJ_PEER_NADAM=1) one fused kernel over peer memory
-    allreduce, peer = parallel.make_step_exchange(eng, world)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def max_over_ranks(ms):
-        return parallel.max_over_ranks(ms, "cuda")
+    def over_ranks(ms):
+        """(max, min, all) of a per-rank device time."""
+        if world <= 1:
+            return ms, ms, [ms]
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        out = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        v = [float(x.item()) for x in out]
+        return max(v), min(v), v
+    return barrier, over_ranks, parallel
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# algorithmic HBM bytes of one training step in the layout the kernels actually use (DESIGN.md section 3)
+# ----------------------------------------------------------------------------------------------------------------
+def step_algorithmic_bytes(mcfg, B, T, mixed):
+    """Per LSTM layer and activation row (K = padded input width, U units, Up = units of the layer below):
+      forward   producer reads h_below 4Up, writes A (bf16 hi [+ lo]) 2K [4K]; gate GEMM reads it back 2K [4K], writes
+                Z fp32 16U; scan reads Z 16U, writes gates 16U + h 4U + c 4U + 16-bit h_{t-1} 2U
+      backward  scan reads gates 16U + c 4U + dY 4U, writes bf16 dZ 8U; data-gradient GEMM reads dZ 8U, writes dA fp32 4K;
+                weight-gradient GEMMs read A_hi 2K + dZ 8U and h_{t-1} 2U + dZ 8U; style reduction reads dA 4K
+      = (14K [18K]) + 116U + 4Up bytes per row; heads add 4U read + 4U dX written + 24 B; rows = B*T*48."""
+    rows = B * T * N_NOTES
+    total = 0
+    up = 0
+    for L in mcfg.layers():
+        K = (L["F"] + 31) // 32 * 32
+        U = L["U"]
+        total += (18 if mixed else 14) * K + 116 * U + 4 * up
+        up = U
+    total += 8 * mcfg.note_axis_units + 24
+    return total * rows
+
+
+def _run_train(args):
+    import torch.distributed as dist
+    import music_generator_b200  # noqa: F401
+    from music_generator_b200.config import ModelConfig
+    from music_generator_b200.engine import Engine
+    import dataset
+
+    from music_generator_b200 import parallel
+    rank, world, local = parallel.env_world()
+    torch.cuda.set_device(local)
+    parallel.init_distributed("nccl")
+    barrier, over_ranks, _ = _dist_helpers(world)
+    K, W = args.steps, max(args.warmup, 3)
+    scaled = args.workload == "scaled"
+    T = 512 if scaled else 128
+    mcfg = ModelConfig(time_axis_units=512, note_axis_units=256, seq_len=512) if scaled else ModelConfig()
+    B = args.batch if args.batch else (16 if scaled else BATCH)
+    if args.scaling == "strong":
+        assert B % world == 0, "strong scaling splits the global batch evenly"
+        B //= world
+    eng = Engine(mcfg, precision=args.precision)
+    eng.init_params(0)
+    x, y = dataset.synthetic_all(B, T, seed=1234 + rank)
+    host = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in (x[0], x[1], x[2], x[3], y[0])]
+    dev = [h.cuda(non_blocking=True) for h in host]
+    # gradient exchange: one fused kernel over peer memory, or (DJ_PEER_NADAM=0) NCCL all-reduce + Nadam kernel
+    allreduce, peer = parallel.make_step_exchange(eng, world)
 
     # ---------------- device-resident arm (value)
     for i in range(W):
@@ -220,7 +336,7 @@ def _run_ours(args):
         loss = eng.train_step(*dev, seed=100 + i, allreduce=allreduce, world=world)
     e1.record()
     barrier()
-    ms = max_over_ranks(e0.elapsed_time(e1))
+    ms, ms_min, ms_all = over_ranks(e0.elapsed_time(e1))
     launches = eng.launches - launches0
     dom = eng.profile_summary().get(DOM, [0, 0.0])
     eng.profile, eng.profile_only = None, None
@@ -259,10 +375,25 @@ def _run_ours(args):
     lossv = e2e_steps(K, 200)
     e1.record()
     barrier()
-    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
-    sampler.stop_flag = True
-    sampler.join(timeout=2)
+    ms_e2e, _, _ = over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.finish()
     e2e = world * B * K / (ms_e2e * 1e-3)
+
+    # ---------------- per-entry-point device times of 3 more steps (events around every launch: the two backward
+    # streams are serialised here, so these are kernel times, not the step's critical path)
+    kernels = None
+    if rank == 0 and not args.no_kernel_table:
+        eng.profile, eng.profile_only = [], None
+    if not args.no_kernel_table:
+        for i in range(3):
+            eng.train_step(*dev, seed=300 + i, allreduce=allreduce, world=world)
+        barrier()
+    if rank == 0 and not args.no_kernel_table:
+        agg = eng.profile_summary()
+        eng.profile = None
+        kernels = {k: {"launches_per_step": v[0] / 3, "ms_per_step": round(v[1] / 3, 4)}
+                   for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:14]}
+
     exchange = "NCCL all-reduce of the flat gradient + Nadam kernel"
     if peer is not None:
         exchange = "fused reduce-scatter + Nadam + all-gather kernel over peer memory (CUDA IPC)"
@@ -274,70 +405,204 @@ def _run_ours(args):
             dist.destroy_process_group()
         return None
 
-    # ---------------- roofline of the dominant kernel (time-axis reverse scan, layer 1)
-    # algorithmic bytes per row: gates 16U + c 4U + dY 4U read, dZ(bf16) 8U written, U=256
-    U, M = mcfg.time_axis_units, B * T * 48
+    # ---------------- roofline of the dominant kernel (time-axis reverse scan, layer 1) and of the whole step
+    # algorithmic bytes per row of that kernel: gates 16U + c 4U + dY 4U read, dZ (bf16) 8U written
+    U, M = mcfg.time_axis_units, B * T * N_NOTES
     alg_bytes = 32 * U * M
     peak, how = peaks()
     dom_ms = dom[1] / max(dom[0], 1)
     achieved = alg_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else None
-    kname = "scan_tc_bwd_kernel<512,16,32,time>" if scaled else "scan_tc_bwd_kernel<256,48,64,time>"
+    kname = f"scan_tc_bwd_kernel<{U},time> B={B} T={T}"
+    traffic, traffic_src = measured_traffic(kname)
     roofline = {"kernel": kname + " (dj_lstm_scan_tc_bwd, time-axis layer 1 reverse scan)", "bound": "hbm",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape from the ncu --set full
-                # capture summarised in profiles/r01_scan_tc_bwd_time.md (2.418 GB + 0.786 GB per launch)
-                "traffic": 3.204e9 if (B == 64 and not scaled) else None, "peak_source": how, "avg_launch_ms": dom_ms, "launches_timed": dom[0],
-                "algorithmic_bytes_per_launch": alg_bytes,
-                "note": "sequential recurrence: bound by the per-step publish/TMA/MMA latency chain, not by HBM; timed inside the "
-                        "step, where it shares the GPU with the weight-gradient GEMMs of the second stream (alone: 0.87 ms), "
-                        "see DESIGN.md section 4"}
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": how, "avg_launch_ms": dom_ms,
+                "launches_timed": dom[0], "algorithmic_bytes_per_launch": alg_bytes,
+                "note": "sequential recurrence: bound by the per-step publish/TMA/MMA latency chain, not by HBM; timed "
+                        "inside the step, where it shares the GPU with the weight-gradient GEMMs of the second stream"}
+    step_bytes = step_algorithmic_bytes(mcfg, B, T, args.precision == "mixed")
+    step_roofline = {"bound": "hbm", "algorithmic_bytes_per_step": step_bytes,
+                     "achieved": step_bytes / (ms / K * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": step_bytes / (ms / K * 1e-3) / 1e9 / peak,
+                     "formula": "(18K|14K)+116U+4Up bytes per row and LSTM layer (mixed|bf16), see step_algorithmic_bytes"}
 
-    # ---------------- generation probe (configs[1])
+    # ---------------- generation (configs[1], and one GPU's share of configs[3])
     gen = None
-    if not args.no_generation and not scaled:
-        ge = Engine(ModelConfig(), precision="fp32")
-        ge.init_params(0)
-        sty = np.mean([np.eye(23)[i] for i in (0, 5, 12)], axis=0)
-        gsteps = 32
-        u = np.random.RandomState(42).random_sample(2 * 48 * gsteps)
-        generate_events(ge, [sty], 4, u)
-        torch.cuda.synchronize()
-        rates = []
-        for _ in range(3):                       # the one-sequence loop is launch-heavy: median of three runs
-            t0 = time.time()
-            generate_events(ge, [sty], gsteps, u)
-            torch.cuda.synchronize()
-            rates.append(gsteps / (time.time() - t0))
-        gen = {"timesteps_per_s": sorted(rates)[1], "sequences": 1, "timesteps": gsteps, "runs": [round(r, 1) for r in rates],
-               "workload": "generate.py path, 1 style-mixed sequence, full 128-step window recompute per timestep"}
-        # configs[3] per-GPU share: 128 independent sequences (4 predict-chunks of 32), indexed uniform stream
-        Gb, bsteps = 128, 4
-        stys = [np.eye(23)[i % 23] for i in range(Gb)]
-        ub = np.random.RandomState(7).random_sample((bsteps, Gb, 48, 2))
-        generate_events(ge, stys, 1, ub[:1], stream_mode=1)
-        torch.cuda.synchronize()
-        t0 = time.time()
-        generate_events(ge, stys, bsteps, ub, stream_mode=1)
-        torch.cuda.synchronize()
-        gen["batched"] = {"sequences": Gb, "timesteps": bsteps, "timesteps_per_s": Gb * bsteps / (time.time() - t0)}
+    if not args.no_generation and not scaled and world == 1:
+        gen = generation_probe(args)
 
     # ---------------- CPU baseline on this box's host cores (bounded sample)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        rate, threads = cpu_oracle_rate(5, 1, REF_SAMPLE_B)
-        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"median of 5 steps of {REF_SAMPLE_B} sequences after 1 warm-up, fp32 torch-CPU oracle of model.py"}
+        sb = 2 if scaled else REF_SAMPLE_B
+        rate, threads = cpu_train_rate(3, 1, sb, scaled)
+        cpu = {"value": rate, "unit": "seqs/s", "cores": threads, "kind": "port",
+               "sample": f"median of 3 steps of {sb} sequences after 1 warm-up, fp32 torch-CPU oracle of model.py "
+                         f"(forward+loss+autograd backward+Nadam), {threads} threads"}
 
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16 gate-GEMM operands, f32 accumulate/recurrence", "data": "synthetic",
-            "config": workload_config(scaled, B, T, world),
-            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+    dtype = {"mixed": "bf16 hi+lo split gate-GEMM operands (fp32-grade product), f16 h / f16 hi+lo U in the recurrence, "
+                      "bf16 dZ in backward; f32 accumulate, state and activations",
+             "bf16": "bf16 operands in the gate GEMMs AND the recurrence, f32 accumulate/state (fast mode, outside the 1e-3 "
+                     "output tolerance)",
+             "fp32": "f32"}[args.precision]
+    line = {"metric": "train_seqs_per_sec", "value": value, "unit": "seqs/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+            "dtype": dtype, "precision": args.precision, "data": "synthetic",
+            "config": workload_config(args, B, T, world),
+            "e2e": {"value": e2e, "unit": "seqs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / K},
-            "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roofline, "cpu_baseline": cpu,
-            "generation": gen, "loss": lossv}
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "step_roofline": step_roofline,
+            "rank_ms_per_step": {"max": ms / K, "min": ms_min / K, "all": [round(v / K, 4) for v in ms_all]},
+            "kernels": kernels, "cpu_baseline": cpu, "generation": gen, "loss": lossv}
     if world > 1:
         line["config"]["exchange"] = exchange
+        dist.destroy_process_group()
+    return line
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# generation workloads
+# ----------------------------------------------------------------------------------------------------------------
+def _gen_styles(G, seed=0):
+    """the three genre mixtures (dataset.compute_genre) cycled with random 3-composer mixtures."""
+    import dataset
+    rs = np.random.RandomState(seed)
+    out = []
+    for g in range(G):
+        if g % 2 == 0:
+            out.append(np.asarray(dataset.compute_genre((g // 2) % 3), dtype=np.float64))
+        else:
+            out.append(np.mean([np.eye(23)[i] for i in rs.choice(23, 3, replace=False)], axis=0))
+    return out
+
+
+def _timed_generation(eng, styles, steps, warmup, u, stream_mode):
+    """Device time of `steps` generated timesteps after `warmup` untimed ones (state carried over), CUDA events."""
+    from music_generator_b200.sampler import GenerationRun
+    run = GenerationRun(eng, styles, warmup + steps, u, stream_mode)
+    for t in range(warmup):
+        run.step(t)
+    torch.cuda.synchronize()
+    l0 = eng.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for t in range(warmup, warmup + steps):
+        run.step(t)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1), eng.launches - l0, run
+
+
+def generation_probe(args):
+    """configs[1] (one sequence, 512 timesteps) and one GPU's share of configs[3] (128 sequences), with the CPU oracle's
+    literal loop beside them and a lock-step bit-exactness check of the first timesteps."""
+    from music_generator_b200.config import ModelConfig
+    from music_generator_b200.engine import Engine
+    from music_generator_b200.sampler import generate_events
+    from oracle import deepj_oracle as O
+    ge = Engine(ModelConfig(), precision="fp32")
+    ge.init_params(0)
+    sty = np.mean([np.eye(23)[i] for i in (0, 5, 12)], axis=0)
+    gsteps, check = 512, 16
+    u = np.random.RandomState(42).random_sample(2 * N_NOTES * (gsteps + 4))
+    rates = []
+    for _ in range(3):                       # the one-sequence loop is launch-heavy: median of three runs
+        ms, launches, run = _timed_generation(ge, [sty], gsteps, 4, u, 0)
+        rates.append(gsteps / (ms * 1e-3))
+    # bit-exactness: the oracle replays the first `check` timesteps in lock-step on the device's events
+    ev, info = generate_events(ge, [sty], check, u, stream_mode=0)
+    p32 = {k: torch.tensor(v) for k, v in ge.get_params().items()}
+    _, oinfo = O.generate(p32, O.Config(), [sty], check, u, mode="incremental", forced_events=ev, return_probs=True)
+    exact = bool(np.array_equal(oinfo["decisions"][..., :2], ev[..., :2]) and info["uniforms_used"] == oinfo["uniforms_used"])
+    gen = {"timesteps_per_s": sorted(rates)[1], "sequences": 1, "timesteps": gsteps, "runs": [round(r, 1) for r in rates],
+           "gpu_launches_per_timestep": launches / gsteps,
+           "events_equal_oracle": exact, "events_checked_timesteps": check,
+           "max_prob_err_vs_oracle": float(np.abs(info["probs"] - oinfo["probs"]).max()),
+           "workload": "generate.py path, 1 style-mixed sequence, 32 bars, full 128-step window recompute per timestep"}
+    Gb, bsteps = 128, 6
+    ub = np.random.RandomState(7).random_sample((bsteps + 2, Gb, N_NOTES, 2))
+    ms, launches, _ = _timed_generation(ge, _gen_styles(Gb), bsteps, 2, ub, 1)
+    gen["batched"] = {"sequences": Gb, "timesteps": bsteps, "timesteps_per_s": Gb * bsteps / (ms * 1e-3),
+                      "gpu_launches_per_timestep": launches / bsteps}
+    if not args.no_cpu_baseline:
+        rate, threads = cpu_generation_rate(1, 6)
+        gen["cpu_baseline"] = {"value": rate, "unit": "timesteps/s", "cores": threads, "kind": "port",
+                               "sample": "6 timesteps of 1 sequence after 1 warm-up, fp32 torch-CPU oracle in the reference's "
+                                         "literal call structure (49 predicts per timestep, generate.py:104-121)"}
+    return gen
+
+
+def _run_generation(args):
+    import torch.distributed as dist
+    import music_generator_b200  # noqa: F401
+    from music_generator_b200.config import ModelConfig
+    from music_generator_b200.engine import Engine
+    from music_generator_b200.sampler import generate_events
+    from music_generator_b200 import parallel
+    rank, world, local = parallel.env_world()
+    torch.cuda.set_device(local)
+    parallel.init_distributed("nccl")        # only for the barrier and the max over ranks: generation has no collective
+    barrier, over_ranks, _ = _dist_helpers(world)
+    single = args.workload == "gen1"
+    K = args.steps if args.steps_given else (512 if single else 16)
+    W = max(args.warmup, 3)
+    G = 1 if single else 128
+    eng = Engine(ModelConfig(), precision="fp32")
+    eng.init_params(0)
+    if single:
+        styles = [np.mean([np.eye(23)[i] for i in (0, 5, 12)], axis=0)]
+        u = np.random.RandomState(42).random_sample(2 * N_NOTES * (K + W))
+        mode = 0
+    else:
+        # every rank draws the WHOLE batch's indexed stream and keeps its own sequences (what generate_batch does)
+        styles = _gen_styles(G * world)[rank * G:(rank + 1) * G]
+        u = np.random.RandomState(7).random_sample((K + W, G * world, N_NOTES, 2))[:, rank * G:(rank + 1) * G]
+        u = np.ascontiguousarray(u)
+        mode = 1
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms_local, launches, run = _timed_generation(eng, styles, K, W, u, mode)
+    barrier()
+    ms, ms_min, ms_all = over_ranks(ms_local)
+    value = world * G * K / (ms * 1e-3)
+    # ---- end to end through the public call: numpy styles + uniforms in, numpy events out (H2D / D2H inside)
+    generate_events(eng, styles, 2, u[:2] if mode == 1 else u, stream_mode=mode)
+    barrier()
+    t0 = time.time()
+    ev, _ = generate_events(eng, styles, K, u[:K] if mode == 1 else u, stream_mode=mode)
+    torch.cuda.synchronize()
+    ms_e2e, _, _ = over_ranks((time.time() - t0) * 1e3)
+    clocks = sampler.finish()
+    e2e = world * G * K / (ms_e2e * 1e-3)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return None
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        Gc = 1 if single else 4
+        rate, threads = cpu_generation_rate(Gc, 6)
+        cpu = {"value": rate, "unit": "timesteps/s", "cores": threads, "kind": "port",
+               "sample": f"6 timesteps of {Gc} sequence(s) after 1 warm-up, fp32 torch-CPU oracle in the reference's literal "
+                         f"call structure (generate.py:104-121), {threads} threads"}
+    # algorithmic work of one timestep of one sequence (SURVEY 8d): 10.93 GFLOP, sequential depth 256 + 96 LSTM steps
+    flops = 10.93e9 * G * K / (ms * 1e-3)
+    line = {"metric": "generated_timesteps_per_sec", "value": value, "unit": "timesteps/s", "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic (random-init weights, seeded uniform stream)",
+            "config": workload_config(args, G, 128, world),
+            "e2e": {"value": e2e, "unit": "timesteps/s", "h2d_bytes_per_step": int(u.nbytes // max(K + W, 1)) if mode == 1 else 16 * N_NOTES,
+                    "d2h_bytes_per_step": G * N_NOTES * 3 * 4, "ms_per_step": ms_e2e / K},
+            "gpu_launches": launches, "clocks": clocks,
+            "roofline": {"kernel": "time-axis window recompute (2 LSTM layers x 128 steps per generated timestep)",
+                         "bound": "tensor" if eng.gen_tc else "fma", "achieved": flops / 1e12, "unit": "TFLOP/s",
+                         "peak": 74.4, "frac": flops / 1e12 / 74.4, "traffic": None,
+                         "note": "peak = fp32 FMA rate of the CUDA cores (148 SMs x 128 lanes x 2 x 1.965 GHz): the sampled "
+                                 "events must be bit-exact against the fp32 model, so the path computes at fp32 grade; "
+                                 "at 1 sequence the path is a latency chain of 352 dependent LSTM steps per timestep"},
+            "rank_ms_per_step": {"max": ms / K, "min": ms_min / K, "all": [round(v / K, 4) for v in ms_all]},
+            "cpu_baseline": cpu, "played_notes": int(ev[..., 0].sum())}
     if world > 1:
         dist.destroy_process_group()
     return line
@@ -346,14 +611,22 @@ def _run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=BATCH)
-    ap.add_argument("--workload", default="default", choices=["default", "scaled"])
+    ap.add_argument("--batch", type=int, default=0, help="sequences per GPU (default 64; 16 for the scaled model)")
+    ap.add_argument("--workload", default="train", choices=["train", "default", "scaled", "gen1", "gen1024"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--precision", default="mixed", choices=["mixed", "bf16"])
     ap.add_argument("--no-generation", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-kernel-table", action="store_true")
     args = ap.parse_args()
+    if args.workload == "default":
+        args.workload = "train"
+    args.steps_given = args.steps is not None
+    if args.steps is None:
+        args.steps = 10
     if args.impl == "reference":
         run_reference(args)
     else:

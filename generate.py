@@ -43,22 +43,34 @@ def generate(models, num_bars, styles, uniforms=None, default_temp=1):
 def generate_batch(models, num_bars, styles, seed=0, default_temp=1):
     """Many independent style-conditioned sequences (BASELINE configs[3]): every (timestep, sequence,
     note) owns its two uniforms U[t,g,n,:] -- drawn from RandomState(seed) for the WHOLE batch -- so the
-    result does not depend on how the sequences are sharded.  Under torchrun each rank generates the
-    sequences rank, rank+world, ... (multiples of the 32-sequence predict chunk keep the pitch-bins scope
-    of a single-GPU run); no collective is involved.  Returns (indices, events[steps, len(indices), 48, 3])."""
+    result does not depend on how the sequences are sharded.  Under torchrun rank r generates the 32-sequence
+    predict chunks r, r+world, ... (whole chunks keep the pitch-bins scope of a single-GPU run, model.py:43-49);
+    no collective is involved.  Returns (indices, events[steps, len(indices), 48, 3])."""
     from music_generator_b200 import parallel
     rank, world, local = parallel.env_world()
     eng = models[1].engine
     steps = NOTES_PER_BAR * num_bars
     G = len(styles)
     u = np.random.RandomState(seed).random_sample((steps, G, NUM_NOTES, 2))
-    chunk = 32
-    mine = [g for g in range(G) if (g // chunk) % world == rank]
+    mine = parallel.shard_sequence_chunks(G, rank, world)
     if not mine:
         return mine, np.zeros((steps, 0, NUM_NOTES, NOTE_UNITS), dtype=np.float32)
     events, _ = generate_events(eng, [styles[g] for g in mine], steps, np.ascontiguousarray(u[:, mine]),
                                 stream_mode=1, default_temp=default_temp)
     return mine, events
+
+
+def batch_styles(G, seed=0):
+    """Styles of a batched run: the three genre mixtures of dataset.compute_genre cycled with random 3-composer
+    mixtures."""
+    rs = np.random.RandomState(seed)
+    out = []
+    for g in range(G):
+        if g % 2 == 0:
+            out.append(compute_genre((g // 2) % len(genre)))
+        else:
+            out.append(np.mean([one_hot(i, NUM_STYLES) for i in rs.choice(NUM_STYLES, 3, replace=False)], axis=0))
+    return out
 
 
 def write_file(name, results):
@@ -78,12 +90,28 @@ def main():
     parser.add_argument('--styles', default=None, type=int, nargs='+', help='Styles to mix together')
     parser.add_argument('--batch', default=0, type=int,
                         help='Generate this many independent sequences (sharded over ranks under torchrun)')
+    parser.add_argument('--seed', default=0, type=int, help='Seed of the indexed uniform stream of --batch')
     args = parser.parse_args()
     if args.batch:
+        # BASELINE configs[3]: N independent style-conditioned sequences; under torchrun every rank generates its
+        # own share (whole 32-sequence predict chunks, no collective) and writes its own, globally numbered files
         import torch
         from music_generator_b200 import parallel
-        torch.cuda.set_device(parallel.env_world()[2])
+        rank, world, local = parallel.env_world()
+        torch.cuda.set_device(local)
+        models = build_or_load()
+        styles = batch_styles(args.batch, args.seed)
+        mine, events = generate_batch(models, args.bars, styles, seed=args.seed)
+        for j, g in enumerate(mine):
+            fpath = os.path.join(SAMPLES_DIR, 'batch_' + str(g) + '.mid')
+            os.makedirs(os.path.dirname(fpath), exist_ok=True)
+            midi.write_midifile(fpath, midi_encode(unclamp_midi(events[:, j])))
+        print('rank', rank, 'wrote', len(mine), 'of', args.batch, 'sequences to', SAMPLES_DIR)
+        return
 
+    from music_generator_b200 import parallel
+    if parallel.env_world()[0] != 0:
+        return                      # the 1..3 sequence path is one GPU's work: only rank 0 generates and writes
     models = build_or_load()
     styles = [compute_genre(i) for i in range(len(genre))]
     if args.styles:

@@ -35,9 +35,11 @@ extern "C" {
 #define DJ_STYLE_UNITS 64    /* constants.py:71 */
 #define DJ_FEAT0 94          /* model.py:61-67: 1+12+1+64+16 */
 
-/* dtype tags for GEMM operands produced by the glue kernels */
+/* dtype tags for GEMM operands produced by the glue kernels; DJ_F16 = IEEE half
+ * (the 16-bit operand formats of tcgen05 kind::f16 are bf16 and half, per operand) */
 #define DJ_F32 0
 #define DJ_BF16 1
+#define DJ_F16 2
 
 /* One dropout site (model.py:58,80,85,116,123,136-138).  mode 0 = inactive
  * (predict), 1 = one hash word per 4 elements (rate*256 integral), 2 = one
@@ -71,11 +73,12 @@ int dj_style_fwd(const float* style_in, int64_t style_bstride, int64_t style_tst
  * (model.py:22-49, including the reshape scramble over the LOCAL batch), the
  * beat RepeatVector, Concatenate, Permute (model.py:61-72) and the layer-0
  * style Add (model.py:78-82).  Writes the time-axis layer-0 GEMM A operand
- * A0[M, ldA] (cols >= 94 zero). */
+ * A0[M, ldA] (cols >= 94 zero).  A0_lo (nullable, DJ_BF16 only) receives the
+ * bf16 residual A - bf16(A): the second operand of the split gate GEMM. */
 int dj_frontend_fwd(const float* notes_in, int64_t notes_bstride, const float* beat_in,
                     int64_t beat_bstride, int B, int T, const float* Wc, const float* bc,
                     const float* sp0, dj_dropout d_notes, dj_dropout d_beat, dj_dropout d_conv,
-                    dj_dropout d_sp, void* A0, int ldA, int a_dtype, void* stream);
+                    dj_dropout d_sp, void* A0, void* A0_lo, int ldA, int a_dtype, void* stream);
 /* dj_layer_input replaces, for every LSTM layer but the first, the Dropout of
  * the previous layer output (model.py:85,123), the style Add (model.py:82,117)
  * and -- for note-axis layer 0 -- shift_chosen + Concatenate (model.py:101-106,
@@ -83,10 +86,10 @@ int dj_frontend_fwd(const float* notes_in, int64_t notes_bstride, const float* b
  *   h_prev row for (b,t,n) = h_row0 + b*h_b_rows + t*48 + n, Uprev columns
  *   chosen_in (nullable) [B,T,48,3] with batch stride chosen_bstride
  *   A[M, ldA]: cols [0,Uprev) = drop(h) + drop(sp); cols [Uprev,F) = shifted
- *   chosen + drop(sp); cols >= F zero. */
+ *   chosen + drop(sp); cols >= F zero.  A_lo as in dj_frontend_fwd. */
 int dj_layer_input(const float* h_prev, int Uprev, int64_t h_row0, int64_t h_b_rows, dj_dropout d_h,
                    const float* sp, int F, dj_dropout d_sp, const float* chosen_in,
-                   int64_t chosen_bstride, dj_dropout d_chosen, int B, int T, void* A, int ldA,
+                   int64_t chosen_bstride, dj_dropout d_chosen, int B, int T, void* A, void* A_lo, int ldA,
                    int a_dtype, void* stream);
 
 /* ---- gate projections (the dense part of keras LSTM: x.W + b, model.py:84,120)
@@ -105,17 +108,33 @@ int dj_gemm_simt(const void* A, int a_dtype, int64_t a_sm, int64_t a_sk, const v
  *   lda/ldb in elements (multiples of 8), K padded with zeros up to lda. */
 int dj_gate_gemm_bf16(const void* A, int64_t lda, const void* Bt, int64_t ldb, float* C, int64_t ldc,
                       const float* bias, int M, int N, int K, void* stream);
+/* The same kernel with per-operand 16-bit formats (DJ_BF16 / DJ_F16) and, when
+ * A_lo and Bt_lo are given, the fp32-grade SPLIT product in three tcgen05 passes
+ * over the same TMEM accumulator:
+ *   C = A.Bt^T + A_lo.Bt^T + A.Bt_lo^T + bias,   X_lo = 16-bit(X - 16-bit(X))
+ * (the lo.lo term, 2^-16 relative, is dropped).  The forward x.W+b of training
+ * runs this way: north_star's 1e-3 tolerance on the outputs is not reachable
+ * with single bf16 operands (tools/precision_study.py). */
+int dj_gate_gemm_16(const void* A, const void* A_lo, int a_fmt, int64_t lda, const void* Bt,
+                    const void* Bt_lo, int b_fmt, int64_t ldb, float* C, int64_t ldc, const float* bias,
+                    int M, int N, int K, void* stream);
 /* tcgen05 weight-gradient GEMM (contraction over the M rows, split across CTAs,
  * fp32 global reductions):  C[Ka,Nb] += A[M,Ka]^T . B[M,Nb]   (bf16, MN-major).
  * The h_{step-1} operand of dU comes pre-shifted from dj_lstm_scan_fwd. */
 int dj_wgrad_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, float* C, int64_t ldc,
                        int Ka, int Nb, int64_t M, void* stream);
+/* per-operand formats: dU = H_{step-1}^T.dZ multiplies the half-precision h the
+ * forward scan saved with the bf16 dZ of the reverse scan */
+int dj_wgrad_gemm_16(const void* A, int a_fmt, int64_t lda, const void* B, int b_fmt, int64_t ldb, float* C,
+                     int64_t ldc, int Ka, int Nb, int64_t M, void* stream);
 /* fp32 -> bf16 operand copies: out[r, c] = in[r, c] (c<cols) else 0, out ld = ldo;
  * transpose!=0 writes out[c, r] (ldo >= rows). */
 int dj_cast_bf16(const float* in, int rows, int cols, void* out, int ldo, int transpose, void* stream);
-/* the same for up to 16 tensors in one launch (all operand copies of a training step) */
-int dj_cast_bf16_multi(int n, const float* const* in, const int* rows, const int* cols, void* const* out,
-                       const int* ldo, const int* transpose, void* stream);
+/* the same for up to 16 tensors in one launch (all operand copies of a training step):
+ * fmt[i] = DJ_BF16 / DJ_F16; out_lo (nullable array, nullable entries) receives the
+ * 16-bit residual in - 16-bit(in) in the same layout. */
+int dj_cast16_multi(int n, const float* const* in, const int* rows, const int* cols, void* const* out,
+                    void* const* out_lo, const int* ldo, const int* transpose, const int* fmt, void* stream);
 
 /* ---- recurrence (the sequential part of keras LSTM, model.py:84,120) ---------
  * Persistent thread-block-cluster kernel: the recurrent weights U [units,4*units]
@@ -133,20 +152,25 @@ int dj_cast_bf16_multi(int n, const float* const* in, const int* rows, const int
 int dj_lstm_scan_fwd(float* Z, float* h_out, float* c_out, void* h_prev_bf16, const float* Uw, int S,
                      int steps, int units, int seq_inner, int64_t seq_outer_stride,
                      int64_t seq_inner_stride, int64_t step_stride, int hard, void* stream);
-/* Tensor-core variant of the forward recurrence (training path, bf16 operands for
+/* Tensor-core variant of the forward recurrence (training path, 16-bit operands for
  * h.U, fp32 accumulate/state): same contract as dj_lstm_scan_fwd, but U is passed as
- * Ut_bf16 [4*units, units] (bf16, transposed, gate-interleaved rows) and
- * h_prev_bf16 is REQUIRED (it doubles as the inter-CTA exchange buffer).  Only the
- * two maps of the model are supported: units=256 with the time-axis map, units=128
- * with the note-axis map. */
-int dj_lstm_scan_tc_fwd(float* Z, float* h_out, float* c_out, void* h_prev_bf16, const void* Ut_bf16,
-                        int S, int steps, int units, int seq_inner, int64_t seq_outer_stride,
-                        int64_t seq_inner_stride, int64_t step_stride, int hard, void* stream);
+ * Ut_16 [4*units, units] (transposed, gate-interleaved rows) in format `fmt`
+ * (DJ_BF16 / DJ_F16), h_prev_16 (same format) is REQUIRED (it doubles as the
+ * inter-CTA exchange buffer), and Ut_lo (nullable) is the 16-bit residual
+ * U^T - fmt(U^T): with it every step runs a second MMA pass h.U_lo, so the recurrent
+ * weights enter with ~22 mantissa bits and only h is rounded (to half: 2^-12).
+ * Only the two maps of the model are supported: units 256/512 with the time-axis
+ * map, units 128/256 with the note-axis map. */
+int dj_lstm_scan_tc_fwd(float* Z, float* h_out, float* c_out, void* h_prev_16, const void* Ut_16,
+                        const void* Ut_lo, int fmt, int S, int steps, int units, int seq_inner,
+                        int64_t seq_outer_stride, int64_t seq_inner_stride, int64_t step_stride, int hard,
+                        void* stream);
 /* Tensor-core variant of the reverse scan (dz.U^T on tcgen05): U is passed as
- * Un_bf16 [units, 4*units] (bf16, natural, gate-interleaved columns); dZ is bf16
- * and doubles as the inter-CTA exchange buffer; db accumulates with fp32 atomics. */
+ * Un_16 [units, 4*units] (u_fmt = DJ_BF16 / DJ_F16, natural, gate-interleaved columns);
+ * dZ is bf16 (gradients need the exponent range; kind::f16 mixes the two formats) and
+ * doubles as the inter-CTA exchange buffer; db accumulates with fp32 atomics. */
 int dj_lstm_scan_tc_bwd(const float* gates, const float* c, const float* dY, int64_t ldY, dj_dropout d_y,
-                        const void* Un_bf16, void* dZ_bf16, float* db, int S, int steps, int units,
+                        const void* Un_16, int u_fmt, void* dZ_bf16, float* db, int S, int steps, int units,
                         int seq_inner, int64_t seq_outer_stride, int64_t seq_inner_stride,
                         int64_t step_stride, int hard, void* stream);
 /* reverse scan: consumes gates/c and dY (gradient w.r.t. the DROPPED-OUT layer

@@ -38,7 +38,9 @@ def midi_encode(note_seq, resolution=NOTES_PER_BEAT, step=1):
         changed = np.nonzero((on_now != on_before) | (on_now & on_before & (replay[t] > 0)))[0]
         for p in changed:
             delta = (t - last_tick) * step
-            vel = int(volume[t][p] * MAX_VELOCITY)
+            # the volume head is linear and unbounded (model.py:95): clamp instead of letting 128 wrap to 0 or a
+            # negative value wrap to a loud note in the 7-bit data byte
+            vel = min(max(int(volume[t][p] * MAX_VELOCITY), 0), MAX_VELOCITY)
             if on_now[p] and not on_before[p]:
                 track.append(midi.NoteOnEvent(tick=delta, velocity=vel, pitch=int(p)))
             elif on_before[p] and not on_now[p]:

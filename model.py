@@ -9,7 +9,7 @@ from music_generator_b200.keras_like import NoteModel, TimeModel, TrainModel
 from music_generator_b200.keras_like import primary_loss  # noqa: F401  (model.py:14-20)
 
 
-def build_models(time_steps=SEQ_LEN, input_dropout=0.2, dropout=0.5, precision='bf16', seed=0,
+def build_models(time_steps=SEQ_LEN, input_dropout=0.2, dropout=0.5, precision='mixed', seed=0,
                  recurrent_activation='hard_sigmoid'):
     """reference model.py:128-169 -> (model, time_model, note_model) sharing one
     set of weights.  `time_steps` is taken from the arrays at call time; it is

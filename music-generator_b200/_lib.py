@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdeepj_sm100.so")
 BUILD_SCRIPT = os.path.join(_HERE, "csrc", "build.sh")
 
-DJ_F32, DJ_BF16 = 0, 1
+DJ_F32, DJ_BF16, DJ_F16 = 0, 1, 2
 
 
 class Dropout(C.Structure):
@@ -33,19 +33,21 @@ SIGNATURES = {
     "dj_style_fwd": (_i, [_p, _i64, _i64, _i, _i, _i, _p, _p, _i, C.POINTER(_p), C.POINTER(_p),
                           C.POINTER(_i), _p, C.POINTER(_p), _p]),
     "dj_frontend_fwd": (_i, [_p, _i64, _p, _i64, _i, _i, _p, _p, _p, Dropout, Dropout, Dropout, Dropout,
-                             _p, _i, _i, _p]),
-    "dj_layer_input": (_i, [_p, _i, _i64, _i64, Dropout, _p, _i, Dropout, _p, _i64, Dropout, _i, _i, _p,
+                             _p, _p, _i, _i, _p]),
+    "dj_layer_input": (_i, [_p, _i, _i64, _i64, Dropout, _p, _i, Dropout, _p, _i64, Dropout, _i, _i, _p, _p,
                             _i, _i, _p]),
     "dj_gemm_simt": (_i, [_p, _i, _i64, _i64, _p, _i, _i64, _i64, _p, _i64, _p, _i, _i, _i, _i, _i64,
                           _i64, _p]),
     "dj_gate_gemm_bf16": (_i, [_p, _i64, _p, _i64, _p, _i64, _p, _i, _i, _i, _p]),
+    "dj_gate_gemm_16": (_i, [_p, _p, _i, _i64, _p, _p, _i, _i64, _p, _i64, _p, _i, _i, _i, _p]),
     "dj_wgrad_gemm_bf16": (_i, [_p, _i64, _p, _i64, _p, _i64, _i, _i, _i64, _p]),
+    "dj_wgrad_gemm_16": (_i, [_p, _i, _i64, _p, _i, _i64, _p, _i64, _i, _i, _i64, _p]),
     "dj_cast_bf16": (_i, [_p, _i, _i, _p, _i, _i, _p]),
-    "dj_cast_bf16_multi": (_i, [_i, C.POINTER(_p), C.POINTER(_i), C.POINTER(_i), C.POINTER(_p), C.POINTER(_i),
-                                C.POINTER(_i), _p]),
+    "dj_cast16_multi": (_i, [_i, C.POINTER(_p), C.POINTER(_i), C.POINTER(_i), C.POINTER(_p), C.POINTER(_p),
+                             C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), _p]),
     "dj_lstm_scan_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i64, _i64, _i64, _i, _p]),
-    "dj_lstm_scan_tc_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i64, _i64, _i64, _i, _p]),
-    "dj_lstm_scan_tc_bwd": (_i, [_p, _p, _p, _i64, Dropout, _p, _p, _p, _i, _i, _i, _i, _i64, _i64, _i64, _i, _p]),
+    "dj_lstm_scan_tc_fwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i64, _i64, _i64, _i, _p]),
+    "dj_lstm_scan_tc_bwd": (_i, [_p, _p, _p, _i64, Dropout, _p, _i, _p, _p, _i, _i, _i, _i, _i64, _i64, _i64, _i, _p]),
     "dj_lstm_scan_bwd": (_i, [_p, _p, _p, _i64, Dropout, _p, _p, _i, _p, _i, _i, _i, _i, _i64, _i64,
                               _i64, _i, _p]),
     "dj_head_partials_size": (_i64, [_i]),

@@ -2,6 +2,8 @@
 // Replaces model.py:22-49,56-82,101-117,136-142 of the reference (Keras Lambda /
 // Conv1D / Dense / Dropout / Concatenate / Permute layers) with fused kernels
 // that write the LSTM gate-GEMM A operands directly in canonical row order.
+#include <cuda_fp16.h>
+
 #include "dj_common.cuh"
 
 namespace {
@@ -25,6 +27,16 @@ __device__ __forceinline__ void store4(__nv_bfloat16* p, const float v[4]) {
   u.y = *reinterpret_cast<uint32_t*>(&b);
   *reinterpret_cast<uint2*>(p) = u;
 }
+
+// residual of the bf16 rounding, itself rounded to bf16: hi + lo carries 16 mantissa bits, which is what the
+// 3-pass split gate GEMM (dj_gate_gemm_16) multiplies
+__device__ __forceinline__ void store4_lo(__nv_bfloat16* p, const float v[4]) {
+  float r[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) r[j] = v[j] - __bfloat162float(__float2bfloat16_rn(v[j]));
+  store4(p, r);
+}
+__device__ __forceinline__ void store4_lo(float*, const float[4]) {}   // fp32 operands have no residual
 
 // ---------------------------------------------------------------------------
 // style embedding + the four tanh style projections; 8 (b,t) rows per block
@@ -88,7 +100,7 @@ __global__ void __launch_bounds__(256) frontend_fwd_kernel(
     const float* __restrict__ notes_in, int64_t notes_bstride, const float* __restrict__ beat_in,
     int64_t beat_bstride, int B, int T, const float* __restrict__ Wc, const float* __restrict__ bc,
     const float* __restrict__ sp0, dj_dropout d_notes, dj_dropout d_beat, dj_dropout d_conv,
-    dj_dropout d_sp, TA* __restrict__ A0, int ldA) {
+    dj_dropout d_sp, TA* __restrict__ A0, TA* __restrict__ A0lo, int ldA) {
   __shared__ __align__(16) float Wc_s[CK_ * NU_ * OU_];
   __shared__ float bc_s[OU_];
   __shared__ float xs[(N_ + CK_ - 1) * NU_];
@@ -189,11 +201,13 @@ __global__ void __launch_bounds__(256) frontend_fwd_kernel(
         if (f < F0_) v[j] = fmaf(sp0[(int64_t)bt * F0_ + f], m[j], v[j]);
       }
       store4(A0 + (int64_t)row * ldA + f4, v);
+      if (A0lo != nullptr) store4_lo(A0lo + (int64_t)row * ldA + f4, v);
     }
     for (int i = tid; i < N_ * ((ldA - F0P_) / 4); i += 256) {   // zero any extra padding
       const int w = (ldA - F0P_) / 4, n = i / w, f4 = F0P_ + (i % w) * 4;
       const float z[4] = {0.f, 0.f, 0.f, 0.f};
       store4(A0 + ((int64_t)bt * N_ + n) * ldA + f4, z);
+      if (A0lo != nullptr) store4(A0lo + ((int64_t)bt * N_ + n) * ldA + f4, z);
     }
     __syncthreads();
   }
@@ -209,7 +223,7 @@ template <typename TA>
 __global__ void __launch_bounds__(256) layer_input_kernel(
     const float* __restrict__ h_prev, int Uprev, int64_t h_row0, int64_t h_b_rows, dj_dropout d_h,
     const float* __restrict__ sp, int F, dj_dropout d_sp, const float* __restrict__ chosen_in,
-    int64_t chosen_bstride, dj_dropout d_chosen, int B, int T, TA* __restrict__ A, int ldA) {
+    int64_t chosen_bstride, dj_dropout d_chosen, int B, int T, TA* __restrict__ A, TA* __restrict__ Alo, int ldA) {
   const int ld4 = (F + 3) & ~3;
   const int lane = threadIdx.x & 31;
   const uint32_t rows = (uint32_t)B * (uint32_t)T * N_;
@@ -251,6 +265,11 @@ __global__ void __launch_bounds__(256) layer_input_kernel(
       TA* out = A + (int64_t)row * ldA + f8;
       store4(out, v);
       store4(out + 4, v + 4);
+      if (Alo != nullptr) {
+        TA* olo = Alo + (int64_t)row * ldA + f8;
+        store4_lo(olo, v);
+        store4_lo(olo + 4, v + 4);
+      }
     }
   }
 }
@@ -282,15 +301,23 @@ __global__ void cast_bf16_kernel(const float* __restrict__ in, int rows, int col
 
 struct CastBatch {
   const float* in[16];
-  __nv_bfloat16* out[16];
-  int rows[16], cols[16], ldo[16], transpose[16];
+  uint16_t* out[16];
+  uint16_t* out_lo[16];      // nullable: 16-bit residual v - hi (same format)
+  int rows[16], cols[16], ldo[16], transpose[16], fmt[16];
 };
-// all bf16 operand copies of a step in one launch: blockIdx.y selects the tensor
+__device__ __forceinline__ uint16_t to16(float v, int fmt, float& back) {
+  if (fmt == DJ_F16) { const __half h = __float2half_rn(v); back = __half2float(h); return __half_as_ushort(h); }
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  back = __bfloat162float(h);
+  return __bfloat16_as_ushort(h);
+}
+// all 16-bit operand copies of a step in one launch: blockIdx.y selects the tensor
 __global__ void cast_bf16_multi_kernel(CastBatch b) {
   const int e = blockIdx.y;
   const float* __restrict__ in = b.in[e];
-  __nv_bfloat16* __restrict__ out = b.out[e];
-  const int rows = b.rows[e], cols = b.cols[e], ldo = b.ldo[e], tr = b.transpose[e];
+  uint16_t* __restrict__ out = b.out[e];
+  uint16_t* __restrict__ out_lo = b.out_lo[e];
+  const int rows = b.rows[e], cols = b.cols[e], ldo = b.ldo[e], tr = b.transpose[e], fmt = b.fmt[e];
   const int orows = tr ? cols : rows;
   const int64_t total = (int64_t)orows * ldo;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -298,7 +325,9 @@ __global__ void cast_bf16_multi_kernel(CastBatch b) {
     float v = 0.f;
     if (!tr) { if (co < cols) v = in[(int64_t)ro * cols + co]; }
     else { if (co < rows) v = in[(int64_t)co * cols + ro]; }
-    out[i] = __float2bfloat16_rn(v);
+    float back, back2;
+    out[i] = to16(v, fmt, back);
+    if (out_lo != nullptr) out_lo[i] = to16(v - back, fmt, back2);
   }
 }
 
@@ -353,8 +382,9 @@ extern "C" int dj_style_fwd(const float* style_in, int64_t style_bstride, int64_
 extern "C" int dj_frontend_fwd(const float* notes_in, int64_t notes_bstride, const float* beat_in,
                                int64_t beat_bstride, int B, int T, const float* Wc, const float* bc,
                                const float* sp0, dj_dropout d_notes, dj_dropout d_beat, dj_dropout d_conv,
-                               dj_dropout d_sp, void* A0, int ldA, int a_dtype, void* stream) {
+                               dj_dropout d_sp, void* A0, void* A0_lo, int ldA, int a_dtype, void* stream) {
   DJ_CHECK_ARG(notes_in && beat_in && Wc && bc && sp0 && A0, "dj_frontend_fwd: NULL pointer");
+  DJ_CHECK_ARG(A0_lo == nullptr || a_dtype == DJ_BF16, "dj_frontend_fwd: the residual operand A0_lo exists for DJ_BF16 only");
   DJ_CHECK_ARG(B > 0 && T > 0, "dj_frontend_fwd: bad B/T");
   DJ_CHECK_ARG(ldA >= F0P_ && ldA % 8 == 0, "dj_frontend_fwd: ldA %d must be >=96 and a multiple of 8", ldA);
   DJ_CHECK_ARG((int64_t)B * T * N_ * F0P_ < (int64_t)4294967296LL, "dj_frontend_fwd: batch too large");
@@ -362,11 +392,11 @@ extern "C" int dj_frontend_fwd(const float* notes_in, int64_t notes_bstride, con
   cudaStream_t st = (cudaStream_t)stream;
   if (a_dtype == DJ_F32)
     frontend_fwd_kernel<float><<<grid, 256, 0, st>>>(notes_in, notes_bstride, beat_in, beat_bstride, B, T, Wc,
-                                                     bc, sp0, d_notes, d_beat, d_conv, d_sp, (float*)A0, ldA);
+                                                     bc, sp0, d_notes, d_beat, d_conv, d_sp, (float*)A0, (float*)nullptr, ldA);
   else if (a_dtype == DJ_BF16)
     frontend_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(notes_in, notes_bstride, beat_in, beat_bstride, B,
                                                              T, Wc, bc, sp0, d_notes, d_beat, d_conv, d_sp,
-                                                             (__nv_bfloat16*)A0, ldA);
+                                                             (__nv_bfloat16*)A0, (__nv_bfloat16*)A0_lo, ldA);
   else DJ_CHECK_ARG(false, "dj_frontend_fwd: unknown dtype %d", a_dtype);
   DJ_LAUNCH_CHECK();
   return 0;
@@ -375,8 +405,9 @@ extern "C" int dj_frontend_fwd(const float* notes_in, int64_t notes_bstride, con
 extern "C" int dj_layer_input(const float* h_prev, int Uprev, int64_t h_row0, int64_t h_b_rows,
                               dj_dropout d_h, const float* sp, int F, dj_dropout d_sp,
                               const float* chosen_in, int64_t chosen_bstride, dj_dropout d_chosen, int B,
-                              int T, void* A, int ldA, int a_dtype, void* stream) {
+                              int T, void* A, void* A_lo, int ldA, int a_dtype, void* stream) {
   DJ_CHECK_ARG(h_prev && sp && A, "dj_layer_input: NULL pointer");
+  DJ_CHECK_ARG(A_lo == nullptr || a_dtype == DJ_BF16, "dj_layer_input: the residual operand A_lo exists for DJ_BF16 only");
   DJ_CHECK_ARG(Uprev > 0 && Uprev % 4 == 0 && F >= Uprev, "dj_layer_input: bad Uprev %d / F %d", Uprev, F);
   DJ_CHECK_ARG(F == Uprev || (chosen_in && F == Uprev + NU_), "dj_layer_input: F must be Uprev or Uprev+3 with chosen");
   DJ_CHECK_ARG(ldA >= ((F + 3) & ~3) && ldA % 8 == 0, "dj_layer_input: ldA %d too small or not a multiple of 8", ldA);
@@ -386,11 +417,11 @@ extern "C" int dj_layer_input(const float* h_prev, int Uprev, int64_t h_row0, in
   cudaStream_t st = (cudaStream_t)stream;
   if (a_dtype == DJ_F32)
     layer_input_kernel<float><<<grid, 256, 0, st>>>(h_prev, Uprev, h_row0, h_b_rows, d_h, sp, F, d_sp,
-                                                    chosen_in, chosen_bstride, d_chosen, B, T, (float*)A, ldA);
+                                                    chosen_in, chosen_bstride, d_chosen, B, T, (float*)A, (float*)nullptr, ldA);
   else if (a_dtype == DJ_BF16)
     layer_input_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(h_prev, Uprev, h_row0, h_b_rows, d_h, sp, F, d_sp,
                                                             chosen_in, chosen_bstride, d_chosen, B, T,
-                                                            (__nv_bfloat16*)A, ldA);
+                                                            (__nv_bfloat16*)A, (__nv_bfloat16*)A_lo, ldA);
   else DJ_CHECK_ARG(false, "dj_layer_input: unknown dtype %d", a_dtype);
   DJ_LAUNCH_CHECK();
   return 0;
@@ -407,15 +438,16 @@ extern "C" int dj_cast_bf16(const float* in, int rows, int cols, void* out, int 
   return 0;
 }
 
-extern "C" int dj_cast_bf16_multi(int n, const float* const* in, const int* rows, const int* cols, void* const* out,
-                                  const int* ldo, const int* transpose, void* stream) {
-  DJ_CHECK_ARG(n > 0 && n <= 16 && in && rows && cols && out && ldo && transpose, "dj_cast_bf16_multi: bad arguments");
+extern "C" int dj_cast16_multi(int n, const float* const* in, const int* rows, const int* cols, void* const* out,
+                               void* const* out_lo, const int* ldo, const int* transpose, const int* fmt, void* stream) {
+  DJ_CHECK_ARG(n > 0 && n <= 16 && in && rows && cols && out && ldo && transpose && fmt, "dj_cast16_multi: bad arguments");
   CastBatch b{};
   for (int i = 0; i < n; ++i) {
-    DJ_CHECK_ARG(in[i] && out[i] && rows[i] > 0 && cols[i] > 0 && ldo[i] >= (transpose[i] ? rows[i] : cols[i]),
-                 "dj_cast_bf16_multi: entry %d invalid", i);
-    b.in[i] = in[i]; b.out[i] = (__nv_bfloat16*)out[i];
-    b.rows[i] = rows[i]; b.cols[i] = cols[i]; b.ldo[i] = ldo[i]; b.transpose[i] = transpose[i];
+    DJ_CHECK_ARG(in[i] && out[i] && rows[i] > 0 && cols[i] > 0 && ldo[i] >= (transpose[i] ? rows[i] : cols[i]) &&
+                     (fmt[i] == DJ_BF16 || fmt[i] == DJ_F16),
+                 "dj_cast16_multi: entry %d invalid", i);
+    b.in[i] = in[i]; b.out[i] = (uint16_t*)out[i]; b.out_lo[i] = out_lo ? (uint16_t*)out_lo[i] : nullptr;
+    b.rows[i] = rows[i]; b.cols[i] = cols[i]; b.ldo[i] = ldo[i]; b.transpose[i] = transpose[i]; b.fmt[i] = fmt[i];
   }
   cast_bf16_multi_kernel<<<dim3(64, n), 256, 0, (cudaStream_t)stream>>>(b);
   DJ_LAUNCH_CHECK();

@@ -37,8 +37,10 @@ struct GemmSmem {
 // C = A . Bt^T + bias, both operands K-major
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gate_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias, int M, int N, int K) {
+gate_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
+                 const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
+                 const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias, int M, int N, int K,
+                 int npass, uint32_t idesc) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const uint32_t sbase = smem_u32(smem);
@@ -55,6 +57,7 @@ gate_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA); prefetch_tmap(&tmB); prefetch_tmap(&tmC);
+    if (npass > 1) { prefetch_tmap(&tmAlo); prefetch_tmap(&tmBlo); }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
@@ -75,24 +78,29 @@ gate_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m0 = (tile / num_n) * BM, n0 = (tile % num_n) * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(empty_bar(stage), phase ^ 1);
-          mbar_expect_tx(full_bar(stage), A_BYTES + B_BYTES);
-          tma_load_2d(sbase + GemmSmem::A_OFF + stage * A_BYTES, &tmA, full_bar(stage), kb * BK, m0);
-          tma_load_2d(sbase + GemmSmem::B_OFF + stage * B_BYTES, &tmB, full_bar(stage), kb * BK, n0);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        // split-operand passes (fp32-grade product from 16-bit operands): hi.hi, then lo.hi, then hi.lo
+        for (int pass = 0; pass < npass; ++pass) {
+          const CUtensorMap* mA = (pass == 1) ? &tmAlo : &tmA;
+          const CUtensorMap* mB = (pass == 2) ? &tmBlo : &tmB;
+          for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(empty_bar(stage), phase ^ 1);
+            mbar_expect_tx(full_bar(stage), A_BYTES + B_BYTES);
+            tma_load_2d(sbase + GemmSmem::A_OFF + stage * A_BYTES, mA, full_bar(stage), kb * BK, m0);
+            tma_load_2d(sbase + GemmSmem::B_OFF + stage * B_BYTES, mB, full_bar(stage), kb * BK, n0);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {   // ===== MMA issuer =====
-      constexpr uint32_t idesc = make_idesc(BM, BN, 0, 0);
       int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t aphase = 0;
+      const int num_it = npass * num_kb;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(tempty_bar(acc), aphase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = 0; kb < num_it; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint64_t adesc = make_smem_desc(sbase + GemmSmem::A_OFF + stage * A_BYTES, 16, 1024);
@@ -184,7 +192,8 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                  float* __restrict__ C, int64_t ldc, int Ka, int Nb, int64_t M, int num_tiles, int kb_per_split) {
+                  float* __restrict__ C, int64_t ldc, int Ka, int Nb, int64_t M, int num_tiles, int kb_per_split,
+                  uint32_t idesc) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const uint32_t sbase = smem_u32(smem);
@@ -233,7 +242,6 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (warp == 1) {
     if (lane == 0 && nkb > 0) {   // ===== MMA issuer =====
-      constexpr uint32_t idesc = make_idesc(WG_BM, WG_BN, 1, 1);
       int stage = 0; uint32_t phase = 0;
       for (int i = 0; i < nkb; ++i) {
         mbar_wait(full_bar(stage), phase);
@@ -283,43 +291,73 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
 }  // namespace
 
-extern "C" int dj_gate_gemm_bf16(const void* A, int64_t lda, const void* Bt, int64_t ldb, float* C, int64_t ldc,
-                                 const float* bias, int M, int N, int K, void* stream) {
-  DJ_CHECK_ARG(A && Bt && C, "dj_gate_gemm_bf16: NULL pointer");
-  DJ_CHECK_ARG(M > 0 && N > 0 && K > 0, "dj_gate_gemm_bf16: bad shape");
+// kind::f16 operand formats in the instruction descriptor: bits 7-9 (A) / 10-12 (B): 0 = f16, 1 = bf16.
+// make_idesc() sets both to bf16; this clears the bit of every operand that is IEEE half.
+static inline bool fmt16_ok(int f) { return f == DJ_BF16 || f == DJ_F16; }
+static inline uint32_t idesc_with_formats(uint32_t idesc, int a_fmt, int b_fmt) {
+  if (a_fmt == DJ_F16) idesc &= ~(1u << 7);
+  if (b_fmt == DJ_F16) idesc &= ~(1u << 10);
+  return idesc;
+}
+static inline CUtensorMapDataType tmap_dtype(int fmt) {
+  return fmt == DJ_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+}
+
+extern "C" int dj_gate_gemm_16(const void* A, const void* A_lo, int a_fmt, int64_t lda, const void* Bt,
+                               const void* Bt_lo, int b_fmt, int64_t ldb, float* C, int64_t ldc, const float* bias,
+                               int M, int N, int K, void* stream) {
+  DJ_CHECK_ARG(A && Bt && C, "dj_gate_gemm_16: NULL pointer");
+  DJ_CHECK_ARG((A_lo == nullptr) == (Bt_lo == nullptr), "dj_gate_gemm_16: A_lo and Bt_lo come together (3-pass split product)");
+  DJ_CHECK_ARG(fmt16_ok(a_fmt) && fmt16_ok(b_fmt), "dj_gate_gemm_16: operand formats must be DJ_BF16 or DJ_F16");
+  DJ_CHECK_ARG(M > 0 && N > 0 && K > 0, "dj_gate_gemm_16: bad shape");
   DJ_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0 && ldc % 4 == 0 && lda >= K && ldb >= K && ldc >= N,
-               "dj_gate_gemm_bf16: leading dimensions must be 16-byte multiples and cover K/N (lda=%lld ldb=%lld ldc=%lld)",
+               "dj_gate_gemm_16: leading dimensions must be 16-byte multiples and cover K/N (lda=%lld ldb=%lld ldc=%lld)",
                (long long)lda, (long long)ldb, (long long)ldc);
-  DJ_CHECK_ARG(bias == nullptr || N <= MAX_BIAS_N, "dj_gate_gemm_bf16: N=%d exceeds the bias staging capacity %d", N, MAX_BIAS_N);
+  DJ_CHECK_ARG(bias == nullptr || N <= MAX_BIAS_N, "dj_gate_gemm_16: N=%d exceeds the bias staging capacity %d", N, MAX_BIAS_N);
   DJ_CHECK_ARG(((uintptr_t)A % 16) == 0 && ((uintptr_t)Bt % 16) == 0 && ((uintptr_t)C % 16) == 0 &&
+                   ((uintptr_t)A_lo % 16) == 0 && ((uintptr_t)Bt_lo % 16) == 0 &&
                    (bias == nullptr || ((uintptr_t)bias % 16) == 0),
-               "dj_gate_gemm_bf16: pointers must be 16-byte aligned");
-  CUtensorMap tmA, tmB, tmC;
+               "dj_gate_gemm_16: pointers must be 16-byte aligned");
+  const int npass = A_lo ? 3 : 1;
+  CUtensorMap tmA, tmAlo, tmB, tmBlo, tmC;
   int rc;
-  if ((rc = make_map_2d(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, BM))) return rc;
-  if ((rc = make_map_2d(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Bt, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BK, BN))) return rc;
+  if ((rc = make_map_2d(&tmA, tmap_dtype(a_fmt), 2, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, BM))) return rc;
+  if ((rc = make_map_2d(&tmB, tmap_dtype(b_fmt), 2, Bt, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BK, BN))) return rc;
+  tmAlo = tmA; tmBlo = tmB;
+  if (npass == 3) {
+    if ((rc = make_map_2d(&tmAlo, tmap_dtype(a_fmt), 2, A_lo, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, BM))) return rc;
+    if ((rc = make_map_2d(&tmBlo, tmap_dtype(b_fmt), 2, Bt_lo, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BK, BN))) return rc;
+  }
   if ((rc = make_map_2d(&tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, C, (uint64_t)N, (uint64_t)M, (uint64_t)ldc, 32, 32))) return rc;
   DJ_CUDA(cudaFuncSetAttribute((const void*)gate_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem::TOTAL));
   const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   int grid = dj_num_sms();
   if (grid > tiles) grid = tiles;
-  gate_gemm_kernel<<<grid, NUM_THREADS, GemmSmem::TOTAL, (cudaStream_t)stream>>>(tmA, tmB, tmC, bias, M, N, K);
+  const uint32_t idesc = idesc_with_formats(make_idesc(BM, BN, 0, 0), a_fmt, b_fmt);
+  gate_gemm_kernel<<<grid, NUM_THREADS, GemmSmem::TOTAL, (cudaStream_t)stream>>>(tmA, tmAlo, tmB, tmBlo, tmC, bias, M, N, K,
+                                                                                 npass, idesc);
   DJ_LAUNCH_CHECK();
   return 0;
 }
 
-extern "C" int dj_wgrad_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, float* C, int64_t ldc,
-                                  int Ka, int Nb, int64_t M, void* stream) {
-  DJ_CHECK_ARG(A && B && C, "dj_wgrad_gemm_bf16: NULL pointer");
-  DJ_CHECK_ARG(Ka > 0 && Nb > 0 && M > 0, "dj_wgrad_gemm_bf16: bad shape");
+extern "C" int dj_gate_gemm_bf16(const void* A, int64_t lda, const void* Bt, int64_t ldb, float* C, int64_t ldc,
+                                 const float* bias, int M, int N, int K, void* stream) {
+  return dj_gate_gemm_16(A, nullptr, DJ_BF16, lda, Bt, nullptr, DJ_BF16, ldb, C, ldc, bias, M, N, K, stream);
+}
+
+extern "C" int dj_wgrad_gemm_16(const void* A, int a_fmt, int64_t lda, const void* B, int b_fmt, int64_t ldb, float* C,
+                                int64_t ldc, int Ka, int Nb, int64_t M, void* stream) {
+  DJ_CHECK_ARG(A && B && C, "dj_wgrad_gemm_16: NULL pointer");
+  DJ_CHECK_ARG(fmt16_ok(a_fmt) && fmt16_ok(b_fmt), "dj_wgrad_gemm_16: operand formats must be DJ_BF16 or DJ_F16");
+  DJ_CHECK_ARG(Ka > 0 && Nb > 0 && M > 0, "dj_wgrad_gemm_16: bad shape");
   DJ_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0 && ldc % 4 == 0 && lda >= Ka && ldb >= Nb && ldc >= Nb,
-               "dj_wgrad_gemm_bf16: leading dimensions must be 16-byte multiples and cover the widths");
+               "dj_wgrad_gemm_16: leading dimensions must be 16-byte multiples and cover the widths");
   DJ_CHECK_ARG(((uintptr_t)A % 16) == 0 && ((uintptr_t)B % 16) == 0 && ((uintptr_t)C % 16) == 0,
-               "dj_wgrad_gemm_bf16: pointers must be 16-byte aligned");
+               "dj_wgrad_gemm_16: pointers must be 16-byte aligned");
   CUtensorMap tmA, tmB;
   int rc;
-  if ((rc = make_map_2d(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, A, (uint64_t)Ka, (uint64_t)M, (uint64_t)lda, 64, WG_BK))) return rc;
-  if ((rc = make_map_2d(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, B, (uint64_t)Nb, (uint64_t)M, (uint64_t)ldb, 64, WG_BK))) return rc;
+  if ((rc = make_map_2d(&tmA, tmap_dtype(a_fmt), 2, A, (uint64_t)Ka, (uint64_t)M, (uint64_t)lda, 64, WG_BK))) return rc;
+  if ((rc = make_map_2d(&tmB, tmap_dtype(b_fmt), 2, B, (uint64_t)Nb, (uint64_t)M, (uint64_t)ldb, 64, WG_BK))) return rc;
   DJ_CUDA(cudaFuncSetAttribute((const void*)wgrad_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WgradSmem::TOTAL));
   const int tiles = ((Ka + WG_BM - 1) / WG_BM) * ((Nb + WG_BN - 1) / WG_BN);
   const int total_kb = (int)((M + WG_BK - 1) / WG_BK);
@@ -328,8 +366,14 @@ extern "C" int dj_wgrad_gemm_bf16(const void* A, int64_t lda, const void* B, int
   if (splits > total_kb) splits = total_kb;
   const int kbps = (total_kb + splits - 1) / splits;
   splits = (total_kb + kbps - 1) / kbps;
+  const uint32_t idesc = idesc_with_formats(make_idesc(WG_BM, WG_BN, 1, 1), a_fmt, b_fmt);
   wgrad_gemm_kernel<<<tiles * splits, NUM_THREADS, WgradSmem::TOTAL, (cudaStream_t)stream>>>(tmA, tmB, C, ldc, Ka, Nb, M,
-                                                                                             tiles, kbps);
+                                                                                             tiles, kbps, idesc);
   DJ_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int dj_wgrad_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, float* C, int64_t ldc,
+                                  int Ka, int Nb, int64_t M, void* stream) {
+  return dj_wgrad_gemm_16(A, DJ_BF16, lda, B, DJ_BF16, ldb, C, ldc, Ka, Nb, M, stream);
 }

@@ -22,6 +22,7 @@
 // `hprev` is needed anyway as the A operand of dU = H_{t-1}^T.dZ, so the all-gather
 // costs no extra HBM traffic and avoids the ~20 B/clk DSMEM store path.
 #include <cooperative_groups.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 #include "dj_tc.cuh"
@@ -133,7 +134,8 @@ template <int U, int BS, bool TIME, bool HARD, int NB, int NS, bool ATM>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 scan_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmH,
                    float* __restrict__ Z, float* __restrict__ Hout, float* __restrict__ Cout,
-                   __nv_bfloat16* __restrict__ Hprev, const uint32_t* __restrict__ Ut_words, int steps, TcMap map) {
+                   uint16_t* __restrict__ Hprev, const uint32_t* __restrict__ Ut_words, int steps, TcMap map,
+                   int f16, int has_lo) {
   constexpr uint32_t SSTR = TIME ? 1u : 48u, TSTR = TIME ? 48u : 1u;
   constexpr int C = U / 32;            // cluster size
   constexpr int KA = U / 64;           // 64-wide K atoms
@@ -148,7 +150,13 @@ scan_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
   constexpr uint32_t A_COL0 = D_COLS;                                                   // A operand: columns [A_COL0, +U/2)
   constexpr uint32_t NEED = ATM ? D_COLS + U / 2 : D_COLS;
   constexpr uint32_t TMEM_COLS = NEED <= 32 ? 32 : NEED <= 64 ? 64 : NEED <= 128 ? 128 : NEED <= 256 ? 256 : 512;
-  static_assert(BS % 16 == 0 && BS <= 256 && (!ATM || TMEM_COLS <= 256), "tile shape / two CTAs share 512 TMEM columns");
+  // U = 512 needs 176 KB of shared memory, so only one CTA is resident per SM and it may take all 512 columns
+  static_assert(BS % 16 == 0 && BS <= 256 && (!ATM || TMEM_COLS <= 256 || U == 512), "tile shape / two CTAs share 512 TMEM columns");
+  // h and U operands: bf16 or IEEE half (kind::f16 format bits 7 / 10 of the instruction descriptor: 0 = f16)
+  const uint32_t idesc = f16 ? (make_idesc(128, HB, 0, 0) & ~((1u << 7) | (1u << 10))) : make_idesc(128, HB, 0, 0);
+  // has_lo (ATM only): shared memory holds the 16-bit residual U - hi(U) of this CTA's slice; a second MMA pass adds
+  // h.U_lo so the recurrent weights enter the product with ~22 mantissa bits
+  const bool smem_a = !ATM || has_lo;
   using SM = TcFwdSmem<U, BS>;
 
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -206,7 +214,7 @@ scan_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
     // ================= issuer + publisher of half-tile hf =================
     // the whole warp walks the loop converged; single-thread work sits under elect_one()
     const int hf = (warp == 0) ? 0 : 1;
-    if (!ATM && warp == 0 && elect_one()) {   // resident A operand in shared memory: rows [128*rank, +128) of U^T
+    if (smem_a && warp == 0 && elect_one()) {   // resident shared-memory A operand (U^T, or its residual): rows [128*rank, +128)
       mbar_expect_tx(bar_a, SM::A_BYTES);
 #pragma unroll
       for (int ka = 0; ka < KA; ++ka)
@@ -235,12 +243,11 @@ scan_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
                            (uint16_t)((1u << C) - 1u));
         }
         __syncwarp();
-        if (!ATM && t == 0) mbar_wait(bar_a, 0);
+        if (smem_a && t == 0) mbar_wait(bar_a, 0);
         mbar_wait(bar_h, par);                            // all C slices of this half landed
         DJ_TR(t, 4 * hf + 2);
         tc_fence_after();
         if (elect_one()) {
-          constexpr uint32_t idesc = make_idesc(128, HB, 0, 0);
           const uint64_t adesc0 = make_smem_desc(sbase + SM::A_OFF, 16, 1024);
           const uint64_t bdesc0 = make_smem_desc(sbase + SM::H_OFF + hf * (HB * 128), 16, 1024);
 #pragma unroll
@@ -255,6 +262,14 @@ scan_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
                 umma_bf16(tmem_base + (uint32_t)(hf * HB), adesc0 + (uint64_t)((ka * 16384 + k * 32) >> 4), bdesc,
                           idesc, (ka | k) != 0);
             }
+          if (ATM && has_lo) {
+#pragma unroll
+            for (int ka = 0; ka < KA; ++ka)
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_bf16(tmem_base + (uint32_t)(hf * HB), adesc0 + (uint64_t)((ka * 16384 + k * 32) >> 4),
+                          bdesc0 + (uint64_t)((ka * (BS * 128) + k * 32) >> 4), idesc, 1);
+          }
           umma_commit(bar_acc);
         }
         __syncwarp();
@@ -327,7 +342,7 @@ scan_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
           const size_t o1 = (size_t)row_c * U + col;
           float* const hp = Hout + o1;
           float* const cp = Cout + o1;                       // only dereferenced when Cout != nullptr
-          __nv_bfloat16* const hb = Hprev + o1;
+          uint16_t* const hb = Hprev + o1;
 #pragma unroll
           for (int blk = 0; blk < 2; ++blk) {
             // 4x4 transpose across the 4 lanes of a unit: lane g ends with i,f,g,o of sequence 4*blk+g
@@ -348,8 +363,9 @@ scan_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
 
             constexpr size_t RO = (size_t)4 * SSTR;          // rows between consecutive blocks
             // h_t (bf16) at the NEXT step's row: the A operand of dU = H_{t-1}^T.dZ
-            if (not_last) hb[(blk * RO + TSTR) * U] = __float2bfloat16_rn(hn);
-            if (t == 0) hb[blk * RO * U] = __float2bfloat16_rn(0.f);
+            if (not_last)
+              hb[(blk * RO + TSTR) * U] = f16 ? __half_as_ushort(__float2half_rn(hn)) : __bfloat16_as_ushort(__float2bfloat16_rn(hn));
+            if (t == 0) hb[blk * RO * U] = 0;
 #ifndef DJ_EXP
 #define DJ_EXP 0   // timing experiments only: bit0/1/2 drop the gate / h / c stores
 #endif
@@ -384,15 +400,21 @@ inline bool fwd_atm_enabled() {   // DJ_FWD_ATM=0 keeps the A operand in shared 
 }
 
 template <int U, int BS, bool TIME, bool HARD, int NB, int NS>
-int launch_tc_fwd_inst(const void* Ut_bf, float* Z, float* h_out, float* c_out, void* hprev, int S, int steps,
-                       const TcMap& map_in, cudaStream_t st) {
+int launch_tc_fwd_inst(const void* Ut_bf, const void* Ut_lo, int f16, float* Z, float* h_out, float* c_out, void* hprev,
+                       int S, int steps, const TcMap& map_in, cudaStream_t st) {
   constexpr int C = U / 32;
   using SM = TcFwdSmem<U, BS>;
   DJ_CHECK_ARG(S % BS == 0, "dj_lstm_scan_tc_fwd: the number of sequences (%d) must be a multiple of %d", S, BS);
   TcMap map = map_in;
   CUtensorMap tmU, tmH;
   int rc;
-  if ((rc = make_map_2d(&tmU, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Ut_bf, (uint64_t)U, (uint64_t)4 * U, (uint64_t)U, 64, 128)))
+  // U <= 256: A operand in tensor memory unless DJ_FWD_ATM=0; U = 512: only when the residual pass needs the shared-memory slot
+  constexpr bool CAN_ATM = true;
+  const bool atm = (U <= 256) ? fwd_atm_enabled() : (Ut_lo != nullptr);
+  DJ_CHECK_ARG(Ut_lo == nullptr || atm, "dj_lstm_scan_tc_fwd: the residual pass (Ut_lo) needs the tensor-memory A operand (DJ_FWD_ATM=0 is set)");
+  // the shared-memory A slot holds U^T (A not in tensor memory) or the residual U^T - hi(U^T)
+  if ((rc = make_map_2d(&tmU, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (atm && Ut_lo) ? Ut_lo : Ut_bf, (uint64_t)U, (uint64_t)4 * U,
+                        (uint64_t)U, 64, 128)))
     return rc;
   constexpr int RH = BS / 2;
   if (TIME) {   // hprev viewed as [b][t*48+n][U]
@@ -409,8 +431,6 @@ int launch_tc_fwd_inst(const void* Ut_bf, float* Z, float* h_out, float* c_out, 
     map.step1 = 1; map.off1 = 0; map.base2 = BS; map.off2 = RH;
     map.seq_stride = map.outer_stride;
   }
-  constexpr bool CAN_ATM = (U <= 256);
-  const bool atm = CAN_ATM && fwd_atm_enabled();
   auto kernel = scan_tc_fwd_kernel<U, BS, TIME, HARD, NB, NS, false>;
   if constexpr (CAN_ATM) {
     if (atm) kernel = scan_tc_fwd_kernel<U, BS, TIME, HARD, NB, NS, true>;
@@ -431,9 +451,10 @@ int launch_tc_fwd_inst(const void* Ut_bf, float* Z, float* h_out, float* c_out, 
     cudaOccupancyMaxActiveClusters(&n, (const void*)kernel, &cfg);
     fprintf(stderr, "scan_tc_fwd<%d,%d>: %d clusters of %d launched, %d can be resident\n", U, BS, S / BS, C, n);
   }
-  __nv_bfloat16* hp = (__nv_bfloat16*)hprev;
+  uint16_t* hp = (uint16_t*)hprev;
   const uint32_t* utw = (const uint32_t*)Ut_bf;
-  DJ_CUDA(cudaLaunchKernelEx(&cfg, kernel, tmU, tmH, Z, h_out, c_out, hp, utw, steps, map));
+  const int has_lo = Ut_lo != nullptr ? 1 : 0;
+  DJ_CUDA(cudaLaunchKernelEx(&cfg, kernel, tmU, tmH, Z, h_out, c_out, hp, utw, steps, map, f16, has_lo));
   return 0;
 }
 
@@ -459,8 +480,8 @@ inline bool fwd_split_enabled() {
 }
 
 template <int U, int BS, bool TIME>
-int launch_tc_fwd(const void* Ut_bf, float* Z, float* h_out, float* c_out, void* hprev, int S, int steps,
-                  const TcMap& map, int /*axis_time*/, int hard, cudaStream_t st) {
+int launch_tc_fwd(const void* Ut_bf, const void* Ut_lo, int f16, float* Z, float* h_out, float* c_out, void* hprev, int S,
+                  int steps, const TcMap& map, int /*axis_time*/, int hard, cudaStream_t st) {
   constexpr int NCH = BS / 16;
   constexpr bool CAN_SPLIT = (NCH % 2 == 0);
   constexpr int NB_DEF = (NCH % 2 == 0) ? 2 : 1;
@@ -469,8 +490,8 @@ int launch_tc_fwd(const void* Ut_bf, float* Z, float* h_out, float* c_out, void*
 #define DJ_FWD_CASE(NBV, NSV)                                                                                       \
   if constexpr (NCH % NBV == 0 && (NSV == 1 || CAN_SPLIT)) {                                                        \
     if (nb == NBV && split == (NSV == 2))                                                                           \
-      return hard ? launch_tc_fwd_inst<U, BS, TIME, true, NBV, NSV>(Ut_bf, Z, h_out, c_out, hprev, S, steps, map, st) \
-                  : launch_tc_fwd_inst<U, BS, TIME, false, NBV, NSV>(Ut_bf, Z, h_out, c_out, hprev, S, steps, map, st); \
+      return hard ? launch_tc_fwd_inst<U, BS, TIME, true, NBV, NSV>(Ut_bf, Ut_lo, f16, Z, h_out, c_out, hprev, S, steps, map, st) \
+                  : launch_tc_fwd_inst<U, BS, TIME, false, NBV, NSV>(Ut_bf, Ut_lo, f16, Z, h_out, c_out, hprev, S, steps, map, st); \
   }
   DJ_FWD_CASE(1, 1)
   DJ_FWD_CASE(1, 2)
@@ -521,7 +542,7 @@ __global__ void __launch_bounds__(TCB_THREADS, (U == 128 && BS <= 32) ? 2 : 1)
 scan_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmZ,
                    const float* __restrict__ G, const float* __restrict__ Cst, const float* __restrict__ dY,
                    uint32_t ldY, dj_dropout d_y, __nv_bfloat16* __restrict__ dZ, float* __restrict__ db,
-                   int steps, TcMap map, int hard) {
+                   int steps, TcMap map, int hard, int u_f16) {
   constexpr int C = U / UPC;            // cluster size
   constexpr int KA = 4 * U / 64;        // K atoms of the contraction (gate columns)
   constexpr int ATOM = UPC * 128;       // bytes of one resident K atom of U (UPC rows x 128 B)
@@ -608,7 +629,8 @@ scan_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
         DJ_TR(t, 4 * hf + 2);
         tc_fence_after();
         if (elect_one()) {
-          constexpr uint32_t idesc = make_idesc(64, HB, 0, 0);
+          // A = U (bf16, or IEEE half: format bit 7 cleared), B = dz (always bf16: gradients need the exponent range)
+          const uint32_t idesc = u_f16 ? (make_idesc(64, HB, 0, 0) & ~(1u << 7)) : make_idesc(64, HB, 0, 0);
           const uint64_t adesc0 = make_smem_desc(sbase + SM::A_OFF, 16, 1024);
           const uint64_t bdesc0 = make_smem_desc(b_half, 16, 1024);
 #pragma unroll
@@ -746,7 +768,7 @@ inline bool bwd_split_enabled() {   // DJ_BWD_NS=1 forces the unsplit tile (expe
 
 template <int U, int BS, int UPC, bool AXIS_TIME, int NS>
 int launch_tc_bwd_inst(const void* Un_bf, const float* gates, const float* c, const float* dY, int64_t ldY, dj_dropout d_y,
-                       void* dZ, float* db, int S, int steps, const TcMap& map_in, int hard, cudaStream_t st) {
+                       void* dZ, float* db, int S, int steps, const TcMap& map_in, int hard, int u_f16, cudaStream_t st) {
   constexpr int C = U / UPC;
   constexpr int HB = BS / NS;
   using SM = TcBwdSmem<U, BS, UPC>;
@@ -791,24 +813,27 @@ int launch_tc_bwd_inst(const void* Un_bf, const float* gates, const float* c, co
   }
   __nv_bfloat16* dzp = (__nv_bfloat16*)dZ;
   const uint32_t ldy32 = (uint32_t)ldY;
-  DJ_CUDA(cudaLaunchKernelEx(&cfg, kernel, tmU, tmZ, gates, c, dY, ldy32, d_y, dzp, db, steps, map, hard));
+  DJ_CUDA(cudaLaunchKernelEx(&cfg, kernel, tmU, tmZ, gates, c, dY, ldy32, d_y, dzp, db, steps, map, hard, u_f16));
   return 0;
 }
 
 template <int U, int BS, int UPC, bool AXIS_TIME>
 int launch_tc_bwd(const void* Un_bf, const float* gates, const float* c, const float* dY, int64_t ldY, dj_dropout d_y,
-                  void* dZ, float* db, int S, int steps, const TcMap& map, int hard, cudaStream_t st) {
+                  void* dZ, float* db, int S, int steps, const TcMap& map, int hard, int u_f16, cudaStream_t st) {
   if (bwd_split_enabled())
-    return launch_tc_bwd_inst<U, BS, UPC, AXIS_TIME, 2>(Un_bf, gates, c, dY, ldY, d_y, dZ, db, S, steps, map, hard, st);
-  return launch_tc_bwd_inst<U, BS, UPC, AXIS_TIME, 1>(Un_bf, gates, c, dY, ldY, d_y, dZ, db, S, steps, map, hard, st);
+    return launch_tc_bwd_inst<U, BS, UPC, AXIS_TIME, 2>(Un_bf, gates, c, dY, ldY, d_y, dZ, db, S, steps, map, hard, u_f16, st);
+  return launch_tc_bwd_inst<U, BS, UPC, AXIS_TIME, 1>(Un_bf, gates, c, dY, ldY, d_y, dZ, db, S, steps, map, hard, u_f16, st);
 }
 
 }  // namespace
 
-extern "C" int dj_lstm_scan_tc_fwd(float* Z, float* h_out, float* c_out, void* h_prev_bf16, const void* Ut_bf16, int S,
-                                   int steps, int units, int seq_inner, int64_t seq_outer_stride,
-                                   int64_t seq_inner_stride, int64_t step_stride, int hard, void* stream) {
+extern "C" int dj_lstm_scan_tc_fwd(float* Z, float* h_out, float* c_out, void* h_prev_bf16, const void* Ut_bf16,
+                                   const void* Ut_lo, int fmt, int S, int steps, int units, int seq_inner,
+                                   int64_t seq_outer_stride, int64_t seq_inner_stride, int64_t step_stride, int hard,
+                                   void* stream) {
   DJ_CHECK_ARG(Z && h_out && h_prev_bf16 && Ut_bf16, "dj_lstm_scan_tc_fwd: NULL pointer");
+  DJ_CHECK_ARG(fmt == DJ_BF16 || fmt == DJ_F16, "dj_lstm_scan_tc_fwd: operand format must be DJ_BF16 or DJ_F16");
+  const int f16 = (fmt == DJ_F16) ? 1 : 0;
   DJ_CHECK_ARG(S > 0 && steps > 0, "dj_lstm_scan_tc_fwd: bad sizes");
   TcMap map{seq_inner, seq_outer_stride, seq_inner_stride, step_stride, 0, 0, 0, 0, 0};
   cudaStream_t st = (cudaStream_t)stream;
@@ -819,26 +844,28 @@ extern "C" int dj_lstm_scan_tc_fwd(float* Z, float* h_out, float* c_out, void* h
     // 2 CTAs/SM x 16 resident 8-CTA clusters = 32 tile slots: beyond that, double the tile (two batch
     // elements per cluster) so the whole layer still runs as one wave of step chains
     if (S % 96 == 0 && S / 48 > 32)
-      return launch_tc_fwd<256, 96, true>(Ut_bf16, Z, h_out, c_out, h_prev_bf16, S, steps, map, 1, hard, st);
-    return launch_tc_fwd<256, 48, true>(Ut_bf16, Z, h_out, c_out, h_prev_bf16, S, steps, map, 1, hard, st);
+      return launch_tc_fwd<256, 96, true>(Ut_bf16, Ut_lo, f16, Z, h_out, c_out, h_prev_bf16, S, steps, map, 1, hard, st);
+    return launch_tc_fwd<256, 48, true>(Ut_bf16, Ut_lo, f16, Z, h_out, c_out, h_prev_bf16, S, steps, map, 1, hard, st);
   } else if (time_map && units == 512) {   // scaled model (BASELINE configs[4]): 16-CTA clusters
-    return launch_tc_fwd<512, 48, true>(Ut_bf16, Z, h_out, c_out, h_prev_bf16, S, steps, map, 1, hard, st);
+    return launch_tc_fwd<512, 48, true>(Ut_bf16, Ut_lo, f16, Z, h_out, c_out, h_prev_bf16, S, steps, map, 1, hard, st);
   } else if (note_map && units == 128) {
     if (S % 128 == 0 && S / 64 > 74)
-      return launch_tc_fwd<128, 128, false>(Ut_bf16, Z, h_out, c_out, h_prev_bf16, S, steps, map, 0, hard, st);
-    return launch_tc_fwd<128, 64, false>(Ut_bf16, Z, h_out, c_out, h_prev_bf16, S, steps, map, 0, hard, st);
+      return launch_tc_fwd<128, 128, false>(Ut_bf16, Ut_lo, f16, Z, h_out, c_out, h_prev_bf16, S, steps, map, 0, hard, st);
+    return launch_tc_fwd<128, 64, false>(Ut_bf16, Ut_lo, f16, Z, h_out, c_out, h_prev_bf16, S, steps, map, 0, hard, st);
   } else if (note_map && units == 256) {   // scaled model, note axis
-    return launch_tc_fwd<256, 64, false>(Ut_bf16, Z, h_out, c_out, h_prev_bf16, S, steps, map, 0, hard, st);
+    return launch_tc_fwd<256, 64, false>(Ut_bf16, Ut_lo, f16, Z, h_out, c_out, h_prev_bf16, S, steps, map, 0, hard, st);
   }
   DJ_CHECK_ARG(false, "dj_lstm_scan_tc_fwd: units=%d unsupported on this axis (time: 256/512, note: 128/256)", units);
   return -1;
 }
 
 extern "C" int dj_lstm_scan_tc_bwd(const float* gates, const float* c, const float* dY, int64_t ldY, dj_dropout d_y,
-                                   const void* Un_bf16, void* dZ_bf16, float* db, int S, int steps, int units,
+                                   const void* Un_bf16, int u_fmt, void* dZ_bf16, float* db, int S, int steps, int units,
                                    int seq_inner, int64_t seq_outer_stride, int64_t seq_inner_stride,
                                    int64_t step_stride, int hard, void* stream) {
   DJ_CHECK_ARG(gates && c && dY && Un_bf16 && dZ_bf16 && db, "dj_lstm_scan_tc_bwd: NULL pointer");
+  DJ_CHECK_ARG(u_fmt == DJ_BF16 || u_fmt == DJ_F16, "dj_lstm_scan_tc_bwd: U format must be DJ_BF16 or DJ_F16");
+  const int u_f16 = (u_fmt == DJ_F16) ? 1 : 0;
   DJ_CHECK_ARG(S > 0 && steps > 0 && ldY >= units, "dj_lstm_scan_tc_bwd: bad sizes");
   TcMap map{seq_inner, seq_outer_stride, seq_inner_stride, step_stride, 0, 0, 0, 0, 0};
   cudaStream_t st = (cudaStream_t)stream;
@@ -846,13 +873,13 @@ extern "C" int dj_lstm_scan_tc_bwd(const float* gates, const float* c, const flo
   const bool note_map = (seq_inner == 1 && seq_outer_stride == 48 && step_stride == 1 && steps <= 48);
   DJ_CHECK_ARG(time_map || note_map, "dj_lstm_scan_tc_bwd: only the time-axis (seq=(b,n)) and note-axis (seq=(b,t)) maps are supported");
   if (time_map && units == 256)
-    return launch_tc_bwd<256, 48, 64, true>(Un_bf16, gates, c, dY, ldY, d_y, dZ_bf16, db, S, steps, map, hard, st);
+    return launch_tc_bwd<256, 48, 64, true>(Un_bf16, gates, c, dY, ldY, d_y, dZ_bf16, db, S, steps, map, hard, u_f16, st);
   if (time_map && units == 512)   // scaled model: 32 units per CTA, 16-CTA clusters, a third of a batch element per tile
-    return launch_tc_bwd<512, 16, 32, true>(Un_bf16, gates, c, dY, ldY, d_y, dZ_bf16, db, S, steps, map, hard, st);
+    return launch_tc_bwd<512, 16, 32, true>(Un_bf16, gates, c, dY, ldY, d_y, dZ_bf16, db, S, steps, map, hard, u_f16, st);
   if (note_map && units == 128)
-    return launch_tc_bwd<128, 32, 64, false>(Un_bf16, gates, c, dY, ldY, d_y, dZ_bf16, db, S, steps, map, hard, st);
+    return launch_tc_bwd<128, 32, 64, false>(Un_bf16, gates, c, dY, ldY, d_y, dZ_bf16, db, S, steps, map, hard, u_f16, st);
   if (note_map && units == 256)   // scaled model, note axis
-    return launch_tc_bwd<256, 32, 64, false>(Un_bf16, gates, c, dY, ldY, d_y, dZ_bf16, db, S, steps, map, hard, st);
+    return launch_tc_bwd<256, 32, 64, false>(Un_bf16, gates, c, dY, ldY, d_y, dZ_bf16, db, S, steps, map, hard, u_f16, st);
   DJ_CHECK_ARG(false, "dj_lstm_scan_tc_bwd: units=%d unsupported on this axis (time: 256/512, note: 128/256)", units);
   return -1;
 }

@@ -50,16 +50,18 @@ __device__ __forceinline__ float4 ld_peer_f4(const float* p) {
 
 // Spin until the local flag word reaches `epoch` (epochs only grow; compared as a signed difference so the counter
 // may wrap).  Bounded: after timeout_ns the launch gives up and raises the status word instead of hanging.
-__device__ __forceinline__ void wait_flag(uint32_t* flag, uint32_t epoch, uint32_t* status,
+// Returns false on a timeout.
+__device__ __forceinline__ bool wait_flag(uint32_t* flag, uint32_t epoch, uint32_t* status,
                                           unsigned long long timeout_ns) {
   const unsigned long long t0 = globaltimer_ns();
   while ((int32_t)(ld_acquire_sys(flag) - epoch) < 0) {
     __nanosleep(64);
     if (globaltimer_ns() - t0 > timeout_ns) {
       atomicExch(status, 1u);
-      break;
+      return false;
     }
   }
+  return true;
 }
 
 __global__ void __launch_bounds__(256) peer_nadam_kernel(PeerPtrs pp, int rank, int world, float* __restrict__ m,
@@ -75,11 +77,17 @@ __global__ void __launch_bounds__(256) peer_nadam_kernel(PeerPtrs pp, int rank, 
   if (blockIdx.x == 0 && tid < world) st_release_sys(pp.flags[tid] + FLAG_A + rank, epoch);
   if (tid < world) wait_flag(my + FLAG_A + tid, epoch, my + FLAG_STATUS, timeout_ns);
   __syncthreads();
+  // A timeout is NOT destructive: if any wait of this launch -- or of an earlier one: the status word is sticky --
+  // gave up, the gradient of some rank is missing, so this CTA touches neither the moments nor anybody's weights.
+  // (A rank that never arrives makes every CTA of every rank time out alike; the host reads the status word once per
+  // epoch, before the checkpoint callback, and aborts: PeerNadam.raise_if_timed_out.)
+  const bool healthy = (ld_acquire_sys(my + FLAG_STATUS) == 0u);
 
   // ---- 2.+3. reduce my slice over the ranks, Nadam, broadcast the new weights
   const float* gl = pp.g[rank];
   float* pl = pp.p[rank];
-  for (int64_t i = lo + 4 * ((int64_t)blockIdx.x * blockDim.x + tid); i < hi; i += 4 * (int64_t)gridDim.x * blockDim.x) {
+  for (int64_t i = lo + 4 * ((int64_t)blockIdx.x * blockDim.x + tid); healthy && i < hi;
+       i += 4 * (int64_t)gridDim.x * blockDim.x) {
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int r = 0; r < world; ++r) {
       const float4 x = (r == rank) ? *reinterpret_cast<const float4*>(gl + i) : ld_peer_f4(pp.g[r] + i);

@@ -17,7 +17,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import DJ_BF16, DJ_F32, NO_DROPOUT, Dropout, check
+from ._lib import DJ_BF16, DJ_F16, DJ_F32, NO_DROPOUT, Dropout, check
 from .config import ModelConfig, param_shapes, round_up
 
 N = 48
@@ -34,24 +34,29 @@ def _stream():
 class Workspace:
     """Activation / gradient buffers for one (B, T, precision, train) shape."""
 
-    def __init__(self, cfg: ModelConfig, B: int, T: int, bf16: bool, train: bool, dev):
+    def __init__(self, cfg: ModelConfig, B: int, T: int, prec: str, train: bool, dev):
         self.B, self.T, self.M = B, T, B * T * N
+        bf16, mixed = prec in ("bf16", "mixed"), prec == "mixed"
         M, BT = self.M, B * T
         f32 = dict(dtype=torch.float32, device=dev)
         adt = torch.bfloat16 if bf16 else torch.float32
         self.emb = torch.empty(BT, cfg.style_units, **f32)
         self.sp, self.A, self.Z, self.h, self.c = [], [], [], [], []
+        self.A_lo = []      # mixed: bf16 residual of A (second operand of the split gate GEMM)
         self.ld = []
         for L in cfg.layers():
             ld = round_up(L["F"], 32)
             self.ld.append(ld)
             self.sp.append(torch.empty(BT, L["F"], **f32))
             self.A.append(torch.empty(M, ld, dtype=adt, device=dev))
+            self.A_lo.append(torch.empty(M, ld, dtype=adt, device=dev) if mixed else None)
             self.Z.append(torch.empty(M, 4 * L["U"], **f32))
             self.h.append(torch.empty(M, L["U"], **f32))
             self.c.append(torch.empty(M, L["U"], **f32) if train else None)
-        # h_{step-1} in bf16: A operand of the tcgen05 recurrent-weight gradient
-        self.hprev = [torch.empty(M, L["U"], dtype=torch.bfloat16, device=dev) if (train and bf16) else None
+        # h_{step-1} in 16 bits (half in mixed precision): B operand of the tensor-core recurrence and A operand of
+        # the recurrent-weight gradient
+        hdt = torch.float16 if mixed else torch.bfloat16
+        self.hprev = [torch.empty(M, L["U"], dtype=hdt, device=dev) if (train and bf16) else None
                       for L in cfg.layers()]
         self.probs = torch.empty(M, 3, **f32)
         if train:
@@ -61,7 +66,7 @@ class Workspace:
             self.loss = torch.zeros(1, **f32)
             # one dZ per layer: the weight-gradient GEMMs of layer l run on a second stream while the
             # reverse scan of layer l-1 is already writing its own dZ
-            self.dZ = [torch.empty(M, 4 * L["U"], dtype=adt, device=dev) for L in cfg.layers()]
+            self.dZ = [torch.empty(M, 4 * L["U"], dtype=adt, device=dev) for L in cfg.layers()]   # bf16 (range)
             self.dA = [torch.empty(M, ld, **f32) for ld in self.ld]
             self.ds = [torch.empty(BT, L["F"], **f32) for L in cfg.layers()]
             self.demb = torch.empty(BT, cfg.style_units, **f32)
@@ -69,11 +74,15 @@ class Workspace:
 
 class Engine:
     def __init__(self, cfg: ModelConfig = ModelConfig(), device: Optional[torch.device] = None,
-                 precision: str = "bf16", recurrent_activation: str = "hard_sigmoid",
+                 precision: str = "mixed", recurrent_activation: str = "hard_sigmoid",
                  input_dropout: float = 0.2, dropout: float = 0.5):
         if not torch.cuda.is_available():
             raise RuntimeError("the DeepJ B200 engine needs a CUDA device; there is no CPU fallback")
-        assert precision in ("bf16", "fp32")
+        # "mixed" (training default): tensor cores at fp32 grade where the outputs need it -- split bf16 hi+lo gate
+        #     GEMM (3 passes), half-precision h and hi+lo half-precision U in the recurrence; bf16 in the backward pass.
+        # "bf16": every tensor-core operand one bf16 (fastest; outside north_star's 1e-3 tolerance).
+        # "fp32": CUDA-core kernels throughout (generation, reference-grade checks).
+        assert precision in ("mixed", "bf16", "fp32")
         self.lib = _lib.load()
         self.cfg = cfg
         self.dev = device or torch.device("cuda", torch.cuda.current_device())
@@ -102,17 +111,19 @@ class Engine:
         self._ws: Dict[tuple, Workspace] = {}
         self._wbf: Dict[str, torch.Tensor] = {}
         self._wbf_version = -1
+        self._wbf_mixed = None
         self._version = 0
         self.launches = 0   # kernels of ours enqueued (bench.py reports it)
         self.profile = None
         self.profile_only = None
-        self.tc_scan = True   # bf16 training: recurrence on tcgen05 (False = fp32 CUDA-core scans)
+        self.tc_scan = True   # tensor-core training: recurrence on tcgen05 (False: debugging, precision "bf16" only)
         # backward runs on two streams: the dependency chain (reverse scan -> data gradient -> next layer's
         # reverse scan) on a high-priority stream, the weight / style / conv gradients behind it on the caller's
         self.overlap = os.environ.get("DJ_NO_OVERLAP", "") == ""
         self._hi = None
         self._tag = ""
         self.peer = None      # parallel.PeerNadam: fused gradient exchange + Nadam over peer memory
+        self.gen_tc = False   # generation projections on the tensor cores (split operands); False = CUDA-core fp32 GEMM
 
     # ------------------------------------------------------------------ params
     def _view(self, flat, k):
@@ -218,12 +229,14 @@ class Engine:
         self.profile = []
         return agg
 
-    def _refresh_bf16(self):
-        """bf16 copies of the LSTM kernels: transposed [4U, ld] (forward B operand,
-        K-major) and natural [F, 4U] (data-gradient B operand)."""
-        if self._wbf_version == self._version:
+    def _refresh_bf16(self, mixed: bool):
+        """16-bit operand copies of the LSTM kernels: transposed [4U, ld] (forward B operand, K-major) and natural
+        [F, 4U] (data-gradient B operand).  Mixed precision adds the residuals W^T - bf16(W^T) and keeps the recurrent
+        kernel of the forward scan as IEEE half hi + lo."""
+        if self._wbf_version == self._version and self._wbf_mixed == mixed:
             return
-        ents = []   # (src, rows, cols, dst, ldo, transpose)
+        ents = []   # (src, rows, cols, dst, dst_lo, ldo, transpose, fmt)
+        rfmt = DJ_F16 if mixed else DJ_BF16
         for li, L in enumerate(self.layers):
             W = self.params[f"{L['name']}.lstm.W"]
             Um = self.params[f"{L['name']}.lstm.U"]
@@ -231,19 +244,25 @@ class Engine:
             U, ld = L["U"], round_up(F, 32)
             n = L["name"]
             if f"{n}.Wt" not in self._wbf:
-                bf = dict(dtype=torch.bfloat16, device=self.dev)
-                self._wbf[f"{n}.Wt"] = torch.empty(U4, ld, **bf)   # W^T  [4U, ld]: forward B operand (K-major)
-                self._wbf[f"{n}.Wn"] = torch.empty(F, U4, **bf)    # W    [F, 4U]: data-gradient B operand
-                self._wbf[f"{n}.Ut"] = torch.empty(U4, U, **bf)    # U^T  [4U, U]: resident A operand, forward scan
-                self._wbf[f"{n}.Un"] = torch.empty(U, U4, **bf)    # U    [U, 4U]: resident A operand, reverse scan
-            ents += [(W, F, U4, self._wbf[f"{n}.Wt"], ld, 1), (W, F, U4, self._wbf[f"{n}.Wn"], U4, 0),
-                     (Um, U, U4, self._wbf[f"{n}.Ut"], U, 1), (Um, U, U4, self._wbf[f"{n}.Un"], U4, 0)]
+                w16 = dict(dtype=torch.int16, device=self.dev)     # raw 16-bit words: bf16 or half by mode
+                self._wbf[f"{n}.Wt"] = torch.empty(U4, ld, **w16)     # W^T  [4U, ld]: forward B operand (K-major)
+                self._wbf[f"{n}.Wt_lo"] = torch.empty(U4, ld, **w16)  #       its bf16 residual (split gate GEMM)
+                self._wbf[f"{n}.Wn"] = torch.empty(F, U4, **w16)      # W    [F, 4U]: data-gradient B operand
+                self._wbf[f"{n}.Ut"] = torch.empty(U4, U, **w16)      # U^T  [4U, U]: resident A operand, forward scan
+                self._wbf[f"{n}.Ut_lo"] = torch.empty(U4, U, **w16)   #       its residual (second MMA pass)
+                self._wbf[f"{n}.Un"] = torch.empty(U, U4, **w16)      # U    [U, 4U]: resident A operand, reverse scan
+            lo = (lambda k: self._wbf[k]) if mixed else (lambda k: None)
+            ents += [(W, F, U4, self._wbf[f"{n}.Wt"], lo(f"{n}.Wt_lo"), ld, 1, DJ_BF16),
+                     (W, F, U4, self._wbf[f"{n}.Wn"], None, U4, 0, rfmt),
+                     (Um, U, U4, self._wbf[f"{n}.Ut"], lo(f"{n}.Ut_lo"), U, 1, rfmt),
+                     (Um, U, U4, self._wbf[f"{n}.Un"], None, U4, 0, rfmt)]
         k = len(ents)
-        self._call("dj_cast_bf16_multi", k, (C.c_void_p * k)(*[e[0].data_ptr() for e in ents]),
-                   (C.c_int * k)(*[e[1] for e in ents]), (C.c_int * k)(*[e[2] for e in ents]),
-                   (C.c_void_p * k)(*[e[3].data_ptr() for e in ents]), (C.c_int * k)(*[e[4] for e in ents]),
-                   (C.c_int * k)(*[e[5] for e in ents]), _stream())
-        self._wbf_version = self._version
+        ints = lambda j: (C.c_int * k)(*[e[j] for e in ents])
+        self._call("dj_cast16_multi", k, (C.c_void_p * k)(*[e[0].data_ptr() for e in ents]), ints(1), ints(2),
+                   (C.c_void_p * k)(*[e[3].data_ptr() for e in ents]),
+                   (C.c_void_p * k)(*[None if e[4] is None else e[4].data_ptr() for e in ents]),
+                   ints(5), ints(6), ints(7), _stream())
+        self._wbf_version, self._wbf_mixed = self._version, mixed
 
     # --------------------------------------------------------------- dropout
     def _drops(self, train: bool, seed: int) -> Dict[int, Dropout]:
@@ -272,10 +291,10 @@ class Engine:
         return out
 
     # --------------------------------------------------------------- forward
-    def workspace(self, B: int, T: int, bf16: bool, train: bool) -> Workspace:
-        key = (B, T, bf16, train)
+    def workspace(self, B: int, T: int, prec: str, train: bool) -> Workspace:
+        key = (B, T, prec, train)
         if key not in self._ws:
-            self._ws[key] = Workspace(self.cfg, B, T, bf16, train, self.dev)
+            self._ws[key] = Workspace(self.cfg, B, T, prec, train, self.dev)
         return self._ws[key]
 
     def _style(self, ws: Workspace, style, bstride, tstride, B, T):
@@ -294,16 +313,25 @@ class Engine:
         bias = P[f"{L['name']}.lstm.b"]
         self._tag = ":" + L["name"]
         if bf16:
-            self._call("dj_gate_gemm_bf16", _ptr(ws.A[li]), ld, _ptr(self._wbf[f"{L['name']}.Wt"]), ld,
-                       _ptr(ws.Z[li]), U4, _ptr(bias), M, U4, ld, _stream())
+            mixed = ws.A_lo[li] is not None     # split product: A.W + A_lo.W + A.W_lo on the same TMEM accumulator
+            self._call("dj_gate_gemm_16", _ptr(ws.A[li]), _ptr(ws.A_lo[li]), DJ_BF16, ld,
+                       _ptr(self._wbf[f"{L['name']}.Wt"]), _ptr(self._wbf[f"{L['name']}.Wt_lo"]) if mixed else None,
+                       DJ_BF16, ld, _ptr(ws.Z[li]), U4, _ptr(bias), M, U4, ld, _stream())
         else:
             self._call("dj_gemm_simt", _ptr(ws.A[li]), DJ_F32, ld, 1, _ptr(P[f"{L['name']}.lstm.W"]), DJ_F32,
                        U4, 1, _ptr(ws.Z[li]), U4, _ptr(bias), M, U4, L["F"], 0, 0, 0, _stream())
 
     def _tc_ok(self, B: int, T: int) -> bool:
-        """The tensor-core scans work on whole tiles: 48 time-axis sequences (always whole: B*48) and
-        64 note-axis sequences (B*T % 64 == 0); other shapes use the fp32 CUDA-core scans."""
-        return self.tc_scan and (B * T) % 64 == 0
+        """The tensor-core scans work on whole tiles: 48 time-axis sequences (always whole: B*48) and 64 note-axis
+        sequences (B*T % 64 == 0: any batch size at the model's 128-step windows).  There is no second code path:
+        training any other shape in a tensor-core precision is an error (`tc_scan = False` is a debugging switch
+        that runs the bf16 GEMMs with the CUDA-core scans)."""
+        if not self.tc_scan:
+            return False
+        if (B * T) % 64 != 0:
+            raise ValueError(f"tensor-core training needs batch*time_steps to be a multiple of 64 (got {B}*{T}); "
+                             "use precision='fp32' for other shapes")
+        return True
 
     def _scan_map(self, axis: str, B: int, T: int):
         if axis == "time":   # sequences (b,n), steps t
@@ -315,8 +343,10 @@ class Engine:
         m = self._scan_map(L["axis"], B, T)
         self._tag = ":" + L["name"]
         if train and ws.hprev[li] is not None and self._tc_ok(B, T):
+            mixed = ws.A_lo[li] is not None
             self._call("dj_lstm_scan_tc_fwd", _ptr(ws.Z[li]), _ptr(ws.h[li]), _ptr(ws.c[li]), _ptr(ws.hprev[li]),
-                       _ptr(self._wbf[f"{L['name']}.Ut"]), m["S"], m["steps"], L["U"], m["inner"], m["outer"],
+                       _ptr(self._wbf[f"{L['name']}.Ut"]), _ptr(self._wbf[f"{L['name']}.Ut_lo"]) if mixed else None,
+                       DJ_F16 if mixed else DJ_BF16, m["S"], m["steps"], L["U"], m["inner"], m["outer"],
                        m["inner_stride"], m["step"], self.hard, _stream())
         else:
             self._call("dj_lstm_scan_fwd", _ptr(ws.Z[li]), _ptr(ws.h[li]), _ptr(ws.c[li]) if train else None,
@@ -331,18 +361,18 @@ class Engine:
         P = self.params
         adt = DJ_BF16 if bf16 else DJ_F32
         if bf16:
-            self._refresh_bf16()
+            self._refresh_bf16(ws.A_lo[0] is not None)
         if not style_done:
             self._style(ws, style, style_bstride, style_tstride, B, T)
         self._call("dj_frontend_fwd", _ptr(notes), notes_bstride, _ptr(beat), beat_bstride, B, T,
                    _ptr(P["conv.W"]), _ptr(P["conv.b"]), _ptr(ws.sp[0]), d[1], d[2], d[4], d[5], _ptr(ws.A[0]),
-                   ws.ld[0], adt, _stream())
+                   _ptr(ws.A_lo[0]), ws.ld[0], adt, _stream())
         M = B * T * N
         self._gate_gemm(0, ws, bf16, M)
         self._scan_fwd(0, ws, B, T, train)
         L1 = self.layers[1]
         self._call("dj_layer_input", _ptr(ws.h[0]), self.layers[0]["U"], 0, T * N, d[6], _ptr(ws.sp[1]), L1["F"],
-                   d[7], None, 0, NO_DROPOUT, B, T, _ptr(ws.A[1]), ws.ld[1], adt, _stream())
+                   d[7], None, 0, NO_DROPOUT, B, T, _ptr(ws.A[1]), _ptr(ws.A_lo[1]), ws.ld[1], adt, _stream())
         self._gate_gemm(1, ws, bf16, M)
         self._scan_fwd(1, ws, B, T, train)
 
@@ -352,15 +382,16 @@ class Engine:
         P, cfg = self.params, self.cfg
         adt = DJ_BF16 if bf16 else DJ_F32
         if bf16:
-            self._refresh_bf16()
+            self._refresh_bf16(ws.A_lo[2] is not None)
         M = B * T * N
         L2, L3 = self.layers[2], self.layers[3]
         self._call("dj_layer_input", _ptr(h_time), cfg.time_axis_units, h_row0, h_b_rows, d[8], _ptr(ws.sp[2]),
-                   L2["F"], d[9], _ptr(chosen), chosen_bstride, d[3], B, T, _ptr(ws.A[2]), ws.ld[2], adt, _stream())
+                   L2["F"], d[9], _ptr(chosen), chosen_bstride, d[3], B, T, _ptr(ws.A[2]), _ptr(ws.A_lo[2]), ws.ld[2], adt,
+                   _stream())
         self._gate_gemm(2, ws, bf16, M)
         self._scan_fwd(2, ws, B, T, train)
         self._call("dj_layer_input", _ptr(ws.h[2]), L2["U"], 0, T * N, d[10], _ptr(ws.sp[3]), L3["F"], d[11],
-                   None, 0, NO_DROPOUT, B, T, _ptr(ws.A[3]), ws.ld[3], adt, _stream())
+                   None, 0, NO_DROPOUT, B, T, _ptr(ws.A[3]), _ptr(ws.A_lo[3]), ws.ld[3], adt, _stream())
         self._gate_gemm(3, ws, bf16, M)
         self._scan_fwd(3, ws, B, T, train)
         self._call("dj_head_loss", _ptr(ws.h[3]), cfg.note_axis_units, d[12], _ptr(P["note_dense.W"]),
@@ -372,11 +403,14 @@ class Engine:
         """`model([notes, chosen, beat, style])` of model.py:151 on device tensors
         [B,T,48,3], [B,T,48,3], [B,T,16], [B,T,23] (fp32, contiguous).  Returns
         the workspace; ws.probs is the [B*T*48, 3] output."""
-        bf16 = (precision or self.precision) == "bf16"
+        prec = precision or self.precision
+        bf16 = prec in ("bf16", "mixed")         # tensor-core path (16-bit operands)
+        if prec == "mixed" and not self.tc_scan:
+            raise ValueError("tc_scan = False (CUDA-core scans under the tensor-core GEMMs) exists for precision 'bf16' only")
         B, T = notes.shape[0], notes.shape[1]
-        ws = self.workspace(B, T, bf16, target is not None)
+        ws = self.workspace(B, T, prec, target is not None)
         d = self._drops(train, seed)
-        self._last = dict(ws=ws, d=d, bf16=bf16, notes=notes, style=style, B=B, T=T)
+        self._last = dict(ws=ws, d=d, bf16=bf16, prec=prec, notes=notes, style=style, B=B, T=T)
         self.forward_time(ws, notes, T * N * 3, beat, T * 16, B, T, d, bf16, target is not None, style=style,
                           style_bstride=T * self.cfg.num_styles, style_tstride=self.cfg.num_styles)
         self.forward_note(ws, ws.h[1], 0, T * N, chosen, T * N * 3, B, T, d, bf16, target is not None, target)
@@ -392,6 +426,9 @@ class Engine:
         P, G, cfg = self.params, self.grads, self.cfg
         M, BT = B * T * N, B * T
         zdt = DJ_BF16 if bf16 else DJ_F32
+        # backward weight operands (U of the reverse scan, W of the data gradient): half in mixed precision (8x finer
+        # than bf16; weights need no exponent range), always against bf16 dZ
+        wfmt = DJ_F16 if st["prec"] == "mixed" else DJ_BF16
         self.gflat.zero_()
         self._call("dj_head_finalize", _ptr(ws.partials), cfg.note_axis_units, _ptr(ws.loss),
                    _ptr(G["note_dense.W"]), _ptr(G["note_dense.b"]), _ptr(G["volume_dense.W"]),
@@ -416,7 +453,7 @@ class Engine:
                 # ---- critical chain: reverse scan, then the data gradient the next layer's scan consumes
                 if bf16 and self._tc_ok(B, T):
                     self._call("dj_lstm_scan_tc_bwd", _ptr(ws.Z[li]), _ptr(ws.c[li]), _ptr(dY), ldY, d[L["site_out"]],
-                               _ptr(self._wbf[f"{name}.Un"]), _ptr(dZ), _ptr(G[f"{name}.lstm.b"]), m["S"], m["steps"],
+                               _ptr(self._wbf[f"{name}.Un"]), wfmt, _ptr(dZ), _ptr(G[f"{name}.lstm.b"]), m["S"], m["steps"],
                                U, m["inner"], m["outer"], m["inner_stride"], m["step"], self.hard, _stream())
                 else:
                     self._call("dj_lstm_scan_bwd", _ptr(ws.Z[li]), _ptr(ws.c[li]), _ptr(dY), ldY, d[L["site_out"]],
@@ -427,8 +464,8 @@ class Engine:
                     ev_scan.record(chain)
                 # data gradient dA = dZ . W^T
                 if bf16:
-                    self._call("dj_gate_gemm_bf16", _ptr(dZ), U4, _ptr(self._wbf[f"{name}.Wn"]), U4, _ptr(ws.dA[li]),
-                               ld, None, M, F, U4, _stream())
+                    self._call("dj_gate_gemm_16", _ptr(dZ), None, DJ_BF16, U4, _ptr(self._wbf[f"{name}.Wn"]), None, wfmt,
+                               U4, _ptr(ws.dA[li]), ld, None, M, F, U4, _stream())
                 else:
                     self._call("dj_gemm_simt", _ptr(dZ), DJ_F32, U4, 1, _ptr(P[f"{name}.lstm.W"]), DJ_F32, 1, U4,
                                _ptr(ws.dA[li]), ld, None, M, F, U4, 0, 0, 0, _stream())
@@ -441,8 +478,9 @@ class Engine:
             if bf16:
                 self._call("dj_wgrad_gemm_bf16", _ptr(ws.A[li]), ld, _ptr(dZ), U4, _ptr(G[f"{name}.lstm.W"]), U4,
                            F, U4, M, _stream())
-                self._call("dj_wgrad_gemm_bf16", _ptr(ws.hprev[li]), U, _ptr(dZ), U4, _ptr(G[f"{name}.lstm.U"]),
-                           U4, U, U4, M, _stream())
+                self._call("dj_wgrad_gemm_16", _ptr(ws.hprev[li]),
+                           DJ_F16 if ws.hprev[li].dtype == torch.float16 else DJ_BF16, U, _ptr(dZ), DJ_BF16, U4,
+                           _ptr(G[f"{name}.lstm.U"]), U4, U, U4, M, _stream())
             else:
                 self._call("dj_gemm_simt", _ptr(ws.A[li]), DJ_F32, 1, ld, _ptr(dZ), zdt, U4, 1,
                            _ptr(G[f"{name}.lstm.W"]), U4, None, F, U4, M, 1, 0, 0, _stream())

@@ -72,7 +72,7 @@ class _Base:
             def __call__(self_inner, style_vectors):
                 sv = np.ascontiguousarray(style_vectors, dtype=np.float32)
                 n, ns = sv.shape
-                ws = eng.workspace(n, 1, False, False)
+                ws = eng.workspace(n, 1, "fp32", False)
                 eng._style(ws, _dev(eng, sv), ns, 0, n, 1)     # dj_style_fwd: emb = style.W + b (linear)
                 torch.cuda.synchronize()
                 return ws.emb[:n].cpu().numpy().copy()
@@ -161,8 +161,14 @@ class TrainModel(_Base):
             if world > 1:
                 # every rank must see the same epoch loss, or rank-local callbacks (early stopping) would make the
                 # ranks leave the epoch loop at different times and the next gradient exchange would wait forever
+                # The same all-reduce carries the health of the fused gradient exchange: if any rank's bounded wait
+                # gave up during this epoch, every rank stops HERE, before ModelCheckpoint could save anything.
                 from . import parallel
-                tot_n = parallel.sum_over_ranks(torch.stack([tot, torch.full_like(tot, float(n))]))
+                bad = e.peer.status_word().double().reshape(()) if e.peer is not None else torch.zeros_like(tot)
+                tot_n = parallel.sum_over_ranks(torch.stack([tot, torch.full_like(tot, float(n)), bad]))
+                if float(tot_n[2].item()) != 0.0:
+                    raise RuntimeError("the peer-memory gradient exchange timed out on at least one rank during this epoch; "
+                                       "no update was applied after that step and nothing was saved")
                 logs = {"loss": float(tot_n[0].item()) / max(float(tot_n[1].item()), 1.0)}
             else:
                 logs = {"loss": float(tot.item()) / max(n, 1)}
@@ -189,7 +195,7 @@ class TimeModel(_Base):
         for s in range(0, len(notes), batch_size):
             n_, b_, s_ = [_dev(e, a[s:s + batch_size]) for a in (notes, beat, style)]
             B, T = n_.shape[0], n_.shape[1]
-            ws = e.workspace(B, T, False, False)
+            ws = e.workspace(B, T, "fp32", False)
             e.forward_time(ws, n_, T * N * 3, b_, T * 16, B, T, d, False, False, style=s_,
                            style_bstride=T * e.cfg.num_styles, style_tstride=e.cfg.num_styles)
             outs.append(ws.h[1].view(B, T, N, -1).cpu().numpy())
@@ -208,7 +214,7 @@ class NoteModel(_Base):
         for s in range(0, len(feats), batch_size):
             f_, c_, s_ = [_dev(e, a[s:s + batch_size]) for a in (feats, chosen, style)]
             B, T = f_.shape[0], f_.shape[1]
-            ws = e.workspace(B, T, False, False)
+            ws = e.workspace(B, T, "fp32", False)
             e._style(ws, s_, T * e.cfg.num_styles, e.cfg.num_styles, B, T)
             e.forward_note(ws, f_.view(B * T * N, -1), 0, T * N, c_, T * N * 3, B, T, d, False, False)
             outs.append(ws.probs.view(B, T, N, 3).cpu().numpy())

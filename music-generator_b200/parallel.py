@@ -37,6 +37,13 @@ def shard_indices(n: int, rank: int, world: int) -> np.ndarray:
     return np.arange(rank, n, world)
 
 
+def shard_sequence_chunks(G: int, rank: int, world: int, chunk: int = 32) -> List[int]:
+    """Generation shard of rank `rank`: the sequences of the predict chunks rank, rank+world, ... (chunk = Keras'
+    predict batch of 32, which scopes the pitch_bins scramble of model.py:43-49, so a sharded run computes exactly
+    what one GPU walking all chunks computes).  Every sequence lands on exactly one rank."""
+    return [g for g in range(G) if (g // chunk) % world == rank]
+
+
 def allreduce_flat(flat: torch.Tensor) -> torch.Tensor:
     """Sum the flat gradient buffer over ranks in place (one collective per step).
     The 1/world average is applied by the Nadam kernel (gscale)."""
@@ -90,21 +97,50 @@ class PeerNadam:
         self.n = n
         self.flag_words = int(self.lib.dj_peer_flag_words())
         nbytes = (2 * n + self.flag_words) * 4
+        # Setting up is a COLLECTIVE decision: a rank whose allocation or whose mapping of one peer fails must not
+        # leave the others waiting in a collective (or running the peer kernel alone), so after each phase the
+        # ranks exchange success flags and either all go on or all release what they hold and raise.
         own, handle = C.c_void_p(), C.create_string_buffer(64)
-        self.check(self.lib.dj_peer_alloc(nbytes, C.byref(own), handle), "dj_peer_alloc")
-        stage("allocated")
-        handles: List[Optional[bytes]] = [None] * self.world
+        rc = self.lib.dj_peer_alloc(nbytes, C.byref(own), handle)
+        err = None if rc == 0 else self.lib.dj_last_error().decode("utf-8", "replace")
+        stage("allocated" if rc == 0 else f"allocation failed: {err}")
+        gathered: List[Optional[tuple]] = [None] * self.world
         if self.world > 1:
-            dist.all_gather_object(handles, handle.raw)
+            dist.all_gather_object(gathered, (rc == 0, handle.raw, err))
+        else:
+            gathered[0] = (rc == 0, handle.raw, err)
+        if not all(g[0] for g in gathered):
+            if rc == 0:
+                self.lib.dj_peer_free(own)
+            bad = {r: g[2] for r, g in enumerate(gathered) if not g[0]}
+            raise RuntimeError(f"dj_peer_alloc failed on rank(s) {bad}")
+        handles = [g[1] for g in gathered]
         stage("handles exchanged")
         self.bases: List[int] = []
+        opened, err = [], None
         for r in range(self.world):
             if r == self.rank:
                 self.bases.append(own.value)
-            else:
-                q = C.c_void_p()
-                self.check(self.lib.dj_peer_open(handles[r], C.byref(q)), "dj_peer_open")
-                self.bases.append(q.value)
+                continue
+            q = C.c_void_p()
+            rc = self.lib.dj_peer_open(handles[r], C.byref(q))
+            if rc != 0:
+                err = f"dj_peer_open(rank {r}): " + self.lib.dj_last_error().decode("utf-8", "replace")
+                break
+            opened.append(q.value)
+            self.bases.append(q.value)
+        oks: List[Optional[tuple]] = [None] * self.world
+        if self.world > 1:
+            dist.all_gather_object(oks, (err is None, err))
+        else:
+            oks[0] = (err is None, err)
+        if not all(o[0] for o in oks):
+            for b in opened:
+                self.lib.dj_peer_close(C.c_void_p(b))
+            if self.world > 1:
+                dist.barrier()            # nobody frees a block a peer still has mapped
+            self.lib.dj_peer_free(own)
+            raise RuntimeError(f"peer mapping failed: {[o[1] for o in oks if not o[0]]}")
         stage("peers opened")
         base = own.value
         self.flat = torch.as_tensor(_DeviceBlock(base, n, "<f4"), device=eng.dev)
@@ -129,11 +165,16 @@ class PeerNadam:
         eng._call("dj_nadam_allreduce_peer", self._p, self._g, self._f, self.rank, self.world, eng.m.data_ptr(),
                   eng.v.data_ptr(), self.n, self.epoch, 1.0 / self.world, *scalars, stream)
 
+    def status_word(self) -> torch.Tensor:
+        """Device view of the sticky status word (0 = healthy, 1 = a bounded wait gave up); no synchronisation."""
+        return self.flags[self.flag_words - 1]
+
     def raise_if_timed_out(self) -> None:
-        """Host check (synchronises) of the status word a bounded wait sets when a peer never showed up."""
-        if int(self.flags[self.flag_words - 1].item()) != 0:
+        """Host check (synchronises) of the status word a bounded wait sets when a peer never showed up.  From that
+        launch on the kernel skips every update, so the weights are those of the last good step."""
+        if int(self.status_word().item()) != 0:
             raise RuntimeError("dj_nadam_allreduce_peer: a rank did not reach the exchange within the time limit; "
-                               "the weights of this run are invalid")
+                               "training stopped updating at that step")
 
     def close(self, eng=None) -> None:
         if self.closed:
@@ -164,6 +205,6 @@ def make_step_exchange(eng, world: int):
     if os.environ.get("DJ_PEER_NADAM", "1") != "0" and torch.cuda.is_available():
         try:
             return None, PeerNadam(eng)
-        except RuntimeError as e:      # CUDA IPC / peer access not available here: every rank fails alike
+        except RuntimeError as e:      # raised on EVERY rank or on none (PeerNadam.__init__ decides collectively)
             print(f"[deepj] peer-memory exchange unavailable ({e}); using NCCL all-reduce", file=sys.stderr)
     return allreduce_flat, None

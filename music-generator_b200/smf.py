@@ -171,7 +171,9 @@ def _encode_track(track: List[Event]) -> bytes:
         elif isinstance(ev, SysexEvent):
             out += bytes([0xF0]) + _write_varlen(len(ev.data)) + bytes(ev.data)
         else:
-            out += bytes([ev.status | ev.channel]) + bytes(d & 0x7F for d in ev.data)
+            if any(not 0 <= d <= 0x7F for d in ev.data):
+                raise ValueError(f"MIDI data byte out of range 0..127 in {type(ev).__name__}: {list(ev.data)}")
+            out += bytes([ev.status | ev.channel]) + bytes(ev.data)
     if not track or not isinstance(track[-1], EndOfTrackEvent):
         out += b"\x00\xff\x2f\x00"
     return bytes(out)

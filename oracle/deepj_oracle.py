@@ -498,9 +498,10 @@ def generate(p, cfg: Config, styles: Sequence[np.ndarray], num_steps: int, unifo
     gens = [Generation(cfg, s, default_temp) for s in styles]
     G, N, Ut = len(gens), cfg.num_notes, cfg.time_axis_units
     act = recurrent_activation
-    out_steps, prob_steps, decision_steps = [], [], []
+    out_steps, prob_steps, decision_steps, temp_steps = [], [], [], []
     with torch.no_grad():
         for t in range(num_steps):
+            temp_steps.append([g.temperature for g in gens])      # temperature in effect while step t is sampled
             notes = torch.tensor(np.stack([g.notes_memory for g in gens]), dtype=dtype)
             beat = torch.tensor(np.stack([g.beat_memory for g in gens]), dtype=dtype)
             sty = torch.tensor(np.stack([g.style_memory for g in gens]), dtype=dtype)
@@ -555,6 +556,9 @@ def generate(p, cfg: Config, styles: Sequence[np.ndarray], num_steps: int, unifo
     events = np.stack(out_steps)            # [steps, G, N, 3]
     info = {"uniforms_used": rand.pos, "min_margin": min(g.min_margin for g in gens)}
     info["decisions"] = np.stack(decision_steps)   # the oracle's own draws (== events unless forced)
+    info["temperature_trace"] = np.array(temp_steps, dtype=np.float64)          # [steps, G]
+    info["temperature"] = np.array([g.temperature for g in gens], dtype=np.float64)
+    info["silent_time"] = np.array([g.silent_time for g in gens])
     if return_probs:
         info["probs"] = np.stack(prob_steps)
     return events, info

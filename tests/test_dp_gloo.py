@@ -109,3 +109,16 @@ def test_training_shards_are_equal_and_disjoint():
         assert all(len(s) == n // world for s in shards)
         allidx = np.concatenate(shards)
         assert len(set(allidx.tolist())) == len(allidx) and allidx.max(initial=-1) < n
+
+
+def test_generation_shards_are_whole_predict_chunks():
+    """Generation sharding (no collective): every sequence on exactly one rank, whole chunks of 32 together."""
+    from music_generator_b200 import parallel
+    for G in (1, 31, 32, 70, 1024):
+        for world in (1, 2, 8):
+            shards = [parallel.shard_sequence_chunks(G, r, world) for r in range(world)]
+            assert sorted(sum(shards, [])) == list(range(G))
+            for sh in shards:
+                for g in sh:
+                    assert all(h in sh for h in range(32 * (g // 32), min(32 * (g // 32) + 32, G)))
+    assert len(parallel.shard_sequence_chunks(1024, 3, 8)) == 128

@@ -19,7 +19,7 @@ K = 10
 for i in range(K):
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
     ev[0].record()
-    ws = e.workspace(B, 128, True, True)
+    ws = e.workspace(B, 128, e.precision, True)
     d = e._drops(True, 10 + i)
     e._last = dict(ws=ws, d=d, bf16=True, notes=dev[0], style=dev[3], B=B, T=128)
     e.forward_time(ws, dev[0], 128 * 48 * 3, dev[2], 128 * 16, B, 128, d, True, True, style=dev[3],
