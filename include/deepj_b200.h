@@ -108,7 +108,9 @@ int dj_gemm_simt(const void* A, int a_dtype, int64_t a_sm, int64_t a_sk, const v
  *   lda/ldb in elements (multiples of 8), K padded with zeros up to lda. */
 int dj_gate_gemm_bf16(const void* A, int64_t lda, const void* Bt, int64_t ldb, float* C, int64_t ldc,
                       const float* bias, int M, int N, int K, void* stream);
-/* The same kernel with per-operand 16-bit formats (DJ_BF16 / DJ_F16) and, when
+/* The same kernel with a choice of 16-bit format (DJ_BF16 / DJ_F16, the SAME for both
+ * operands: tcgen05 kind::f16 raises an illegal-instruction fault on B200 when one
+ * operand is half and the other bf16, so a_fmt != b_fmt is rejected) and, when
  * A_lo and Bt_lo are given, the fp32-grade SPLIT product in three tcgen05 passes
  * over the same TMEM accumulator:
  *   C = A.Bt^T + A_lo.Bt^T + A.Bt_lo^T + bias,   X_lo = 16-bit(X - 16-bit(X))
@@ -123,10 +125,13 @@ int dj_gate_gemm_16(const void* A, const void* A_lo, int a_fmt, int64_t lda, con
  * The h_{step-1} operand of dU comes pre-shifted from dj_lstm_scan_fwd. */
 int dj_wgrad_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, float* C, int64_t ldc,
                        int Ka, int Nb, int64_t M, void* stream);
-/* per-operand formats: dU = H_{step-1}^T.dZ multiplies the half-precision h the
- * forward scan saved with the bf16 dZ of the reverse scan */
+/* the same with a choice of format (a_fmt == b_fmt, see dj_gate_gemm_16) */
 int dj_wgrad_gemm_16(const void* A, int a_fmt, int64_t lda, const void* B, int b_fmt, int64_t ldb, float* C,
                      int64_t ldc, int Ka, int Nb, int64_t M, void* stream);
+/* In-place IEEE half -> bf16 of n elements.  The forward scan keeps h_{step-1} in half
+ * (4 more mantissa bits in the recurrence); its weight gradient dU = H_{step-1}^T.dZ
+ * multiplies it with the bf16 dZ, so after the forward pass the buffer is converted. */
+int dj_half_to_bf16_inplace(void* buf, int64_t n, void* stream);
 /* fp32 -> bf16 operand copies: out[r, c] = in[r, c] (c<cols) else 0, out ld = ldo;
  * transpose!=0 writes out[c, r] (ldo >= rows). */
 int dj_cast_bf16(const float* in, int rows, int cols, void* out, int ldo, int transpose, void* stream);
@@ -166,11 +171,11 @@ int dj_lstm_scan_tc_fwd(float* Z, float* h_out, float* c_out, void* h_prev_16, c
                         int64_t seq_outer_stride, int64_t seq_inner_stride, int64_t step_stride, int hard,
                         void* stream);
 /* Tensor-core variant of the reverse scan (dz.U^T on tcgen05): U is passed as
- * Un_16 [units, 4*units] (u_fmt = DJ_BF16 / DJ_F16, natural, gate-interleaved columns);
- * dZ is bf16 (gradients need the exponent range; kind::f16 mixes the two formats) and
- * doubles as the inter-CTA exchange buffer; db accumulates with fp32 atomics. */
+ * Un_bf16 [units, 4*units] (bf16, natural, gate-interleaved columns); dZ is bf16
+ * (gradients need its exponent range) and doubles as the inter-CTA exchange buffer;
+ * db accumulates with fp32 atomics. */
 int dj_lstm_scan_tc_bwd(const float* gates, const float* c, const float* dY, int64_t ldY, dj_dropout d_y,
-                        const void* Un_16, int u_fmt, void* dZ_bf16, float* db, int S, int steps, int units,
+                        const void* Un_bf16, void* dZ_bf16, float* db, int S, int steps, int units,
                         int seq_inner, int64_t seq_outer_stride, int64_t seq_inner_stride,
                         int64_t step_stride, int hard, void* stream);
 /* reverse scan: consumes gates/c and dY (gradient w.r.t. the DROPPED-OUT layer

@@ -331,6 +331,21 @@ __global__ void cast_bf16_multi_kernel(CastBatch b) {
   }
 }
 
+// 8 elements (one 16-byte vector) per thread and trip
+__global__ void half_to_bf16_kernel(uint4* __restrict__ buf, int64_t nvec) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    uint4 q = buf[i];
+    uint32_t* w = reinterpret_cast<uint32_t*>(&q);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __half2 h = *reinterpret_cast<const __half2*>(&w[j]);
+      const __nv_bfloat162 b = __floats2bfloat162_rn(__low2float(h), __high2float(h));
+      w[j] = *reinterpret_cast<const uint32_t*>(&b);
+    }
+    buf[i] = q;
+  }
+}
+
 inline int grid_for(int64_t total, int threads, int max_blocks) {
   int64_t b = (total + threads - 1) / threads;
   if (b < 1) b = 1;
@@ -434,6 +449,13 @@ extern "C" int dj_cast_bf16(const float* in, int rows, int cols, void* out, int 
   DJ_CHECK_ARG(ldo >= (transpose ? rows : cols), "dj_cast_bf16: ldo %d too small", ldo);
   cast_bf16_kernel<<<grid_for((int64_t)orows * ldo, 256, dj_num_sms() * 8), 256, 0, (cudaStream_t)stream>>>(
       in, rows, cols, (__nv_bfloat16*)out, ldo, transpose, orows);
+  DJ_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int dj_half_to_bf16_inplace(void* buf, int64_t n, void* stream) {
+  DJ_CHECK_ARG(buf && n > 0 && n % 8 == 0 && ((uintptr_t)buf % 16) == 0, "dj_half_to_bf16_inplace: needs a 16-byte aligned buffer of 8k elements");
+  half_to_bf16_kernel<<<grid_for(n / 8, 256, dj_num_sms() * 8), 256, 0, (cudaStream_t)stream>>>((uint4*)buf, n / 8);
   DJ_LAUNCH_CHECK();
   return 0;
 }

@@ -308,7 +308,8 @@ extern "C" int dj_gate_gemm_16(const void* A, const void* A_lo, int a_fmt, int64
                                int M, int N, int K, void* stream) {
   DJ_CHECK_ARG(A && Bt && C, "dj_gate_gemm_16: NULL pointer");
   DJ_CHECK_ARG((A_lo == nullptr) == (Bt_lo == nullptr), "dj_gate_gemm_16: A_lo and Bt_lo come together (3-pass split product)");
-  DJ_CHECK_ARG(fmt16_ok(a_fmt) && fmt16_ok(b_fmt), "dj_gate_gemm_16: operand formats must be DJ_BF16 or DJ_F16");
+  DJ_CHECK_ARG(fmt16_ok(a_fmt) && a_fmt == b_fmt,
+               "dj_gate_gemm_16: operand formats must be DJ_BF16 or DJ_F16 and equal (kind::f16 cannot mix half with bf16)");
   DJ_CHECK_ARG(M > 0 && N > 0 && K > 0, "dj_gate_gemm_16: bad shape");
   DJ_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0 && ldc % 4 == 0 && lda >= K && ldb >= K && ldc >= N,
                "dj_gate_gemm_16: leading dimensions must be 16-byte multiples and cover K/N (lda=%lld ldb=%lld ldc=%lld)",
@@ -348,7 +349,8 @@ extern "C" int dj_gate_gemm_bf16(const void* A, int64_t lda, const void* Bt, int
 extern "C" int dj_wgrad_gemm_16(const void* A, int a_fmt, int64_t lda, const void* B, int b_fmt, int64_t ldb, float* C,
                                 int64_t ldc, int Ka, int Nb, int64_t M, void* stream) {
   DJ_CHECK_ARG(A && B && C, "dj_wgrad_gemm_16: NULL pointer");
-  DJ_CHECK_ARG(fmt16_ok(a_fmt) && fmt16_ok(b_fmt), "dj_wgrad_gemm_16: operand formats must be DJ_BF16 or DJ_F16");
+  DJ_CHECK_ARG(fmt16_ok(a_fmt) && a_fmt == b_fmt,
+               "dj_wgrad_gemm_16: operand formats must be DJ_BF16 or DJ_F16 and equal (kind::f16 cannot mix half with bf16)");
   DJ_CHECK_ARG(Ka > 0 && Nb > 0 && M > 0, "dj_wgrad_gemm_16: bad shape");
   DJ_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0 && ldc % 4 == 0 && lda >= Ka && ldb >= Nb && ldc >= Nb,
                "dj_wgrad_gemm_16: leading dimensions must be 16-byte multiples and cover the widths");

@@ -514,10 +514,11 @@ int launch_tc_fwd(const void* Ut_bf, const void* Ut_lo, int f16, float* Z, float
 // ---------------------------------------------------------------------------
 // UPC = hidden units owned by one CTA: 64 (M = 64 fully used) or 32 (U = 512: only 32 rows of U fit; the
 // M = 64 MMA then reads 32 further rows of the next K atom, whose accumulator rows are never read).
-template <int U, int BS, int UPC>
+// SHARED: the two half-tiles take turns in ONE operand staging buffer (HB rows), so a tile can be twice as large
+template <int U, int BS, int UPC, bool SHARED = false>
 struct TcBwdSmem {
   static constexpr int A_BYTES = UPC * 4 * U * 2;
-  static constexpr int B_BYTES = BS * 4 * U * 2;
+  static constexpr int B_BYTES = (SHARED ? BS / 2 : BS) * 4 * U * 2;
   static constexpr int A_OFF = 0, B_OFF = A_BYTES, BAR_OFF = A_BYTES + B_BYTES;
   static constexpr int TOTAL = BAR_OFF + 128 + 1024;
 };
@@ -537,12 +538,23 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t v[4]) {
 // dz columns--> bar_z[hf] of every CTA --MMA--> bar_acc[hf]; the MMA commit also multicasts to free[hf] of every CTA
 // ("my operand tile may be overwritten").  A CTA's dz is only ever read from memory by that CTA's own TMA, so the
 // chain contains no gpu-scope membar and no cluster barrier.
-template <int U, int BS, int UPC, bool AXIS_TIME, int NS>
+//
+// SHARED (time axis at large batch: one wave instead of two).  Shared memory holds the resident U slice (128 KB)
+// and ONE staging buffer of 48 sequences x 1024 gate columns (96 KB); with two buffers a cluster could own only 48
+// sequences and 64 sequences per GPU needed 64 clusters where 33-37 are resident.  Here a cluster owns 96 sequences
+// = two half-tiles of 48 (one batch element each) that ALTERNATE in the single staging buffer: the multicast of half
+// B's dz waits until every CTA's MMAs over half A's dz have retired (free[A], signalled by the multicast
+// tcgen05.commit) and vice versa.  The MMA time per half is set by re-reading the resident U slice, not by N, so
+// 48-wide halves cost about what the 24-wide halves of the two-wave variant cost: per step and SM the tensor pipe
+// does half the work of before.  The epilogue then owns 24 cells per lane: only ONE half's gate / c / dY operands
+// are held in registers at a time (loaded from L2 right after the other half's epilogue; the lines are pulled into
+// L2 by prefetches issued a whole half-step earlier).
+template <int U, int BS, int UPC, bool AXIS_TIME, int NS, bool SHARED = false>
 __global__ void __launch_bounds__(TCB_THREADS, (U == 128 && BS <= 32) ? 2 : 1)
 scan_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmZ,
                    const float* __restrict__ G, const float* __restrict__ Cst, const float* __restrict__ dY,
                    uint32_t ldY, dj_dropout d_y, __nv_bfloat16* __restrict__ dZ, float* __restrict__ db,
-                   int steps, TcMap map, int hard, int u_f16) {
+                   int steps, TcMap map, int hard) {
   constexpr int C = U / UPC;            // cluster size
   constexpr int KA = 4 * U / 64;        // K atoms of the contraction (gate columns)
   constexpr int ATOM = UPC * 128;       // bytes of one resident K atom of U (UPC rows x 128 B)
@@ -555,7 +567,8 @@ scan_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
   constexpr uint32_t TMEM_COLS = BS <= 32 ? 32 : BS <= 64 ? 64 : BS <= 128 ? 128 : 256;
   static_assert(NS == 1 || NS == 2, "one tile or two half-tiles");
   static_assert(HB % 8 == 0 && WC % 4 == 0, "half-tiles are whole 8-row swizzle groups; columns load in 4-column pieces");
-  using SM = TcBwdSmem<U, BS, UPC>;
+  static_assert(!SHARED || (NS == 2 && AXIS_TIME && HB == 48), "shared staging: two half-tiles of one batch element each");
+  using SM = TcBwdSmem<U, BS, UPC, SHARED>;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -603,10 +616,15 @@ scan_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
     __syncwarp();
     const uint32_t bar_z = sbase + BAR_Z + 8 * hf, bar_acc = sbase + BAR_ACC + 8 * hf,
                    bar_done = sbase + BAR_DONE + 8 * hf, bar_free = sbase + BAR_FREE + 8 * hf;
-    const uint32_t b_half = sbase + SM::B_OFF + hf * HALF_BYTES;
+    // the barrier that says "the staging I am about to overwrite is no longer being read": my own half's MMAs of the
+    // previous round, or (shared staging) the OTHER half's MMAs, which were the last to read it
+    const uint32_t bar_free_wait = SHARED ? sbase + BAR_FREE + 8 * (hf ^ 1) : bar_free;
+    const uint32_t b_half = sbase + SM::B_OFF + (SHARED ? 0 : hf * HALF_BYTES);
     // TMA coordinates of this half-tile: rows (time axis: within the batch element) / sequences (note axis)
-    const int c_row0 = AXIS_TIME ? (tile % map.off2) * BS + hf * HB : tile * BS + hf * HB;
-    const int c_outer = AXIS_TIME ? tile / map.off2 : 0;
+    int c_row0, c_outer;
+    if constexpr (!AXIS_TIME) { c_row0 = tile * BS + hf * HB; c_outer = 0; }
+    else if constexpr (BS <= 48) { c_row0 = (tile % (48 / BS)) * BS + hf * HB; c_outer = tile / (48 / BS); }
+    else { c_row0 = 0; c_outer = tile * (BS / 48) + hf * (HB / 48); }       // a half-tile = whole batch elements
     if (hf < NS) {
       uint32_t par = 0;
       for (int t = steps - 1; t > 0; --t, par ^= 1u) {   // round: dz_t in, dh of step t-1 out
@@ -615,7 +633,13 @@ scan_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
         // Nobody else reads this CTA's dz_t from memory: THIS CTA's TMA multicasts it into every CTA's operand tile,
         // so no gpu-scope release and no cluster-wide "published" round trip is needed -- only the guarantee that
         // every peer's MMAs of the previous round have finished reading the tile we are about to overwrite.
-        if (t != steps - 1) mbar_wait(bar_free, par ^ 1u);   // (orders TMA writes after MMA reads: no data to acquire)
+        // (orders TMA writes after MMA reads: no data to acquire)
+        if constexpr (SHARED) {
+          if (hf == 1) mbar_wait(bar_free_wait, par);                        // half A's MMAs of THIS round
+          else if (t != steps - 1) mbar_wait(bar_free_wait, par ^ 1u);       // half B's MMAs of the previous round
+        } else {
+          if (t != steps - 1) mbar_wait(bar_free_wait, par ^ 1u);
+        }
         DJ_TR(t, 4 * hf + 1);
         if (elect_one()) {
           mbar_expect_tx(bar_z, HALF_BYTES);
@@ -629,8 +653,8 @@ scan_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
         DJ_TR(t, 4 * hf + 2);
         tc_fence_after();
         if (elect_one()) {
-          // A = U (bf16, or IEEE half: format bit 7 cleared), B = dz (always bf16: gradients need the exponent range)
-          const uint32_t idesc = u_f16 ? (make_idesc(64, HB, 0, 0) & ~(1u << 7)) : make_idesc(64, HB, 0, 0);
+          // both operands bf16: dz needs bf16's exponent range and kind::f16 cannot mix half with bf16
+          constexpr uint32_t idesc = make_idesc(64, HB, 0, 0);
           const uint64_t adesc0 = make_smem_desc(sbase + SM::A_OFF, 16, 1024);
           const uint64_t bdesc0 = make_smem_desc(b_half, 16, 1024);
 #pragma unroll
@@ -646,7 +670,7 @@ scan_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
         DJ_TR(t, 4 * hf + 3);
       }
       // drain the peers' last multicast arrives before this CTA can exit
-      if (steps > 1) mbar_wait(bar_free, par ^ 1u);
+      if (steps > 1) mbar_wait(bar_free_wait, par ^ 1u);
     }
   } else {
     // ================= epilogue: gate derivatives =================
@@ -658,24 +682,41 @@ scan_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
     const uint32_t col = UPC * rank + 16 * q + (lane & 15);       // global hidden unit
     const bool active = (16 * q < UPC);                            // UPC = 32: only TMEM quarters 0,1 hold real rows
     const uint32_t sstr = (uint32_t)map.seq_stride, tstr = (uint32_t)map.step_stride;
-    const uint32_t row_tile = (uint32_t)tc_row0(map, tile * BS);
     uint32_t row00[NS];                                            // row of this lane's first sequence of each half, step 0
 #pragma unroll
-    for (int hf = 0; hf < NS; ++hf) row00[hf] = row_tile + (uint32_t)(hf * HB + w2 * WC + sh * CPL) * sstr;
+    for (int hf = 0; hf < NS; ++hf)   // a half-tile never straddles a batch element
+      row00[hf] = (uint32_t)tc_row0(map, tile * BS + hf * HB) + (uint32_t)(w2 * WC + sh * CPL) * sstr;
     float dbacc[4] = {0.f, 0.f, 0.f, 0.f};
-    float dcn[NS][CPL], ct[NS][CPL], cpv[NS][CPL], dyv[NS][CPL];
-    float4 gv[NS][CPL];
+    constexpr int LSN = SHARED ? 1 : NS;                           // operand sets held in registers at a time
+    float dcn[NS][CPL], ct[NS][CPL], cpv[LSN][CPL], dyv[LSN][CPL];
+    float4 gv[LSN][CPL];
     // Pure loads only: anything computed on a just-loaded value would serialise the loads (each use
     // waits for its own DRAM round trip).  Masks and the t==0 special case are applied at use time.
     auto issue_loads = [&](int hf, int t) {   // everything of (half hf, step t) that does not depend on the recurrence
       const uint32_t tp = (t > 0) ? (uint32_t)(t - 1) : 0u;      // clamped: row of c_{t-1} (ignored at t == 0)
+      const int ls = SHARED ? 0 : hf;
       if (!active) return;
 #pragma unroll
       for (int j = 0; j < CPL; ++j) {
         const uint32_t r = row00[hf] + j * sstr + (uint32_t)t * tstr;
-        gv[hf][j] = __ldg(reinterpret_cast<const float4*>(G + (size_t)r * (4 * U) + 4 * col));
-        cpv[hf][j] = __ldg(Cst + (size_t)(row00[hf] + j * sstr + tp * tstr) * U + col);
-        dyv[hf][j] = __ldg(dY + (size_t)r * ldY + col);
+        gv[ls][j] = __ldg(reinterpret_cast<const float4*>(G + (size_t)r * (4 * U) + 4 * col));
+        cpv[ls][j] = __ldg(Cst + (size_t)(row00[hf] + j * sstr + tp * tstr) * U + col);
+        dyv[ls][j] = __ldg(dY + (size_t)r * ldY + col);
+      }
+    };
+    // pull the lines issue_loads(hf, t) will read into L2: per cell the 16 lanes of a unit group read 256 B of gates
+    // (lanes 0 and 8 of the group prefetch a 128-byte line each) and 64 B each of c and dY (lane 0 of the group)
+    auto prefetch_l2 = [&](int hf, int t) {
+      const uint32_t tp = (t > 0) ? (uint32_t)(t - 1) : 0u;
+      if (!active) return;
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) {
+        const uint32_t r = row00[hf] + j * sstr + (uint32_t)t * tstr;
+        if ((lane & 7) == 0) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(G + (size_t)r * (4 * U) + 4 * col));
+        if ((lane & 15) == 0) {
+          asm volatile("prefetch.global.L2 [%0];\n" ::"l"(Cst + (size_t)(row00[hf] + j * sstr + tp * tstr) * U + col));
+          asm volatile("prefetch.global.L2 [%0];\n" ::"l"(dY + (size_t)r * ldY + col));
+        }
       }
     };
 #pragma unroll
@@ -684,10 +725,15 @@ scan_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
       for (int j = 0; j < CPL; ++j) {
         dcn[hf][j] = 0.f;
         ct[hf][j] = active ? Cst[(size_t)(row00[hf] + j * sstr + (uint32_t)(steps - 1) * tstr) * U + col] : 0.f;
-        gv[hf][j] = make_float4(0.f, 0.f, 0.f, 0.f); cpv[hf][j] = 0.f; dyv[hf][j] = 0.f;
       }
-      issue_loads(hf, steps - 1);
     }
+#pragma unroll
+    for (int ls = 0; ls < LSN; ++ls) {
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) { gv[ls][j] = make_float4(0.f, 0.f, 0.f, 0.f); cpv[ls][j] = 0.f; dyv[ls][j] = 0.f; }
+      issue_loads(ls, steps - 1);
+    }
+    if constexpr (SHARED) prefetch_l2(1, steps - 1);
     const bool tr = (warp == 1 && lane == 0);
     uint32_t par = 0;
     for (int t = steps - 1; t >= 0; --t) {
@@ -716,9 +762,11 @@ scan_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
         for (int j = 0; j < CPL; ++j) {
           if (!active) break;
           const uint32_t r = row00[hf] + j * sstr + (uint32_t)t * tstr;
-          const float4 g4 = gv[hf][j];
-          const float cprev = (t > 0) ? cpv[hf][j] : 0.f;
-          const float dht = fmaf(dyv[hf][j], dj_dropmul(d_y, r * U + col), dh[j]);
+          constexpr int LS_ = SHARED ? 0 : -1;
+          const int ls = (LS_ == 0) ? 0 : hf;
+          const float4 g4 = gv[ls][j];
+          const float cprev = (t > 0) ? cpv[ls][j] : 0.f;
+          const float dht = fmaf(dyv[ls][j], dj_dropmul(d_y, r * U + col), dh[j]);
           const float tc = fast_tanh(ct[hf][j]);
           const float d_o = dht * tc;
           const float dc = fmaf(dht * g4.w, 1.f - tc * tc, dcn[hf][j]);
@@ -741,7 +789,13 @@ scan_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
           fence_proxy_async_all();          // dz_t (generic-proxy global stores) -> later TMA (async proxy) reads
           __syncwarp();
           if (lane == 0) mbar_arrive(sbase + BAR_DONE + 8 * hf);   // release.cta: hands this warp's stores to the issuer
-          issue_loads(hf, t - 1);           // land during this half's publish / TMA / MMA chain
+          if constexpr (!SHARED) issue_loads(hf, t - 1);   // land during this half's publish / TMA / MMA chain
+        }
+        if constexpr (SHARED) {
+          // one operand set in registers: load what the NEXT epilogue in program order needs (its lines were
+          // prefetched into L2 one epilogue ago), and prefetch for the one after it
+          if (hf == 0) { issue_loads(1, t); if (t > 0) prefetch_l2(0, t - 1); }
+          else if (t > 0) { issue_loads(0, t - 1); prefetch_l2(1, t - 1); }
         }
         if (tr) DJ_TR(t, 10 + 3 * hf);
       }
@@ -766,12 +820,12 @@ inline bool bwd_split_enabled() {   // DJ_BWD_NS=1 forces the unsplit tile (expe
   return env != 0;
 }
 
-template <int U, int BS, int UPC, bool AXIS_TIME, int NS>
+template <int U, int BS, int UPC, bool AXIS_TIME, int NS, bool SHARED = false>
 int launch_tc_bwd_inst(const void* Un_bf, const float* gates, const float* c, const float* dY, int64_t ldY, dj_dropout d_y,
-                       void* dZ, float* db, int S, int steps, const TcMap& map_in, int hard, int u_f16, cudaStream_t st) {
+                       void* dZ, float* db, int S, int steps, const TcMap& map_in, int hard, cudaStream_t st) {
   constexpr int C = U / UPC;
   constexpr int HB = BS / NS;
-  using SM = TcBwdSmem<U, BS, UPC>;
+  using SM = TcBwdSmem<U, BS, UPC, SHARED>;
   DJ_CHECK_ARG(S % BS == 0, "dj_lstm_scan_tc_bwd: the number of sequences (%d) must be a multiple of %d", S, BS);
   TcMap map = map_in;
   CUtensorMap tmU, tmZ;
@@ -780,12 +834,13 @@ int launch_tc_bwd_inst(const void* Un_bf, const float* gates, const float* c, co
     return rc;
   constexpr int KA = 4 * U / 64, KPC = KA / C;
   if (AXIS_TIME) {   // dZ viewed as [b][t*48+n][atom][64]; a tile is BS consecutive notes of one batch element
-    static_assert(!AXIS_TIME || 48 % BS == 0, "time-axis tiles divide a batch element");
+    static_assert(!AXIS_TIME || 48 % BS == 0 || (BS % 48 == 0 && HB % 48 == 0),
+                  "time-axis tiles divide a batch element, or their halves are whole batch elements");
     const uint64_t rows_per_b = (uint64_t)map.outer_stride, B = (uint64_t)(S / 48);
     const uint64_t dims[4] = {64, rows_per_b, (uint64_t)KA, B}, str[3] = {(uint64_t)4 * U, 64, rows_per_b * 4 * U};
     const uint32_t box[4] = {64, (uint32_t)HB, (uint32_t)KPC, 1};
     if ((rc = make_map(&tmZ, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dZ, 4, dims, str, box))) return rc;
-    map.step1 = 48; map.off1 = BS; map.base2 = 1; map.off2 = 48 / BS;
+    map.step1 = 48; map.off1 = BS; map.base2 = 1; map.off2 = BS <= 48 ? 48 / BS : 1;
     map.seq_stride = map.inner_stride;
   } else {           // dZ viewed as [n][atom][seq][64] (strides: seq 48*4U, atom 64, n 4U)
     const uint64_t dims[4] = {64, (uint64_t)S, (uint64_t)KA, 48}, str[3] = {(uint64_t)48 * 4 * U, 64, (uint64_t)4 * U};
@@ -794,7 +849,7 @@ int launch_tc_bwd_inst(const void* Un_bf, const float* gates, const float* c, co
     map.step1 = 1; map.off1 = 0; map.base2 = BS; map.off2 = 1;
     map.seq_stride = map.outer_stride;
   }
-  auto kernel = scan_tc_bwd_kernel<U, BS, UPC, AXIS_TIME, NS>;
+  auto kernel = scan_tc_bwd_kernel<U, BS, UPC, AXIS_TIME, NS, SHARED>;
   DJ_CUDA(cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
   if (C > 8) DJ_CUDA(cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   cudaLaunchConfig_t cfg{};
@@ -813,16 +868,16 @@ int launch_tc_bwd_inst(const void* Un_bf, const float* gates, const float* c, co
   }
   __nv_bfloat16* dzp = (__nv_bfloat16*)dZ;
   const uint32_t ldy32 = (uint32_t)ldY;
-  DJ_CUDA(cudaLaunchKernelEx(&cfg, kernel, tmU, tmZ, gates, c, dY, ldy32, d_y, dzp, db, steps, map, hard, u_f16));
+  DJ_CUDA(cudaLaunchKernelEx(&cfg, kernel, tmU, tmZ, gates, c, dY, ldy32, d_y, dzp, db, steps, map, hard));
   return 0;
 }
 
 template <int U, int BS, int UPC, bool AXIS_TIME>
 int launch_tc_bwd(const void* Un_bf, const float* gates, const float* c, const float* dY, int64_t ldY, dj_dropout d_y,
-                  void* dZ, float* db, int S, int steps, const TcMap& map, int hard, int u_f16, cudaStream_t st) {
+                  void* dZ, float* db, int S, int steps, const TcMap& map, int hard, cudaStream_t st) {
   if (bwd_split_enabled())
-    return launch_tc_bwd_inst<U, BS, UPC, AXIS_TIME, 2>(Un_bf, gates, c, dY, ldY, d_y, dZ, db, S, steps, map, hard, u_f16, st);
-  return launch_tc_bwd_inst<U, BS, UPC, AXIS_TIME, 1>(Un_bf, gates, c, dY, ldY, d_y, dZ, db, S, steps, map, hard, u_f16, st);
+    return launch_tc_bwd_inst<U, BS, UPC, AXIS_TIME, 2>(Un_bf, gates, c, dY, ldY, d_y, dZ, db, S, steps, map, hard, st);
+  return launch_tc_bwd_inst<U, BS, UPC, AXIS_TIME, 1>(Un_bf, gates, c, dY, ldY, d_y, dZ, db, S, steps, map, hard, st);
 }
 
 }  // namespace
@@ -860,26 +915,32 @@ extern "C" int dj_lstm_scan_tc_fwd(float* Z, float* h_out, float* c_out, void* h
 }
 
 extern "C" int dj_lstm_scan_tc_bwd(const float* gates, const float* c, const float* dY, int64_t ldY, dj_dropout d_y,
-                                   const void* Un_bf16, int u_fmt, void* dZ_bf16, float* db, int S, int steps, int units,
+                                   const void* Un_bf16, void* dZ_bf16, float* db, int S, int steps, int units,
                                    int seq_inner, int64_t seq_outer_stride, int64_t seq_inner_stride,
                                    int64_t step_stride, int hard, void* stream) {
   DJ_CHECK_ARG(gates && c && dY && Un_bf16 && dZ_bf16 && db, "dj_lstm_scan_tc_bwd: NULL pointer");
-  DJ_CHECK_ARG(u_fmt == DJ_BF16 || u_fmt == DJ_F16, "dj_lstm_scan_tc_bwd: U format must be DJ_BF16 or DJ_F16");
-  const int u_f16 = (u_fmt == DJ_F16) ? 1 : 0;
   DJ_CHECK_ARG(S > 0 && steps > 0 && ldY >= units, "dj_lstm_scan_tc_bwd: bad sizes");
   TcMap map{seq_inner, seq_outer_stride, seq_inner_stride, step_stride, 0, 0, 0, 0, 0};
   cudaStream_t st = (cudaStream_t)stream;
   const bool time_map = (seq_inner == 48 && seq_inner_stride == 1 && step_stride == 48 && S % 48 == 0);
   const bool note_map = (seq_inner == 1 && seq_outer_stride == 48 && step_stride == 1 && steps <= 48);
   DJ_CHECK_ARG(time_map || note_map, "dj_lstm_scan_tc_bwd: only the time-axis (seq=(b,n)) and note-axis (seq=(b,t)) maps are supported");
-  if (time_map && units == 256)
-    return launch_tc_bwd<256, 48, 64, true>(Un_bf16, gates, c, dY, ldY, d_y, dZ_bf16, db, S, steps, map, hard, u_f16, st);
+  if (time_map && units == 256) {
+    // 64 units per CTA, clusters of 4: 33-37 clusters are resident.  Up to that many 48-sequence tiles run as one
+    // wave; beyond it a cluster takes 96 sequences through one shared staging buffer (one wave up to ~66 sequences
+    // per GPU instead of two), if the batch is even
+    static int one_wave = -1;
+    if (one_wave < 0) { const char* e = getenv("DJ_BWD_SHARED"); one_wave = (e && atoi(e) == 1) ? 1 : 0; }   // experiment: off
+    if (one_wave && S % 96 == 0 && S / 48 > 33)
+      return launch_tc_bwd_inst<256, 96, 64, true, 2, true>(Un_bf16, gates, c, dY, ldY, d_y, dZ_bf16, db, S, steps, map, hard, st);
+    return launch_tc_bwd<256, 48, 64, true>(Un_bf16, gates, c, dY, ldY, d_y, dZ_bf16, db, S, steps, map, hard, st);
+  }
   if (time_map && units == 512)   // scaled model: 32 units per CTA, 16-CTA clusters, a third of a batch element per tile
-    return launch_tc_bwd<512, 16, 32, true>(Un_bf16, gates, c, dY, ldY, d_y, dZ_bf16, db, S, steps, map, hard, u_f16, st);
+    return launch_tc_bwd<512, 16, 32, true>(Un_bf16, gates, c, dY, ldY, d_y, dZ_bf16, db, S, steps, map, hard, st);
   if (note_map && units == 128)
-    return launch_tc_bwd<128, 32, 64, false>(Un_bf16, gates, c, dY, ldY, d_y, dZ_bf16, db, S, steps, map, hard, u_f16, st);
+    return launch_tc_bwd<128, 32, 64, false>(Un_bf16, gates, c, dY, ldY, d_y, dZ_bf16, db, S, steps, map, hard, st);
   if (note_map && units == 256)   // scaled model, note axis
-    return launch_tc_bwd<256, 32, 64, false>(Un_bf16, gates, c, dY, ldY, d_y, dZ_bf16, db, S, steps, map, hard, u_f16, st);
+    return launch_tc_bwd<256, 32, 64, false>(Un_bf16, gates, c, dY, ldY, d_y, dZ_bf16, db, S, steps, map, hard, st);
   DJ_CHECK_ARG(false, "dj_lstm_scan_tc_bwd: units=%d unsupported on this axis (time: 256/512, note: 128/256)", units);
   return -1;
 }

@@ -253,9 +253,9 @@ class Engine:
                 self._wbf[f"{n}.Un"] = torch.empty(U, U4, **w16)      # U    [U, 4U]: resident A operand, reverse scan
             lo = (lambda k: self._wbf[k]) if mixed else (lambda k: None)
             ents += [(W, F, U4, self._wbf[f"{n}.Wt"], lo(f"{n}.Wt_lo"), ld, 1, DJ_BF16),
-                     (W, F, U4, self._wbf[f"{n}.Wn"], None, U4, 0, rfmt),
+                     (W, F, U4, self._wbf[f"{n}.Wn"], None, U4, 0, DJ_BF16),
                      (Um, U, U4, self._wbf[f"{n}.Ut"], lo(f"{n}.Ut_lo"), U, 1, rfmt),
-                     (Um, U, U4, self._wbf[f"{n}.Un"], None, U4, 0, rfmt)]
+                     (Um, U, U4, self._wbf[f"{n}.Un"], None, U4, 0, DJ_BF16)]
         k = len(ents)
         ints = lambda j: (C.c_int * k)(*[e[j] for e in ents])
         self._call("dj_cast16_multi", k, (C.c_void_p * k)(*[e[0].data_ptr() for e in ents]), ints(1), ints(2),
@@ -426,9 +426,6 @@ class Engine:
         P, G, cfg = self.params, self.grads, self.cfg
         M, BT = B * T * N, B * T
         zdt = DJ_BF16 if bf16 else DJ_F32
-        # backward weight operands (U of the reverse scan, W of the data gradient): half in mixed precision (8x finer
-        # than bf16; weights need no exponent range), always against bf16 dZ
-        wfmt = DJ_F16 if st["prec"] == "mixed" else DJ_BF16
         self.gflat.zero_()
         self._call("dj_head_finalize", _ptr(ws.partials), cfg.note_axis_units, _ptr(ws.loss),
                    _ptr(G["note_dense.W"]), _ptr(G["note_dense.b"]), _ptr(G["volume_dense.W"]),
@@ -453,7 +450,7 @@ class Engine:
                 # ---- critical chain: reverse scan, then the data gradient the next layer's scan consumes
                 if bf16 and self._tc_ok(B, T):
                     self._call("dj_lstm_scan_tc_bwd", _ptr(ws.Z[li]), _ptr(ws.c[li]), _ptr(dY), ldY, d[L["site_out"]],
-                               _ptr(self._wbf[f"{name}.Un"]), wfmt, _ptr(dZ), _ptr(G[f"{name}.lstm.b"]), m["S"], m["steps"],
+                               _ptr(self._wbf[f"{name}.Un"]), _ptr(dZ), _ptr(G[f"{name}.lstm.b"]), m["S"], m["steps"],
                                U, m["inner"], m["outer"], m["inner_stride"], m["step"], self.hard, _stream())
                 else:
                     self._call("dj_lstm_scan_bwd", _ptr(ws.Z[li]), _ptr(ws.c[li]), _ptr(dY), ldY, d[L["site_out"]],
@@ -464,8 +461,8 @@ class Engine:
                     ev_scan.record(chain)
                 # data gradient dA = dZ . W^T
                 if bf16:
-                    self._call("dj_gate_gemm_16", _ptr(dZ), None, DJ_BF16, U4, _ptr(self._wbf[f"{name}.Wn"]), None, wfmt,
-                               U4, _ptr(ws.dA[li]), ld, None, M, F, U4, _stream())
+                    self._call("dj_gate_gemm_bf16", _ptr(dZ), U4, _ptr(self._wbf[f"{name}.Wn"]), U4, _ptr(ws.dA[li]),
+                               ld, None, M, F, U4, _stream())
                 else:
                     self._call("dj_gemm_simt", _ptr(dZ), DJ_F32, U4, 1, _ptr(P[f"{name}.lstm.W"]), DJ_F32, 1, U4,
                                _ptr(ws.dA[li]), ld, None, M, F, U4, 0, 0, 0, _stream())
@@ -478,9 +475,12 @@ class Engine:
             if bf16:
                 self._call("dj_wgrad_gemm_bf16", _ptr(ws.A[li]), ld, _ptr(dZ), U4, _ptr(G[f"{name}.lstm.W"]), U4,
                            F, U4, M, _stream())
-                self._call("dj_wgrad_gemm_16", _ptr(ws.hprev[li]),
-                           DJ_F16 if ws.hprev[li].dtype == torch.float16 else DJ_BF16, U, _ptr(dZ), DJ_BF16, U4,
-                           _ptr(G[f"{name}.lstm.U"]), U4, U, U4, M, _stream())
+                if ws.hprev[li].dtype == torch.float16:
+                    # the recurrence kept h_{step-1} in half; dZ is bf16 and tcgen05 kind::f16 cannot mix the two
+                    # formats, so the buffer is converted in place (the forward pass is done with it)
+                    self._call("dj_half_to_bf16_inplace", _ptr(ws.hprev[li]), M * U, _stream())
+                self._call("dj_wgrad_gemm_bf16", _ptr(ws.hprev[li]), U, _ptr(dZ), U4, _ptr(G[f"{name}.lstm.U"]),
+                           U4, U, U4, M, _stream())
             else:
                 self._call("dj_gemm_simt", _ptr(ws.A[li]), DJ_F32, 1, ld, _ptr(dZ), zdt, U4, 1,
                            _ptr(G[f"{name}.lstm.W"]), U4, None, F, U4, M, 1, 0, 0, _stream())
@@ -517,13 +517,16 @@ class Engine:
         (lr, beta_1, beta_2, eps, mu_t, mu_t1, m_schedule_new, m_schedule_next, 1-beta_2^t)."""
         o = self.nadam
         t = self.iterations + 1
-        mu_t = o["beta_1"] * (1.0 - 0.5 * (0.96 ** (t * o["schedule_decay"])))
-        mu_t1 = o["beta_1"] * (1.0 - 0.5 * (0.96 ** ((t + 1) * o["schedule_decay"])))
+        # Keras holds lr / beta_1 / beta_2 as float32 variables: the schedule and the bias correction are functions of
+        # the ROUNDED values (1 - float32(0.999)^t, not 1 - 0.999^t: 1.3e-5 apart at t = 1)
+        b1, b2 = float(np.float32(o["beta_1"])), float(np.float32(o["beta_2"]))
+        mu_t = b1 * (1.0 - 0.5 * (0.96 ** (t * o["schedule_decay"])))
+        mu_t1 = b1 * (1.0 - 0.5 * (0.96 ** ((t + 1) * o["schedule_decay"])))
         ms_new = self.m_schedule * mu_t
         ms_next = self.m_schedule * mu_t * mu_t1
         self.iterations, self.m_schedule = t, ms_new
         self._version += 1
-        return (o["lr"], o["beta_1"], o["beta_2"], o["eps"], mu_t, mu_t1, ms_new, ms_next, 1.0 - o["beta_2"] ** t)
+        return (o["lr"], b1, b2, o["eps"], mu_t, mu_t1, ms_new, ms_next, 1.0 - b2 ** t)
 
     def nadam_step(self, gscale: float = 1.0):
         """keras.optimizers.Nadam.get_updates on the flat buffers (model.py:152)."""

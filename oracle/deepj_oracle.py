@@ -343,11 +343,18 @@ def note_model_predict(p, cfg: Config, note_features, chosen, style_in,
 # --------------------------------------------------------------------------
 # training step: loss, autograd gradients, Keras-2 Nadam (model.py:152)
 # --------------------------------------------------------------------------
+def _f32(x: float) -> float:
+    return float(np.float32(x))
+
+
 @dataclass
 class NadamState:
-    lr: float = 0.002
-    beta_1: float = 0.9
-    beta_2: float = 0.999
+    # keras.optimizers.Nadam.__init__ stores lr / beta_1 / beta_2 as K.variable(...) of floatx = float32, so the graph
+    # computes with the float32-ROUNDED values: 1 - beta_2 is 0.00099998713, not 0.001 (1.3e-5 relative, visible in
+    # the first updates).  The oracle keeps its arithmetic in the caller's dtype but uses those rounded constants.
+    lr: float = _f32(0.002)
+    beta_1: float = _f32(0.9)
+    beta_2: float = _f32(0.999)
     eps: float = 1e-8            # Keras <= 2.1.2; K.epsilon()=1e-7 from 2.1.3
     schedule_decay: float = 0.004
     iterations: int = 0

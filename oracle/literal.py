@@ -90,7 +90,9 @@ def primary_loss_loops(y_true, y_pred, eps=1e-7):
 
 
 def nadam_scalar_loop(p, grads_seq, lr=0.002, b1=0.9, b2=0.999, eps=1e-8, sd=0.004):
-    """keras.optimizers.Nadam.get_updates for one scalar parameter."""
+    """keras.optimizers.Nadam.get_updates for one scalar parameter.  lr / beta_1 / beta_2 are float32 K.variables in
+    Keras: the update is a function of their float32-rounded values."""
+    lr, b1, b2 = (float(np.float32(x)) for x in (lr, b1, b2))
     m = v = 0.0
     m_schedule = 1.0
     for it, g in enumerate(grads_seq):

@@ -146,10 +146,28 @@ def test_gate_gemm_split_is_fp32_grade(lib, shape):
     assert err_split < 2e-5 and err_single > 20 * err_split, (err_split, err_single)
 
 
-@pytest.mark.parametrize("fmts", [(2, 2), (2, 1), (1, 2)])
-def test_gemm_operand_formats_half_and_mixed(lib, fmts):
-    """kind::f16 takes IEEE half or bf16 PER OPERAND: half x half, and the mixed products the training step uses
-    (half h_{t-1} against bf16 dZ in dU = H^T.dZ)."""
+def test_gemm_rejects_mixed_operand_formats(lib):
+    """tcgen05 kind::f16 with one half and one bf16 operand raises an illegal-instruction fault on B200 (measured in
+    round 2), so the ABI refuses the combination instead of launching it."""
+    a = torch.zeros(128, 64, device="cuda", dtype=torch.float16)
+    c = torch.zeros(128, 128, device="cuda")
+    assert lib.dj_gate_gemm_16(P(a), None, 2, 64, P(a), None, 1, 64, P(c), 128, None, 128, 128, 64, None) == -1
+    assert b"cannot mix" in lib.dj_last_error()
+    assert lib.dj_wgrad_gemm_16(P(a), 1, 64, P(a), 2, 64, P(c), 128, 64, 64, 128, None) == -1
+
+
+def test_half_to_bf16_inplace(lib):
+    from music_generator_b200 import _lib
+    x = (torch.randn(4096 * 8, generator=torch.Generator().manual_seed(3)) * 0.7).half()
+    buf = x.cuda()
+    _lib.check(lib.dj_half_to_bf16_inplace(P(buf), buf.numel(), None))
+    torch.cuda.synchronize()
+    assert torch.equal(buf.view(torch.bfloat16).float().cpu(), x.float().bfloat16().float())
+
+
+@pytest.mark.parametrize("fmts", [(2, 2), (1, 1)])
+def test_gemm_operand_formats_half(lib, fmts):
+    """kind::f16 with both operands IEEE half (the forward recurrence's format) or both bf16."""
     from music_generator_b200 import _lib
     dts = {1: torch.bfloat16, 2: torch.float16}
     g = torch.Generator().manual_seed(13)
@@ -256,7 +274,8 @@ def test_lstm_scan_tcgen05_matches_fp32_scan(lib, axis, B, T, mode):
 
 
 @pytest.mark.parametrize("axis,B,T", [("time", 3, 8), ("note", 2, 32), ("note", 40, 128), ("note256", 2, 32),
-                                      ("time", 40, 6)])   # 40 batch elements: the streaming 96-sequence-tile variant
+                                      ("time", 40, 6), ("time", 64, 5),   # > 33 tiles: 96-sequence tiles, shared staging
+                                      ("time", 35, 4)])                    # odd batch: two waves of 48-sequence tiles
 def test_lstm_scan_bwd_tcgen05_matches_fp32_scan(lib, axis, B, T):
     """Reverse scan on tcgen05 (bf16 dz.U^T) against the fp32 CUDA-core reverse scan."""
     from music_generator_b200 import _lib
@@ -281,7 +300,7 @@ def test_lstm_scan_bwd_tcgen05_matches_fp32_scan(lib, axis, B, T):
     Un = Uw.bfloat16().cuda()
     dZt = torch.zeros(M, 4 * U, device="cuda").bfloat16()
     dbt = torch.zeros(4 * U, device="cuda")
-    _lib.check(lib.dj_lstm_scan_tc_bwd(P(Z), P(c), P(dY), ld, d, P(Un), 1, P(dZt), P(dbt), S, steps, U, *m, 1, None))
+    _lib.check(lib.dj_lstm_scan_tc_bwd(P(Z), P(c), P(dY), ld, d, P(Un), P(dZt), P(dbt), S, steps, U, *m, 1, None))
     torch.cuda.synchronize()
     a, b = dZt.float().cpu().numpy(), dZr.cpu().numpy()
     assert np.isfinite(a).all()

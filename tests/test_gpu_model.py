@@ -135,7 +135,8 @@ def test_train_step_fp32_matches_oracle_autograd():
     for k in ("style.W", "conv.W", "time0.lstm.U", "note1.lstm.W", "note_dense.W"):
         p0 = p64[k].numpy().ravel()[:16]
         upd, ref = new[k].ravel()[:16] - p0, z[f"nadam_head/{k}"] - p0
-        assert np.abs(upd - ref).max() < 2e-3 * np.abs(ref).max(), (k, upd, ref)
+        # (the fixture's starting point is the fp64 initialiser, the engine's its fp32 rounding: 1e-8 of slack)
+        assert np.abs(upd - ref).max() < 1e-3 * 0.002 + 1e-8, (k, upd, ref)
 
 
 def test_nadam_ten_steps_match_oracle():

@@ -48,7 +48,7 @@ def test_peer_nadam_train_step_world1_tracks_plain_path():
     import numpy as np
     import dataset
     from music_generator_b200 import parallel
-    x, y = dataset.synthetic_all(4, 8, seed=3)
+    x, y = dataset.synthetic_all(4, 16, seed=3)      # B*T = 64: whole tensor-core tiles
     dev = [torch.from_numpy(np.ascontiguousarray(t)).cuda() for t in (x[0], x[1], x[2], x[3], y[0])]
     a, b = _engine(), _engine()
     peer = parallel.PeerNadam(b)

@@ -28,7 +28,7 @@ for axis, U in (("time", 256), ("note", 128)):
         fmt = 1 if mode == "bf16" else 2
         Ut = Uw.t().contiguous().to(dt)
         Ut_lo = (Uw.t().contiguous() - Ut.float()).to(dt)
-        Un = Uw.to(dt)
+        Un = Uw.bfloat16()
         hp = torch.zeros(M, U, device="cuda").to(dt)
         for rep in range(3):
             Z = Z0.clone()
@@ -39,7 +39,7 @@ for axis, U in (("time", 256), ("note", 128)):
                                                    S, steps, U, *m, 1, None))
             e1.record()
             if which in ("all", "bwd"):
-                _lib.check(lib.dj_lstm_scan_tc_bwd(P(Z), P(c), P(dY), U, _lib.NO_DROPOUT, P(Un), fmt, P(dZ), P(db), S, steps, U,
+                _lib.check(lib.dj_lstm_scan_tc_bwd(P(Z), P(c), P(dY), U, _lib.NO_DROPOUT, P(Un), P(dZ), P(db), S, steps, U,
                                                    *m, 1, None))
             e2.record()
             torch.cuda.synchronize()
