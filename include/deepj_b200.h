@@ -120,6 +120,12 @@ int dj_gate_gemm_bf16(const void* A, int64_t lda, const void* Bt, int64_t ldb, f
 int dj_gate_gemm_16(const void* A, const void* A_lo, int a_fmt, int64_t lda, const void* Bt,
                     const void* Bt_lo, int b_fmt, int64_t ldb, float* C, int64_t ldc, const float* bias,
                     int M, int N, int K, void* stream);
+/* ... and with the accumulator multiplied by out_scale before the bias is added: the generation path splits
+ * operands into IEEE half hi+lo (22 mantissa bits) after scaling the weights by a power of two, which keeps the
+ * residuals out of half's subnormal range; out_scale undoes it exactly. */
+int dj_gate_gemm_16s(const void* A, const void* A_lo, int a_fmt, int64_t lda, const void* Bt,
+                     const void* Bt_lo, int b_fmt, int64_t ldb, float* C, int64_t ldc, const float* bias,
+                     float out_scale, int M, int N, int K, void* stream);
 /* tcgen05 weight-gradient GEMM (contraction over the M rows, split across CTAs,
  * fp32 global reductions):  C[Ka,Nb] += A[M,Ka]^T . B[M,Nb]   (bf16, MN-major).
  * The h_{step-1} operand of dU comes pre-shifted from dj_lstm_scan_fwd. */
@@ -139,7 +145,8 @@ int dj_cast_bf16(const float* in, int rows, int cols, void* out, int ldo, int tr
  * fmt[i] = DJ_BF16 / DJ_F16; out_lo (nullable array, nullable entries) receives the
  * 16-bit residual in - 16-bit(in) in the same layout. */
 int dj_cast16_multi(int n, const float* const* in, const int* rows, const int* cols, void* const* out,
-                    void* const* out_lo, const int* ldo, const int* transpose, const int* fmt, void* stream);
+                    void* const* out_lo, const int* ldo, const int* transpose, const int* fmt,
+                    const float* scale /* nullable: per-entry power-of-two pre-scale */, void* stream);
 
 /* ---- recurrence (the sequential part of keras LSTM, model.py:84,120) ---------
  * Persistent thread-block-cluster kernel: the recurrent weights U [units,4*units]
@@ -170,6 +177,16 @@ int dj_lstm_scan_tc_fwd(float* Z, float* h_out, float* c_out, void* h_prev_16, c
                         const void* Ut_lo, int fmt, int S, int steps, int units, int seq_inner,
                         int64_t seq_outer_stride, int64_t seq_inner_stride, int64_t step_stride, int hard,
                         void* stream);
+/* Inference variant for the generation window (generate.py:106-109: both time-axis layers over
+ * the 128-step window from zero state, every generated timestep).  The sampled events must equal
+ * the fp32 model's, so h.U is fp32-grade: U as half hi + lo (pre-scaled by 1/acc_scale, a power of
+ * two, so the residual stays normal), h_{t-1} as half hi + lo exchanged through h_hi / h_lo
+ * [M, units], three MMA passes per step (U_hi.h_hi + U_lo.h_hi + U_hi.h_lo, fp32 accumulators in
+ * tensor memory).  Z is read only; nothing is saved for a backward pass.  Time-axis map, 256 units. */
+int dj_lstm_scan_tc_infer(const float* Z, float* h_out, void* h_hi, void* h_lo, const void* Ut_hi,
+                          const void* Ut_lo, float acc_scale, int S, int steps, int units, int seq_inner,
+                          int64_t seq_outer_stride, int64_t seq_inner_stride, int64_t step_stride, int hard,
+                          void* stream);
 /* Tensor-core variant of the reverse scan (dz.U^T on tcgen05): U is passed as
  * Un_bf16 [units, 4*units] (bf16, natural, gate-interleaved columns); dZ is bf16
  * (gradients need its exponent range) and doubles as the inter-CTA exchange buffer;

@@ -40,12 +40,14 @@ SIGNATURES = {
                           _i64, _p]),
     "dj_gate_gemm_bf16": (_i, [_p, _i64, _p, _i64, _p, _i64, _p, _i, _i, _i, _p]),
     "dj_gate_gemm_16": (_i, [_p, _p, _i, _i64, _p, _p, _i, _i64, _p, _i64, _p, _i, _i, _i, _p]),
+    "dj_gate_gemm_16s": (_i, [_p, _p, _i, _i64, _p, _p, _i, _i64, _p, _i64, _p, _f, _i, _i, _i, _p]),
     "dj_wgrad_gemm_bf16": (_i, [_p, _i64, _p, _i64, _p, _i64, _i, _i, _i64, _p]),
     "dj_wgrad_gemm_16": (_i, [_p, _i, _i64, _p, _i, _i64, _p, _i64, _i, _i, _i64, _p]),
     "dj_cast_bf16": (_i, [_p, _i, _i, _p, _i, _i, _p]),
     "dj_half_to_bf16_inplace": (_i, [_p, _i64, _p]),
     "dj_cast16_multi": (_i, [_i, C.POINTER(_p), C.POINTER(_i), C.POINTER(_i), C.POINTER(_p), C.POINTER(_p),
-                             C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), _p]),
+                             C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_f), _p]),
+    "dj_lstm_scan_tc_infer": (_i, [_p, _p, _p, _p, _p, _p, _f, _i, _i, _i, _i, _i64, _i64, _i64, _i, _p]),
     "dj_lstm_scan_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i64, _i64, _i64, _i, _p]),
     "dj_lstm_scan_tc_fwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i64, _i64, _i64, _i, _p]),
     "dj_lstm_scan_tc_bwd": (_i, [_p, _p, _p, _i64, Dropout, _p, _p, _p, _i, _i, _i, _i, _i64, _i64, _i64, _i, _p]),

@@ -28,6 +28,19 @@ __device__ __forceinline__ void store4(__nv_bfloat16* p, const float v[4]) {
   *reinterpret_cast<uint2*>(p) = u;
 }
 
+__device__ __forceinline__ void store4(__half* p, const float v[4]) {
+  const __half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], v[3]);
+  uint2 u;
+  u.x = *reinterpret_cast<const uint32_t*>(&a);
+  u.y = *reinterpret_cast<const uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+__device__ __forceinline__ void store4_lo(__half* p, const float v[4]) {   // half hi + lo: ~22 mantissa bits
+  float r[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) r[j] = v[j] - __half2float(__float2half_rn(v[j]));
+  store4(p, r);
+}
 // residual of the bf16 rounding, itself rounded to bf16: hi + lo carries 16 mantissa bits, which is what the
 // 3-pass split gate GEMM (dj_gate_gemm_16) multiplies
 __device__ __forceinline__ void store4_lo(__nv_bfloat16* p, const float v[4]) {
@@ -304,6 +317,7 @@ struct CastBatch {
   uint16_t* out[16];
   uint16_t* out_lo[16];      // nullable: 16-bit residual v - hi (same format)
   int rows[16], cols[16], ldo[16], transpose[16], fmt[16];
+  float scale[16];           // the value is multiplied by this (a power of two) before the split
 };
 __device__ __forceinline__ uint16_t to16(float v, int fmt, float& back) {
   if (fmt == DJ_F16) { const __half h = __float2half_rn(v); back = __half2float(h); return __half_as_ushort(h); }
@@ -326,6 +340,7 @@ __global__ void cast_bf16_multi_kernel(CastBatch b) {
     if (!tr) { if (co < cols) v = in[(int64_t)ro * cols + co]; }
     else { if (co < rows) v = in[(int64_t)co * cols + ro]; }
     float back, back2;
+    v *= b.scale[e];
     out[i] = to16(v, fmt, back);
     if (out_lo != nullptr) out_lo[i] = to16(v - back, fmt, back2);
   }
@@ -399,7 +414,7 @@ extern "C" int dj_frontend_fwd(const float* notes_in, int64_t notes_bstride, con
                                const float* sp0, dj_dropout d_notes, dj_dropout d_beat, dj_dropout d_conv,
                                dj_dropout d_sp, void* A0, void* A0_lo, int ldA, int a_dtype, void* stream) {
   DJ_CHECK_ARG(notes_in && beat_in && Wc && bc && sp0 && A0, "dj_frontend_fwd: NULL pointer");
-  DJ_CHECK_ARG(A0_lo == nullptr || a_dtype == DJ_BF16, "dj_frontend_fwd: the residual operand A0_lo exists for DJ_BF16 only");
+  DJ_CHECK_ARG(A0_lo == nullptr || a_dtype == DJ_BF16 || a_dtype == DJ_F16, "dj_frontend_fwd: the residual operand A0_lo exists for 16-bit operands only");
   DJ_CHECK_ARG(B > 0 && T > 0, "dj_frontend_fwd: bad B/T");
   DJ_CHECK_ARG(ldA >= F0P_ && ldA % 8 == 0, "dj_frontend_fwd: ldA %d must be >=96 and a multiple of 8", ldA);
   DJ_CHECK_ARG((int64_t)B * T * N_ * F0P_ < (int64_t)4294967296LL, "dj_frontend_fwd: batch too large");
@@ -412,6 +427,9 @@ extern "C" int dj_frontend_fwd(const float* notes_in, int64_t notes_bstride, con
     frontend_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(notes_in, notes_bstride, beat_in, beat_bstride, B,
                                                              T, Wc, bc, sp0, d_notes, d_beat, d_conv, d_sp,
                                                              (__nv_bfloat16*)A0, (__nv_bfloat16*)A0_lo, ldA);
+  else if (a_dtype == DJ_F16)
+    frontend_fwd_kernel<__half><<<grid, 256, 0, st>>>(notes_in, notes_bstride, beat_in, beat_bstride, B, T, Wc, bc, sp0,
+                                                      d_notes, d_beat, d_conv, d_sp, (__half*)A0, (__half*)A0_lo, ldA);
   else DJ_CHECK_ARG(false, "dj_frontend_fwd: unknown dtype %d", a_dtype);
   DJ_LAUNCH_CHECK();
   return 0;
@@ -422,7 +440,7 @@ extern "C" int dj_layer_input(const float* h_prev, int Uprev, int64_t h_row0, in
                               const float* chosen_in, int64_t chosen_bstride, dj_dropout d_chosen, int B,
                               int T, void* A, void* A_lo, int ldA, int a_dtype, void* stream) {
   DJ_CHECK_ARG(h_prev && sp && A, "dj_layer_input: NULL pointer");
-  DJ_CHECK_ARG(A_lo == nullptr || a_dtype == DJ_BF16, "dj_layer_input: the residual operand A_lo exists for DJ_BF16 only");
+  DJ_CHECK_ARG(A_lo == nullptr || a_dtype == DJ_BF16 || a_dtype == DJ_F16, "dj_layer_input: the residual operand A_lo exists for 16-bit operands only");
   DJ_CHECK_ARG(Uprev > 0 && Uprev % 4 == 0 && F >= Uprev, "dj_layer_input: bad Uprev %d / F %d", Uprev, F);
   DJ_CHECK_ARG(F == Uprev || (chosen_in && F == Uprev + NU_), "dj_layer_input: F must be Uprev or Uprev+3 with chosen");
   DJ_CHECK_ARG(ldA >= ((F + 3) & ~3) && ldA % 8 == 0, "dj_layer_input: ldA %d too small or not a multiple of 8", ldA);
@@ -437,6 +455,9 @@ extern "C" int dj_layer_input(const float* h_prev, int Uprev, int64_t h_row0, in
     layer_input_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(h_prev, Uprev, h_row0, h_b_rows, d_h, sp, F, d_sp,
                                                             chosen_in, chosen_bstride, d_chosen, B, T,
                                                             (__nv_bfloat16*)A, (__nv_bfloat16*)A_lo, ldA);
+  else if (a_dtype == DJ_F16)
+    layer_input_kernel<__half><<<grid, 256, 0, st>>>(h_prev, Uprev, h_row0, h_b_rows, d_h, sp, F, d_sp, chosen_in,
+                                                     chosen_bstride, d_chosen, B, T, (__half*)A, (__half*)A_lo, ldA);
   else DJ_CHECK_ARG(false, "dj_layer_input: unknown dtype %d", a_dtype);
   DJ_LAUNCH_CHECK();
   return 0;
@@ -461,7 +482,8 @@ extern "C" int dj_half_to_bf16_inplace(void* buf, int64_t n, void* stream) {
 }
 
 extern "C" int dj_cast16_multi(int n, const float* const* in, const int* rows, const int* cols, void* const* out,
-                               void* const* out_lo, const int* ldo, const int* transpose, const int* fmt, void* stream) {
+                               void* const* out_lo, const int* ldo, const int* transpose, const int* fmt,
+                               const float* scale, void* stream) {
   DJ_CHECK_ARG(n > 0 && n <= 16 && in && rows && cols && out && ldo && transpose && fmt, "dj_cast16_multi: bad arguments");
   CastBatch b{};
   for (int i = 0; i < n; ++i) {
@@ -470,6 +492,7 @@ extern "C" int dj_cast16_multi(int n, const float* const* in, const int* rows, c
                  "dj_cast16_multi: entry %d invalid", i);
     b.in[i] = in[i]; b.out[i] = (uint16_t*)out[i]; b.out_lo[i] = out_lo ? (uint16_t*)out_lo[i] : nullptr;
     b.rows[i] = rows[i]; b.cols[i] = cols[i]; b.ldo[i] = ldo[i]; b.transpose[i] = transpose[i]; b.fmt[i] = fmt[i];
+    b.scale[i] = scale ? scale[i] : 1.0f;
   }
   cast_bf16_multi_kernel<<<dim3(64, n), 256, 0, (cudaStream_t)stream>>>(b);
   DJ_LAUNCH_CHECK();

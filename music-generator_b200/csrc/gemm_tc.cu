@@ -12,19 +12,26 @@
 // tiles written by TMA and read by the tensor core through shared-memory matrix
 // descriptors; full/empty mbarriers pipeline TMA against MMA, tmem_full/empty
 // pipeline MMA against the epilogue (two accumulator stages).
+#include <stdlib.h>
+
 #include "dj_tc.cuh"
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 64;
-constexpr int STAGES = 4, ACC_STAGES = 2;
-constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
+constexpr int BM = 128, BK = 64;
+constexpr int ACC_STAGES = 2;
+constexpr int A_BYTES = BM * BK * 2;
 constexpr int EPI_BOXES = 4;                     // 32x32 fp32 staging boxes per epilogue warp (TMA stores in flight)
 constexpr int EPI_WARP_BYTES = EPI_BOXES * 32 * 128;
 constexpr int NUM_THREADS = 256;
 
 constexpr int MAX_BIAS_N = 2048;                  // bias is staged in shared memory once per CTA
-struct GemmSmem {
+// BN = 128: four stages; BN = 256 (one 128x256x16 MMA feeds the tensor core twice as long per byte of A read from
+// shared memory: the tile of the 3-pass split product, which is bound by the MMA loop, not by writing C): three
+// stages of 48 KB and all 512 tensor-memory columns for the two accumulator stages
+template <int BN> struct GemmSmem {
+  static constexpr int STAGES = BN == 256 ? 3 : 4;
+  static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int A_OFF = 0;
   static constexpr int B_OFF = STAGES * A_BYTES;
   static constexpr int EPI_OFF = B_OFF + STAGES * B_BYTES;
@@ -36,20 +43,23 @@ struct GemmSmem {
 // ---------------------------------------------------------------------------
 // C = A . Bt^T + bias, both operands K-major
 // ---------------------------------------------------------------------------
+template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gate_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
                  const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias, int M, int N, int K,
-                 int npass, uint32_t idesc) {
+                 int npass, uint32_t idesc, float out_scale) {
+  using SM = GemmSmem<BN>;
+  constexpr int STAGES = SM::STAGES, B_BYTES = SM::B_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const uint32_t sbase = smem_u32(smem);
-  const uint32_t bars = sbase + GemmSmem::BAR_OFF;
+  const uint32_t bars = sbase + SM::BAR_OFF;
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
   auto tfull_bar = [&](int a) { return bars + 8u * (2 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bars + 8u * (2 * STAGES + ACC_STAGES + a); };
-  uint32_t* tmem_slot = (uint32_t*)(smem + GemmSmem::BAR_OFF + 8 * (2 * STAGES + 2 * ACC_STAGES));
+  uint32_t* tmem_slot = (uint32_t*)(smem + SM::BAR_OFF + 8 * (2 * STAGES + 2 * ACC_STAGES));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_n = (N + BN - 1) / BN, num_m = (M + BM - 1) / BM;
@@ -65,7 +75,7 @@ gate_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(smem_u32(tmem_slot), ACC_STAGES * BN);
-  float* bias_s = reinterpret_cast<float*>(smem + GemmSmem::BIAS_OFF);
+  float* bias_s = reinterpret_cast<float*>(smem + SM::BIAS_OFF);
   if (bias != nullptr)   // one global read of the bias per CTA; the epilogue then reads it from shared memory
     for (int i = threadIdx.x; i < ((N + 127) / 128) * 128; i += NUM_THREADS) bias_s[i] = (i < N) ? bias[i] : 0.f;
   tc_fence_before();
@@ -85,8 +95,8 @@ gate_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int kb = 0; kb < num_kb; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1);
             mbar_expect_tx(full_bar(stage), A_BYTES + B_BYTES);
-            tma_load_2d(sbase + GemmSmem::A_OFF + stage * A_BYTES, mA, full_bar(stage), kb * BK, m0);
-            tma_load_2d(sbase + GemmSmem::B_OFF + stage * B_BYTES, mB, full_bar(stage), kb * BK, n0);
+            tma_load_2d(sbase + SM::A_OFF + stage * A_BYTES, mA, full_bar(stage), kb * BK, m0);
+            tma_load_2d(sbase + SM::B_OFF + stage * B_BYTES, mB, full_bar(stage), kb * BK, n0);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -103,8 +113,8 @@ gate_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int kb = 0; kb < num_it; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint64_t adesc = make_smem_desc(sbase + GemmSmem::A_OFF + stage * A_BYTES, 16, 1024);
-          const uint64_t bdesc = make_smem_desc(sbase + GemmSmem::B_OFF + stage * B_BYTES, 16, 1024);
+          const uint64_t adesc = make_smem_desc(sbase + SM::A_OFF + stage * A_BYTES, 16, 1024);
+          const uint64_t bdesc = make_smem_desc(sbase + SM::B_OFF + stage * B_BYTES, 16, 1024);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)   // UMMA_K = 16 bf16 = 32 B inside the 128 B swizzle row
             umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
@@ -117,7 +127,7 @@ gate_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp >= 4) {   // ===== epilogue =====
     const int e = warp - 4;
-    uint8_t* ebuf = smem + GemmSmem::EPI_OFF + e * EPI_WARP_BYTES;
+    uint8_t* ebuf = smem + SM::EPI_OFF + e * EPI_WARP_BYTES;
     const uint32_t ebuf_s = smem_u32(ebuf);
     int acc = 0; uint32_t aphase = 0; int nbuf = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -137,6 +147,7 @@ gate_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           float4 o;
           o.x = __uint_as_float(v[4 * q + 0]); o.y = __uint_as_float(v[4 * q + 1]);
           o.z = __uint_as_float(v[4 * q + 2]); o.w = __uint_as_float(v[4 * q + 3]);
+          o.x *= out_scale; o.y *= out_scale; o.z *= out_scale; o.w *= out_scale;   // exact for the power-of-two scales used
           if (bias != nullptr) {
             const float4 bv = *reinterpret_cast<const float4*>(bias_s + ncol + 4 * q);   // broadcast smem read
             o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
@@ -303,42 +314,68 @@ static inline CUtensorMapDataType tmap_dtype(int fmt) {
   return fmt == DJ_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
 }
 
-extern "C" int dj_gate_gemm_16(const void* A, const void* A_lo, int a_fmt, int64_t lda, const void* Bt,
-                               const void* Bt_lo, int b_fmt, int64_t ldb, float* C, int64_t ldc, const float* bias,
-                               int M, int N, int K, void* stream) {
-  DJ_CHECK_ARG(A && Bt && C, "dj_gate_gemm_16: NULL pointer");
-  DJ_CHECK_ARG((A_lo == nullptr) == (Bt_lo == nullptr), "dj_gate_gemm_16: A_lo and Bt_lo come together (3-pass split product)");
-  DJ_CHECK_ARG(fmt16_ok(a_fmt) && a_fmt == b_fmt,
-               "dj_gate_gemm_16: operand formats must be DJ_BF16 or DJ_F16 and equal (kind::f16 cannot mix half with bf16)");
-  DJ_CHECK_ARG(M > 0 && N > 0 && K > 0, "dj_gate_gemm_16: bad shape");
-  DJ_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0 && ldc % 4 == 0 && lda >= K && ldb >= K && ldc >= N,
-               "dj_gate_gemm_16: leading dimensions must be 16-byte multiples and cover K/N (lda=%lld ldb=%lld ldc=%lld)",
-               (long long)lda, (long long)ldb, (long long)ldc);
-  DJ_CHECK_ARG(bias == nullptr || N <= MAX_BIAS_N, "dj_gate_gemm_16: N=%d exceeds the bias staging capacity %d", N, MAX_BIAS_N);
-  DJ_CHECK_ARG(((uintptr_t)A % 16) == 0 && ((uintptr_t)Bt % 16) == 0 && ((uintptr_t)C % 16) == 0 &&
-                   ((uintptr_t)A_lo % 16) == 0 && ((uintptr_t)Bt_lo % 16) == 0 &&
-                   (bias == nullptr || ((uintptr_t)bias % 16) == 0),
-               "dj_gate_gemm_16: pointers must be 16-byte aligned");
-  const int npass = A_lo ? 3 : 1;
-  CUtensorMap tmA, tmAlo, tmB, tmBlo, tmC;
+template <int BN>
+static int launch_gate_gemm(const CUtensorMap& tmA, const CUtensorMap& tmAlo, const void* Bt, const void* Bt_lo, int b_fmt,
+                            int64_t ldb, const CUtensorMap& tmC, const float* bias, int M, int N, int K, int npass,
+                            uint32_t idesc_fmt_mask, float out_scale, cudaStream_t st) {
+  CUtensorMap tmB, tmBlo;
   int rc;
-  if ((rc = make_map_2d(&tmA, tmap_dtype(a_fmt), 2, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, BM))) return rc;
   if ((rc = make_map_2d(&tmB, tmap_dtype(b_fmt), 2, Bt, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BK, BN))) return rc;
-  tmAlo = tmA; tmBlo = tmB;
-  if (npass == 3) {
-    if ((rc = make_map_2d(&tmAlo, tmap_dtype(a_fmt), 2, A_lo, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, BM))) return rc;
-    if ((rc = make_map_2d(&tmBlo, tmap_dtype(b_fmt), 2, Bt_lo, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BK, BN))) return rc;
-  }
-  if ((rc = make_map_2d(&tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, C, (uint64_t)N, (uint64_t)M, (uint64_t)ldc, 32, 32))) return rc;
-  DJ_CUDA(cudaFuncSetAttribute((const void*)gate_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem::TOTAL));
+  tmBlo = tmB;
+  if (npass == 3 && (rc = make_map_2d(&tmBlo, tmap_dtype(b_fmt), 2, Bt_lo, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BK, BN)))
+    return rc;
+  DJ_CUDA(cudaFuncSetAttribute((const void*)gate_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               GemmSmem<BN>::TOTAL));
   const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   int grid = dj_num_sms();
   if (grid > tiles) grid = tiles;
-  const uint32_t idesc = idesc_with_formats(make_idesc(BM, BN, 0, 0), a_fmt, b_fmt);
-  gate_gemm_kernel<<<grid, NUM_THREADS, GemmSmem::TOTAL, (cudaStream_t)stream>>>(tmA, tmAlo, tmB, tmBlo, tmC, bias, M, N, K,
-                                                                                 npass, idesc);
+  const uint32_t idesc = make_idesc(BM, BN, 0, 0) & idesc_fmt_mask;
+  gate_gemm_kernel<BN><<<grid, NUM_THREADS, GemmSmem<BN>::TOTAL, st>>>(tmA, tmAlo, tmB, tmBlo, tmC, bias, M, N, K, npass, idesc,
+                                                                      out_scale);
   DJ_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int dj_gate_gemm_16s(const void* A, const void* A_lo, int a_fmt, int64_t lda, const void* Bt,
+                                const void* Bt_lo, int b_fmt, int64_t ldb, float* C, int64_t ldc, const float* bias,
+                                float out_scale, int M, int N, int K, void* stream) {
+  DJ_CHECK_ARG(A && Bt && C, "dj_gate_gemm_16s: NULL pointer");
+  DJ_CHECK_ARG((A_lo == nullptr) == (Bt_lo == nullptr), "dj_gate_gemm_16s: A_lo and Bt_lo come together (3-pass split product)");
+  DJ_CHECK_ARG(fmt16_ok(a_fmt) && a_fmt == b_fmt,
+               "dj_gate_gemm_16s: operand formats must be DJ_BF16 or DJ_F16 and equal (kind::f16 cannot mix half with bf16)");
+  DJ_CHECK_ARG(M > 0 && N > 0 && K > 0, "dj_gate_gemm_16s: bad shape");
+  DJ_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0 && ldc % 4 == 0 && lda >= K && ldb >= K && ldc >= N,
+               "dj_gate_gemm_16s: leading dimensions must be 16-byte multiples and cover K/N (lda=%lld ldb=%lld ldc=%lld)",
+               (long long)lda, (long long)ldb, (long long)ldc);
+  DJ_CHECK_ARG(bias == nullptr || N <= MAX_BIAS_N, "dj_gate_gemm_16s: N=%d exceeds the bias staging capacity %d", N, MAX_BIAS_N);
+  DJ_CHECK_ARG(((uintptr_t)A % 16) == 0 && ((uintptr_t)Bt % 16) == 0 && ((uintptr_t)C % 16) == 0 &&
+                   ((uintptr_t)A_lo % 16) == 0 && ((uintptr_t)Bt_lo % 16) == 0 &&
+                   (bias == nullptr || ((uintptr_t)bias % 16) == 0),
+               "dj_gate_gemm_16s: pointers must be 16-byte aligned");
+  const int npass = A_lo ? 3 : 1;
+  CUtensorMap tmA, tmAlo, tmC;
+  int rc;
+  if ((rc = make_map_2d(&tmA, tmap_dtype(a_fmt), 2, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, BM))) return rc;
+  tmAlo = tmA;
+  if (npass == 3 && (rc = make_map_2d(&tmAlo, tmap_dtype(a_fmt), 2, A_lo, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, BM)))
+    return rc;
+  if ((rc = make_map_2d(&tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, C, (uint64_t)N, (uint64_t)M, (uint64_t)ldc, 32, 32))) return rc;
+  const uint32_t fmt_mask = idesc_with_formats(0xFFFFFFFFu, a_fmt, b_fmt);
+  // the split product is bound by its MMA loop: 128x256 tiles when N allows (DJ_GEMM_BN=128 forces the small tile)
+  static int bn_env = -1;
+  if (bn_env < 0) { const char* e = getenv("DJ_GEMM_BN"); bn_env = e ? atoi(e) : 0; }
+  const bool wide = (npass == 3 && N % 256 == 0 && bn_env != 128) || bn_env == 256;
+  if (wide)
+    return launch_gate_gemm<256>(tmA, tmAlo, Bt, Bt_lo, b_fmt, ldb, tmC, bias, M, N, K, npass, fmt_mask, out_scale,
+                                 (cudaStream_t)stream);
+  return launch_gate_gemm<128>(tmA, tmAlo, Bt, Bt_lo, b_fmt, ldb, tmC, bias, M, N, K, npass, fmt_mask, out_scale,
+                               (cudaStream_t)stream);
+}
+
+extern "C" int dj_gate_gemm_16(const void* A, const void* A_lo, int a_fmt, int64_t lda, const void* Bt,
+                               const void* Bt_lo, int b_fmt, int64_t ldb, float* C, int64_t ldc, const float* bias,
+                               int M, int N, int K, void* stream) {
+  return dj_gate_gemm_16s(A, A_lo, a_fmt, lda, Bt, Bt_lo, b_fmt, ldb, C, ldc, bias, 1.0f, M, N, K, stream);
 }
 
 extern "C" int dj_gate_gemm_bf16(const void* A, int64_t lda, const void* Bt, int64_t ldb, float* C, int64_t ldc,

@@ -73,10 +73,11 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t v[8]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
 
-template <int U, int BS>
+// INFER: the B operand is h as IEEE half hi + lo (two tiles)
+template <int U, int BS, bool INFER = false>
 struct TcFwdSmem {
   static constexpr int A_BYTES = 128 * U * 2;
-  static constexpr int H_BYTES = BS * U * 2;
+  static constexpr int H_BYTES = BS * U * 2 * (INFER ? 2 : 1);
   static constexpr int A_OFF = 0, H_OFF = A_BYTES, BAR_OFF = A_BYTES + H_BYTES;
   static constexpr int TOTAL = BAR_OFF + 96;          // no static smem: two CTAs must fit one SM
 };
@@ -130,12 +131,17 @@ __device__ __forceinline__ int64_t tc_row0(const TcMap& m, int seq) {
 // (tcgen05.mma with A from TMEM): the per-step MMAs then read only the small B operand from shared memory.  With A
 // in shared memory the 16 MMAs of a half-step are bound by re-reading the 64 KB of weights (~80 cycles per MMA
 // against a 24-cycle floor).  Needs 2 x (BS + U/2 rounded up) <= 512 TMEM columns for two CTAs per SM: U <= 256.
-template <int U, int BS, bool TIME, bool HARD, int NB, int NS, bool ATM>
+// INFER (generation: the sampled events must equal the fp32 model's, so the recurrence has to be fp32-grade):
+// h_{t-1} enters as IEEE half hi + lo and U as half hi + lo (both ~22 mantissa bits; U pre-scaled by a power of
+// two, undone by acc_scale, so its residual stays out of half's subnormal range), three MMA passes per step on the
+// same accumulator: U_hi.h_hi + U_lo.h_hi + U_hi.h_lo.  Nothing is saved for a backward pass: no gate / c stores.
+template <int U, int BS, bool TIME, bool HARD, int NB, int NS, bool ATM, bool INFER = false>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 scan_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmH,
-                   float* __restrict__ Z, float* __restrict__ Hout, float* __restrict__ Cout,
-                   uint16_t* __restrict__ Hprev, const uint32_t* __restrict__ Ut_words, int steps, TcMap map,
-                   int f16, int has_lo) {
+                   const __grid_constant__ CUtensorMap tmHlo, float* __restrict__ Z, float* __restrict__ Hout,
+                   float* __restrict__ Cout, uint16_t* __restrict__ Hprev, uint16_t* __restrict__ Hprev_lo,
+                   const uint32_t* __restrict__ Ut_words, int steps, TcMap map, int f16, int has_lo, float acc_scale) {
+  static_assert(!INFER || ATM, "inference mode keeps the A operand in tensor memory");
   constexpr uint32_t SSTR = TIME ? 1u : 48u, TSTR = TIME ? 48u : 1u;
   constexpr int C = U / 32;            // cluster size
   constexpr int KA = U / 64;           // 64-wide K atoms
@@ -157,7 +163,8 @@ scan_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
   // has_lo (ATM only): shared memory holds the 16-bit residual U - hi(U) of this CTA's slice; a second MMA pass adds
   // h.U_lo so the recurrent weights enter the product with ~22 mantissa bits
   const bool smem_a = !ATM || has_lo;
-  using SM = TcFwdSmem<U, BS>;
+  using SM = TcFwdSmem<U, BS, INFER>;
+  constexpr int HLO_OFF = BS * U * 2;     // INFER: the lo tiles follow the hi tiles inside the H region
 
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
@@ -175,6 +182,7 @@ scan_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
     if (lane == 0) {
       if (sbase & 1023u) { printf("deepj scan_tc_fwd: dynamic smem not 1024-aligned\n"); __trap(); }
       prefetch_tmap(&tmU); prefetch_tmap(&tmH);
+      if (INFER) prefetch_tmap(&tmHlo);
       mbar_init(bar_a, 1);
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
@@ -236,11 +244,16 @@ scan_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
         mbar_wait(bar_pub, par);
         DJ_TR(t, 4 * hf + 1);
         if (elect_one()) {
-          mbar_expect_tx(bar_h, HB * U * 2);
-          if (NS == 1 || my_hh == hf)
+          mbar_expect_tx(bar_h, HB * U * 2 * (INFER ? 2 : 1));
+          if (NS == 1 || my_hh == hf) {
             tma_load_3d_mc(sbase + SM::H_OFF + my_ka * (BS * 128) + my_hh * (RH * 128), &tmH, bar_h, my_ka * 64,
                            (t + 1) * map.step1 + my_hh * map.off1, tile * map.base2 + my_hh * map.off2,
                            (uint16_t)((1u << C) - 1u));
+            if constexpr (INFER)
+              tma_load_3d_mc(sbase + SM::H_OFF + HLO_OFF + my_ka * (BS * 128) + my_hh * (RH * 128), &tmHlo, bar_h,
+                             my_ka * 64, (t + 1) * map.step1 + my_hh * map.off1, tile * map.base2 + my_hh * map.off2,
+                             (uint16_t)((1u << C) - 1u));
+          }
         }
         __syncwarp();
         if (smem_a && t == 0) mbar_wait(bar_a, 0);
@@ -269,6 +282,14 @@ scan_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
               for (int k = 0; k < 4; ++k)
                 umma_bf16(tmem_base + (uint32_t)(hf * HB), adesc0 + (uint64_t)((ka * 16384 + k * 32) >> 4),
                           bdesc0 + (uint64_t)((ka * (BS * 128) + k * 32) >> 4), idesc, 1);
+          }
+          if constexpr (INFER) {   // U_hi . h_lo
+#pragma unroll
+            for (int ka = 0; ka < KA; ++ka)
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_bf16_ts(tmem_base + (uint32_t)(hf * HB), tmem_base + A_COL0 + (uint32_t)(ka * 32 + k * 8),
+                             bdesc0 + (uint64_t)((HLO_OFF + ka * (BS * 128) + k * 32) >> 4), idesc, 1);
           }
           umma_commit(bar_acc);
         }
@@ -328,7 +349,7 @@ scan_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
             tmem_ld8(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(ci * 16 + 8 * w2), acc);
             tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(acc[j]) + zreg[ci % NB][j];
+            for (int j = 0; j < 8; ++j) v[j] = fmaf(__uint_as_float(acc[j]), acc_scale, zreg[ci % NB][j]);
           } else {
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] = zreg[ci % NB][j];
@@ -343,6 +364,7 @@ scan_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
           float* const hp = Hout + o1;
           float* const cp = Cout + o1;                       // only dereferenced when Cout != nullptr
           uint16_t* const hb = Hprev + o1;
+          uint16_t* const hbl = Hprev_lo + o1;                // INFER only
 #pragma unroll
           for (int blk = 0; blk < 2; ++blk) {
             // 4x4 transpose across the 4 lanes of a unit: lane g ends with i,f,g,o of sequence 4*blk+g
@@ -363,15 +385,23 @@ scan_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
 
             constexpr size_t RO = (size_t)4 * SSTR;          // rows between consecutive blocks
             // h_t (bf16) at the NEXT step's row: the A operand of dU = H_{t-1}^T.dZ
-            if (not_last)
-              hb[(blk * RO + TSTR) * U] = f16 ? __half_as_ushort(__float2half_rn(hn)) : __bfloat16_as_ushort(__float2bfloat16_rn(hn));
-            if (t == 0) hb[blk * RO * U] = 0;
+            if constexpr (INFER) {
+              if (not_last) {
+                const __half hh = __float2half_rn(hn);
+                hb[(blk * RO + TSTR) * U] = __half_as_ushort(hh);
+                hbl[(blk * RO + TSTR) * U] = __half_as_ushort(__float2half_rn(hn - __half2float(hh)));
+              }
+            } else {
+              if (not_last)
+                hb[(blk * RO + TSTR) * U] = f16 ? __half_as_ushort(__float2half_rn(hn)) : __bfloat16_as_ushort(__float2bfloat16_rn(hn));
+              if (t == 0) hb[blk * RO * U] = 0;
+            }
 #ifndef DJ_EXP
 #define DJ_EXP 0   // timing experiments only: bit0/1/2 drop the gate / h / c stores
 #endif
-            if (!(DJ_EXP & 1)) *reinterpret_cast<float4*>(zg + blk * RO * (4 * U)) = make_float4(gi, gf, gg, go);
+            if (!INFER && !(DJ_EXP & 1)) *reinterpret_cast<float4*>(zg + blk * RO * (4 * U)) = make_float4(gi, gf, gg, go);
             if (!(DJ_EXP & 2)) hp[blk * RO * U] = hn;
-            if (!(DJ_EXP & 4) && Cout != nullptr) cp[blk * RO * U] = cn;
+            if (!INFER && !(DJ_EXP & 4) && Cout != nullptr) cp[blk * RO * U] = cn;
           }
         }
         if (tr) DJ_TR(t, 9 + 4 * hf);
@@ -399,14 +429,15 @@ inline bool fwd_atm_enabled() {   // DJ_FWD_ATM=0 keeps the A operand in shared 
   return env != 0;
 }
 
-template <int U, int BS, bool TIME, bool HARD, int NB, int NS>
+template <int U, int BS, bool TIME, bool HARD, int NB, int NS, bool INFER = false>
 int launch_tc_fwd_inst(const void* Ut_bf, const void* Ut_lo, int f16, float* Z, float* h_out, float* c_out, void* hprev,
-                       int S, int steps, const TcMap& map_in, cudaStream_t st) {
+                       int S, int steps, const TcMap& map_in, cudaStream_t st, void* hprev_lo = nullptr,
+                       float acc_scale = 1.0f) {
   constexpr int C = U / 32;
-  using SM = TcFwdSmem<U, BS>;
+  using SM = TcFwdSmem<U, BS, INFER>;
   DJ_CHECK_ARG(S % BS == 0, "dj_lstm_scan_tc_fwd: the number of sequences (%d) must be a multiple of %d", S, BS);
   TcMap map = map_in;
-  CUtensorMap tmU, tmH;
+  CUtensorMap tmU, tmH, tmHlo;
   int rc;
   // U <= 256: A operand in tensor memory unless DJ_FWD_ATM=0; U = 512: only when the residual pass needs the shared-memory slot
   constexpr bool CAN_ATM = true;
@@ -422,18 +453,27 @@ int launch_tc_fwd_inst(const void* Ut_bf, const void* Ut_lo, int f16, float* Z, 
     const uint64_t dims[3] = {(uint64_t)U, rows_per_b, B}, str[2] = {(uint64_t)U, rows_per_b * U};
     const uint32_t box[3] = {64, (uint32_t)(RH <= 48 ? RH : 48), (uint32_t)(RH <= 48 ? 1 : RH / 48)};
     if ((rc = make_map(&tmH, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, hprev, 3, dims, str, box))) return rc;
+    tmHlo = tmH;
+    if (INFER && (rc = make_map(&tmHlo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, hprev_lo, 3, dims, str, box))) return rc;
     map.step1 = 48; map.off1 = (RH % 48); map.base2 = BS / 48; map.off2 = RH / 48;
     map.seq_stride = map.inner_stride;
   } else {           // hprev viewed as [seq][n][U]
     const uint64_t dims[3] = {(uint64_t)U, 48, (uint64_t)S}, str[2] = {(uint64_t)U, (uint64_t)48 * U};
     const uint32_t box[3] = {64, 1, (uint32_t)RH};
     if ((rc = make_map(&tmH, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, hprev, 3, dims, str, box))) return rc;
+    tmHlo = tmH;
+    if (INFER && (rc = make_map(&tmHlo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, hprev_lo, 3, dims, str, box))) return rc;
     map.step1 = 1; map.off1 = 0; map.base2 = BS; map.off2 = RH;
     map.seq_stride = map.outer_stride;
   }
-  auto kernel = scan_tc_fwd_kernel<U, BS, TIME, HARD, NB, NS, false>;
-  if constexpr (CAN_ATM) {
-    if (atm) kernel = scan_tc_fwd_kernel<U, BS, TIME, HARD, NB, NS, true>;
+  auto kernel = scan_tc_fwd_kernel<U, BS, TIME, HARD, NB, NS, INFER, INFER>;   // (INFER: the only instance, ATM = true)
+  if constexpr (!INFER) {
+    kernel = scan_tc_fwd_kernel<U, BS, TIME, HARD, NB, NS, false, false>;
+    if constexpr (CAN_ATM) {
+      if (atm) kernel = scan_tc_fwd_kernel<U, BS, TIME, HARD, NB, NS, true, false>;
+    }
+  } else {
+    DJ_CHECK_ARG(atm && Ut_lo && hprev_lo, "dj_lstm_scan_tc_infer: needs Ut_lo, h_lo and the tensor-memory A operand");
   }
   DJ_CUDA(cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
   if (C > 8) DJ_CUDA(cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
@@ -454,7 +494,8 @@ int launch_tc_fwd_inst(const void* Ut_bf, const void* Ut_lo, int f16, float* Z, 
   uint16_t* hp = (uint16_t*)hprev;
   const uint32_t* utw = (const uint32_t*)Ut_bf;
   const int has_lo = Ut_lo != nullptr ? 1 : 0;
-  DJ_CUDA(cudaLaunchKernelEx(&cfg, kernel, tmU, tmH, Z, h_out, c_out, hp, utw, steps, map, f16, has_lo));
+  uint16_t* hpl = (uint16_t*)hprev_lo;
+  DJ_CUDA(cudaLaunchKernelEx(&cfg, kernel, tmU, tmH, tmHlo, Z, h_out, c_out, hp, hpl, utw, steps, map, f16, has_lo, acc_scale));
   return 0;
 }
 
@@ -912,6 +953,25 @@ extern "C" int dj_lstm_scan_tc_fwd(float* Z, float* h_out, float* c_out, void* h
   }
   DJ_CHECK_ARG(false, "dj_lstm_scan_tc_fwd: units=%d unsupported on this axis (time: 256/512, note: 128/256)", units);
   return -1;
+}
+
+extern "C" int dj_lstm_scan_tc_infer(const float* Z, float* h_out, void* h_hi, void* h_lo, const void* Ut_hi,
+                                     const void* Ut_lo, float acc_scale, int S, int steps, int units, int seq_inner,
+                                     int64_t seq_outer_stride, int64_t seq_inner_stride, int64_t step_stride, int hard,
+                                     void* stream) {
+  DJ_CHECK_ARG(Z && h_out && h_hi && h_lo && Ut_hi && Ut_lo, "dj_lstm_scan_tc_infer: NULL pointer");
+  DJ_CHECK_ARG(S > 0 && steps > 0 && acc_scale > 0.f, "dj_lstm_scan_tc_infer: bad sizes");
+  TcMap map{seq_inner, seq_outer_stride, seq_inner_stride, step_stride, 0, 0, 0, 0, 0};
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool time_map = (seq_inner == 48 && seq_inner_stride == 1 && step_stride == 48 && S % 48 == 0);
+  DJ_CHECK_ARG(time_map && units == 256, "dj_lstm_scan_tc_infer: the time-axis map with 256 units is the supported shape");
+  float* Zm = const_cast<float*>(Z);     // inference mode never writes the pre-activations
+  if (S % 96 == 0 && S / 48 > 32) {
+    if (hard) return launch_tc_fwd_inst<256, 96, true, true, 2, 2, true>(Ut_hi, Ut_lo, 1, Zm, h_out, nullptr, h_hi, S, steps, map, st, h_lo, acc_scale);
+    return launch_tc_fwd_inst<256, 96, true, false, 2, 2, true>(Ut_hi, Ut_lo, 1, Zm, h_out, nullptr, h_hi, S, steps, map, st, h_lo, acc_scale);
+  }
+  if (hard) return launch_tc_fwd_inst<256, 48, true, true, 1, 1, true>(Ut_hi, Ut_lo, 1, Zm, h_out, nullptr, h_hi, S, steps, map, st, h_lo, acc_scale);
+  return launch_tc_fwd_inst<256, 48, true, false, 1, 1, true>(Ut_hi, Ut_lo, 1, Zm, h_out, nullptr, h_hi, S, steps, map, st, h_lo, acc_scale);
 }
 
 extern "C" int dj_lstm_scan_tc_bwd(const float* gates, const float* c, const float* dY, int64_t ldY, dj_dropout d_y,

@@ -37,9 +37,12 @@ class Workspace:
     def __init__(self, cfg: ModelConfig, B: int, T: int, prec: str, train: bool, dev):
         self.B, self.T, self.M = B, T, B * T * N
         bf16, mixed = prec in ("bf16", "mixed"), prec == "mixed"
+        gen = prec == "gen"     # generation window: fp32-grade tensor-core path (half hi+lo operands), time axis only
         M, BT = self.M, B * T
         f32 = dict(dtype=torch.float32, device=dev)
-        adt = torch.bfloat16 if bf16 else torch.float32
+        adt = torch.bfloat16 if bf16 else torch.float16 if gen else torch.float32
+        self.gen = gen
+        self.h_hi, self.h_lo = [], []     # gen: h_{t-1} as half hi / lo, the exchange buffers of the inference scan
         self.emb = torch.empty(BT, cfg.style_units, **f32)
         self.sp, self.A, self.Z, self.h, self.c = [], [], [], [], []
         self.A_lo = []      # mixed: bf16 residual of A (second operand of the split gate GEMM)
@@ -49,7 +52,10 @@ class Workspace:
             self.ld.append(ld)
             self.sp.append(torch.empty(BT, L["F"], **f32))
             self.A.append(torch.empty(M, ld, dtype=adt, device=dev))
-            self.A_lo.append(torch.empty(M, ld, dtype=adt, device=dev) if mixed else None)
+            self.A_lo.append(torch.empty(M, ld, dtype=adt, device=dev) if (mixed or gen) else None)
+            tl = gen and L["axis"] == "time"
+            self.h_hi.append(torch.empty(M, L["U"], dtype=torch.float16, device=dev) if tl else None)
+            self.h_lo.append(torch.empty(M, L["U"], dtype=torch.float16, device=dev) if tl else None)
             self.Z.append(torch.empty(M, 4 * L["U"], **f32))
             self.h.append(torch.empty(M, L["U"], **f32))
             self.c.append(torch.empty(M, L["U"], **f32) if train else None)
@@ -123,7 +129,9 @@ class Engine:
         self._hi = None
         self._tag = ""
         self.peer = None      # parallel.PeerNadam: fused gradient exchange + Nadam over peer memory
-        self.gen_tc = False   # generation projections on the tensor cores (split operands); False = CUDA-core fp32 GEMM
+        # generation window on the tensor cores at fp32 grade (half hi+lo operands, 3 MMA passes); DJ_GEN_TC=0 = the
+        # CUDA-core fp32 kernels
+        self.gen_tc = os.environ.get("DJ_GEN_TC", "1") != "0"
 
     # ------------------------------------------------------------------ params
     def _view(self, flat, k):
@@ -261,8 +269,36 @@ class Engine:
         self._call("dj_cast16_multi", k, (C.c_void_p * k)(*[e[0].data_ptr() for e in ents]), ints(1), ints(2),
                    (C.c_void_p * k)(*[e[3].data_ptr() for e in ents]),
                    (C.c_void_p * k)(*[None if e[4] is None else e[4].data_ptr() for e in ents]),
-                   ints(5), ints(6), ints(7), _stream())
+                   ints(5), ints(6), ints(7), None, _stream())
         self._wbf_version, self._wbf_mixed = self._version, mixed
+
+    GEN_SCALE = 1024.0      # power of two: keeps the half-precision residuals of W and U out of the subnormal range
+
+    def _refresh_gen(self):
+        """Generation window on the tensor cores at fp32 grade: the time-axis kernels W^T and U^T as IEEE half hi + lo
+        (~22 mantissa bits), pre-scaled by GEN_SCALE (undone exactly in the kernels' epilogues)."""
+        if getattr(self, "_wgen_version", -1) == self._version:
+            return
+        ents = []
+        for L in self.layers:
+            if L["axis"] != "time":
+                continue
+            n = L["name"]
+            W, Um = self.params[f"{n}.lstm.W"], self.params[f"{n}.lstm.U"]
+            F, U4 = W.shape
+            U, ld = L["U"], round_up(F, 32)
+            if f"{n}.gWt" not in self._wbf:
+                w16 = dict(dtype=torch.float16, device=self.dev)
+                for k, shp in (("gWt", (U4, ld)), ("gWt_lo", (U4, ld)), ("gUt", (U4, U)), ("gUt_lo", (U4, U))):
+                    self._wbf[f"{n}.{k}"] = torch.empty(*shp, **w16)
+            ents += [(W, F, U4, self._wbf[f"{n}.gWt"], self._wbf[f"{n}.gWt_lo"], ld, 1, DJ_F16),
+                     (Um, U, U4, self._wbf[f"{n}.gUt"], self._wbf[f"{n}.gUt_lo"], U, 1, DJ_F16)]
+        k = len(ents)
+        ints = lambda j: (C.c_int * k)(*[e[j] for e in ents])
+        self._call("dj_cast16_multi", k, (C.c_void_p * k)(*[e[0].data_ptr() for e in ents]), ints(1), ints(2),
+                   (C.c_void_p * k)(*[e[3].data_ptr() for e in ents]), (C.c_void_p * k)(*[e[4].data_ptr() for e in ents]),
+                   ints(5), ints(6), ints(7), (C.c_float * k)(*[self.GEN_SCALE] * k), _stream())
+        self._wgen_version = self._version
 
     # --------------------------------------------------------------- dropout
     def _drops(self, train: bool, seed: int) -> Dict[int, Dropout]:
@@ -312,7 +348,11 @@ class Engine:
         U4, ld = 4 * L["U"], ws.ld[li]
         bias = P[f"{L['name']}.lstm.b"]
         self._tag = ":" + L["name"]
-        if bf16:
+        if ws.gen and L["axis"] == "time":      # half hi+lo operands, weights pre-scaled by GEN_SCALE
+            self._call("dj_gate_gemm_16s", _ptr(ws.A[li]), _ptr(ws.A_lo[li]), DJ_F16, ld,
+                       _ptr(self._wbf[f"{L['name']}.gWt"]), _ptr(self._wbf[f"{L['name']}.gWt_lo"]), DJ_F16, ld,
+                       _ptr(ws.Z[li]), U4, _ptr(bias), 1.0 / self.GEN_SCALE, M, U4, ld, _stream())
+        elif bf16:
             mixed = ws.A_lo[li] is not None     # split product: A.W + A_lo.W + A.W_lo on the same TMEM accumulator
             self._call("dj_gate_gemm_16", _ptr(ws.A[li]), _ptr(ws.A_lo[li]), DJ_BF16, ld,
                        _ptr(self._wbf[f"{L['name']}.Wt"]), _ptr(self._wbf[f"{L['name']}.Wt_lo"]) if mixed else None,
@@ -342,7 +382,12 @@ class Engine:
         L = self.layers[li]
         m = self._scan_map(L["axis"], B, T)
         self._tag = ":" + L["name"]
-        if train and ws.hprev[li] is not None and self._tc_ok(B, T):
+        if ws.gen and L["axis"] == "time":
+            self._call("dj_lstm_scan_tc_infer", _ptr(ws.Z[li]), _ptr(ws.h[li]), _ptr(ws.h_hi[li]), _ptr(ws.h_lo[li]),
+                       _ptr(self._wbf[f"{L['name']}.gUt"]), _ptr(self._wbf[f"{L['name']}.gUt_lo"]), 1.0 / self.GEN_SCALE,
+                       m["S"], m["steps"], L["U"], m["inner"], m["outer"], m["inner_stride"], m["step"], self.hard,
+                       _stream())
+        elif train and ws.hprev[li] is not None and self._tc_ok(B, T):
             mixed = ws.A_lo[li] is not None
             self._call("dj_lstm_scan_tc_fwd", _ptr(ws.Z[li]), _ptr(ws.h[li]), _ptr(ws.c[li]), _ptr(ws.hprev[li]),
                        _ptr(self._wbf[f"{L['name']}.Ut"]), _ptr(self._wbf[f"{L['name']}.Ut_lo"]) if mixed else None,
@@ -359,9 +404,11 @@ class Engine:
                      style_done: bool = False, style=None, style_bstride=0, style_tstride=0):
         """time_axis of model.py:51-89 -> ws.h[1] ([M, Ut] canonical rows)."""
         P = self.params
-        adt = DJ_BF16 if bf16 else DJ_F32
+        adt = DJ_BF16 if bf16 else DJ_F16 if ws.gen else DJ_F32
         if bf16:
             self._refresh_bf16(ws.A_lo[0] is not None)
+        if ws.gen:
+            self._refresh_gen()
         if not style_done:
             self._style(ws, style, style_bstride, style_tstride, B, T)
         self._call("dj_frontend_fwd", _ptr(notes), notes_bstride, _ptr(beat), beat_bstride, B, T,

@@ -42,7 +42,8 @@ class DeviceGeneration:
         self.events = torch.zeros(G, N, 3, **f32)
         self.margin = torch.full((G,), 1e300, dtype=torch.float64, device=dev)
         self.cursor = torch.zeros(1, dtype=torch.int64, device=dev)
-        self.ws_time = Workspace(cfg, G, L, "fp32", False, dev)
+        # eng.gen_tc: the window recompute on the tensor cores at fp32 grade (half hi+lo operands); else CUDA-core fp32
+        self.ws_time = Workspace(cfg, G, L, "gen" if eng.gen_tc else "fp32", False, dev)
         self.ws_note = Workspace(cfg, G, 1, "fp32", False, dev)
         self.zero_chosen = torch.zeros(G, 1, N, 3, **f32)
         self.probs = torch.zeros(num_steps, G, N, 3, **f32)

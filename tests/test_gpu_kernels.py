@@ -190,6 +190,59 @@ def test_gemm_operand_formats_half(lib, fmts):
     assert helpers.rel_err(Cw.cpu().numpy(), ref) < 5e-5
 
 
+@pytest.mark.parametrize("shape", [(6144, 1024, 96), (6144, 1024, 256), (1536 * 128, 1024, 256)])
+def test_gate_gemm_half_split_scaled_is_fp32_grade(lib, shape):
+    """The generation path's projection: IEEE half hi+lo operands, weights pre-scaled by 2^10 (undone by out_scale):
+    fp32-grade (the operands carry ~22 bits; what is left is the tensor core's truncating fp32 accumulation)."""
+    from music_generator_b200 import _lib
+    M, N, K = shape
+    g = torch.Generator().manual_seed(14)
+    A = torch.randn(M, K, generator=g) * torch.rand(M, 1, generator=g)          # rows of very different sizes
+    Bt = torch.randn(N, K, generator=g) * 0.07
+    bias = torch.randn(N, generator=g)
+    ref = (A.double() @ Bt.double().t() + bias.double()).numpy()
+    Ah, Al = _split16(A, torch.float16)
+    Bh, Bl = _split16(Bt * 1024.0, torch.float16)
+    Cd = torch.full((M, N), float("nan"), device="cuda")
+    dev = [t.cuda() for t in (Ah, Al, Bh, Bl, bias)]
+    _lib.check(lib.dj_gate_gemm_16s(P(dev[0]), P(dev[1]), 2, K, P(dev[2]), P(dev[3]), 2, K, P(Cd), N, P(dev[4]),
+                                    1.0 / 1024.0, M, N, K, None))
+    torch.cuda.synchronize()
+    got = Cd.cpu().numpy()
+    err = float(np.abs(got - ref).max())
+    ref32 = float(np.abs((A @ Bt.t() + bias).numpy() - ref).max())            # torch's fp32 CPU matmul, for scale
+    print(f"half-split GEMM {shape}: max abs err {err:.2e} (fp32 CPU matmul: {ref32:.2e})")
+    # not 2^-23: tcgen05 accumulates the fp32 partial sums with truncation, a bias of up to an ulp per MMA (48 - 144
+    # MMAs deep here), i.e. a few 1e-6 relative -- measured 3-4x the error of an fp32 FMA-chain matmul
+    assert np.isfinite(got).all() and err < 4e-5 and err < 8 * ref32
+
+
+@pytest.mark.parametrize("B,T", [(1, 128), (3, 16), (32, 128), (40, 8)])
+def test_lstm_scan_tcgen05_inference_is_fp32_grade(lib, B, T):
+    """dj_lstm_scan_tc_infer (generation window: h and U as half hi+lo, three MMA passes) against the fp32 CUDA-core
+    recurrence: the two must agree like two fp32 implementations do (1e-6), and Z must be left untouched."""
+    from music_generator_b200 import _lib
+    g = torch.Generator().manual_seed(15)
+    U, M = 256, B * T * 48
+    Z0 = torch.randn(M, 4 * U, generator=g)
+    Uw = torch.randn(U, 4 * U, generator=g) * 0.06
+    S, steps, m = B * 48, T, (48, T * 48, 1, 48)
+    Zr, Zt, Ud = Z0.cuda(), Z0.cuda(), Uw.cuda()
+    Ut, Ut_lo = _split16(Uw.t().contiguous() * 1024.0, torch.float16)
+    Ut, Ut_lo = Ut.cuda(), Ut_lo.cuda()
+    hr, cr = torch.empty(M, U, device="cuda"), torch.empty(M, U, device="cuda")
+    ht = torch.zeros(M, U, device="cuda")
+    hhi = torch.zeros(M, U, device="cuda", dtype=torch.float16)
+    hlo = torch.zeros(M, U, device="cuda", dtype=torch.float16)
+    _lib.check(lib.dj_lstm_scan_fwd(P(Zr), P(hr), P(cr), None, P(Ud), S, steps, U, *m, 1, None))
+    _lib.check(lib.dj_lstm_scan_tc_infer(P(Zt), P(ht), P(hhi), P(hlo), P(Ut), P(Ut_lo), 1.0 / 1024.0, S, steps, U, *m, 1, None))
+    torch.cuda.synchronize()
+    dh = float((ht - hr).abs().max())
+    print(f"scan_tc_infer[B={B},T={T}]: max|dh| {dh:.2e}")
+    assert torch.isfinite(ht).all() and dh < 2e-6
+    assert torch.equal(Zt.cpu(), Z0)
+
+
 @pytest.mark.parametrize("axis,B,T", [("time", 1, 12), ("time", 5, 7), ("time", 8, 6), ("note", 1, 5), ("note", 13, 40)])
 def test_lstm_scan_fp32_matches_recurrence(lib, axis, B, T):
     """fp32 CUDA-core forward recurrence (both tilings: 16-sequence tiles / one unit per thread for few

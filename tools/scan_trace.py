@@ -60,7 +60,7 @@ for axis, U in AXES:
         trace.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        _lib.check(lib.dj_lstm_scan_tc_fwd(P(Z), P(h), P(c), P(hp), P(Ut), S, steps, U, *m, 1, None))
+        _lib.check(lib.dj_lstm_scan_tc_fwd(P(Z), P(h), P(c), P(hp), P(Ut), None, 1, S, steps, U, *m, 1, None))
         e1.record()
         torch.cuda.synchronize()
         if rep == 1:
