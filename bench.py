@@ -277,17 +277,17 @@ def _dist_helpers(world):
 def step_algorithmic_bytes(mcfg, B, T, mixed):
     """Per LSTM layer and activation row (K = padded input width, U units, Up = units of the layer below):
       forward   producer reads h_below 4Up, writes A (bf16 hi [+ lo]) 2K [4K]; gate GEMM reads it back 2K [4K], writes
-                Z fp32 16U; scan reads Z 16U, writes gates 16U + h 4U + c 4U + 16-bit h_{t-1} 2U
-      backward  scan reads gates 16U + c 4U + dY 4U, writes bf16 dZ 8U; data-gradient GEMM reads dZ 8U, writes dA fp32 4K;
+                Z fp32 16U; scan reads Z 16U, writes gates (4 halves) 8U + h 4U + c 4U + 16-bit h_{t-1} 2U
+      backward  scan reads gates 8U + c 4U + dY 4U, writes bf16 dZ 8U; data-gradient GEMM reads dZ 8U, writes dA fp32 4K;
                 weight-gradient GEMMs read A_hi 2K + dZ 8U and h_{t-1} 2U + dZ 8U; style reduction reads dA 4K
-      = (14K [18K]) + 116U + 4Up bytes per row; heads add 4U read + 4U dX written + 24 B; rows = B*T*48."""
+      = (14K [18K]) + 100U + 4Up bytes per row; heads add 4U read + 4U dX written + 24 B; rows = B*T*48."""
     rows = B * T * N_NOTES
     total = 0
     up = 0
     for L in mcfg.layers():
         K = (L["F"] + 31) // 32 * 32
         U = L["U"]
-        total += (18 if mixed else 14) * K + 116 * U + 4 * up
+        total += (18 if mixed else 14) * K + 100 * U + 4 * up
         up = U
     total += 8 * mcfg.note_axis_units + 24
     return total * rows
@@ -332,8 +332,10 @@ def _run_train(args):
     launches0 = eng.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    t_host = time.perf_counter()
     for i in range(K):
         loss = eng.train_step(*dev, seed=100 + i, allreduce=allreduce, world=world)
+    host_ms = (time.perf_counter() - t_host) * 1e3 / K     # host time to ENQUEUE a step (no sync inside the loop)
     e1.record()
     barrier()
     ms, ms_min, ms_all = over_ranks(e0.elapsed_time(e1))
@@ -406,9 +408,9 @@ def _run_train(args):
         return None
 
     # ---------------- roofline of the dominant kernel (time-axis reverse scan, layer 1) and of the whole step
-    # algorithmic bytes per row of that kernel: gates 16U + c 4U + dY 4U read, dZ (bf16) 8U written
+    # algorithmic bytes per row of that kernel: gates (4 halves) 8U + c 4U + dY 4U read, dZ (bf16) 8U written
     U, M = mcfg.time_axis_units, B * T * N_NOTES
-    alg_bytes = 32 * U * M
+    alg_bytes = 24 * U * M
     peak, how = peaks()
     dom_ms = dom[1] / max(dom[0], 1)
     achieved = alg_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else None
@@ -418,13 +420,16 @@ def _run_train(args):
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                 "traffic": traffic, "traffic_source": traffic_src, "peak_source": how, "avg_launch_ms": dom_ms,
                 "launches_timed": dom[0], "algorithmic_bytes_per_launch": alg_bytes,
-                "note": "sequential recurrence: bound by the per-step publish/TMA/MMA latency chain, not by HBM; timed "
-                        "inside the step, where it shares the GPU with the weight-gradient GEMMs of the second stream"}
+                "note": "sequential recurrence: every step each SM must ingest the multicast all-gather of the tile's dz "
+                        "(2 KB per sequence and step) before its MMAs can run; that on-chip exchange and the per-step "
+                        "fence/TMA/MMA latency chain bound the kernel, not HBM (DESIGN.md section 4, "
+                        "profiles/r02_scan_bwd_trace.md); timed inside the step, where it shares the GPU with the "
+                        "weight-gradient GEMMs of the second stream"}
     step_bytes = step_algorithmic_bytes(mcfg, B, T, args.precision == "mixed")
     step_roofline = {"bound": "hbm", "algorithmic_bytes_per_step": step_bytes,
                      "achieved": step_bytes / (ms / K * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                      "frac": step_bytes / (ms / K * 1e-3) / 1e9 / peak,
-                     "formula": "(18K|14K)+116U+4Up bytes per row and LSTM layer (mixed|bf16), see step_algorithmic_bytes"}
+                     "formula": "(18K|14K)+100U+4Up bytes per row and LSTM layer (mixed|bf16), see step_algorithmic_bytes"}
 
     # ---------------- generation (configs[1], and one GPU's share of configs[3])
     gen = None
@@ -453,6 +458,9 @@ def _run_train(args):
                     "ms_per_step": ms_e2e / K},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "step_roofline": step_roofline,
             "rank_ms_per_step": {"max": ms / K, "min": ms_min / K, "all": [round(v / K, 4) for v in ms_all]},
+            # the step is enqueued from Python (no CUDA graph): as long as enqueueing a step takes less host time than
+            # the GPU needs to run it, the launches are hidden behind the previous step
+            "host_enqueue_ms_per_step": host_ms, "launches_per_step": launches / K,
             "kernels": kernels, "cpu_baseline": cpu, "generation": gen, "loss": lossv}
     if world > 1:
         line["config"]["exchange"] = exchange
@@ -544,7 +552,7 @@ def _run_generation(args):
     parallel.init_distributed("nccl")        # only for the barrier and the max over ranks: generation has no collective
     barrier, over_ranks, _ = _dist_helpers(world)
     single = args.workload == "gen1"
-    K = args.steps if args.steps_given else (512 if single else 16)
+    K = args.steps if args.steps_given else (512 if single else 32)
     W = max(args.warmup, 3)
     G = 1 if single else 128
     eng = Engine(ModelConfig(), precision="fp32")
@@ -588,6 +596,17 @@ def _run_generation(args):
                          f"call structure (generate.py:104-121), {threads} threads"}
     # algorithmic work of one timestep of one sequence: 10.93 GFLOP, sequential depth 256 + 96 LSTM steps
     flops = 10.93e9 * G * K / (ms * 1e-3)
+    if eng.gen_tc:
+        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"] if os.path.exists(
+            os.path.join(ROOT, "MEASURED_PEAKS.json")) else 1400.0
+        roof = {"bound": "tensor", "peak": pk / 3.0,
+                "note": "fp32-grade products on the tensor cores cost three half-precision MMA passes (hi.hi + lo.hi + hi.lo), "
+                        "so the peak for ALGORITHMIC flops is the measured sustained 16-bit rate / 3; the sampled events must "
+                        "equal the fp32 model's, which rules out single-pass 16-bit operands.  At 1 sequence the path is a "
+                        "latency chain of 352 dependent LSTM steps per timestep, not a throughput problem"}
+    else:
+        roof = {"bound": "fma", "peak": 74.4,
+                "note": "peak = fp32 FMA rate of the CUDA cores (148 SMs x 128 lanes x 2 x 1.965 GHz)"}
     line = {"metric": "generated_timesteps_per_sec", "value": value, "unit": "timesteps/s", "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic (random-init weights, seeded uniform stream)",
@@ -595,12 +614,11 @@ def _run_generation(args):
             "e2e": {"value": e2e, "unit": "timesteps/s", "h2d_bytes_per_step": int(u.nbytes // max(K + W, 1)) if mode == 1 else 16 * N_NOTES,
                     "d2h_bytes_per_step": G * N_NOTES * 3 * 4, "ms_per_step": ms_e2e / K},
             "gpu_launches": launches, "clocks": clocks,
-            "roofline": {"kernel": "time-axis window recompute (2 LSTM layers x 128 steps per generated timestep)",
-                         "bound": "tensor" if eng.gen_tc else "fma", "achieved": flops / 1e12, "unit": "TFLOP/s",
-                         "peak": 74.4, "frac": flops / 1e12 / 74.4, "traffic": None,
-                         "note": "peak = fp32 FMA rate of the CUDA cores (148 SMs x 128 lanes x 2 x 1.965 GHz): the sampled "
-                                 "events must be bit-exact against the fp32 model, so the path computes at fp32 grade; "
-                                 "at 1 sequence the path is a latency chain of 352 dependent LSTM steps per timestep"},
+            "roofline": dict({"kernel": "time-axis window recompute (2 LSTM layers x 128 steps per generated timestep): "
+                                        "dj_gate_gemm_16s + dj_lstm_scan_tc_infer" if eng.gen_tc else
+                                        "time-axis window recompute: dj_gemm_simt + dj_lstm_scan_fwd",
+                              "achieved": flops / 1e12, "unit": "TFLOP/s", "frac": flops / 1e12 / roof["peak"],
+                              "traffic": None}, **roof),
             "rank_ms_per_step": {"max": ms / K, "min": ms_min / K, "all": [round(v / K, 4) for v in ms_all]},
             "cpu_baseline": cpu, "played_notes": int(ev[..., 0].sum())}
     if world > 1:

@@ -165,7 +165,10 @@ int dj_lstm_scan_fwd(float* Z, float* h_out, float* c_out, void* h_prev_bf16, co
                      int steps, int units, int seq_inner, int64_t seq_outer_stride,
                      int64_t seq_inner_stride, int64_t step_stride, int hard, void* stream);
 /* Tensor-core variant of the forward recurrence (training path, 16-bit operands for
- * h.U, fp32 accumulate/state): same contract as dj_lstm_scan_fwd, but U is passed as
+ * h.U, fp32 accumulate/state): same row maps as dj_lstm_scan_fwd, but Z is read only and the
+ * activated gates i,f,g,o are saved to gates16 [M, units] x 4 IEEE halves (8 bytes per cell,
+ * the input of dj_lstm_scan_tc_bwd; a hard-sigmoid gate strictly inside (0,1) is stored
+ * strictly inside, so the derivative's indicator survives the rounding); U is passed as
  * Ut_16 [4*units, units] (transposed, gate-interleaved rows) in format `fmt`
  * (DJ_BF16 / DJ_F16), h_prev_16 (same format) is REQUIRED (it doubles as the
  * inter-CTA exchange buffer), and Ut_lo (nullable) is the 16-bit residual
@@ -173,8 +176,8 @@ int dj_lstm_scan_fwd(float* Z, float* h_out, float* c_out, void* h_prev_bf16, co
  * weights enter with ~22 mantissa bits and only h is rounded (to half: 2^-12).
  * Only the two maps of the model are supported: units 256/512 with the time-axis
  * map, units 128/256 with the note-axis map. */
-int dj_lstm_scan_tc_fwd(float* Z, float* h_out, float* c_out, void* h_prev_16, const void* Ut_16,
-                        const void* Ut_lo, int fmt, int S, int steps, int units, int seq_inner,
+int dj_lstm_scan_tc_fwd(const float* Z, void* gates16, float* h_out, float* c_out, void* h_prev_16,
+                        const void* Ut_16, const void* Ut_lo, int fmt, int S, int steps, int units, int seq_inner,
                         int64_t seq_outer_stride, int64_t seq_inner_stride, int64_t step_stride, int hard,
                         void* stream);
 /* Inference variant for the generation window (generate.py:106-109: both time-axis layers over
@@ -191,7 +194,7 @@ int dj_lstm_scan_tc_infer(const float* Z, float* h_out, void* h_hi, void* h_lo, 
  * Un_bf16 [units, 4*units] (bf16, natural, gate-interleaved columns); dZ is bf16
  * (gradients need its exponent range) and doubles as the inter-CTA exchange buffer;
  * db accumulates with fp32 atomics. */
-int dj_lstm_scan_tc_bwd(const float* gates, const float* c, const float* dY, int64_t ldY, dj_dropout d_y,
+int dj_lstm_scan_tc_bwd(const void* gates16, const float* c, const float* dY, int64_t ldY, dj_dropout d_y,
                         const void* Un_bf16, void* dZ_bf16, float* db, int S, int steps, int units,
                         int seq_inner, int64_t seq_outer_stride, int64_t seq_inner_stride,
                         int64_t step_stride, int hard, void* stream);

@@ -73,10 +73,12 @@ __device__ __forceinline__ float dj_nadam_one(float p, float gi, float& m, float
 
 // ---- counter-based dropout masks --------------------------------------------
 // A mask bit is a pure function of (seed, site, element index), so the backward
-// kernels regenerate it instead of reading a stored mask.  Two lowbias32 rounds
-// per 32-bit word; for rates whose threshold is a whole number of 1/256ths one
-// word serves 4 consecutive elements (one byte each), otherwise one word per
-// element.  tests/ re-implement the same function in numpy.
+// kernels regenerate it instead of reading a stored mask.  One lowbias32 round of
+// (element group + site key) per 32-bit word -- the hash is made for counters, and
+// the glue kernels are bound by these integer instructions (round 1: two rounds,
+// 17 instructions per word); for rates whose threshold is a whole number of
+// 1/256ths one word serves 4 consecutive elements (one byte each), otherwise one
+// word per element.  tests/ re-implement the same function in numpy.
 __host__ __device__ __forceinline__ uint32_t dj_mix32(uint32_t x) {
   x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
   return x;
@@ -87,7 +89,7 @@ __host__ __device__ __forceinline__ uint32_t dj_site_key(uint64_t seed, int site
 }
 // word for element-group q of a site
 __host__ __device__ __forceinline__ uint32_t dj_mask_word(uint32_t key, uint32_t q) {
-  return dj_mix32(dj_mix32(q) + key);
+  return dj_mix32(q + key);
 }
 // single element keep decision (element index e within the site's padded layout)
 __device__ __forceinline__ bool dj_keep(const dj_dropout& d, uint32_t e) {

@@ -102,6 +102,29 @@ template <bool HARD> __device__ __forceinline__ float gate_act_fast(float x) {
   if constexpr (HARD) return hard_sig_sat(x);
   else return rcp_ftz(1.0f + ex2_ftz(x * -1.4426950408889634f));
 }
+// The activated gates are saved for the reverse scan as IEEE half (8 bytes per cell instead of 16: the forward
+// epilogue is bound by the SM's store path and the reverse scan by its loads).  The reverse scan only needs them to
+// ~1e-3, EXCEPT for the hard-sigmoid derivative, which is an indicator of 0 < a < 1: a value strictly inside the
+// interval must not round onto its end, so it is stored as the nearest half strictly inside.
+template <bool HARD> __device__ __forceinline__ uint32_t gate_half(float a) {
+  uint32_t u = __half_as_ushort(__float2half_rn(a));
+  if (HARD) {
+    if (a < 1.0f && u == 0x3C00u) u = 0x3BFFu;     // largest half below 1
+    if (a > 0.0f && u == 0u) u = 1u;               // smallest positive half
+  }
+  return u;
+}
+template <bool HARD> __device__ __forceinline__ uint2 pack_gates16(float gi, float gf, float gg, float go) {
+  uint2 r;
+  r.x = gate_half<HARD>(gi) | (gate_half<HARD>(gf) << 16);
+  r.y = (uint32_t)__half_as_ushort(__float2half_rn(gg)) | (gate_half<HARD>(go) << 16);
+  return r;
+}
+__device__ __forceinline__ float4 unpack_gates16(uint2 r) {
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&r.x));
+  const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
 __device__ __forceinline__ int64_t tc_row0(const TcMap& m, int seq) {
   return (int64_t)(seq / m.seq_inner) * m.outer_stride + (int64_t)(seq % m.seq_inner) * m.inner_stride;
 }
@@ -138,8 +161,9 @@ __device__ __forceinline__ int64_t tc_row0(const TcMap& m, int seq) {
 template <int U, int BS, bool TIME, bool HARD, int NB, int NS, bool ATM, bool INFER = false>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 scan_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmH,
-                   const __grid_constant__ CUtensorMap tmHlo, float* __restrict__ Z, float* __restrict__ Hout,
-                   float* __restrict__ Cout, uint16_t* __restrict__ Hprev, uint16_t* __restrict__ Hprev_lo,
+                   const __grid_constant__ CUtensorMap tmHlo, const float* __restrict__ Z, uint2* __restrict__ G16,
+                   float* __restrict__ Hout, float* __restrict__ Cout, uint16_t* __restrict__ Hprev,
+                   uint16_t* __restrict__ Hprev_lo,
                    const uint32_t* __restrict__ Ut_words, int steps, TcMap map, int f16, int has_lo, float acc_scale) {
   static_assert(!INFER || ATM, "inference mode keeps the A operand in tensor memory");
   constexpr uint32_t SSTR = TIME ? 1u : 48u, TSTR = TIME ? 48u : 1u;
@@ -230,6 +254,9 @@ scan_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
     }
     __syncwarp();
     const int my_ka = rank >> 1, my_hh = rank & 1;       // the slice of h_t this CTA multicasts
+    // time-axis tiles smaller than a batch element (BS < 48): batch element and first row of this tile
+    constexpr int TPB = (TIME && BS < 48) ? 48 / BS : 1;
+    const int tile_b = tile / TPB, tile_r = (tile % TPB) * BS;
     const uint32_t bar_done = bar_done0 + 8 * hf, bar_pub = bar_pub0 + 8 * hf, bar_h = bar_h0 + 8 * hf,
                    bar_acc = bar_acc0 + 8 * hf;
     if (hf < NS) {
@@ -247,12 +274,12 @@ scan_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
           mbar_expect_tx(bar_h, HB * U * 2 * (INFER ? 2 : 1));
           if (NS == 1 || my_hh == hf) {
             tma_load_3d_mc(sbase + SM::H_OFF + my_ka * (BS * 128) + my_hh * (RH * 128), &tmH, bar_h, my_ka * 64,
-                           (t + 1) * map.step1 + my_hh * map.off1, tile * map.base2 + my_hh * map.off2,
+                           (t + 1) * map.step1 + tile_r + my_hh * map.off1, tile_b * map.base2 + my_hh * map.off2,
                            (uint16_t)((1u << C) - 1u));
             if constexpr (INFER)
               tma_load_3d_mc(sbase + SM::H_OFF + HLO_OFF + my_ka * (BS * 128) + my_hh * (RH * 128), &tmHlo, bar_h,
-                             my_ka * 64, (t + 1) * map.step1 + my_hh * map.off1, tile * map.base2 + my_hh * map.off2,
-                             (uint16_t)((1u << C) - 1u));
+                             my_ka * 64, (t + 1) * map.step1 + tile_r + my_hh * map.off1,
+                             tile_b * map.base2 + my_hh * map.off2, (uint16_t)((1u << C) - 1u));
           }
         }
         __syncwarp();
@@ -359,8 +386,8 @@ scan_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
           else if (not_last) load_z(ci + NB - NCH, t + 1);
           // this lane's cell after the transpose: sequence 16*ci + 8*w2 + 4*blk + g, unit `col`
           const uint32_t row_c = rowb[ci] + (uint32_t)g * SSTR + (uint32_t)t * TSTR;
-          float* const zg = Z + (size_t)row_c * (4 * U) + 4 * col;
           const size_t o1 = (size_t)row_c * U + col;
+          uint2* const g16 = G16 + o1;                       // the four activated gates of this cell as IEEE half
           float* const hp = Hout + o1;
           float* const cp = Cout + o1;                       // only dereferenced when Cout != nullptr
           uint16_t* const hb = Hprev + o1;
@@ -399,7 +426,7 @@ scan_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
 #ifndef DJ_EXP
 #define DJ_EXP 0   // timing experiments only: bit0/1/2 drop the gate / h / c stores
 #endif
-            if (!INFER && !(DJ_EXP & 1)) *reinterpret_cast<float4*>(zg + blk * RO * (4 * U)) = make_float4(gi, gf, gg, go);
+            if (!INFER && !(DJ_EXP & 1)) g16[blk * RO * U] = pack_gates16<HARD>(gi, gf, gg, go);
             if (!(DJ_EXP & 2)) hp[blk * RO * U] = hn;
             if (!INFER && !(DJ_EXP & 4) && Cout != nullptr) cp[blk * RO * U] = cn;
           }
@@ -430,9 +457,9 @@ inline bool fwd_atm_enabled() {   // DJ_FWD_ATM=0 keeps the A operand in shared 
 }
 
 template <int U, int BS, bool TIME, bool HARD, int NB, int NS, bool INFER = false>
-int launch_tc_fwd_inst(const void* Ut_bf, const void* Ut_lo, int f16, float* Z, float* h_out, float* c_out, void* hprev,
-                       int S, int steps, const TcMap& map_in, cudaStream_t st, void* hprev_lo = nullptr,
-                       float acc_scale = 1.0f) {
+int launch_tc_fwd_inst(const void* Ut_bf, const void* Ut_lo, int f16, const float* Z, void* gates16, float* h_out,
+                       float* c_out, void* hprev, int S, int steps, const TcMap& map_in, cudaStream_t st,
+                       void* hprev_lo = nullptr, float acc_scale = 1.0f) {
   constexpr int C = U / 32;
   using SM = TcFwdSmem<U, BS, INFER>;
   DJ_CHECK_ARG(S % BS == 0, "dj_lstm_scan_tc_fwd: the number of sequences (%d) must be a multiple of %d", S, BS);
@@ -440,7 +467,6 @@ int launch_tc_fwd_inst(const void* Ut_bf, const void* Ut_lo, int f16, float* Z, 
   CUtensorMap tmU, tmH, tmHlo;
   int rc;
   // U <= 256: A operand in tensor memory unless DJ_FWD_ATM=0; U = 512: only when the residual pass needs the shared-memory slot
-  constexpr bool CAN_ATM = true;
   const bool atm = (U <= 256) ? fwd_atm_enabled() : (Ut_lo != nullptr);
   DJ_CHECK_ARG(Ut_lo == nullptr || atm, "dj_lstm_scan_tc_fwd: the residual pass (Ut_lo) needs the tensor-memory A operand (DJ_FWD_ATM=0 is set)");
   // the shared-memory A slot holds U^T (A not in tensor memory) or the residual U^T - hi(U^T)
@@ -455,7 +481,7 @@ int launch_tc_fwd_inst(const void* Ut_bf, const void* Ut_lo, int f16, float* Z, 
     if ((rc = make_map(&tmH, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, hprev, 3, dims, str, box))) return rc;
     tmHlo = tmH;
     if (INFER && (rc = make_map(&tmHlo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, hprev_lo, 3, dims, str, box))) return rc;
-    map.step1 = 48; map.off1 = (RH % 48); map.base2 = BS / 48; map.off2 = RH / 48;
+    map.step1 = 48; map.off1 = (RH % 48); map.base2 = BS >= 48 ? BS / 48 : 1; map.off2 = RH / 48;
     map.seq_stride = map.inner_stride;
   } else {           // hprev viewed as [seq][n][U]
     const uint64_t dims[3] = {(uint64_t)U, 48, (uint64_t)S}, str[2] = {(uint64_t)U, (uint64_t)48 * U};
@@ -466,14 +492,20 @@ int launch_tc_fwd_inst(const void* Ut_bf, const void* Ut_lo, int f16, float* Z, 
     map.step1 = 1; map.off1 = 0; map.base2 = BS; map.off2 = RH;
     map.seq_stride = map.outer_stride;
   }
-  auto kernel = scan_tc_fwd_kernel<U, BS, TIME, HARD, NB, NS, INFER, INFER>;   // (INFER: the only instance, ATM = true)
-  if constexpr (!INFER) {
-    kernel = scan_tc_fwd_kernel<U, BS, TIME, HARD, NB, NS, false, false>;
-    if constexpr (CAN_ATM) {
-      if (atm) kernel = scan_tc_fwd_kernel<U, BS, TIME, HARD, NB, NS, true, false>;
-    }
-  } else {
+  // Shipped instances: A operand in tensor memory (U <= 256 always; U = 512 when the residual pass needs the
+  // shared-memory slot, else A in shared memory).  The other placement is an experiment (-DDJ_EXPERIMENTS).
+  constexpr bool SHIP_SMEM_A = (U > 256) && !INFER;
+  auto kernel = scan_tc_fwd_kernel<U, BS, TIME, HARD, NB, NS, !SHIP_SMEM_A, INFER>;
+  if constexpr (INFER) {
     DJ_CHECK_ARG(atm && Ut_lo && hprev_lo, "dj_lstm_scan_tc_infer: needs Ut_lo, h_lo and the tensor-memory A operand");
+  } else if constexpr (SHIP_SMEM_A) {
+    if (atm) kernel = scan_tc_fwd_kernel<U, BS, TIME, HARD, NB, NS, true, false>;
+  } else {
+#ifdef DJ_EXPERIMENTS
+    if (!atm) kernel = scan_tc_fwd_kernel<U, BS, TIME, HARD, NB, NS, false, false>;
+#else
+    DJ_CHECK_ARG(atm, "dj_lstm_scan_tc_fwd: DJ_FWD_ATM=0 needs a build with -DDJ_EXPERIMENTS");
+#endif
   }
   DJ_CUDA(cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
   if (C > 8) DJ_CUDA(cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
@@ -495,12 +527,13 @@ int launch_tc_fwd_inst(const void* Ut_bf, const void* Ut_lo, int f16, float* Z, 
   const uint32_t* utw = (const uint32_t*)Ut_bf;
   const int has_lo = Ut_lo != nullptr ? 1 : 0;
   uint16_t* hpl = (uint16_t*)hprev_lo;
-  DJ_CUDA(cudaLaunchKernelEx(&cfg, kernel, tmU, tmH, tmHlo, Z, h_out, c_out, hp, hpl, utw, steps, map, f16, has_lo, acc_scale));
+  uint2* g16 = (uint2*)gates16;
+  DJ_CUDA(cudaLaunchKernelEx(&cfg, kernel, tmU, tmH, tmHlo, Z, g16, h_out, c_out, hp, hpl, utw, steps, map, f16, has_lo, acc_scale));
   return 0;
 }
 
 // prefetch depth of the x.W pre-activations, in 16-sequence chunks (DJ_FWD_NB overrides for experiments)
-inline int fwd_prefetch_depth(int nch, int dflt) {
+[[maybe_unused]] inline int fwd_prefetch_depth(int nch, int dflt) {
   static int env = -1;
   if (env < 0) {
     const char* e = getenv("DJ_FWD_NB");
@@ -511,7 +544,7 @@ inline int fwd_prefetch_depth(int nch, int dflt) {
 }
 
 // DJ_FWD_NS=1 forces the unsplit tile (experiments)
-inline bool fwd_split_enabled() {
+[[maybe_unused]] inline bool fwd_split_enabled() {
   static int env = -1;
   if (env < 0) {
     const char* e = getenv("DJ_FWD_NS");
@@ -521,18 +554,23 @@ inline bool fwd_split_enabled() {
 }
 
 template <int U, int BS, bool TIME>
-int launch_tc_fwd(const void* Ut_bf, const void* Ut_lo, int f16, float* Z, float* h_out, float* c_out, void* hprev, int S,
-                  int steps, const TcMap& map, int /*axis_time*/, int hard, cudaStream_t st) {
+int launch_tc_fwd(const void* Ut_bf, const void* Ut_lo, int f16, const float* Z, void* gates16, float* h_out, float* c_out,
+                  void* hprev, int S, int steps, const TcMap& map, int /*axis_time*/, int hard, cudaStream_t st) {
   constexpr int NCH = BS / 16;
   constexpr bool CAN_SPLIT = (NCH % 2 == 0);
   constexpr int NB_DEF = (NCH % 2 == 0) ? 2 : 1;
+#ifndef DJ_EXPERIMENTS
+  // shipped: two half-tiles when the tile is an even number of chunks, prefetch depth 2 then (else 1)
+  return hard ? launch_tc_fwd_inst<U, BS, TIME, true, NB_DEF, CAN_SPLIT ? 2 : 1>(Ut_bf, Ut_lo, f16, Z, gates16, h_out, c_out, hprev, S, steps, map, st)
+              : launch_tc_fwd_inst<U, BS, TIME, false, NB_DEF, CAN_SPLIT ? 2 : 1>(Ut_bf, Ut_lo, f16, Z, gates16, h_out, c_out, hprev, S, steps, map, st);
+#else
   const int nb = fwd_prefetch_depth(NCH, NB_DEF);
   const bool split = CAN_SPLIT && fwd_split_enabled();
 #define DJ_FWD_CASE(NBV, NSV)                                                                                       \
   if constexpr (NCH % NBV == 0 && (NSV == 1 || CAN_SPLIT)) {                                                        \
     if (nb == NBV && split == (NSV == 2))                                                                           \
-      return hard ? launch_tc_fwd_inst<U, BS, TIME, true, NBV, NSV>(Ut_bf, Ut_lo, f16, Z, h_out, c_out, hprev, S, steps, map, st) \
-                  : launch_tc_fwd_inst<U, BS, TIME, false, NBV, NSV>(Ut_bf, Ut_lo, f16, Z, h_out, c_out, hprev, S, steps, map, st); \
+      return hard ? launch_tc_fwd_inst<U, BS, TIME, true, NBV, NSV>(Ut_bf, Ut_lo, f16, Z, gates16, h_out, c_out, hprev, S, steps, map, st) \
+                  : launch_tc_fwd_inst<U, BS, TIME, false, NBV, NSV>(Ut_bf, Ut_lo, f16, Z, gates16, h_out, c_out, hprev, S, steps, map, st); \
   }
   DJ_FWD_CASE(1, 1)
   DJ_FWD_CASE(1, 2)
@@ -541,6 +579,7 @@ int launch_tc_fwd(const void* Ut_bf, const void* Ut_lo, int f16, float* Z, float
 #undef DJ_FWD_CASE
   DJ_CHECK_ARG(false, "dj_lstm_scan_tc_fwd: no kernel instance for prefetch depth %d", nb);
   return -1;
+#endif
 }
 
 // ---------------------------------------------------------------------------
@@ -593,7 +632,7 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t v[4]) {
 template <int U, int BS, int UPC, bool AXIS_TIME, int NS, bool SHARED = false>
 __global__ void __launch_bounds__(TCB_THREADS, (U == 128 && BS <= 32) ? 2 : 1)
 scan_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmZ,
-                   const float* __restrict__ G, const float* __restrict__ Cst, const float* __restrict__ dY,
+                   const uint2* __restrict__ G16, const float* __restrict__ Cst, const float* __restrict__ dY,
                    uint32_t ldY, dj_dropout d_y, __nv_bfloat16* __restrict__ dZ, float* __restrict__ db,
                    int steps, TcMap map, int hard) {
   constexpr int C = U / UPC;            // cluster size
@@ -730,7 +769,7 @@ scan_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
     float dbacc[4] = {0.f, 0.f, 0.f, 0.f};
     constexpr int LSN = SHARED ? 1 : NS;                           // operand sets held in registers at a time
     float dcn[NS][CPL], ct[NS][CPL], cpv[LSN][CPL], dyv[LSN][CPL];
-    float4 gv[LSN][CPL];
+    uint2 gv[LSN][CPL];                                            // four gates of a cell as IEEE half
     // Pure loads only: anything computed on a just-loaded value would serialise the loads (each use
     // waits for its own DRAM round trip).  Masks and the t==0 special case are applied at use time.
     auto issue_loads = [&](int hf, int t) {   // everything of (half hf, step t) that does not depend on the recurrence
@@ -740,7 +779,7 @@ scan_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
 #pragma unroll
       for (int j = 0; j < CPL; ++j) {
         const uint32_t r = row00[hf] + j * sstr + (uint32_t)t * tstr;
-        gv[ls][j] = __ldg(reinterpret_cast<const float4*>(G + (size_t)r * (4 * U) + 4 * col));
+        gv[ls][j] = __ldg(G16 + (size_t)r * U + col);
         cpv[ls][j] = __ldg(Cst + (size_t)(row00[hf] + j * sstr + tp * tstr) * U + col);
         dyv[ls][j] = __ldg(dY + (size_t)r * ldY + col);
       }
@@ -753,7 +792,7 @@ scan_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
 #pragma unroll
       for (int j = 0; j < CPL; ++j) {
         const uint32_t r = row00[hf] + j * sstr + (uint32_t)t * tstr;
-        if ((lane & 7) == 0) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(G + (size_t)r * (4 * U) + 4 * col));
+        if ((lane & 15) == 0) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(G16 + (size_t)r * U + col));
         if ((lane & 15) == 0) {
           asm volatile("prefetch.global.L2 [%0];\n" ::"l"(Cst + (size_t)(row00[hf] + j * sstr + tp * tstr) * U + col));
           asm volatile("prefetch.global.L2 [%0];\n" ::"l"(dY + (size_t)r * ldY + col));
@@ -771,7 +810,7 @@ scan_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
 #pragma unroll
     for (int ls = 0; ls < LSN; ++ls) {
 #pragma unroll
-      for (int j = 0; j < CPL; ++j) { gv[ls][j] = make_float4(0.f, 0.f, 0.f, 0.f); cpv[ls][j] = 0.f; dyv[ls][j] = 0.f; }
+      for (int j = 0; j < CPL; ++j) { gv[ls][j] = make_uint2(0u, 0u); cpv[ls][j] = 0.f; dyv[ls][j] = 0.f; }
       issue_loads(ls, steps - 1);
     }
     if constexpr (SHARED) prefetch_l2(1, steps - 1);
@@ -805,7 +844,7 @@ scan_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
           const uint32_t r = row00[hf] + j * sstr + (uint32_t)t * tstr;
           constexpr int LS_ = SHARED ? 0 : -1;
           const int ls = (LS_ == 0) ? 0 : hf;
-          const float4 g4 = gv[ls][j];
+          const float4 g4 = unpack_gates16(gv[ls][j]);
           const float cprev = (t > 0) ? cpv[ls][j] : 0.f;
           const float dht = fmaf(dyv[ls][j], dj_dropmul(d_y, r * U + col), dh[j]);
           const float tc = fast_tanh(ct[hf][j]);
@@ -852,7 +891,7 @@ scan_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
   if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-inline bool bwd_split_enabled() {   // DJ_BWD_NS=1 forces the unsplit tile (experiments)
+[[maybe_unused]] inline bool bwd_split_enabled() {   // DJ_BWD_NS=1 forces the unsplit tile (experiments)
   static int env = -1;
   if (env < 0) {
     const char* e = getenv("DJ_BWD_NS");
@@ -862,7 +901,7 @@ inline bool bwd_split_enabled() {   // DJ_BWD_NS=1 forces the unsplit tile (expe
 }
 
 template <int U, int BS, int UPC, bool AXIS_TIME, int NS, bool SHARED = false>
-int launch_tc_bwd_inst(const void* Un_bf, const float* gates, const float* c, const float* dY, int64_t ldY, dj_dropout d_y,
+int launch_tc_bwd_inst(const void* Un_bf, const void* gates, const float* c, const float* dY, int64_t ldY, dj_dropout d_y,
                        void* dZ, float* db, int S, int steps, const TcMap& map_in, int hard, cudaStream_t st) {
   constexpr int C = U / UPC;
   constexpr int HB = BS / NS;
@@ -909,25 +948,28 @@ int launch_tc_bwd_inst(const void* Un_bf, const float* gates, const float* c, co
   }
   __nv_bfloat16* dzp = (__nv_bfloat16*)dZ;
   const uint32_t ldy32 = (uint32_t)ldY;
-  DJ_CUDA(cudaLaunchKernelEx(&cfg, kernel, tmU, tmZ, gates, c, dY, ldy32, d_y, dzp, db, steps, map, hard));
+  const uint2* g16 = (const uint2*)gates;
+  DJ_CUDA(cudaLaunchKernelEx(&cfg, kernel, tmU, tmZ, g16, c, dY, ldy32, d_y, dzp, db, steps, map, hard));
   return 0;
 }
 
 template <int U, int BS, int UPC, bool AXIS_TIME>
-int launch_tc_bwd(const void* Un_bf, const float* gates, const float* c, const float* dY, int64_t ldY, dj_dropout d_y,
+int launch_tc_bwd(const void* Un_bf, const void* gates, const float* c, const float* dY, int64_t ldY, dj_dropout d_y,
                   void* dZ, float* db, int S, int steps, const TcMap& map, int hard, cudaStream_t st) {
-  if (bwd_split_enabled())
-    return launch_tc_bwd_inst<U, BS, UPC, AXIS_TIME, 2>(Un_bf, gates, c, dY, ldY, d_y, dZ, db, S, steps, map, hard, st);
-  return launch_tc_bwd_inst<U, BS, UPC, AXIS_TIME, 1>(Un_bf, gates, c, dY, ldY, d_y, dZ, db, S, steps, map, hard, st);
+#ifdef DJ_EXPERIMENTS
+  if (!bwd_split_enabled())
+    return launch_tc_bwd_inst<U, BS, UPC, AXIS_TIME, 1>(Un_bf, gates, c, dY, ldY, d_y, dZ, db, S, steps, map, hard, st);
+#endif
+  return launch_tc_bwd_inst<U, BS, UPC, AXIS_TIME, 2>(Un_bf, gates, c, dY, ldY, d_y, dZ, db, S, steps, map, hard, st);
 }
 
 }  // namespace
 
-extern "C" int dj_lstm_scan_tc_fwd(float* Z, float* h_out, float* c_out, void* h_prev_bf16, const void* Ut_bf16,
-                                   const void* Ut_lo, int fmt, int S, int steps, int units, int seq_inner,
+extern "C" int dj_lstm_scan_tc_fwd(const float* Z, void* gates16, float* h_out, float* c_out, void* h_prev_bf16,
+                                   const void* Ut_bf16, const void* Ut_lo, int fmt, int S, int steps, int units, int seq_inner,
                                    int64_t seq_outer_stride, int64_t seq_inner_stride, int64_t step_stride, int hard,
                                    void* stream) {
-  DJ_CHECK_ARG(Z && h_out && h_prev_bf16 && Ut_bf16, "dj_lstm_scan_tc_fwd: NULL pointer");
+  DJ_CHECK_ARG(Z && gates16 && h_out && h_prev_bf16 && Ut_bf16, "dj_lstm_scan_tc_fwd: NULL pointer");
   DJ_CHECK_ARG(fmt == DJ_BF16 || fmt == DJ_F16, "dj_lstm_scan_tc_fwd: operand format must be DJ_BF16 or DJ_F16");
   const int f16 = (fmt == DJ_F16) ? 1 : 0;
   DJ_CHECK_ARG(S > 0 && steps > 0, "dj_lstm_scan_tc_fwd: bad sizes");
@@ -940,16 +982,16 @@ extern "C" int dj_lstm_scan_tc_fwd(float* Z, float* h_out, float* c_out, void* h
     // 2 CTAs/SM x 16 resident 8-CTA clusters = 32 tile slots: beyond that, double the tile (two batch
     // elements per cluster) so the whole layer still runs as one wave of step chains
     if (S % 96 == 0 && S / 48 > 32)
-      return launch_tc_fwd<256, 96, true>(Ut_bf16, Ut_lo, f16, Z, h_out, c_out, h_prev_bf16, S, steps, map, 1, hard, st);
-    return launch_tc_fwd<256, 48, true>(Ut_bf16, Ut_lo, f16, Z, h_out, c_out, h_prev_bf16, S, steps, map, 1, hard, st);
+      return launch_tc_fwd<256, 96, true>(Ut_bf16, Ut_lo, f16, Z, gates16, h_out, c_out, h_prev_bf16, S, steps, map, 1, hard, st);
+    return launch_tc_fwd<256, 48, true>(Ut_bf16, Ut_lo, f16, Z, gates16, h_out, c_out, h_prev_bf16, S, steps, map, 1, hard, st);
   } else if (time_map && units == 512) {   // scaled model (BASELINE configs[4]): 16-CTA clusters
-    return launch_tc_fwd<512, 48, true>(Ut_bf16, Ut_lo, f16, Z, h_out, c_out, h_prev_bf16, S, steps, map, 1, hard, st);
+    return launch_tc_fwd<512, 48, true>(Ut_bf16, Ut_lo, f16, Z, gates16, h_out, c_out, h_prev_bf16, S, steps, map, 1, hard, st);
   } else if (note_map && units == 128) {
     if (S % 128 == 0 && S / 64 > 74)
-      return launch_tc_fwd<128, 128, false>(Ut_bf16, Ut_lo, f16, Z, h_out, c_out, h_prev_bf16, S, steps, map, 0, hard, st);
-    return launch_tc_fwd<128, 64, false>(Ut_bf16, Ut_lo, f16, Z, h_out, c_out, h_prev_bf16, S, steps, map, 0, hard, st);
+      return launch_tc_fwd<128, 128, false>(Ut_bf16, Ut_lo, f16, Z, gates16, h_out, c_out, h_prev_bf16, S, steps, map, 0, hard, st);
+    return launch_tc_fwd<128, 64, false>(Ut_bf16, Ut_lo, f16, Z, gates16, h_out, c_out, h_prev_bf16, S, steps, map, 0, hard, st);
   } else if (note_map && units == 256) {   // scaled model, note axis
-    return launch_tc_fwd<256, 64, false>(Ut_bf16, Ut_lo, f16, Z, h_out, c_out, h_prev_bf16, S, steps, map, 0, hard, st);
+    return launch_tc_fwd<256, 64, false>(Ut_bf16, Ut_lo, f16, Z, gates16, h_out, c_out, h_prev_bf16, S, steps, map, 0, hard, st);
   }
   DJ_CHECK_ARG(false, "dj_lstm_scan_tc_fwd: units=%d unsupported on this axis (time: 256/512, note: 128/256)", units);
   return -1;
@@ -965,16 +1007,21 @@ extern "C" int dj_lstm_scan_tc_infer(const float* Z, float* h_out, void* h_hi, v
   cudaStream_t st = (cudaStream_t)stream;
   const bool time_map = (seq_inner == 48 && seq_inner_stride == 1 && step_stride == 48 && S % 48 == 0);
   DJ_CHECK_ARG(time_map && units == 256, "dj_lstm_scan_tc_infer: the time-axis map with 256 units is the supported shape");
-  float* Zm = const_cast<float*>(Z);     // inference mode never writes the pre-activations
   if (S % 96 == 0 && S / 48 > 32) {
-    if (hard) return launch_tc_fwd_inst<256, 96, true, true, 2, 2, true>(Ut_hi, Ut_lo, 1, Zm, h_out, nullptr, h_hi, S, steps, map, st, h_lo, acc_scale);
-    return launch_tc_fwd_inst<256, 96, true, false, 2, 2, true>(Ut_hi, Ut_lo, 1, Zm, h_out, nullptr, h_hi, S, steps, map, st, h_lo, acc_scale);
+    if (hard) return launch_tc_fwd_inst<256, 96, true, true, 2, 2, true>(Ut_hi, Ut_lo, 1, Z, nullptr, h_out, nullptr, h_hi, S, steps, map, st, h_lo, acc_scale);
+    return launch_tc_fwd_inst<256, 96, true, false, 2, 2, true>(Ut_hi, Ut_lo, 1, Z, nullptr, h_out, nullptr, h_hi, S, steps, map, st, h_lo, acc_scale);
   }
-  if (hard) return launch_tc_fwd_inst<256, 48, true, true, 1, 1, true>(Ut_hi, Ut_lo, 1, Zm, h_out, nullptr, h_hi, S, steps, map, st, h_lo, acc_scale);
-  return launch_tc_fwd_inst<256, 48, true, false, 1, 1, true>(Ut_hi, Ut_lo, 1, Zm, h_out, nullptr, h_hi, S, steps, map, st, h_lo, acc_scale);
+  if (S / 48 <= 4) {
+    // a handful of sequences (generate.py's default: 1 to 3): the recurrence is one latency chain per cluster, so the
+    // 48 pitches of a sequence go to three clusters of 16-sequence tiles -- a third of the epilogue per step
+    if (hard) return launch_tc_fwd_inst<256, 16, true, true, 1, 1, true>(Ut_hi, Ut_lo, 1, Z, nullptr, h_out, nullptr, h_hi, S, steps, map, st, h_lo, acc_scale);
+    return launch_tc_fwd_inst<256, 16, true, false, 1, 1, true>(Ut_hi, Ut_lo, 1, Z, nullptr, h_out, nullptr, h_hi, S, steps, map, st, h_lo, acc_scale);
+  }
+  if (hard) return launch_tc_fwd_inst<256, 48, true, true, 1, 1, true>(Ut_hi, Ut_lo, 1, Z, nullptr, h_out, nullptr, h_hi, S, steps, map, st, h_lo, acc_scale);
+  return launch_tc_fwd_inst<256, 48, true, false, 1, 1, true>(Ut_hi, Ut_lo, 1, Z, nullptr, h_out, nullptr, h_hi, S, steps, map, st, h_lo, acc_scale);
 }
 
-extern "C" int dj_lstm_scan_tc_bwd(const float* gates, const float* c, const float* dY, int64_t ldY, dj_dropout d_y,
+extern "C" int dj_lstm_scan_tc_bwd(const void* gates, const float* c, const float* dY, int64_t ldY, dj_dropout d_y,
                                    const void* Un_bf16, void* dZ_bf16, float* db, int S, int steps, int units,
                                    int seq_inner, int64_t seq_outer_stride, int64_t seq_inner_stride,
                                    int64_t step_stride, int hard, void* stream) {
@@ -986,13 +1033,17 @@ extern "C" int dj_lstm_scan_tc_bwd(const float* gates, const float* c, const flo
   const bool note_map = (seq_inner == 1 && seq_outer_stride == 48 && step_stride == 1 && steps <= 48);
   DJ_CHECK_ARG(time_map || note_map, "dj_lstm_scan_tc_bwd: only the time-axis (seq=(b,n)) and note-axis (seq=(b,t)) maps are supported");
   if (time_map && units == 256) {
-    // 64 units per CTA, clusters of 4: 33-37 clusters are resident.  Up to that many 48-sequence tiles run as one
-    // wave; beyond it a cluster takes 96 sequences through one shared staging buffer (one wave up to ~66 sequences
-    // per GPU instead of two), if the batch is even
+    // 64 units per CTA, clusters of 4: 33-37 clusters are resident, so 64 sequences per GPU (64 tiles of 48) run as
+    // two waves.  A one-wave variant (96 sequences per cluster through one shared staging buffer) exists:
+#ifdef DJ_EXPERIMENTS
+    // (measured in round 2: correct but SLOWER than two waves, 1.24 ms against 0.88 ms at 64 sequences per GPU -- the
+    // step is bound by how fast an SM ingests the multicast dz all-gather, ~30 B/clk, and that volume is per
+    // sequence; see DESIGN.md section 4.  Kept as an experiment: DJ_BWD_SHARED=1 in a -DDJ_EXPERIMENTS build.)
     static int one_wave = -1;
-    if (one_wave < 0) { const char* e = getenv("DJ_BWD_SHARED"); one_wave = (e && atoi(e) == 1) ? 1 : 0; }   // experiment: off
+    if (one_wave < 0) { const char* e = getenv("DJ_BWD_SHARED"); one_wave = (e && atoi(e) == 1) ? 1 : 0; }
     if (one_wave && S % 96 == 0 && S / 48 > 33)
       return launch_tc_bwd_inst<256, 96, 64, true, 2, true>(Un_bf16, gates, c, dY, ldY, d_y, dZ_bf16, db, S, steps, map, hard, st);
+#endif
     return launch_tc_bwd<256, 48, 64, true>(Un_bf16, gates, c, dY, ldY, d_y, dZ_bf16, db, S, steps, map, hard, st);
   }
   if (time_map && units == 512)   // scaled model: 32 units per CTA, 16-CTA clusters, a third of a batch element per tile

@@ -64,6 +64,9 @@ class Workspace:
         hdt = torch.float16 if mixed else torch.bfloat16
         self.hprev = [torch.empty(M, L["U"], dtype=hdt, device=dev) if (train and bf16) else None
                       for L in cfg.layers()]
+        # activated gates saved by the tensor-core forward scan for the reverse scan: 4 IEEE halves per cell
+        self.G16 = [torch.empty(M, 4 * L["U"], dtype=torch.float16, device=dev) if (train and bf16) else None
+                    for L in cfg.layers()]
         self.probs = torch.empty(M, 3, **f32)
         if train:
             un = cfg.note_axis_units
@@ -389,7 +392,7 @@ class Engine:
                        _stream())
         elif train and ws.hprev[li] is not None and self._tc_ok(B, T):
             mixed = ws.A_lo[li] is not None
-            self._call("dj_lstm_scan_tc_fwd", _ptr(ws.Z[li]), _ptr(ws.h[li]), _ptr(ws.c[li]), _ptr(ws.hprev[li]),
+            self._call("dj_lstm_scan_tc_fwd", _ptr(ws.Z[li]), _ptr(ws.G16[li]), _ptr(ws.h[li]), _ptr(ws.c[li]), _ptr(ws.hprev[li]),
                        _ptr(self._wbf[f"{L['name']}.Ut"]), _ptr(self._wbf[f"{L['name']}.Ut_lo"]) if mixed else None,
                        DJ_F16 if mixed else DJ_BF16, m["S"], m["steps"], L["U"], m["inner"], m["outer"],
                        m["inner_stride"], m["step"], self.hard, _stream())
@@ -496,7 +499,7 @@ class Engine:
             with torch.cuda.stream(chain):
                 # ---- critical chain: reverse scan, then the data gradient the next layer's scan consumes
                 if bf16 and self._tc_ok(B, T):
-                    self._call("dj_lstm_scan_tc_bwd", _ptr(ws.Z[li]), _ptr(ws.c[li]), _ptr(dY), ldY, d[L["site_out"]],
+                    self._call("dj_lstm_scan_tc_bwd", _ptr(ws.G16[li]), _ptr(ws.c[li]), _ptr(dY), ldY, d[L["site_out"]],
                                _ptr(self._wbf[f"{name}.Un"]), _ptr(dZ), _ptr(G[f"{name}.lstm.b"]), m["S"], m["steps"],
                                U, m["inner"], m["outer"], m["inner_stride"], m["step"], self.hard, _stream())
                 else:

@@ -23,6 +23,46 @@ def _dev(eng: Engine, a) -> torch.Tensor:
     return torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32)).to(eng.dev, non_blocking=True)
 
 
+def _have_h5py() -> bool:
+    try:
+        import h5py  # noqa: F401
+        return True
+    except Exception:
+        return False
+
+
+# Keras auto-names of the reference's layers in model.py creation order (derived from the instantiation
+# order, unverifiable here: neither Keras nor a reference .h5 exists in this environment) -> our tensor prefixes.
+KERAS_H5_MAP = [("style", "style", ("W", "b")), ("conv1d_1", "conv", ("W", "b")),
+                ("dense_1", "time0.sd", ("W", "b")), ("lstm_1", "time0.lstm", ("W", "U", "b")),
+                ("dense_2", "time1.sd", ("W", "b")), ("lstm_2", "time1.lstm", ("W", "U", "b")),
+                ("dense_3", "note0.sd", ("W", "b")), ("lstm_3", "note0.lstm", ("W", "U", "b")),
+                ("dense_4", "note1.sd", ("W", "b")), ("lstm_4", "note1.lstm", ("W", "U", "b")),
+                ("note_dense", "note_dense", ("W", "b")), ("volume_dense", "volume_dense", ("W", "b"))]
+
+
+def _read_keras_h5(f, shapes):
+    """Keras `save_weights` layout: one group per layer holding `kernel:0` / `recurrent_kernel:0` / `bias:0` (possibly one
+    level down, under the layer's own name; TimeDistributed wrappers carry the wrapped layer's weights)."""
+    suffix = {"W": "kernel", "U": "recurrent_kernel", "b": "bias"}
+    found = {}
+
+    def visit(name, obj):
+        if hasattr(obj, "shape"):
+            found[name] = obj
+    f.visititems(visit)
+    state = {}
+    for layer, prefix, parts in KERAS_H5_MAP:
+        for p in parts:
+            want = f"{prefix}.{p}"
+            hits = [n for n in found if layer in n.split("/") and n.split("/")[-1].startswith(suffix[p])
+                    and tuple(found[n].shape) == tuple(shapes[want])]
+            if len(hits) != 1:
+                raise KeyError(f"cannot locate {want} (Keras layer {layer}) in the HDF5 file: {hits}")
+            state[want] = np.asarray(found[hits[0]])
+    return state
+
+
 class History:
     def __init__(self):
         self.history = {"loss": []}
@@ -32,13 +72,41 @@ class _Base:
     def __init__(self, eng: Engine, name: str):
         self.engine, self.name = eng, name
 
-    # -- weights (Keras HDF5 is unavailable here: h5py is not installed; .npz keyed by tensor name)
+    # -- weights.  The reference saves Keras HDF5 (`out/model.h5`, train.py:23 / util.py:19).  With h5py installed a
+    # path ending in .h5 is written / read as an HDF5 file with one dataset per tensor (Keras layouts, the 28 names of
+    # SURVEY 8a; reading also accepts Keras' own layer-group layout through KERAS_H5_MAP).  Without h5py (this image)
+    # nothing is disguised: the weights go to the SAME path with the extension .npz, and loading looks there.
+    @staticmethod
+    def weights_path(path: str) -> str:
+        if path.endswith(".h5") and not _have_h5py():
+            return path[:-3] + ".npz"
+        return path
+
     def save_weights(self, path: str) -> None:
+        path = self.weights_path(path)
         os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
+        state = self.engine.get_params()
+        if path.endswith(".h5"):
+            import h5py
+            with h5py.File(path, "w") as f:
+                for k, v in state.items():
+                    f.create_dataset(k, data=v)
+                f.attrs["format"] = "deepj_b200 flat tensors (Keras layouts)"
+            return
         with open(path, "wb") as f:
-            np.savez(f, **self.engine.get_params())
+            np.savez(f, **state)
 
     def load_weights(self, path: str) -> None:
+        path = self.weights_path(path)
+        if path.endswith(".h5"):
+            import h5py
+            with h5py.File(path, "r") as f:
+                if all(k in f for k in self.engine.shapes):
+                    state = {k: np.asarray(f[k]) for k in self.engine.shapes}
+                else:
+                    state = _read_keras_h5(f, self.engine.shapes)
+            self.engine.set_params(state)
+            return
         with np.load(path) as z:
             self.engine.set_params({k: z[k] for k in self.engine.shapes})
 

@@ -30,10 +30,10 @@ def keep_mask(seed, site, rate, rows, F):
     e = (np.arange(rows, dtype=np.uint64)[:, None] * np.uint64(ld4) + np.arange(F, dtype=np.uint64)[None, :])
     t256 = rate * 256.0
     if t256 == int(t256):
-        w = mix32((mix32(e >> np.uint64(2)) + key) & M32)
+        w = mix32(((e >> np.uint64(2)) + key) & M32)
         byte = (w >> (np.uint64(8) * (e & np.uint64(3)))) & np.uint64(0xFF)
         return (byte >= (thr >> np.uint64(24))).astype(np.float32)
-    w = mix32((mix32(e) + key) & M32)
+    w = mix32((e + key) & M32)
     return (w >= thr).astype(np.float32)
 
 

@@ -23,6 +23,7 @@ for axis, U in (("time", 256), ("note", 128)):
     dY = torch.randn(M, U, device="cuda") * 0.01
     dZ = torch.empty(M, 4 * U, device="cuda").bfloat16()
     db = torch.zeros(4 * U, device="cuda")
+    G16 = torch.rand(M, 4 * U, device="cuda").half()
     for mode in modes:
         dt = torch.bfloat16 if mode == "bf16" else torch.float16
         fmt = 1 if mode == "bf16" else 2
@@ -35,11 +36,11 @@ for axis, U in (("time", 256), ("note", 128)):
             e0, e1, e2, e3 = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
             e0.record()
             if which in ("all", "fwd"):
-                _lib.check(lib.dj_lstm_scan_tc_fwd(P(Z), P(h), P(c), P(hp), P(Ut), P(Ut_lo) if mode != "bf16" else None, fmt,
+                _lib.check(lib.dj_lstm_scan_tc_fwd(P(Z), P(G16), P(h), P(c), P(hp), P(Ut), P(Ut_lo) if mode != "bf16" else None, fmt,
                                                    S, steps, U, *m, 1, None))
             e1.record()
             if which in ("all", "bwd"):
-                _lib.check(lib.dj_lstm_scan_tc_bwd(P(Z), P(c), P(dY), U, _lib.NO_DROPOUT, P(Un), P(dZ), P(db), S, steps, U,
+                _lib.check(lib.dj_lstm_scan_tc_bwd(P(G16), P(c), P(dY), U, _lib.NO_DROPOUT, P(Un), P(dZ), P(db), S, steps, U,
                                                    *m, 1, None))
             e2.record()
             torch.cuda.synchronize()

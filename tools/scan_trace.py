@@ -55,12 +55,13 @@ for axis, U in AXES:
     dY = torch.randn(M, U, device="cuda") * 0.01
     dZ = torch.empty(M, 4 * U, device="cuda").bfloat16()
     db = torch.zeros(4 * U, device="cuda")
+    G16 = torch.rand(M, 4 * U, device="cuda").half()
     for rep in range(2):
         Z = Z0.clone()
         trace.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        _lib.check(lib.dj_lstm_scan_tc_fwd(P(Z), P(h), P(c), P(hp), P(Ut), None, 1, S, steps, U, *m, 1, None))
+        _lib.check(lib.dj_lstm_scan_tc_fwd(P(Z), P(G16), P(h), P(c), P(hp), P(Ut), None, 1, S, steps, U, *m, 1, None))
         e1.record()
         torch.cuda.synchronize()
         if rep == 1:
@@ -68,7 +69,7 @@ for axis, U in AXES:
             report(f"{axis} fwd", steps, False)
         trace.zero_()
         e0.record()
-        _lib.check(lib.dj_lstm_scan_tc_bwd(P(Z), P(c), P(dY), U, _lib.NO_DROPOUT, P(Un), P(dZ), P(db), S, steps, U, *m, 1, None))
+        _lib.check(lib.dj_lstm_scan_tc_bwd(P(G16), P(c), P(dY), U, _lib.NO_DROPOUT, P(Un), P(dZ), P(db), S, steps, U, *m, 1, None))
         e1.record()
         torch.cuda.synchronize()
         if rep == 1:
