@@ -43,13 +43,19 @@ extern "C" {
 
 /* One dropout site (model.py:58,80,85,116,123,136-138).  mode 0 = inactive
  * (predict), 1 = one hash word per 4 elements (rate*256 integral), 2 = one
- * word per element.  Built by dj_make_dropout. */
+ * word per element.  Built by dj_make_dropout.  key_ptr (nullable, DEVICE
+ * pointer): when set, the kernels read the site key from it instead of `key` --
+ * the per-step seed then lives in device memory and a captured CUDA graph of the
+ * training step can be replayed with a new seed every step. */
 typedef struct dj_dropout {
   uint32_t key;
   uint32_t thr;
   float scale;
   int32_t mode;
+  const uint32_t* key_ptr;
 } dj_dropout;
+/* host helper: the site key dj_make_dropout derives from (seed, site) */
+uint32_t dj_dropout_site_key(uint64_t seed, int site);
 
 int dj_version(void);
 const char* dj_last_error(void);
@@ -236,6 +242,10 @@ int dj_nadam_step(float* p, const float* g, float* m, float* v, int64_t n, float
                   float beta1, float beta2, float eps, float mu_t, float mu_t1, float m_sched_new,
                   float m_sched_next, float bias2, void* stream);
 
+/* The same update with the ten per-step scalars read from DEVICE memory (graph replay):
+ * sc = {gscale, lr, beta1, beta2, eps, mu_t, mu_t1, 1/(1-m_sched_new), 1/(1-m_sched_next), 1/bias2}. */
+int dj_nadam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, const float* sc, void* stream);
+
 /* ---- data-parallel step: gradient exchange fused with Nadam over peer memory ----
  * The reference trains on one device (train.py:29 model.fit); SURVEY.md 8e adds
  * data parallelism with one process per GPU.  Instead of an all-reduce followed by
@@ -282,6 +292,11 @@ int dj_gen_sample(const float* zpre, const float* W0c, const float* U0, const fl
                   const double* uniforms, int64_t* ucursor, int stream_mode, double* temperature,
                   int32_t* silent_time, double default_temp, int hard, float* events,
                   float* probs_out, double* margin_out, void* stream);
+
+/* graph-replay form: epoch and the ten scalars of dj_nadam_step_dev come from device memory */
+int dj_nadam_allreduce_peer_dev(float* const* peer_params, const float* const* peer_grads,
+                                uint32_t* const* peer_flags, int rank, int world, float* m, float* v,
+                                int64_t n, const uint32_t* epoch_dev, const float* sc, void* stream);
 
 #ifdef __cplusplus
 }

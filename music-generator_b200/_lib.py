@@ -19,7 +19,8 @@ DJ_F32, DJ_BF16, DJ_F16 = 0, 1, 2
 
 class Dropout(C.Structure):
     """struct dj_dropout"""
-    _fields_ = [("key", C.c_uint32), ("thr", C.c_uint32), ("scale", C.c_float), ("mode", C.c_int32)]
+    _fields_ = [("key", C.c_uint32), ("thr", C.c_uint32), ("scale", C.c_float), ("mode", C.c_int32),
+                ("key_ptr", C.c_void_p)]
 
 
 _p, _i, _i64, _f, _d = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double
@@ -29,6 +30,7 @@ SIGNATURES = {
     "dj_version": (_i, []),
     "dj_last_error": (C.c_char_p, []),
     "dj_make_dropout": (_i, [C.c_uint64, _i, _f, C.POINTER(Dropout)]),
+    "dj_dropout_site_key": (C.c_uint32, [C.c_uint64, _i]),
     "dj_dropout_mask_materialize": (_i, [Dropout, _i64, _i, _p, _p]),
     "dj_style_fwd": (_i, [_p, _i64, _i64, _i, _i, _i, _p, _p, _i, C.POINTER(_p), C.POINTER(_p),
                           C.POINTER(_i), _p, C.POINTER(_p), _p]),
@@ -60,6 +62,8 @@ SIGNATURES = {
     "dj_colsum": (_i, [_p, _i64, _i64, _i, _p, _i, _p]),
     "dj_conv_bwd": (_i, [_p, _i64, _i, _i, _p, _p, Dropout, Dropout, _p, _i64, _p, _p, _p]),
     "dj_nadam_step": (_i, [_p, _p, _p, _p, _i64, _f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _p]),
+    "dj_nadam_step_dev": (_i, [_p, _p, _p, _p, _i64, _p, _p]),
+    "dj_nadam_allreduce_peer_dev": (_i, [C.POINTER(_p), C.POINTER(_p), C.POINTER(_p), _i, _i, _p, _p, _i64, _p, _p, _p]),
     "dj_peer_flag_words": (_i64, []),
     "dj_peer_alloc": (_i, [_i64, C.POINTER(_p), C.c_char_p]),
     "dj_peer_open": (_i, [C.c_char_p, C.POINTER(_p)]),
@@ -115,4 +119,4 @@ def make_dropout(seed: int, site: int, rate: float) -> Dropout:
     return d
 
 
-NO_DROPOUT = Dropout(0, 0, 1.0, 0)
+NO_DROPOUT = Dropout(0, 0, 1.0, 0, None)

@@ -91,6 +91,10 @@ __host__ __device__ __forceinline__ uint32_t dj_site_key(uint64_t seed, int site
 __host__ __device__ __forceinline__ uint32_t dj_mask_word(uint32_t key, uint32_t q) {
   return dj_mix32(q + key);
 }
+// the per-step site key may live in device memory (graph replay: include/deepj_b200.h); call once per kernel
+__device__ __forceinline__ void dj_resolve(dj_dropout& d) {
+  if (d.key_ptr != nullptr) d.key = __ldg(d.key_ptr);
+}
 // single element keep decision (element index e within the site's padded layout)
 __device__ __forceinline__ bool dj_keep(const dj_dropout& d, uint32_t e) {
   if (d.mode == 1) {

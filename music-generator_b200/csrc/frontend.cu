@@ -114,6 +114,7 @@ __global__ void __launch_bounds__(256) frontend_fwd_kernel(
     int64_t beat_bstride, int B, int T, const float* __restrict__ Wc, const float* __restrict__ bc,
     const float* __restrict__ sp0, dj_dropout d_notes, dj_dropout d_beat, dj_dropout d_conv,
     dj_dropout d_sp, TA* __restrict__ A0, TA* __restrict__ A0lo, int ldA) {
+  dj_resolve(d_notes); dj_resolve(d_beat); dj_resolve(d_conv); dj_resolve(d_sp);
   __shared__ __align__(16) float Wc_s[CK_ * NU_ * OU_];
   __shared__ float bc_s[OU_];
   __shared__ float xs[(N_ + CK_ - 1) * NU_];
@@ -237,6 +238,7 @@ __global__ void __launch_bounds__(256) layer_input_kernel(
     const float* __restrict__ h_prev, int Uprev, int64_t h_row0, int64_t h_b_rows, dj_dropout d_h,
     const float* __restrict__ sp, int F, dj_dropout d_sp, const float* __restrict__ chosen_in,
     int64_t chosen_bstride, dj_dropout d_chosen, int B, int T, TA* __restrict__ A, TA* __restrict__ Alo, int ldA) {
+  dj_resolve(d_h); dj_resolve(d_sp); dj_resolve(d_chosen);
   const int ld4 = (F + 3) & ~3;
   const int lane = threadIdx.x & 31;
   const uint32_t rows = (uint32_t)B * (uint32_t)T * N_;
@@ -288,6 +290,7 @@ __global__ void __launch_bounds__(256) layer_input_kernel(
 }
 
 __global__ void mask_materialize_kernel(dj_dropout d, int64_t rows, int F, float* __restrict__ out) {
+  dj_resolve(d);
   const int ld4 = (F + 3) & ~3;
   const int64_t total = rows * F;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -372,6 +375,7 @@ inline int grid_for(int64_t total, int threads, int max_blocks) {
 extern "C" int dj_make_dropout(uint64_t seed, int site, float rate, dj_dropout* out) {
   DJ_CHECK_ARG(out != nullptr, "dj_make_dropout: out is NULL");
   DJ_CHECK_ARG(rate >= 0.f && rate < 1.f, "dj_make_dropout: rate %f outside [0,1)", rate);
+  out->key_ptr = nullptr;
   if (rate == 0.f) { out->key = 0; out->thr = 0; out->scale = 1.f; out->mode = 0; return 0; }
   const double thr = (double)rate * 4294967296.0;
   out->key = dj_site_key(seed, site);
@@ -381,6 +385,8 @@ extern "C" int dj_make_dropout(uint64_t seed, int site, float rate, dj_dropout* 
   out->mode = (t256 == (double)(int)t256) ? 1 : 2;
   return 0;
 }
+
+extern "C" uint32_t dj_dropout_site_key(uint64_t seed, int site) { return dj_site_key(seed, site); }
 
 extern "C" int dj_dropout_mask_materialize(dj_dropout d, int64_t rows, int F, float* out, void* stream) {
   DJ_CHECK_ARG(out && rows > 0 && F > 0, "dj_dropout_mask_materialize: bad arguments");

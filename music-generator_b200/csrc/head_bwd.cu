@@ -24,6 +24,7 @@ __global__ void __launch_bounds__(256) head_loss_kernel(
     const float* __restrict__ h, dj_dropout d_h, const float* __restrict__ Wn, const float* __restrict__ bn,
     const float* __restrict__ Wv, const float* __restrict__ bv, const float* __restrict__ y,
     float* __restrict__ probs, float* __restrict__ dX, float* __restrict__ partials, int64_t M, float inv_M) {
+  dj_resolve(d_h);
   constexpr int UNITS = V * 32;
   constexpr int PSZ = 3 * UNITS + 4;
   __shared__ float red[8][PSZ];
@@ -174,6 +175,7 @@ __global__ void head_finalize_kernel(const float* __restrict__ partials, int uni
 __global__ void __launch_bounds__(128) style_bwd_reduce_kernel(const float* __restrict__ dA, int64_t ldA, int F,
                                                                const float* __restrict__ sp, dj_dropout d_sp,
                                                                float* __restrict__ ds) {
+  dj_resolve(d_sp);
   const int ld4 = (F + 3) & ~3;
   const int64_t bt = blockIdx.x;
   for (int f = threadIdx.x; f < F; f += 128) {
@@ -218,6 +220,7 @@ __global__ void __launch_bounds__(256, 2) conv_bwd_kernel(
     const float* __restrict__ notes_in, int64_t notes_bstride, int B, int T, const float* __restrict__ Wc,
     const float* __restrict__ bc, dj_dropout d_notes, dj_dropout d_conv, const float* __restrict__ dA0,
     int64_t ldA, float* __restrict__ dWc, float* __restrict__ dbc) {
+  dj_resolve(d_notes); dj_resolve(d_conv);
   constexpr int KC = CK_ * NU_;          // 72 (tap, channel-in) pairs
   constexpr int KPT = KC / 4;            // 18 of them per q
   constexpr int NPT = N_ / 4;            // 12 notes per ng
@@ -356,7 +359,30 @@ __global__ void __launch_bounds__(256) nadam_kernel(float* __restrict__ p, const
   }
 }
 
+// the ten per-step scalars from device memory (a replayed CUDA graph gets new ones every step)
+__global__ void __launch_bounds__(256) nadam_dev_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                        float* __restrict__ m, float* __restrict__ v, int64_t n,
+                                                        const float* __restrict__ sc) {
+  const float gscale = sc[0], lr = sc[1], beta1 = sc[2], beta2 = sc[3], eps = sc[4], mu_t = sc[5], mu_t1 = sc[6],
+              i1 = sc[7], i2 = sc[8], ib = sc[9];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float mi = m[i], vi = v[i];
+    p[i] = dj_nadam_one(p[i], __fmul_rn(g[i], gscale), mi, vi, lr, beta1, beta2, eps, mu_t, mu_t1, i1, i2, ib);
+    m[i] = mi;
+    v[i] = vi;
+  }
+}
+
 }  // namespace
+
+extern "C" int dj_nadam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, const float* sc, void* stream) {
+  DJ_CHECK_ARG(p && g && m && v && sc && n > 0, "dj_nadam_step_dev: bad arguments");
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > dj_num_sms() * 8) blocks = dj_num_sms() * 8;
+  nadam_dev_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, sc);
+  DJ_LAUNCH_CHECK();
+  return 0;
+}
 
 extern "C" int64_t dj_head_partials_size(int units) { return (int64_t)HEAD_BLOCKS * (3 * units + 4); }
 

@@ -419,6 +419,7 @@ __global__ void __launch_bounds__((BS / 4) * 16, 1)
 scan_bwd_kernel(const float* __restrict__ G, const float* __restrict__ Cst, const float* __restrict__ dY,
                 int64_t ldY, dj_dropout d_y, const float* __restrict__ Uw, TZ* __restrict__ dZ,
                 float* __restrict__ db, int S, int steps, ScanMap map, int hard) {
+  dj_resolve(d_y);
   static_assert(U / C == UC, "each CTA owns 32 hidden units");
   constexpr int NT = (BS / 4) * 16;
   constexpr int KQ = U / 64;        // k quads per thread in phase B (4 consecutive k each)

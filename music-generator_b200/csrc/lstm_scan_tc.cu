@@ -635,6 +635,7 @@ scan_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
                    const uint2* __restrict__ G16, const float* __restrict__ Cst, const float* __restrict__ dY,
                    uint32_t ldY, dj_dropout d_y, __nv_bfloat16* __restrict__ dZ, float* __restrict__ db,
                    int steps, TcMap map, int hard) {
+  dj_resolve(d_y);
   constexpr int C = U / UPC;            // cluster size
   constexpr int KA = 4 * U / 64;        // K atoms of the contraction (gate columns)
   constexpr int ATOM = UPC * 128;       // bytes of one resident K atom of U (UPC rows x 128 B)

@@ -64,12 +64,20 @@ __device__ __forceinline__ bool wait_flag(uint32_t* flag, uint32_t epoch, uint32
   return true;
 }
 
+// epoch_dev / sc_dev (nullable): the epoch and the ten Nadam scalars of dj_nadam_step_dev read from device memory, so
+// that a captured CUDA graph of the training step replays with the step's own values
 __global__ void __launch_bounds__(256) peer_nadam_kernel(PeerPtrs pp, int rank, int world, float* __restrict__ m,
                                                          float* __restrict__ v, int64_t lo, int64_t hi,
                                                          uint32_t epoch, unsigned long long timeout_ns, float gscale,
                                                          float lr, float beta1, float beta2, float eps, float mu_t, float mu_t1,
                                                          float inv_1m_ms_new, float inv_1m_ms_next,
-                                                         float inv_bias2) {
+                                                         float inv_bias2, const uint32_t* __restrict__ epoch_dev,
+                                                         const float* __restrict__ sc_dev) {
+  if (sc_dev != nullptr) {
+    epoch = *epoch_dev;
+    gscale = sc_dev[0]; lr = sc_dev[1]; beta1 = sc_dev[2]; beta2 = sc_dev[3]; eps = sc_dev[4]; mu_t = sc_dev[5];
+    mu_t1 = sc_dev[6]; inv_1m_ms_new = sc_dev[7]; inv_1m_ms_next = sc_dev[8]; inv_bias2 = sc_dev[9];
+  }
   uint32_t* my = pp.flags[rank];
   const int tid = threadIdx.x;
   // ---- 1. every rank's gradient is complete.  This kernel is stream-ordered behind the local backward pass, so
@@ -166,17 +174,38 @@ extern "C" int dj_peer_free(void* ptr) {
   return 0;
 }
 
+static int peer_launch(float* const* peer_params, const float* const* peer_grads, uint32_t* const* peer_flags, int rank,
+                       int world, float* m, float* v, int64_t n, uint32_t epoch, float gscale, float lr, float beta1,
+                       float beta2, float eps, float mu_t, float mu_t1, float m_sched_new, float m_sched_next, float bias2,
+                       const uint32_t* epoch_dev, const float* sc_dev, void* stream);
+
 extern "C" int dj_nadam_allreduce_peer(float* const* peer_params, const float* const* peer_grads,
                                        uint32_t* const* peer_flags, int rank, int world, float* m, float* v,
                                        int64_t n, uint32_t epoch, float gscale, float lr, float beta1, float beta2,
                                        float eps, float mu_t, float mu_t1, float m_sched_new, float m_sched_next,
                                        float bias2, void* stream) {
+  DJ_CHECK_ARG(epoch != 0, "dj_nadam_allreduce_peer: epoch counts from 1");
+  DJ_CHECK_ARG(m_sched_new < 1.f && m_sched_next < 1.f && bias2 > 0.f, "dj_nadam_allreduce_peer: bad schedule scalars");
+  return peer_launch(peer_params, peer_grads, peer_flags, rank, world, m, v, n, epoch, gscale, lr, beta1, beta2, eps, mu_t,
+                     mu_t1, m_sched_new, m_sched_next, bias2, nullptr, nullptr, stream);
+}
+
+extern "C" int dj_nadam_allreduce_peer_dev(float* const* peer_params, const float* const* peer_grads,
+                                           uint32_t* const* peer_flags, int rank, int world, float* m, float* v,
+                                           int64_t n, const uint32_t* epoch_dev, const float* sc, void* stream) {
+  DJ_CHECK_ARG(epoch_dev && sc, "dj_nadam_allreduce_peer_dev: NULL device parameter block");
+  return peer_launch(peer_params, peer_grads, peer_flags, rank, world, m, v, n, 1u, 1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f,
+                     0.f, 1.f, epoch_dev, sc, stream);
+}
+
+static int peer_launch(float* const* peer_params, const float* const* peer_grads, uint32_t* const* peer_flags, int rank,
+                       int world, float* m, float* v, int64_t n, uint32_t epoch, float gscale, float lr, float beta1,
+                       float beta2, float eps, float mu_t, float mu_t1, float m_sched_new, float m_sched_next, float bias2,
+                       const uint32_t* epoch_dev, const float* sc_dev, void* stream) {
   DJ_CHECK_ARG(peer_params && peer_grads && peer_flags && m && v, "dj_nadam_allreduce_peer: NULL pointer");
   DJ_CHECK_ARG(world >= 1 && world <= PEER_MAX && rank >= 0 && rank < world,
                "dj_nadam_allreduce_peer: rank %d / world %d (at most %d ranks)", rank, world, PEER_MAX);
   DJ_CHECK_ARG(n > 0 && n % 4 == 0, "dj_nadam_allreduce_peer: n must be a positive multiple of 4");
-  DJ_CHECK_ARG(epoch != 0, "dj_nadam_allreduce_peer: epoch counts from 1");
-  DJ_CHECK_ARG(m_sched_new < 1.f && m_sched_next < 1.f && bias2 > 0.f, "dj_nadam_allreduce_peer: bad schedule scalars");
   PeerPtrs pp;
   for (int r = 0; r < world; ++r) {
     DJ_CHECK_ARG(peer_params[r] && peer_grads[r] && peer_flags[r], "dj_nadam_allreduce_peer: rank %d pointers", r);
@@ -201,7 +230,7 @@ extern "C" int dj_nadam_allreduce_peer(float* const* peer_params, const float* c
   }
   peer_nadam_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
       pp, rank, world, m, v, lo, hi, epoch, timeout_ns, gscale, lr, beta1, beta2, eps, mu_t, mu_t1, 1.f / (1.f - m_sched_new),
-      1.f / (1.f - m_sched_next), 1.f / bias2);
+      1.f / (1.f - m_sched_next), 1.f / bias2, epoch_dev, sc_dev);
   DJ_LAUNCH_CHECK();
   return 0;
 }

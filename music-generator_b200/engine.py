@@ -81,6 +81,54 @@ class Workspace:
             self.demb = torch.empty(BT, cfg.style_units, **f32)
 
 
+_M32 = 0xFFFFFFFF
+
+
+def _mix32(x: int) -> int:
+    x ^= x >> 16; x = (x * 0x7feb352d) & _M32
+    x ^= x >> 15; x = (x * 0x846ca68b) & _M32
+    return x ^ (x >> 16)
+
+
+def site_key(seed: int, site: int) -> int:
+    """dj_site_key of csrc/dj_common.cuh (the key dj_make_dropout derives from (seed, site)), on the host."""
+    seed &= 0xFFFFFFFFFFFFFFFF
+    k = _mix32((seed & _M32) ^ ((0x9E3779B9 * (site + 1)) & _M32))
+    return _mix32((k + (seed >> 32)) & _M32)
+
+
+class StepParams:
+    """What changes from one training step to the next and is passed to kernels by VALUE in the eager path -- the 12
+    dropout site keys of the step's seed, the ten Nadam scalars, the exchange epoch -- kept in 128 bytes of device
+    memory instead, so that a captured CUDA graph of the step can be replayed: words 0..14 site keys, word 15 epoch,
+    words 16..25 floats.  Uploads go through a ring of pinned host rows (the host runs ahead of the GPU)."""
+    SLOTS = 64
+
+    def __init__(self, dev):
+        self.buf = torch.zeros(32, dtype=torch.int32, device=dev)
+        self.pinned = torch.zeros(self.SLOTS, 32, dtype=torch.int32).pin_memory()
+        self.rows = self.pinned.numpy()
+        self.events = [None] * self.SLOTS
+        self.i = 0
+        base = self.buf.data_ptr()
+        self.key_ptr = lambda site: base + 4 * site
+        self.epoch_ptr, self.scalar_ptr = base + 4 * 15, base + 4 * 16
+
+    def upload(self, seed: int, epoch: int, scalars) -> None:
+        s = self.i % self.SLOTS
+        self.i += 1
+        if self.events[s] is not None:
+            self.events[s].synchronize()          # the copy that last used this pinned row has been performed
+        row = self.rows[s]
+        row.view(np.uint32)[:15] = [site_key(seed, k) for k in range(15)]
+        row.view(np.uint32)[15] = epoch
+        row.view(np.float32)[16:26] = scalars
+        self.buf.copy_(self.pinned[s], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self.events[s] = ev
+
+
 class Engine:
     def __init__(self, cfg: ModelConfig = ModelConfig(), device: Optional[torch.device] = None,
                  precision: str = "mixed", recurrent_activation: str = "hard_sigmoid",
@@ -132,6 +180,13 @@ class Engine:
         self._hi = None
         self._tag = ""
         self.peer = None      # parallel.PeerNadam: fused gradient exchange + Nadam over peer memory
+        # The training step as ONE CUDA graph launch (DJ_GRAPH=0: ~56 launches from Python).  Per-step values live in
+        # device memory (StepParams); the first step of a shape runs eagerly through the same kernels, the second is
+        # captured, every later one is a replay.
+        self.graph = os.environ.get("DJ_GRAPH", "1") != "0"
+        self._sp: Optional[StepParams] = None
+        self._graphs: Dict[tuple, dict] = {}
+        self._dev_drops = None
         # generation window on the tensor cores at fp32 grade (half hi+lo operands, 3 MMA passes); DJ_GEN_TC=0 = the
         # CUDA-core fp32 kernels
         self.gen_tc = os.environ.get("DJ_GEN_TC", "1") != "0"
@@ -304,9 +359,19 @@ class Engine:
         self._wgen_version = self._version
 
     # --------------------------------------------------------------- dropout
-    def _drops(self, train: bool, seed: int) -> Dict[int, Dropout]:
+    def _drops(self, train: bool, seed) -> Dict[int, Dropout]:
         if not train:
             return {s: NO_DROPOUT for s in range(1, 13)}
+        if seed is None:        # graph path: the site keys are read from device memory (StepParams)
+            if self._dev_drops is None:
+                self._dev_drops = {}
+                for s in range(1, 13):
+                    rate = self.input_dropout if s <= 3 else self.dropout
+                    d = _lib.make_dropout(0, s, rate) if rate > 0 else NO_DROPOUT
+                    if rate > 0:
+                        d.key_ptr = self._sp.key_ptr(s)
+                    self._dev_drops[s] = d
+            return self._dev_drops
         out = {}
         for s in range(1, 13):
             rate = self.input_dropout if s <= 3 else self.dropout
@@ -584,10 +649,60 @@ class Engine:
         self._call("dj_nadam_step", _ptr(self.flat), _ptr(self.gflat), _ptr(self.m), _ptr(self.v), self.flat_size,
                    gscale, *sc, _stream())
 
+    def _step_body_dev(self, gs: dict):
+        """forward + backward + update with every per-step value read from device memory (what the graph captures)."""
+        x = gs["inputs"]
+        self.forward(x[0], x[1], x[2], x[3], target=x[4], train=True, seed=None)
+        loss = self.backward()
+        if self.peer is not None:
+            self.peer.step_dev(self, self._sp.epoch_ptr, self._sp.scalar_ptr, _stream())
+        else:
+            self._call("dj_nadam_step_dev", _ptr(self.flat), _ptr(self.gflat), _ptr(self.m), _ptr(self.v), self.flat_size,
+                       C.c_void_p(self._sp.scalar_ptr), _stream())
+        return loss
+
+    def _train_step_graph(self, tensors, seed: int, world: int):
+        B, T = tensors[0].shape[0], tensors[0].shape[1]
+        if self._sp is None:
+            self._sp = StepParams(self.dev)
+        key = (B, T, self.precision, self.peer is not None)
+        gs = self._graphs.get(key)
+        if gs is None:
+            gs = self._graphs[key] = dict(inputs=[torch.empty_like(t) for t in tensors], graph=None, calls=0, launches=0)
+        for dst, src in zip(gs["inputs"], tensors):
+            if src.data_ptr() != dst.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        lr, b1, b2, eps, mu_t, mu_t1, ms_new, ms_next, bias2 = self._nadam_scalars()
+        f = np.float32          # the reciprocals exactly as the C wrappers of the by-value entry points form them
+        scal = [f(1.0 / world), f(lr), f(b1), f(b2), f(eps), f(mu_t), f(mu_t1), f(1) / (f(1) - f(ms_new)),
+                f(1) / (f(1) - f(ms_next)), f(1) / f(bias2)]
+        self._sp.upload(seed, self.peer.next_epoch() if self.peer is not None else 0, scal)
+        if gs["graph"] is None and gs["calls"] >= 1:
+            l0 = self.launches
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    gs["loss"] = self._step_body_dev(gs)
+                gs["graph"], gs["launches"] = g, self.launches - l0
+                self.launches = l0
+            except Exception as e:   # the launch mechanism, not the arithmetic: log once and keep launching from Python
+                print(f"[deepj] CUDA graph capture of the training step failed ({e}); launching eagerly", flush=True)
+                self.graph = False
+                self._dev_drops = None
+        gs["calls"] += 1
+        if gs["graph"] is not None:
+            gs["graph"].replay()
+            self.launches += gs["launches"]
+            return gs["loss"]
+        return self._step_body_dev(gs)
+
     def train_step(self, notes, chosen, beat, style, target, seed: int, allreduce=None, world: int = 1):
         """One `fit` batch: forward + primary_loss + backward + gradient exchange + Nadam.  The exchange is either
         `allreduce` (NCCL sum of the flat gradient) followed by the Nadam kernel, or -- when a parallel.PeerNadam is
-        attached -- one kernel that does both over peer memory.  Returns the device scalar loss (no sync)."""
+        attached -- one kernel that does both over peer memory.  Returns the device scalar loss (no sync).
+        With `self.graph` (default) and no NCCL collective in the step, the whole step is one CUDA graph launch."""
+        if self.graph and allreduce is None and self.profile is None:
+            return self._train_step_graph((notes, chosen, beat, style, target), seed, world)
         self.forward(notes, chosen, beat, style, target=target, train=True, seed=seed)
         loss = self.backward()
         if self.peer is not None:

@@ -159,6 +159,16 @@ class PeerNadam:
         if self.world > 1:
             dist.barrier()       # every rank's buffers hold its weights before anybody's first step
 
+    def next_epoch(self) -> int:
+        self.epoch = self.epoch % 0xFFFFFFFF + 1
+        return self.epoch
+
+    def step_dev(self, eng, epoch_ptr: int, scalar_ptr: int, stream) -> None:
+        """The same exchange with the epoch and the Nadam scalars read from device memory (Engine.StepParams): the
+        form a captured CUDA graph of the training step replays.  The caller advances the epoch (next_epoch)."""
+        eng._call("dj_nadam_allreduce_peer_dev", self._p, self._g, self._f, self.rank, self.world, eng.m.data_ptr(),
+                  eng.v.data_ptr(), self.n, C.c_void_p(epoch_ptr), C.c_void_p(scalar_ptr), stream)
+
     def step(self, eng, scalars, stream) -> None:
         """One fused exchange + Nadam update; `scalars` = Engine._nadam_scalars()."""
         self.epoch = self.epoch % 0xFFFFFFFF + 1

@@ -246,6 +246,32 @@ def test_training_trajectory_bf16_tracks_fp32():
     assert np.max(np.abs(b - f) / f) < 2e-3, (f, b)
 
 
+def test_graph_replay_equals_eager_steps():
+    """The training step as a replayed CUDA graph (per-step dropout keys, Nadam scalars and exchange epoch read from
+    device memory) against the same steps launched from Python with those values passed by value: same loss every
+    step (each step has its own seed: the masks must really change under replay), same weights after six steps up to
+    the fp32-atomic noise of the gradient reductions."""
+    B, T = 2, 32
+    _, dev = batch_dev(B, T)
+    _, dev2 = batch_dev(B, T, seed=99)
+    out = {}
+    for mode in (False, True):
+        e = make_engine("mixed")
+        e.graph = mode
+        losses = []
+        for step in range(6):
+            batch = dev if step % 2 == 0 else dev2          # the graph's static inputs are refilled every step
+            losses.append(float(e.train_step(*batch, seed=1000 + 17 * step).item()))
+        out[mode] = (np.array(losses), e.flat.detach().clone(), e)
+    le, lg = out[False][0], out[True][0]
+    assert out[True][2]._graphs and all(g["graph"] is not None for g in out[True][2]._graphs.values())
+    assert not out[False][2]._graphs
+    assert np.allclose(le, lg, rtol=2e-5, atol=0), (le, lg)
+    assert len(set(np.round(lg, 6))) == 6
+    diff = (out[False][1] - out[True][1]).abs()
+    assert float(diff.median()) < 1e-6 and float((diff > 1e-4).float().mean()) < 2e-3, float(diff.max())
+
+
 def test_train_step_bf16_single_timestep_and_many_tiles():
     """Edge shapes of the tensor-core scans: a one-step time axis (T = 1: no recurrent MMA at all, B*T = 64 keeps the
     tensor-core path) and a batch whose time-axis tiles exceed one wave of clusters (B = 36 at T = 16)."""
