@@ -59,6 +59,13 @@ uint32_t dj_dropout_site_key(uint64_t seed, int site);
 
 int dj_version(void);
 const char* dj_last_error(void);
+/* Deterministic gradients.  The gradient kernels that sum over CTAs (dj_wgrad_gemm_*, dj_lstm_scan_tc_bwd's db,
+ * dj_conv_bwd, dj_colsum, split-K dj_gemm_simt) add with fp32 atomics by default, so two runs agree only to rounding.
+ * Register a device workspace of `floats` floats for a stream (per calling thread; floats = 0 unregisters) and the
+ * launches on that stream write one partial per CTA there and add them in index order instead: bit-identical
+ * results run to run (also dj_lstm_scan_bwd's db).  A registered workspace too small for a launch makes that launch
+ * fail (<0), it never falls back to the atomics.  8 M floats cover the default and the scaled model at any batch. */
+int dj_set_reduce_workspace(void* stream, float* ws, int64_t floats);
 /* host helper: fills *out for Dropout(rate) at `site` (1..12 = D1..D12 of SURVEY 8a). */
 int dj_make_dropout(uint64_t seed, int site, float rate, dj_dropout* out);
 /* debug: dump the 0/1 keep mask of a site with `rows` rows of F elements

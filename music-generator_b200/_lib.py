@@ -29,6 +29,7 @@ _p, _i, _i64, _f, _d = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double
 SIGNATURES = {
     "dj_version": (_i, []),
     "dj_last_error": (C.c_char_p, []),
+    "dj_set_reduce_workspace": (_i, [_p, _p, _i64]),
     "dj_make_dropout": (_i, [C.c_uint64, _i, _f, C.POINTER(Dropout)]),
     "dj_dropout_site_key": (C.c_uint32, [C.c_uint64, _i]),
     "dj_dropout_mask_materialize": (_i, [Dropout, _i64, _i, _p, _p]),

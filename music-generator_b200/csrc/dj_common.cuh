@@ -23,6 +23,12 @@ void dj_set_error(const char* fmt, ...);
   } while (0)
 #define DJ_LAUNCH_CHECK() DJ_CUDA(cudaGetLastError())
 
+// deterministic-reduction plumbing (api.cu): *out = the workspace registered for a stream (nullptr: none; registered
+// but smaller than need_floats: error), and  out[r*ldo + c] += sum over p < P, in order, of part[p*pstride + r*ldp + c]
+int dj_reduce_workspace(void* stream, int64_t need_floats, float** out);
+int dj_ordered_reduce(const float* part, int P, int64_t pstride, int64_t rows, int cols, int64_t ldp, float* out,
+                      int64_t ldo, void* stream);
+
 static inline int dj_num_sms() {
   static int n = 0;
   if (n == 0) {

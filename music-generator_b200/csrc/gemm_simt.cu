@@ -15,7 +15,7 @@ template <typename TA, typename TB, bool A_KCONTIG, bool B_NCONTIG>
 __global__ void __launch_bounds__(NT) gemm_simt_kernel(
     const TA* __restrict__ A, int64_t a_sm, int64_t a_sk, const TB* __restrict__ B, int64_t b_sk,
     int64_t b_sn, float* __restrict__ C, int64_t ldc, const float* __restrict__ bias, int M, int N, int K,
-    int accumulate, int64_t a_shift, int64_t a_period, int k_per_split, int use_atomic) {
+    int accumulate, int64_t a_shift, int64_t a_period, int k_per_split, int use_atomic, float* __restrict__ part) {
   __shared__ __align__(16) float As[2][BK][BM + 4];
   __shared__ __align__(16) float Bs[2][BK][BN + 4];
   const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
@@ -98,7 +98,8 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(
       float v = acc[i][j];
       if (bias != nullptr && blockIdx.z == 0) v += bias[gn];
       float* dst = C + (int64_t)gm * ldc + gn;
-      if (use_atomic) atomicAdd(dst, v);
+      if (part != nullptr) part[((int64_t)blockIdx.z * M + gm) * N + gn] = v;   // deterministic split-K: added in order later
+      else if (use_atomic) atomicAdd(dst, v);
       else *dst = accumulate ? (*dst + v) : v;
     }
   }
@@ -125,19 +126,22 @@ int launch_simt(const void* A, int64_t a_sm, int64_t a_sk, const void* B, int64_
     if (ldc == N) DJ_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, st));
     else DJ_CUDA(cudaMemset2DAsync(C, sizeof(float) * ldc, 0, sizeof(float) * N, M, st));
   }
+  float* part = nullptr;
+  if (use_atomic && dj_reduce_workspace((void*)st, (int64_t)splits * M * N, &part)) return -1;
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, splits);
   const bool akc = (a_sk == 1), bnc = (b_sn == 1);
   const TA* Ap = (const TA*)A;
   const TB* Bp = (const TB*)B;
 #define LAUNCH(AK, BNc)                                                                                      \
   gemm_simt_kernel<TA, TB, AK, BNc><<<grid, NT, 0, st>>>(Ap, a_sm, a_sk, Bp, b_sk, b_sn, C, ldc, bias, M, N, \
-                                                         K, accumulate, a_shift, a_period, kps, use_atomic)
+                                                         K, accumulate, a_shift, a_period, kps, use_atomic, part)
   if (akc && bnc) LAUNCH(true, true);
   else if (akc && !bnc) LAUNCH(true, false);
   else if (!akc && bnc) LAUNCH(false, true);
   else LAUNCH(false, false);
 #undef LAUNCH
   DJ_LAUNCH_CHECK();
+  if (part != nullptr) return dj_ordered_reduce(part, splits, (int64_t)M * N, M, N, N, C, ldc, (void*)st);
   return 0;
 }
 

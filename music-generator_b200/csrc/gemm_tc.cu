@@ -204,7 +204,7 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   float* __restrict__ C, int64_t ldc, int Ka, int Nb, int64_t M, int num_tiles, int kb_per_split,
-                  uint32_t idesc) {
+                  uint32_t idesc, float* __restrict__ part) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const uint32_t sbase = smem_u32(smem);
@@ -279,7 +279,21 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     for (int c = 0; c < WG_BN / 32; ++c) {
       uint32_t v[32];
       tmem_ld32(tmem_base + ((uint32_t)(32 * e) << 16) + (uint32_t)(c * 32), v);
-      if (row < Ka) {
+      if (row < Ka && part != nullptr) {
+        // deterministic mode: this split's partial tile, added later in split order (dj_ordered_reduce)
+        float* dst = part + ((int64_t)split * Ka + row) * Nb + nb0 + c * 32;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int n = nb0 + c * 32 + 4 * q;
+          if (n + 3 < Nb) {
+            *reinterpret_cast<float4*>(dst + 4 * q) = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                                                                  __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+          } else {
+            for (int j = 0; j < 4; ++j)
+              if (n + j < Nb) dst[4 * q + j] = __uint_as_float(v[4 * q + j]);
+          }
+        }
+      } else if (row < Ka) {
         float* dst = C + (int64_t)row * ldc + nb0 + c * 32;
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
@@ -406,9 +420,13 @@ extern "C" int dj_wgrad_gemm_16(const void* A, int a_fmt, int64_t lda, const voi
   const int kbps = (total_kb + splits - 1) / splits;
   splits = (total_kb + kbps - 1) / kbps;
   const uint32_t idesc = idesc_with_formats(make_idesc(WG_BM, WG_BN, 1, 1), a_fmt, b_fmt);
+  float* part = nullptr;
+  if (dj_reduce_workspace(stream, (int64_t)splits * Ka * Nb, &part)) return -1;
+  DJ_CHECK_ARG(part == nullptr || Nb % 4 == 0, "dj_wgrad_gemm_16: deterministic mode needs Nb %% 4 == 0 (got %d)", Nb);
   wgrad_gemm_kernel<<<tiles * splits, NUM_THREADS, WgradSmem::TOTAL, (cudaStream_t)stream>>>(tmA, tmB, C, ldc, Ka, Nb, M,
-                                                                                             tiles, kbps, idesc);
+                                                                                             tiles, kbps, idesc, part);
   DJ_LAUNCH_CHECK();
+  if (part != nullptr) return dj_ordered_reduce(part, splits, (int64_t)Ka * Nb, Ka, Nb, Nb, C, ldc, stream);
   return 0;
 }
 

@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(128) style_bwd_reduce_kernel(const float* __re
 
 // grid (column blocks of 32, row slices): each block sums its slice, one atomic per column per block
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ X, int64_t ldx, int64_t R, int C,
-                                                     float* __restrict__ out) {
+                                                     float* __restrict__ out, float* __restrict__ part) {
   __shared__ float red[8][33];
   const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5, c = blockIdx.x * 32 + cl;
   const int64_t per = (R + gridDim.y - 1) / gridDim.y;
@@ -205,7 +205,8 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ X
     float t = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) t += red[i][cl];
-    atomicAdd(out + c, t);
+    if (part != nullptr) part[(int64_t)blockIdx.y * C + c] = t;      // deterministic mode: added in slice order later
+    else atomicAdd(out + c, t);
   }
 }
 
@@ -219,7 +220,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ X
 __global__ void __launch_bounds__(256, 2) conv_bwd_kernel(
     const float* __restrict__ notes_in, int64_t notes_bstride, int B, int T, const float* __restrict__ Wc,
     const float* __restrict__ bc, dj_dropout d_notes, dj_dropout d_conv, const float* __restrict__ dA0,
-    int64_t ldA, float* __restrict__ dWc, float* __restrict__ dbc) {
+    int64_t ldA, float* __restrict__ dWc, float* __restrict__ dbc, float* __restrict__ part) {
   dj_resolve(d_notes); dj_resolve(d_conv);
   constexpr int KC = CK_ * NU_;          // 72 (tap, channel-in) pairs
   constexpr int KPT = KC / 4;            // 18 of them per q
@@ -341,6 +342,12 @@ __global__ void __launch_bounds__(256, 2) conv_bwd_kernel(
     }
     __syncthreads();
   }
+  if (part != nullptr) {   // deterministic mode: this block's partial [72*64 weights | 64 biases], added in block order later
+    float* dst = part + (size_t)blockIdx.x * (KC * OU_ + OU_);
+    for (int i = tid; i < KC * OU_; i += 256) dst[i] = red[i];
+    if (tid < OU_) dst[KC * OU_ + tid] = bc_s[tid];
+    return;
+  }
   for (int i = tid; i < KC * OU_; i += 256) atomicAdd(dWc + i, red[i]);
   if (tid < OU_) atomicAdd(dbc + tid, bc_s[tid]);
 }
@@ -426,8 +433,11 @@ extern "C" int dj_colsum(const float* X, int64_t ldx, int64_t R, int C, float* o
   int slices = (int)((R + 127) / 128);
   if (slices > 64) slices = 64;
   if (slices < 1) slices = 1;
-  colsum_kernel<<<dim3((C + 31) / 32, slices), 256, 0, (cudaStream_t)stream>>>(X, ldx, R, C, out);
+  float* part = nullptr;
+  if (slices > 1 && dj_reduce_workspace(stream, (int64_t)slices * C, &part)) return -1;
+  colsum_kernel<<<dim3((C + 31) / 32, slices), 256, 0, (cudaStream_t)stream>>>(X, ldx, R, C, out, part);
   DJ_LAUNCH_CHECK();
+  if (part != nullptr) return dj_ordered_reduce(part, slices, C, 1, C, C, out, C, stream);
   return 0;
 }
 
@@ -438,9 +448,17 @@ extern "C" int dj_conv_bwd(const float* notes_in, int64_t notes_bstride, int B, 
   DJ_CHECK_ARG(B > 0 && T > 0 && ldA >= DJ_FEAT0, "dj_conv_bwd: bad sizes");
   int grid = dj_num_sms() * 2;   // 31 KB smem, 256 threads x <=128 registers: 2 resident blocks overlap the barriers
   if (grid > B * T) grid = B * T;
+  constexpr int PSZ = CK_ * NU_ * OU_ + OU_;
+  float* part = nullptr;
+  if (dj_reduce_workspace(stream, (int64_t)grid * PSZ, &part)) return -1;
   conv_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(notes_in, notes_bstride, B, T, Wc, bc, d_notes, d_conv,
-                                                          dA0, ldA, dWc, dbc);
+                                                          dA0, ldA, dWc, dbc, part);
   DJ_LAUNCH_CHECK();
+  if (part != nullptr) {
+    int rc = dj_ordered_reduce(part, grid, PSZ, 1, CK_ * NU_ * OU_, PSZ, dWc, CK_ * NU_ * OU_, stream);
+    if (rc) return rc;
+    return dj_ordered_reduce(part + CK_ * NU_ * OU_, grid, PSZ, 1, OU_, PSZ, dbc, OU_, stream);
+  }
   return 0;
 }
 

@@ -418,7 +418,7 @@ template <int U, int C, int BS, typename TZ>
 __global__ void __launch_bounds__((BS / 4) * 16, 1)
 scan_bwd_kernel(const float* __restrict__ G, const float* __restrict__ Cst, const float* __restrict__ dY,
                 int64_t ldY, dj_dropout d_y, const float* __restrict__ Uw, TZ* __restrict__ dZ,
-                float* __restrict__ db, int S, int steps, ScanMap map, int hard) {
+                float* __restrict__ db, int S, int steps, ScanMap map, int hard, float* __restrict__ db_part) {
   dj_resolve(d_y);
   static_assert(U / C == UC, "each CTA owns 32 hidden units");
   constexpr int NT = (BS / 4) * 16;
@@ -570,7 +570,9 @@ scan_bwd_kernel(const float* __restrict__ G, const float* __restrict__ Cst, cons
   if (tid < 128) {
     float s = 0.f;
     for (int q = 0; q < BS / 4; ++q) s += dzb[tid * SM::DZS + q];
-    atomicAdd(db + 4 * (unit0 + (tid & 31)) + (tid >> 5), s);
+    const int col = 4 * (unit0 + (tid & 31)) + (tid >> 5);
+    if (db_part != nullptr) db_part[(size_t)cid * (4 * U) + col] = s;   // deterministic mode: one partial per cluster
+    else atomicAdd(db + col, s);
   }
 }
 
@@ -605,7 +607,8 @@ int prepare_cluster_kernel(K kernel, int C, size_t smem) {
 // Persistent clusters: `ntiles` tiles are walked by as many clusters as can be resident, balanced so that every
 // cluster does the same number of rounds.
 template <typename K>
-int launch_cluster(K kernel, int C, int nthreads, size_t smem, int ntiles, cudaStream_t st, void** args) {
+int launch_cluster(K kernel, int C, int nthreads, size_t smem, int ntiles, cudaStream_t st, void** args,
+                   int* ncl_out = nullptr) {
   int rc = prepare_cluster_kernel(kernel, C, smem);
   if (rc) return rc;
   int ncl = max_active_clusters(kernel, C, nthreads, smem);
@@ -622,6 +625,7 @@ int launch_cluster(K kernel, int C, int nthreads, size_t smem, int ntiles, cudaS
   at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
   DJ_CUDA(cudaLaunchKernelExC(&cfg, (const void*)kernel, args));
+  if (ncl_out != nullptr) *ncl_out = ncl;
   return 0;
 }
 
@@ -666,20 +670,30 @@ extern "C" int dj_lstm_scan_bwd(const float* gates, const float* c, const float*
   DJ_CHECK_ARG(S > 0 && steps > 0 && seq_inner > 0 && ldY >= units, "dj_lstm_scan_bwd: bad sizes");
   DJ_CHECK_ARG(dz_dtype == DJ_F32 || dz_dtype == DJ_BF16, "dj_lstm_scan_bwd: unknown dz dtype %d", dz_dtype);
   ScanMap map{seq_inner, seq_outer_stride, seq_inner_stride, step_stride};
-  void* args[] = {(void*)&gates, (void*)&c, (void*)&dY, &ldY, &d_y, (void*)&Uw, &dZ, &db, &S, &steps, &map, &hard};
   cudaStream_t st = (cudaStream_t)stream;
+  const int BSu = units == 256 ? 48 : 64, ntiles = (S + BSu - 1) / BSu;   // tiles; launch_cluster picks the resident cluster count
+  // deterministic mode: one partial bias gradient per cluster, added in cluster order afterwards
+  float* db_part = nullptr;
+  if (dj_reduce_workspace(stream, (int64_t)ntiles * 4 * units, &db_part)) return -1;
+  void* args[] = {(void*)&gates, (void*)&c, (void*)&dY, &ldY, &d_y, (void*)&Uw, &dZ, &db, &S, &steps, &map, &hard, &db_part};
+  int ncl = 0, rc = -1;
   if (units == 256) {
     constexpr int C = 8, BS = 48;
-    const int ncl = (S + BS - 1) / BS;   // tiles; launch_cluster picks the resident cluster count
     if (dz_dtype == DJ_F32)
-      return launch_cluster(scan_bwd_kernel<256, C, BS, float>, C, (BS / 4) * 16, BwdSmem<256, C, BS>::BYTES, ncl, st, args);
-    return launch_cluster(scan_bwd_kernel<256, C, BS, __nv_bfloat16>, C, (BS / 4) * 16, BwdSmem<256, C, BS>::BYTES, ncl, st, args);
+      rc = launch_cluster(scan_bwd_kernel<256, C, BS, float>, C, (BS / 4) * 16, BwdSmem<256, C, BS>::BYTES, ntiles, st, args, &ncl);
+    else
+      rc = launch_cluster(scan_bwd_kernel<256, C, BS, __nv_bfloat16>, C, (BS / 4) * 16, BwdSmem<256, C, BS>::BYTES, ntiles, st, args, &ncl);
   } else if (units == 128) {
     constexpr int C = 4, BS = 64;
-    const int ncl = (S + BS - 1) / BS;   // tiles; launch_cluster picks the resident cluster count
     if (dz_dtype == DJ_F32)
-      return launch_cluster(scan_bwd_kernel<128, C, BS, float>, C, (BS / 4) * 16, BwdSmem<128, C, BS>::BYTES, ncl, st, args);
-    return launch_cluster(scan_bwd_kernel<128, C, BS, __nv_bfloat16>, C, (BS / 4) * 16, BwdSmem<128, C, BS>::BYTES, ncl, st, args);
+      rc = launch_cluster(scan_bwd_kernel<128, C, BS, float>, C, (BS / 4) * 16, BwdSmem<128, C, BS>::BYTES, ntiles, st, args, &ncl);
+    else
+      rc = launch_cluster(scan_bwd_kernel<128, C, BS, __nv_bfloat16>, C, (BS / 4) * 16, BwdSmem<128, C, BS>::BYTES, ntiles, st, args, &ncl);
+  }
+  if (units == 256 || units == 128) {
+    if (rc == 0 && db_part != nullptr)
+      rc = dj_ordered_reduce(db_part, ncl, (int64_t)4 * units, 1, 4 * units, 4 * units, db, 4 * units, stream);
+    return rc;
   }
   DJ_CHECK_ARG(false, "dj_lstm_scan_bwd: units=%d unsupported (128 or 256)", units);
   return -1;

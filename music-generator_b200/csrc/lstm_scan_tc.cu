@@ -634,7 +634,7 @@ __global__ void __launch_bounds__(TCB_THREADS, (U == 128 && BS <= 32) ? 2 : 1)
 scan_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmZ,
                    const uint2* __restrict__ G16, const float* __restrict__ Cst, const float* __restrict__ dY,
                    uint32_t ldY, dj_dropout d_y, __nv_bfloat16* __restrict__ dZ, float* __restrict__ db,
-                   int steps, TcMap map, int hard) {
+                   int steps, TcMap map, int hard, float* __restrict__ db_part) {
   dj_resolve(d_y);
   constexpr int C = U / UPC;            // cluster size
   constexpr int KA = 4 * U / 64;        // K atoms of the contraction (gate columns)
@@ -882,7 +882,12 @@ scan_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
       }
       par ^= 1u;
     }
-    if (active) {
+    if (active && db_part != nullptr) {
+      // deterministic mode: one partial per (tile, sequence group of the CTA), added later in index order; the four
+      // sequence groups (w2, sh) of a CTA and the CTAs of a cluster together cover every column exactly once
+      float* dst = db_part + ((size_t)(tile * 4 + w2 * 2 + sh) * (4 * U)) + 4 * col;
+      *reinterpret_cast<float4*>(dst) = make_float4(dbacc[0], dbacc[1], dbacc[2], dbacc[3]);
+    } else if (active) {
 #pragma unroll
       for (int gq = 0; gq < 4; ++gq) atomicAdd(db + 4 * col + gq, dbacc[gq]);
     }
@@ -950,7 +955,11 @@ int launch_tc_bwd_inst(const void* Un_bf, const void* gates, const float* c, con
   __nv_bfloat16* dzp = (__nv_bfloat16*)dZ;
   const uint32_t ldy32 = (uint32_t)ldY;
   const uint2* g16 = (const uint2*)gates;
-  DJ_CUDA(cudaLaunchKernelEx(&cfg, kernel, tmU, tmZ, g16, c, dY, ldy32, d_y, dzp, db, steps, map, hard));
+  const int tiles = S / BS;
+  float* db_part = nullptr;
+  if (dj_reduce_workspace((void*)st, (int64_t)tiles * 4 * 4 * U, &db_part)) return -1;
+  DJ_CUDA(cudaLaunchKernelEx(&cfg, kernel, tmU, tmZ, g16, c, dY, ldy32, d_y, dzp, db, steps, map, hard, db_part));
+  if (db_part != nullptr) return dj_ordered_reduce(db_part, tiles * 4, (int64_t)4 * U, 1, 4 * U, 4 * U, db, 4 * U, (void*)st);
   return 0;
 }
 

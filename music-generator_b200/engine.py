@@ -132,7 +132,7 @@ class StepParams:
 class Engine:
     def __init__(self, cfg: ModelConfig = ModelConfig(), device: Optional[torch.device] = None,
                  precision: str = "mixed", recurrent_activation: str = "hard_sigmoid",
-                 input_dropout: float = 0.2, dropout: float = 0.5):
+                 input_dropout: float = 0.2, dropout: float = 0.5, deterministic: Optional[bool] = None):
         if not torch.cuda.is_available():
             raise RuntimeError("the DeepJ B200 engine needs a CUDA device; there is no CPU fallback")
         # "mixed" (training default): tensor cores at fp32 grade where the outputs need it -- split bf16 hi+lo gate
@@ -190,6 +190,12 @@ class Engine:
         # generation window on the tensor cores at fp32 grade (half hi+lo operands, 3 MMA passes); DJ_GEN_TC=0 = the
         # CUDA-core fp32 kernels
         self.gen_tc = os.environ.get("DJ_GEN_TC", "1") != "0"
+        # Deterministic gradients (DJ_DETERMINISTIC=1): every sum over CTAs in the backward pass (split weight-gradient
+        # GEMMs, bias / conv / style gradients) goes through per-CTA partials added in index order instead of fp32
+        # atomics, so two runs -- and 1 GPU vs N GPUs on the same shards -- give the same bits.  One workspace per
+        # stream the backward pass launches on (dj_set_reduce_workspace).
+        self.deterministic = (os.environ.get("DJ_DETERMINISTIC", "0") == "1") if deterministic is None else deterministic
+        self._red_ws: Dict[int, torch.Tensor] = {}
 
     # ------------------------------------------------------------------ params
     def _view(self, flat, k):
@@ -532,6 +538,20 @@ class Engine:
         return ws
 
     # -------------------------------------------------------------- backward
+    RED_WS_FLOATS = 8 << 20     # 32 MB: the largest user is the split weight-gradient GEMM (splits x K x 4U partial tiles)
+
+    def _register_reduce_ws(self, stream: "torch.cuda.Stream") -> None:
+        """Deterministic mode: give the library a partial-sum workspace for launches on `stream` (idempotent)."""
+        h = stream.cuda_stream
+        if h not in self._red_ws:
+            self._red_ws[h] = torch.empty(self.RED_WS_FLOATS, dtype=torch.float32, device=self.dev)
+        check(self.lib.dj_set_reduce_workspace(C.c_void_p(h), _ptr(self._red_ws[h]), self.RED_WS_FLOATS),
+              "dj_set_reduce_workspace")
+
+    def _unregister_reduce_ws(self) -> None:
+        for h in self._red_ws:
+            check(self.lib.dj_set_reduce_workspace(C.c_void_p(h), None, 0), "dj_set_reduce_workspace")
+
     def backward(self):
         """tf.gradients of primary_loss w.r.t. the 28 weight tensors, for the last
         forward(target=...).  Fills self.gflat (un-averaged local gradient) and
@@ -550,6 +570,10 @@ class Engine:
         if two and self._hi is None:
             self._hi = torch.cuda.Stream(device=self.dev, priority=-1)
         chain = self._hi if two else main
+        if self.deterministic:
+            self._register_reduce_ws(main)
+            if two:
+                self._register_reduce_ws(chain)
         if two:
             chain.wait_stream(main)           # forward, zeroed gradients
         dY, ldY = ws.dXtop, cfg.note_axis_units
@@ -624,6 +648,8 @@ class Engine:
         self._call("dj_colsum", _ptr(ws.demb), cfg.style_units, BT, cfg.style_units, _ptr(G["style.b"]), 1, _stream())
         if two:
             main.wait_stream(chain)
+        if self.deterministic:
+            self._unregister_reduce_ws()      # the registration is per calling thread and stream: leave none behind
         return ws.loss
 
     # ------------------------------------------------------------- optimizer

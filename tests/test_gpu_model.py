@@ -272,6 +272,61 @@ def test_graph_replay_equals_eager_steps():
     assert float(diff.median()) < 1e-6 and float((diff > 1e-4).float().mean()) < 2e-3, float(diff.max())
 
 
+@pytest.mark.parametrize("prec,graph", [("mixed", False), ("mixed", True), ("fp32", False)])
+def test_deterministic_gradients_are_bitwise_reproducible(prec, graph):
+    """with `deterministic=True` every sum over CTAs of the backward pass (split weight-gradient
+    GEMMs, bias, conv and style gradients) is a fixed-order sum of per-CTA partials, so two runs of the same steps give
+    the same BITS: gradients after one backward pass and weights after four optimizer steps.  The default (fp32
+    atomics) is checked to really differ run to run, so the test cannot pass vacuously."""
+    from music_generator_b200.engine import Engine
+    from music_generator_b200.config import ModelConfig
+    B, T = 4, 32
+    _, dev = batch_dev(B, T)
+    runs = []
+    for _ in range(2):
+        e = Engine(ModelConfig(), precision=prec, deterministic=True)
+        e.init_params(0)
+        e.graph = graph
+        e.forward(*dev[:4], target=dev[4], train=True, seed=5)
+        e.backward()
+        g = e.gflat.detach().clone()
+        for step in range(4):
+            e.train_step(*dev, seed=300 + step)
+        torch.cuda.synchronize()
+        runs.append((g, e.flat.detach().clone(), e.gflat.detach().clone()))
+    assert float(runs[0][0].abs().max()) > 0
+    for a, b in zip(runs[0], runs[1]):
+        assert torch.equal(a, b), float((a - b).abs().max())
+    # same arithmetic as the atomic path up to summation order
+    e = Engine(ModelConfig(), precision=prec, deterministic=False)
+    e.init_params(0)
+    e.forward(*dev[:4], target=dev[4], train=True, seed=5)
+    e.backward()
+    torch.cuda.synchronize()
+    d = (e.gflat - runs[0][0]).abs()
+    assert float(d.max()) <= 2e-4 * float(runs[0][0].abs().max()), float(d.max())
+
+
+def test_deterministic_workspace_too_small_is_an_error():
+    """A registered workspace that cannot hold the partials is an error code, never a silent return to the atomics."""
+    import ctypes as C
+    from music_generator_b200 import _lib
+    lib = _lib.load()
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    ws = torch.empty(64, dtype=torch.float32, device="cuda")
+    X = torch.randn(4096, 96, device="cuda")
+    out = torch.zeros(96, device="cuda")
+    assert lib.dj_set_reduce_workspace(st, C.c_void_p(ws.data_ptr()), 64) == 0
+    try:
+        rc = lib.dj_colsum(C.c_void_p(X.data_ptr()), 96, 4096, 96, C.c_void_p(out.data_ptr()), 0, st)
+        assert rc != 0 and b"workspace" in lib.dj_last_error()
+    finally:
+        assert lib.dj_set_reduce_workspace(st, None, 0) == 0
+    assert lib.dj_colsum(C.c_void_p(X.data_ptr()), 96, 4096, 96, C.c_void_p(out.data_ptr()), 0, st) == 0
+    torch.cuda.synchronize()
+    assert torch.allclose(out, X.sum(0), rtol=1e-4, atol=1e-3)
+
+
 def test_train_step_bf16_single_timestep_and_many_tiles():
     """Edge shapes of the tensor-core scans: a one-step time axis (T = 1: no recurrent MMA at all, B*T = 64 keeps the
     tensor-core path) and a batch whose time-axis tiles exceed one wave of clusters (B = 36 at T = 16)."""
