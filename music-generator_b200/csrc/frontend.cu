@@ -289,6 +289,116 @@ __global__ void __launch_bounds__(256) layer_input_kernel(
   }
 }
 
+// Fast path of the same function for the shapes the engine launches: both dropout sites in byte mode (training) or
+// both off (generation), 16-bit operands, rows laid out b-major without gaps (h row = h_row0 + row, chosen row =
+// row), Uprev a multiple of 8.  One thread per 8-feature chunk over a flat (row, chunk) index -- no idle lanes
+// whatever ldA is --, 16-byte loads of h and of the style projection, 16-byte stores of A and A_lo, the byte test
+// of a mask word done on the word in place.  Same arithmetic, element by element, as layer_input_kernel.
+__device__ __forceinline__ uint4 pack8(const float v[8], __nv_bfloat16) {
+  uint4 u;
+  __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+  __nv_bfloat162 c = __floats2bfloat162_rn(v[4], v[5]), d = __floats2bfloat162_rn(v[6], v[7]);
+  u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
+  u.z = *reinterpret_cast<uint32_t*>(&c); u.w = *reinterpret_cast<uint32_t*>(&d);
+  return u;
+}
+__device__ __forceinline__ uint4 pack8(const float v[8], __half) {
+  uint4 u;
+  __half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], v[3]);
+  __half2 c = __floats2half2_rn(v[4], v[5]), d = __floats2half2_rn(v[6], v[7]);
+  u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
+  u.z = *reinterpret_cast<uint32_t*>(&c); u.w = *reinterpret_cast<uint32_t*>(&d);
+  return u;
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float r[8], __nv_bfloat16) {   // bf16 -> fp32 is a shift
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    r[2 * j] = __uint_as_float(w[j] << 16);
+    r[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000U);
+  }
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float r[8], __half) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
+    r[2 * j] = f.x; r[2 * j + 1] = f.y;
+  }
+}
+// multipliers of the 4 elements of one byte-mode mask word: byte j >= t ? scale : 0 (compared in place)
+__device__ __forceinline__ void mask_mul4(uint32_t w, uint32_t t, float scale, float m[4]) {
+  m[0] = ((w & 0xffU) >= t) ? scale : 0.f;
+  m[1] = ((w & 0xff00U) >= (t << 8)) ? scale : 0.f;
+  m[2] = ((w & 0xff0000U) >= (t << 16)) ? scale : 0.f;
+  m[3] = (w >= (t << 24)) ? scale : 0.f;
+}
+
+template <typename TA, bool CHOSEN, bool DROP>
+__global__ void __launch_bounds__(256) layer_input_fast_kernel(
+    const float* __restrict__ h_prev, uint32_t Uprev, const float* __restrict__ sp, uint32_t F, dj_dropout d_h,
+    dj_dropout d_sp, const float* __restrict__ chosen_in, dj_dropout d_chosen, uint32_t rows, uint32_t ld8,
+    uint32_t ld8_magic, TA* __restrict__ A, TA* __restrict__ Alo) {
+  dj_resolve(d_h); dj_resolve(d_sp); dj_resolve(d_chosen);
+  const uint32_t ld4 = (F + 3) & ~3u, total = rows * ld8;
+  const uint32_t th = d_h.thr >> 24, ts = d_sp.thr >> 24;
+  for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256) {
+    const uint32_t row = __umulhi(i, ld8_magic);        // i / ld8 (exact: host checks total * (magic * ld8 - 2^32) < 2^32)
+    const uint32_t f8 = (i - row * ld8) * 8;
+    const uint32_t bt = row / N_, n = row - bt * N_;
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (f8 < Uprev) {
+      const float4 h0 = __ldg(reinterpret_cast<const float4*>(h_prev + (size_t)row * Uprev + f8));
+      const float4 h1 = __ldg(reinterpret_cast<const float4*>(h_prev + (size_t)row * Uprev + f8 + 4));
+      v[0] = h0.x; v[1] = h0.y; v[2] = h0.z; v[3] = h0.w; v[4] = h1.x; v[5] = h1.y; v[6] = h1.z; v[7] = h1.w;
+      if (DROP) {
+        const uint32_t q = (row * Uprev + f8) >> 2;
+        float m[8];
+        mask_mul4(dj_mask_word(d_h.key, q), th, d_h.scale, m);
+        mask_mul4(dj_mask_word(d_h.key, q + 1), th, d_h.scale, m + 4);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] *= m[j];
+      }
+    } else if (CHOSEN && f8 == Uprev && n > 0) {
+      // shift_chosen (model.py:101): previous NOTE of the same timestep, 3 channels
+      const float* cr = chosen_in + (size_t)(row - 1) * NU_;
+#pragma unroll
+      for (int c = 0; c < NU_; ++c) v[c] = __ldg(cr + c) * dj_dropmul(d_chosen, (row - 1) * 4u + c);
+    }
+    if (f8 < F) {
+      float s[8], m[8];
+      if (!CHOSEN) {      // F == Uprev: whole, 16-byte aligned chunks
+        const float4 s0 = __ldg(reinterpret_cast<const float4*>(sp + (size_t)bt * F + f8));
+        const float4 s1 = __ldg(reinterpret_cast<const float4*>(sp + (size_t)bt * F + f8 + 4));
+        s[0] = s0.x; s[1] = s0.y; s[2] = s0.z; s[3] = s0.w; s[4] = s1.x; s[5] = s1.y; s[6] = s1.z; s[7] = s1.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s[j] = (f8 + j < F) ? __ldg(sp + (size_t)bt * F + f8 + j) : 0.f;
+      }
+      if (DROP) {
+        const uint32_t q = (row * ld4 + f8) >> 2;
+        mask_mul4(dj_mask_word(d_sp.key, q), ts, d_sp.scale, m);
+        mask_mul4(dj_mask_word(d_sp.key, q + 1), ts, d_sp.scale, m + 4);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m[j] = 1.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (!CHOSEN || f8 + j < F) v[j] = fmaf(s[j], m[j], v[j]);
+    }
+    const uint4 hi = pack8(v, TA());
+    *reinterpret_cast<uint4*>(A + (size_t)row * (ld8 * 8) + f8) = hi;
+    if (Alo != nullptr) {   // residual against the rounded values just packed (no second rounding of v)
+      float r[8];
+      unpack8(hi, r, TA());
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] = v[j] - r[j];
+      *reinterpret_cast<uint4*>(Alo + (size_t)row * (ld8 * 8) + f8) = pack8(r, TA());
+    }
+  }
+}
+
 __global__ void mask_materialize_kernel(dj_dropout d, int64_t rows, int F, float* __restrict__ out) {
   dj_resolve(d);
   const int ld4 = (F + 3) & ~3;
@@ -451,9 +561,42 @@ extern "C" int dj_layer_input(const float* h_prev, int Uprev, int64_t h_row0, in
   DJ_CHECK_ARG(F == Uprev || (chosen_in && F == Uprev + NU_), "dj_layer_input: F must be Uprev or Uprev+3 with chosen");
   DJ_CHECK_ARG(ldA >= ((F + 3) & ~3) && ldA % 8 == 0, "dj_layer_input: ldA %d too small or not a multiple of 8", ldA);
   DJ_CHECK_ARG((int64_t)B * T * N_ * ((F + 3) & ~3) < (int64_t)4294967296LL, "dj_layer_input: batch too large");
+  cudaStream_t st = (cudaStream_t)stream;
+  {
+    // fast path (what the engine launches): see layer_input_fast_kernel
+    const bool drop = d_h.mode == 1 && d_sp.mode == 1, nodrop = d_h.mode == 0 && d_sp.mode == 0;
+    const uint32_t rows = (uint32_t)B * T * N_, ld8 = (uint32_t)ldA / 8;
+    const uint64_t magic = ((1ull << 32) + ld8 - 1) / ld8, total8 = (uint64_t)rows * ld8;
+    const bool exact = total8 < (1ull << 32) && total8 * (magic * ld8 - (1ull << 32)) < (1ull << 32) && magic < (1ull << 32);
+    const bool dense = h_b_rows == (int64_t)T * N_ && (chosen_in == nullptr || chosen_bstride == (int64_t)T * N_ * NU_);
+    const bool aligned = Uprev % 8 == 0 && ((uintptr_t)h_prev % 16 == 0) && ((uintptr_t)sp % 16 == 0) &&
+                         ((uintptr_t)A % 16 == 0) && ((uintptr_t)A_lo % 16 == 0);
+    if ((drop || nodrop) && exact && dense && aligned && (a_dtype == DJ_BF16 || a_dtype == DJ_F16) &&
+        (chosen_in != nullptr || F == Uprev)) {
+      const float* hp = h_prev + h_row0 * Uprev;
+      const int grid = grid_for((int64_t)total8, 256, dj_num_sms() * 8);
+#define DJ_LI_FAST(TA, CH, DR)                                                                                      \
+  layer_input_fast_kernel<TA, CH, DR><<<grid, 256, 0, st>>>(hp, (uint32_t)Uprev, sp, (uint32_t)F, d_h, d_sp, chosen_in, \
+                                                            d_chosen, rows, ld8, (uint32_t)magic, (TA*)A, (TA*)A_lo)
+      const bool ch = chosen_in != nullptr;
+      if (a_dtype == DJ_BF16) {
+        if (ch && drop) DJ_LI_FAST(__nv_bfloat16, true, true);
+        else if (ch) DJ_LI_FAST(__nv_bfloat16, true, false);
+        else if (drop) DJ_LI_FAST(__nv_bfloat16, false, true);
+        else DJ_LI_FAST(__nv_bfloat16, false, false);
+      } else {
+        if (ch && drop) DJ_LI_FAST(__half, true, true);
+        else if (ch) DJ_LI_FAST(__half, true, false);
+        else if (drop) DJ_LI_FAST(__half, false, true);
+        else DJ_LI_FAST(__half, false, false);
+      }
+#undef DJ_LI_FAST
+      DJ_LAUNCH_CHECK();
+      return 0;
+    }
+  }
   const int64_t total = (int64_t)B * T * N_ * 32;   // one warp per row
   const int grid = grid_for(total, 256, dj_num_sms() * 16);
-  cudaStream_t st = (cudaStream_t)stream;
   if (a_dtype == DJ_F32)
     layer_input_kernel<float><<<grid, 256, 0, st>>>(h_prev, Uprev, h_row0, h_b_rows, d_h, sp, F, d_sp,
                                                     chosen_in, chosen_bstride, d_chosen, B, T, (float*)A, (float*)nullptr, ldA);

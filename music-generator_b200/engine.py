@@ -578,6 +578,12 @@ class Engine:
             chain.wait_stream(main)           # forward, zeroed gradients
         dY, ldY = ws.dXtop, cfg.note_axis_units
         first_style = True
+        if bf16 and ws.hprev[0].dtype == torch.float16:
+            # the recurrence kept h_{step-1} in half; dZ is bf16 and tcgen05 kind::f16 cannot mix the two formats, so
+            # the buffers are converted in place (the forward pass is done with them) -- all four now, while this
+            # stream would otherwise wait for the first reverse scan, instead of one in front of each dU GEMM
+            for li in range(len(self.layers)):
+                self._call("dj_half_to_bf16_inplace", _ptr(ws.hprev[li]), M * self.layers[li]["U"], _stream())
         for li in (3, 2, 1, 0):
             L = self.layers[li]
             name, U, F, ld = L["name"], L["U"], L["F"], ws.ld[li]
@@ -614,10 +620,6 @@ class Engine:
             if bf16:
                 self._call("dj_wgrad_gemm_bf16", _ptr(ws.A[li]), ld, _ptr(dZ), U4, _ptr(G[f"{name}.lstm.W"]), U4,
                            F, U4, M, _stream())
-                if ws.hprev[li].dtype == torch.float16:
-                    # the recurrence kept h_{step-1} in half; dZ is bf16 and tcgen05 kind::f16 cannot mix the two
-                    # formats, so the buffer is converted in place (the forward pass is done with it)
-                    self._call("dj_half_to_bf16_inplace", _ptr(ws.hprev[li]), M * U, _stream())
                 self._call("dj_wgrad_gemm_bf16", _ptr(ws.hprev[li]), U, _ptr(dZ), U4, _ptr(G[f"{name}.lstm.U"]),
                            U4, U, U4, M, _stream())
             else:

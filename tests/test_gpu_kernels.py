@@ -385,3 +385,54 @@ def test_lstm_scan_bwd_tcgen05_matches_fp32_scan(lib, axis, B, T):
     scale = np.abs(b).max()
     assert np.abs(a - b).max() / scale < 0.03 and np.abs(a - b).mean() / np.abs(b).mean() < 0.02
     assert helpers.rel_err(dbt.cpu().numpy(), dbr.cpu().numpy()) < 0.02
+
+
+@pytest.mark.parametrize("Uprev,chosen", [(256, False), (256, True), (128, False), (512, True)])
+@pytest.mark.parametrize("dtype", ["bf16", "f16"])
+@pytest.mark.parametrize("drop", [True, False])
+def test_layer_input_fast_path_matches_numpy_twin(lib, Uprev, chosen, dtype, drop):
+    """dj_layer_input (model.py:85,101-106,113-117) in the shapes the engine launches -- 16-bit hi + lo operands,
+    byte-mode dropout on both sites or none -- against a NumPy restatement that replays the same masks: the hi
+    operand must be the correctly rounded value bit for bit, the lo operand the rounded residual; the fp32 output of
+    the generic kernel must equal the NumPy value exactly."""
+    from music_generator_b200 import _lib
+    B, T, N = 3, 5, 48
+    rows, F = B * T * N, Uprev + (3 if chosen else 0)
+    ld = (F + 31) // 32 * 32
+    g = torch.Generator().manual_seed(Uprev + chosen)
+    h = torch.randn(rows, Uprev, generator=g)
+    sp = torch.tanh(torch.randn(B * T, F, generator=g))
+    ch = (torch.rand(B, T, N, 3, generator=g) < 0.3).float()
+    seed = 77
+    dh = _lib.make_dropout(seed, 8, 0.5) if drop else _lib.NO_DROPOUT
+    ds = _lib.make_dropout(seed, 9, 0.5) if drop else _lib.NO_DROPOUT
+    dc = _lib.make_dropout(seed, 3, 0.2) if drop else _lib.NO_DROPOUT
+    one = np.float32(1)
+    mh = helpers.keep_mask(seed, 8, 0.5, rows, Uprev).astype(np.float32) * np.float32(2) if drop else one
+    ms = helpers.keep_mask(seed, 9, 0.5, rows, F).astype(np.float32) * np.float32(2) if drop else one
+    mc = helpers.keep_mask(seed, 3, 0.2, rows, 3).astype(np.float32) * np.float32(1.25) if drop else one
+    ref = np.zeros((rows, ld), np.float32)
+    ref[:, :Uprev] = h.numpy() * mh
+    if chosen:
+        c = (ch.numpy().reshape(rows, 3) * mc).astype(np.float32)
+        sh = np.zeros_like(c)
+        sh[1:] = c[:-1]
+        sh[np.arange(rows) % N == 0] = 0          # note 0 has no previous note
+        ref[:, Uprev:F] = sh
+    ref[:, :F] += np.repeat(sp.numpy(), N, axis=0) * ms
+    hd, spd, chd = h.cuda(), sp.cuda(), ch.cuda()
+    out32 = torch.full((rows, ld), 7.0, device="cuda")
+    args = lambda A, Alo, dt: (P(hd), Uprev, 0, T * N, dh, P(spd), F, ds, P(chd) if chosen else None, T * N * 3,
+                               dc, B, T, P(A), None if Alo is None else P(Alo), ld, dt, None)
+    _lib.check(lib.dj_layer_input(*args(out32, None, 0)))
+    tdt, code = (torch.bfloat16, 1) if dtype == "bf16" else (torch.float16, 2)
+    hi = torch.full((rows, ld), 7.0, device="cuda", dtype=tdt)
+    lo = torch.full((rows, ld), 7.0, device="cuda", dtype=tdt)
+    _lib.check(lib.dj_layer_input(*args(hi, lo, code)))
+    torch.cuda.synchronize()
+    assert np.array_equal(out32.cpu().numpy(), ref)
+    r = torch.from_numpy(ref)
+    want_hi = r.to(tdt)
+    want_lo = (r - want_hi.float()).to(tdt)
+    assert torch.equal(hi.cpu(), want_hi)
+    assert torch.equal(lo.cpu(), want_lo)
