@@ -8,6 +8,7 @@ runs in libdeepj_sm100.so through Engine.
 from __future__ import annotations
 
 import os
+import re
 from typing import Callable, List, Optional, Sequence
 
 import numpy as np
@@ -23,43 +24,75 @@ def _dev(eng: Engine, a) -> torch.Tensor:
     return torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32)).to(eng.dev, non_blocking=True)
 
 
-def _have_h5py() -> bool:
-    try:
-        import h5py  # noqa: F401
-        return True
-    except Exception:
-        return False
-
-
-# Keras auto-names of the reference's layers in model.py creation order (derived from the instantiation
-# order, unverifiable here: neither Keras nor a reference .h5 exists in this environment) -> our tensor prefixes.
-KERAS_H5_MAP = [("style", "style", ("W", "b")), ("conv1d_1", "conv", ("W", "b")),
-                ("dense_1", "time0.sd", ("W", "b")), ("lstm_1", "time0.lstm", ("W", "U", "b")),
-                ("dense_2", "time1.sd", ("W", "b")), ("lstm_2", "time1.lstm", ("W", "U", "b")),
-                ("dense_3", "note0.sd", ("W", "b")), ("lstm_3", "note0.lstm", ("W", "U", "b")),
-                ("dense_4", "note1.sd", ("W", "b")), ("lstm_4", "note1.lstm", ("W", "U", "b")),
+# Keras auto-names of the reference's weighted layers, in model.py creation order -> our tensor prefixes.
+# TimeDistributed wrappers own the variables of the layer they wrap (`time_distributed_4/kernel:0` is lstm_1's kernel).
+# Used for WRITING; reading identifies layers by their tensor shapes, which are unique in this model, so a file whose
+# auto-names are shifted (a second build_models() in the same Keras session) still loads.
+KERAS_LAYERS = [("style", "style", ("W", "b")), ("time_distributed_1", "conv", ("W", "b")),
+                ("dense_1", "time0.sd", ("W", "b")), ("time_distributed_4", "time0.lstm", ("W", "U", "b")),
+                ("dense_2", "time1.sd", ("W", "b")), ("time_distributed_6", "time1.lstm", ("W", "U", "b")),
+                ("dense_3", "note0.sd", ("W", "b")), ("time_distributed_8", "note0.lstm", ("W", "U", "b")),
+                ("dense_4", "note1.sd", ("W", "b")), ("time_distributed_10", "note1.lstm", ("W", "U", "b")),
                 ("note_dense", "note_dense", ("W", "b")), ("volume_dense", "volume_dense", ("W", "b"))]
+_KERAS_VAR = {"W": "kernel:0", "U": "recurrent_kernel:0", "b": "bias:0"}
 
 
-def _read_keras_h5(f, shapes):
-    """Keras `save_weights` layout: one group per layer holding `kernel:0` / `recurrent_kernel:0` / `bias:0` (possibly one
-    level down, under the layer's own name; TimeDistributed wrappers carry the wrapped layer's weights)."""
-    suffix = {"W": "kernel", "U": "recurrent_kernel", "b": "bias"}
-    found = {}
+def keras_h5_tree(state) -> dict:
+    """The 28 tensors as the tree `keras.Model.save_weights` writes (Keras 2.0-2.1, TensorFlow backend): root
+    attributes `layer_names`, `backend`, `keras_version`; one group per layer with `weight_names` and the
+    variables below it under their full TensorFlow names (`dense_1/kernel:0` -> group dense_1, dataset kernel:0)."""
+    tree = {"@attrs": {"layer_names": [k for k, _, _ in KERAS_LAYERS], "backend": b"tensorflow",
+                       "keras_version": b"2.0.8"}}
+    for layer, prefix, parts in KERAS_LAYERS:
+        names = [f"{layer}/{_KERAS_VAR[p]}" for p in parts]
+        tree[layer] = {"@attrs": {"weight_names": names},
+                       layer: {_KERAS_VAR[p]: np.asarray(state[f"{prefix}.{p}"], dtype=np.float32) for p in parts}}
+    return tree
 
-    def visit(name, obj):
-        if hasattr(obj, "shape"):
-            found[name] = obj
-    f.visititems(visit)
-    state = {}
-    for layer, prefix, parts in KERAS_H5_MAP:
-        for p in parts:
-            want = f"{prefix}.{p}"
-            hits = [n for n in found if layer in n.split("/") and n.split("/")[-1].startswith(suffix[p])
-                    and tuple(found[n].shape) == tuple(shapes[want])]
-            if len(hits) != 1:
-                raise KeyError(f"cannot locate {want} (Keras layer {layer}) in the HDF5 file: {hits}")
-            state[want] = np.asarray(found[hits[0]])
+
+def read_keras_h5(f, shapes):
+    """Weights from a Keras HDF5 file: `save_weights` layout (layer groups at the root) or a full `model.save` /
+    `ModelCheckpoint` file (the same below `model_weights`), as keras.engine.topology.load_weights_from_hdf5_group
+    reads them.  Each layer group's variables are taken in `weight_names` order; the layer is identified by the shapes
+    of its variables -- (kernel[, recurrent_kernel], bias) -- which are distinct for all 12 weighted layers of
+    model.py, with the numeric suffix of the auto-name as the tie-break.  Also reads this package's round-1 flat
+    layout (one dataset per tensor name)."""
+    from . import h5lite
+    if all(k in f for k in shapes):
+        return {k: f[k].read() for k in shapes}
+    root = f["model_weights"] if ("layer_names" not in f.attrs and "model_weights" in f) else f
+    layers = []
+    for lname in root.keys():
+        g = root[lname]
+        if not isinstance(g, h5lite.Group):
+            continue
+        found = {}
+        g.visititems(lambda n, o: found.__setitem__(n[len(g.name) + 1:], o) if isinstance(o, h5lite.Dataset) else None)
+        if not found:
+            continue
+        wn = g.attrs.get("weight_names")
+        if wn is not None and len(np.atleast_1d(wn)) == len(found):
+            order = [w.decode("utf8") if isinstance(w, bytes) else str(w) for w in np.atleast_1d(wn)]
+        else:
+            rank = lambda n: (0 if "recurrent" not in n and "kernel" in n else 1 if "recurrent" in n else 2, n)
+            order = sorted(found, key=rank)
+        if any(o not in found for o in order):
+            raise KeyError(f"layer {lname}: weight_names {order} do not match the datasets {sorted(found)}")
+        m = re.search(r"_(\d+)$", lname)
+        layers.append((int(m.group(1)) if m else 0, lname, [found[o] for o in order]))
+    state, used = {}, set()
+    for _, prefix, parts in KERAS_LAYERS:
+        want = [tuple(shapes[f"{prefix}.{p}"]) for p in parts]
+        hits = [L for L in layers if [tuple(d.shape) for d in L[2]] == want and L[1] not in used]
+        named = [L for L in hits if L[1] == prefix]            # style / note_dense / volume_dense carry explicit names
+        if named:
+            hits = named
+        if not hits:
+            raise KeyError(f"no layer with variables of shapes {want} (for {prefix}) in the HDF5 file")
+        L = sorted(hits)[0]
+        used.add(L[1])
+        for p, d in zip(parts, L[2]):
+            state[f"{prefix}.{p}"] = d.read().astype(np.float32)
     return state
 
 
@@ -72,41 +105,29 @@ class _Base:
     def __init__(self, eng: Engine, name: str):
         self.engine, self.name = eng, name
 
-    # -- weights.  The reference saves Keras HDF5 (`out/model.h5`, train.py:23 / util.py:19).  With h5py installed a
-    # path ending in .h5 is written / read as an HDF5 file with one dataset per tensor (Keras layouts, the 28 names of
-    # SURVEY 8a; reading also accepts Keras' own layer-group layout through KERAS_H5_MAP).  Without h5py (this image)
-    # nothing is disguised: the weights go to the SAME path with the extension .npz, and loading looks there.
-    @staticmethod
-    def weights_path(path: str) -> str:
-        if path.endswith(".h5") and not _have_h5py():
-            return path[:-3] + ".npz"
-        return path
-
+    # -- weights.  The reference saves Keras HDF5 (`out/model.h5`, train.py:23 / util.py:19).  A path ending in .h5 is
+    # written as a Keras `save_weights` file and read as one (or as a full `model.save` file) through h5lite, this
+    # package's own HDF5 subset -- h5py is not needed.  Any other extension is an .npz keyed by tensor name.
     def save_weights(self, path: str) -> None:
-        path = self.weights_path(path)
+        from . import h5lite
         os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
         state = self.engine.get_params()
-        if path.endswith(".h5"):
-            import h5py
-            with h5py.File(path, "w") as f:
-                for k, v in state.items():
-                    f.create_dataset(k, data=v)
-                f.attrs["format"] = "deepj_b200 flat tensors (Keras layouts)"
+        if path.endswith((".h5", ".hdf5")):
+            h5lite.write(path, keras_h5_tree(state))
             return
         with open(path, "wb") as f:
             np.savez(f, **state)
 
     def load_weights(self, path: str) -> None:
-        path = self.weights_path(path)
-        if path.endswith(".h5"):
-            import h5py
-            with h5py.File(path, "r") as f:
-                if all(k in f for k in self.engine.shapes):
-                    state = {k: np.asarray(f[k]) for k in self.engine.shapes}
-                else:
-                    state = _read_keras_h5(f, self.engine.shapes)
-            self.engine.set_params(state)
-            return
+        from . import h5lite
+        if path.endswith((".h5", ".hdf5")):
+            legacy = path[:path.rfind(".")] + ".npz"       # round 1 wrote .npz beside the .h5 name
+            if not os.path.exists(path) and os.path.exists(legacy):
+                path = legacy
+            else:
+                with h5lite.File(path) as f:
+                    self.engine.set_params(read_keras_h5(f, self.engine.shapes))
+                return
         with np.load(path) as z:
             self.engine.set_params({k: z[k] for k in self.engine.shapes})
 

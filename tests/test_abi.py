@@ -97,30 +97,3 @@ def test_engine_refuses_to_run_without_cuda():
     from music_generator_b200.engine import Engine
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         Engine()
-
-
-def test_weight_files_keep_an_honest_extension_and_keras_h5_layout_maps():
-    """Without h5py `out/model.h5` is not written as a disguised .npz: the path becomes out/model.npz.  The gated HDF5
-    reader maps Keras' layer groups (auto-names in model.py creation order) onto the 28 tensors."""
-    import numpy as np
-    from music_generator_b200 import keras_like as K
-    from music_generator_b200.config import ModelConfig, param_shapes
-    if not K._have_h5py():
-        assert K._Base.weights_path("out/model.h5") == "out/model.npz"
-    assert K._Base.weights_path("out/w.npz") == "out/w.npz"
-    shapes = param_shapes(ModelConfig())
-    rs = np.random.RandomState(0)
-    want = {k: rs.rand(*shp).astype(np.float32) for k, shp in shapes.items()}
-    suffix = {"W": "kernel:0", "U": "recurrent_kernel:0", "b": "bias:0"}
-    tree = {}
-    for layer, prefix, parts in K.KERAS_H5_MAP:
-        outer = layer if not layer.startswith(("lstm", "conv1d")) else f"time_distributed_{layer[-1]}"
-        for p in parts:                      # TimeDistributed wrappers: group/<wrapped layer>/<weight>
-            tree[f"{outer}/{layer}/{suffix[p]}"] = want[f"{prefix}.{p}"]
-
-    class FakeH5:
-        def visititems(self, fn):
-            for name, arr in tree.items():
-                fn(name, arr)
-    got = K._read_keras_h5(FakeH5(), shapes)
-    assert set(got) == set(shapes) and all(np.array_equal(got[k], want[k]) for k in shapes)

@@ -369,6 +369,25 @@ def test_keras_like_predict_api():
     assert np.abs(out - oref.numpy()).max() < 2e-5
 
 
+def test_weights_travel_as_keras_hdf5(tmp_path):
+    """train.py:23 / util.py:19: `save_weights('out/model.h5')` writes a Keras HDF5 weights file (h5lite) and
+    `load_weights` restores the 28 tensors bit for bit into all three models (they share the weights)."""
+    import model as M
+    from music_generator_b200 import h5lite
+    models = M.build_models(precision="fp32")
+    before = models[0].engine.get_params()
+    path = str(tmp_path / "model.h5")
+    models[0].save_weights(path)
+    assert open(path, "rb").read(8) == h5lite.SIG
+    models[0].engine.init_params(123)
+    assert any(not np.array_equal(before[k], v) for k, v in models[0].engine.get_params().items())
+    models[0].load_weights(path)
+    after = models[2].engine.get_params()
+    assert all(np.array_equal(before[k], after[k]) for k in before)
+    with h5lite.File(path) as f:
+        assert f["time_distributed_8/time_distributed_8/kernel:0"].shape == (259, 512)
+
+
 def test_fit_pipeline_equals_per_batch_training():
     """fit() (pinned staging, async H2D on a copy stream, loss read back once per epoch) must train exactly like a
     loop of train_on_batch over the same shuffled mini-batches, including the short last batch."""
