@@ -143,6 +143,49 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
       "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accum)
       : "memory");
 }
+// ---- CTA pairs (cta_group::2): the two CTAs of a cluster with ranks 2p, 2p+1 run ONE MMA of M = 128 or 256; each
+// holds its own half of A's rows and of B's rows (= N columns) in its shared memory at the same offsets, and gets its
+// half of D's rows in its tensor memory.  For M = 128 a CTA's 64 rows sit in lanes 0..63 for the columns of the
+// leader's B half and in lanes 64..127 for the columns of the peer's B half, N/2 tensor-memory columns in all
+// (checked on B200 by tools/micro/pair_mma.cu).  Both CTAs allocate / free; only the even-ranked leader issues.
+__device__ __forceinline__ void tmem_alloc2(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// commit of the pair's MMAs: arrives on the barrier at the same offset in every CTA of `cta_mask` (cluster ranks)
+__device__ __forceinline__ void umma2_commit_mc(uint32_t bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(bar),
+               "h"(cta_mask)
+               : "memory");
+}
+// TMA loads of a pair: with .cta_group::2 the mbarrier operand may name the barrier of the destination CTA's peer.
+// Bit 24 of a shared::cluster address is the low bit of the CTA rank (checked by tools/micro/pair_mma.cu), so clearing
+// it makes every load -- also the multicast copies landing in odd CTAs -- signal the barrier of the pair's LEADER.
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::"r"(dst),
+      "l"(map), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_mc_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                                    int c3, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+      "[%0], [%1, {%3, %4, %5, %6}], [%2], %7;\n" ::"r"(dst),
+      "l"(map), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(cta_mask)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t v[16]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "

@@ -762,7 +762,10 @@ scan_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
     const int sh = lane >> 4;
     const uint32_t col = UPC * rank + 16 * q + (lane & 15);       // global hidden unit
     const bool active = (16 * q < UPC);                            // UPC = 32: only TMEM quarters 0,1 hold real rows
-    const uint32_t sstr = (uint32_t)map.seq_stride, tstr = (uint32_t)map.step_stride;
+    // the row strides of the canonical layout are fixed per axis (the ABI accepts only these two maps), so every
+    // per-cell offset below is an immediate off ONE base address per array, half-tile and step
+    constexpr uint32_t sstr = AXIS_TIME ? 1u : 48u, tstr = AXIS_TIME ? 48u : 1u;
+    const uint32_t ystep = sstr * ldY;                             // dY floats between consecutive sequences
     uint32_t row00[NS];                                            // row of this lane's first sequence of each half, step 0
 #pragma unroll
     for (int hf = 0; hf < NS; ++hf)   // a half-tile never straddles a batch element
@@ -777,12 +780,15 @@ scan_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
       const uint32_t tp = (t > 0) ? (uint32_t)(t - 1) : 0u;      // clamped: row of c_{t-1} (ignored at t == 0)
       const int ls = SHARED ? 0 : hf;
       if (!active) return;
+      const uint32_t r0 = row00[hf] + (uint32_t)t * tstr;
+      const uint2* gp = G16 + (size_t)r0 * U + col;
+      const float* cp = Cst + (size_t)(row00[hf] + tp * tstr) * U + col;
+      const float* yp = dY + (size_t)r0 * ldY + col;
 #pragma unroll
       for (int j = 0; j < CPL; ++j) {
-        const uint32_t r = row00[hf] + j * sstr + (uint32_t)t * tstr;
-        gv[ls][j] = __ldg(G16 + (size_t)r * U + col);
-        cpv[ls][j] = __ldg(Cst + (size_t)(row00[hf] + j * sstr + tp * tstr) * U + col);
-        dyv[ls][j] = __ldg(dY + (size_t)r * ldY + col);
+        gv[ls][j] = __ldg(gp + (size_t)j * (sstr * U));
+        cpv[ls][j] = __ldg(cp + (size_t)j * (sstr * U));
+        dyv[ls][j] = __ldg(yp + (size_t)j * ystep);
       }
     };
     // pull the lines issue_loads(hf, t) will read into L2: per cell the 16 lanes of a unit group read 256 B of gates
@@ -790,13 +796,16 @@ scan_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
     auto prefetch_l2 = [&](int hf, int t) {
       const uint32_t tp = (t > 0) ? (uint32_t)(t - 1) : 0u;
       if (!active) return;
+      const uint32_t r0 = row00[hf] + (uint32_t)t * tstr;
+      const uint2* gp = G16 + (size_t)r0 * U + col;
+      const float* cp = Cst + (size_t)(row00[hf] + tp * tstr) * U + col;
+      const float* yp = dY + (size_t)r0 * ldY + col;
 #pragma unroll
       for (int j = 0; j < CPL; ++j) {
-        const uint32_t r = row00[hf] + j * sstr + (uint32_t)t * tstr;
-        if ((lane & 15) == 0) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(G16 + (size_t)r * U + col));
+        if ((lane & 15) == 0) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(gp + (size_t)j * (sstr * U)));
         if ((lane & 15) == 0) {
-          asm volatile("prefetch.global.L2 [%0];\n" ::"l"(Cst + (size_t)(row00[hf] + j * sstr + tp * tstr) * U + col));
-          asm volatile("prefetch.global.L2 [%0];\n" ::"l"(dY + (size_t)r * ldY + col));
+          asm volatile("prefetch.global.L2 [%0];\n" ::"l"(cp + (size_t)j * (sstr * U)));
+          asm volatile("prefetch.global.L2 [%0];\n" ::"l"(yp + (size_t)j * ystep));
         }
       }
     };
@@ -805,7 +814,7 @@ scan_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
 #pragma unroll
       for (int j = 0; j < CPL; ++j) {
         dcn[hf][j] = 0.f;
-        ct[hf][j] = active ? Cst[(size_t)(row00[hf] + j * sstr + (uint32_t)(steps - 1) * tstr) * U + col] : 0.f;
+        ct[hf][j] = active ? Cst[(size_t)(row00[hf] + (uint32_t)(steps - 1) * tstr) * U + col + (size_t)j * (sstr * U)] : 0.f;
       }
     }
 #pragma unroll
@@ -839,15 +848,17 @@ scan_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
 #pragma unroll
           for (int j = 0; j < CPL; ++j) dh[j] = 0.f;
         }
+        const uint32_t r0 = row00[hf] + (uint32_t)t * tstr;
+        const uint32_t e0 = r0 * U + col;               // dropout element index of the first cell (32-bit by contract)
+        __nv_bfloat16* const zp = dZ + (size_t)r0 * (4 * U) + 4 * col;
 #pragma unroll
         for (int j = 0; j < CPL; ++j) {
           if (!active) break;
-          const uint32_t r = row00[hf] + j * sstr + (uint32_t)t * tstr;
           constexpr int LS_ = SHARED ? 0 : -1;
           const int ls = (LS_ == 0) ? 0 : hf;
           const float4 g4 = unpack_gates16(gv[ls][j]);
           const float cprev = (t > 0) ? cpv[ls][j] : 0.f;
-          const float dht = fmaf(dyv[ls][j], dj_dropmul(d_y, r * U + col), dh[j]);
+          const float dht = fmaf(dyv[ls][j], dj_dropmul(d_y, e0 + (uint32_t)j * (sstr * U)), dh[j]);
           const float tc = fast_tanh(ct[hf][j]);
           const float d_o = dht * tc;
           const float dc = fmaf(dht * g4.w, 1.f - tc * tc, dcn[hf][j]);
@@ -860,7 +871,7 @@ scan_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
           uint2 pk;
           pk.x = *reinterpret_cast<uint32_t*>(&lo);
           pk.y = *reinterpret_cast<uint32_t*>(&hi);
-          *reinterpret_cast<uint2*>(dZ + (size_t)r * (4 * U) + 4 * col) = pk;
+          *reinterpret_cast<uint2*>(zp + (size_t)j * (sstr * 4 * U)) = pk;
           dbacc[0] += dz0; dbacc[1] += dz1; dbacc[2] += dz2; dbacc[3] += dz3;
           ct[hf][j] = cprev;                // c_{t-1} is the cell state of the next (earlier) step
         }
@@ -896,6 +907,314 @@ scan_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
   cluster.sync();
   if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
 }
+
+#ifdef DJ_EXPERIMENTS
+// ---------------------------------------------------------------------------
+// reverse scan on CTA PAIRS (tcgen05.mma.cta_group::2).
+// The reverse scan above is bound by every SM ingesting the whole dz half-tile each step (2 KB per sequence), so a
+// larger tile does not help it.  Here the C = U/64 CTAs of a cluster form C/2 pairs; a pair runs ONE M = 128 MMA
+// (each CTA its own 64 rows of U), and the B operand -- the dz half-tile -- is split between the two CTAs of a pair
+// by sequence: CTA 2p stages sequences [0, NH) of the half-tile, CTA 2p+1 sequences [NH, 2 NH).  Each CTA therefore
+// stages and ingests HALF of what it did, so a tile twice as large (96 time-axis sequences = two batch elements,
+// 64 note-axis sequences) costs the same shared memory and the same ingest per step, and a layer that needed two
+// waves of clusters runs as one.  Per half-step:
+//   epilogue --done[hf]--> issuer (every CTA): wait free[hf] (all pairs have read the previous round's tiles), two
+//   multicast TMAs of this CTA's own dz columns (sequences [0,NH) -> the even CTAs, [NH,2NH) -> the odd CTAs)
+//   --> z[hf] of the destination pair's LEADER (cta_group::2 TMA: loads landing in the odd CTA signal the even one, so
+//   nothing is forwarded); the leader issues the pair's 4U/16 MMAs and commits to acc[hf] of its pair and to free[hf]
+//   of every CTA.
+// Accumulator (M = 128 pair layout, dj_tc.cuh): unit u of this CTA in lane u (sequences of the leader's half) and
+// lane 64 + u (the peer's half), columns [hf*NH, +NH).  The 8 epilogue warps: quarter q = lanes [32q, +32) -> units
+// 32*(q&1) + lane, sequence side q>>1; the two warps of a quarter split the NH columns.  Every lane owns CPL = NH/2
+// cells per half-tile; one operand set (gates, c, dY of the NEXT epilogue in program order) is held in registers.
+// ---------------------------------------------------------------------------
+template <int U, int BS>
+struct TcBwdPairSmem {
+  static constexpr int A_BYTES = 64 * 4 * U * 2;
+  static constexpr int B_BYTES = (BS / 2) * 4 * U * 2;      // two half-tiles x NH = BS/4 sequences x 4U columns
+  static constexpr int A_OFF = 0, B_OFF = A_BYTES, BAR_OFF = A_BYTES + B_BYTES;
+  static constexpr int TOTAL = BAR_OFF + 128 + 1024;
+};
+
+// DIRECT: operand loads signal the leader's barriers (cta_group::2 TMA); else the odd CTA waits for its own half and
+// forwards one remote arrive to its leader (measured faster for the single-pair note-axis clusters).
+template <int U, int BS, bool AXIS_TIME, int LSN, bool DIRECT>
+__global__ void __launch_bounds__(TCB_THREADS, (U == 128) ? 2 : 1)
+scan_tc_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmZ,
+                        const uint2* __restrict__ G16, const float* __restrict__ Cst, const float* __restrict__ dY,
+                        uint32_t ldY, dj_dropout d_y, __nv_bfloat16* __restrict__ dZ, float* __restrict__ db,
+                        int steps, TcMap map, int hard, float* __restrict__ db_part) {
+  dj_resolve(d_y);
+  constexpr int C = U / 64;             // cluster size (CTAs), C/2 pairs
+  constexpr int KA = 4 * U / 64;        // K atoms of the contraction (gate columns)
+  constexpr int ATOM = 64 * 128;        // bytes of one resident K atom of U (64 rows x 128 B)
+  constexpr int KPC = KA / C;           // atoms each CTA multicasts per step
+  constexpr int HB = BS / 2;            // sequences per half-tile (= MMA N)
+  constexpr int NH = HB / 2;            // sequences of a half-tile staged in one CTA of a pair
+  constexpr int CPL = NH / 2;           // cells per lane and half-tile
+  constexpr int HALF_BYTES = KA * NH * 128;   // one CTA's share of a half-tile's B operand: [KA atoms][NH rows][128 B]
+  constexpr uint32_t TMEM_COLS = 2 * NH <= 32 ? 32 : 64;
+  // row strides of the canonical layout (row = (b*T + t)*48 + n) are fixed per axis, so every per-cell offset below
+  // is an immediate: time axis = sequences (b, n) one row apart, steps 48 rows apart; note axis the other way round
+  constexpr uint32_t SSTR = AXIS_TIME ? 1u : 48u, TSTR = AXIS_TIME ? 48u : 1u;
+  static_assert(C == 2 || C == 4, "one or two pairs per cluster");
+  static_assert(NH % 8 == 0 && CPL % 4 == 0 && 2 * NH <= 64, "whole swizzle groups; columns load in 4-column pieces");
+  static_assert(LSN == 1 || LSN == 2, "operand sets held in registers");
+  using SM = TcBwdPairSmem<U, BS>;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const uint32_t sbase = smem_u32(smem);
+  // barriers: a | z[2] | acc[2] | done[2] | free[2] | peer[2] | tmem slot
+  constexpr uint32_t BAR_Z = SM::BAR_OFF + 8, BAR_ACC = SM::BAR_OFF + 24, BAR_DONE = SM::BAR_OFF + 40,
+                     BAR_FREE = SM::BAR_OFF + 56, BAR_PEER = SM::BAR_OFF + 72;
+  const uint32_t bar_a = sbase + SM::BAR_OFF;
+  uint32_t* tmem_slot = (uint32_t*)(smem + SM::BAR_OFF + 88);
+
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const bool leader = (rank & 1) == 0;
+  const int tile = blockIdx.x / C;
+  const int warp = uniform_warp_id(), lane = threadIdx.x & 31;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      prefetch_tmap(&tmU); prefetch_tmap(&tmZ);
+      mbar_init(bar_a, 1);
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        mbar_init(sbase + BAR_Z + 8 * hf, 1); mbar_init(sbase + BAR_ACC + 8 * hf, 1);
+        mbar_init(sbase + BAR_DONE + 8 * hf, 8); mbar_init(sbase + BAR_FREE + 8 * hf, C / 2);
+        mbar_init(sbase + BAR_PEER + 8 * hf, 1);
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc2(smem_u32(tmem_slot), TMEM_COLS);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  cluster.sync();
+
+  if (warp == 0 || warp == 9) {
+    // ================= issuer of half-tile hf (every CTA multicasts; the leader of a pair also multiplies) =================
+    // Every operand load is a cta_group::2 TMA whose mbarrier operand names the LEADER's barrier (dj_tc.cuh), so the
+    // leader's a / z[hf] barriers count the bytes landing in both CTAs of the pair and the odd CTA never waits for,
+    // or forwards, anything.
+    const int hf = (warp == 0) ? 0 : 1;
+    if (warp == 0 && elect_one()) {   // resident A operand: rows [64*rank, +64) of U, all 4U columns
+      if (DIRECT) {
+        if (leader) mbar_expect_tx(bar_a, 2 * SM::A_BYTES);
+        for (int ja = 0; ja < KA; ++ja)
+          tma_load_2d_pair(sbase + SM::A_OFF + ja * ATOM, &tmU, bar_a, ja * 64, 64 * rank);
+      } else {
+        mbar_expect_tx(bar_a, SM::A_BYTES);
+        for (int ja = 0; ja < KA; ++ja)
+          tma_load_2d(sbase + SM::A_OFF + ja * ATOM, &tmU, bar_a, ja * 64, 64 * rank);
+      }
+    }
+    __syncwarp();
+    const uint32_t bar_z = sbase + BAR_Z + 8 * hf, bar_acc = sbase + BAR_ACC + 8 * hf,
+                   bar_done = sbase + BAR_DONE + 8 * hf, bar_free = sbase + BAR_FREE + 8 * hf,
+                   bar_peer = sbase + BAR_PEER + 8 * hf;
+    const uint32_t b_half = sbase + SM::B_OFF + hf * HALF_BYTES;
+    constexpr uint16_t MASK_ALL = (uint16_t)((1u << C) - 1u), MASK_EVEN = (uint16_t)(0x5555u & MASK_ALL),
+                       MASK_ODD = (uint16_t)(0xAAAAu & MASK_ALL);
+    const uint16_t mask_pair = (uint16_t)(3u << (rank & ~1));
+    // TMA coordinates of this half-tile: rows (time axis: one batch element per half-tile) / sequences (note axis)
+    int c_row0, c_outer;
+    if constexpr (AXIS_TIME) { c_row0 = 0; c_outer = tile * 2 + hf; }
+    else { c_row0 = tile * BS + hf * HB; c_outer = 0; }
+    uint32_t par = 0;
+    for (int t = steps - 1; t > 0; --t, par ^= 1u) {   // round: dz_t in, dh of step t-1 out
+      mbar_wait(bar_done, par);                         // this CTA's epilogue warps stored (and proxy-fenced) their dz_t
+      DJ_TR(t, 4 * hf + 0);
+      if (t != steps - 1) mbar_wait(bar_free, par ^ 1u);   // every pair's MMAs of the previous round have read their tiles
+      DJ_TR(t, 4 * hf + 1);
+      if (elect_one()) {
+        // this CTA's KPC atoms of dz_t, as {64 columns, NH rows, KPC atoms} boxes: sequences [0, NH) of the half-tile
+        // to the even CTAs, [NH, 2 NH) to the odd CTAs
+        const int r1 = AXIS_TIME ? t * 48 + c_row0 : c_row0, r3 = AXIS_TIME ? c_outer : t;
+        if (DIRECT) {
+          if (leader) mbar_expect_tx(bar_z, 2 * HALF_BYTES);
+          tma_load_4d_mc_pair(b_half + rank * KPC * (NH * 128), &tmZ, bar_z, 0, r1, rank * KPC, r3, MASK_EVEN);
+          tma_load_4d_mc_pair(b_half + rank * KPC * (NH * 128), &tmZ, bar_z, 0, r1 + NH, rank * KPC, r3, MASK_ODD);
+        } else {
+          mbar_expect_tx(bar_z, HALF_BYTES);
+          tma_load_4d_mc(b_half + rank * KPC * (NH * 128), &tmZ, bar_z, 0, r1, rank * KPC, r3, MASK_EVEN);
+          tma_load_4d_mc(b_half + rank * KPC * (NH * 128), &tmZ, bar_z, 0, r1 + NH, rank * KPC, r3, MASK_ODD);
+        }
+      }
+      __syncwarp();
+      if (!DIRECT && !leader) {       // forwarded signalling: the odd CTA tells its leader that its half landed
+        if (t == steps - 1) mbar_wait(bar_a, 0);
+        mbar_wait(bar_z, par);
+        if (elect_one()) mbar_arrive_remote(bar_peer, (uint32_t)(rank & ~1));   // release.cluster
+        __syncwarp();
+      }
+      if (leader) {
+        if (t == steps - 1) mbar_wait(bar_a, 0);
+        mbar_wait(bar_z, par);                          // all C CTAs' columns of the pair's sequences landed
+        if (!DIRECT) mbar_wait_cluster(bar_peer, par);
+        DJ_TR(t, 4 * hf + 2);
+        tc_fence_after();
+        if (elect_one()) {
+          constexpr uint32_t idesc = make_idesc(128, HB, 0, 0);
+          const uint64_t adesc0 = make_smem_desc(sbase + SM::A_OFF, 16, 1024);
+          const uint64_t bdesc0 = make_smem_desc(b_half, 16, 1024);
+#pragma unroll
+          for (int ja = 0; ja < KA; ++ja)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)   // descriptor start addresses are in 16-byte units
+              umma2_bf16(tmem_base + (uint32_t)(hf * NH), adesc0 + (uint64_t)((ja * ATOM + k * 32) >> 4),
+                         bdesc0 + (uint64_t)((ja * (NH * 128) + k * 32) >> 4), idesc, (ja | k) != 0);
+          umma2_commit_mc(bar_acc, mask_pair);          // -> the epilogues of both CTAs of the pair
+          umma2_commit_mc(bar_free, MASK_ALL);          // -> every CTA: this pair's operand tiles may be rewritten
+        }
+        __syncwarp();
+      }
+      DJ_TR(t, 4 * hf + 3);
+    }
+    // drain the last multicast arrives on this CTA's barriers before it can exit
+    if (steps > 1) mbar_wait(bar_free, par ^ 1u);
+  } else {
+    // ================= epilogue: gate derivatives =================
+    const int q = warp & 3;                          // TMEM lane quarter this warp may access
+    const int w2 = (warp - 1) >> 2;                  // which half of the NH columns
+    const int side = q >> 1;                         // sequences staged in the leader (0) or in the peer (1)
+    const uint32_t col = 64 * rank + 32 * (q & 1) + lane;          // global hidden unit
+    uint32_t row00[2];                               // row of this lane's first sequence of each half-tile, step 0
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf)
+      row00[hf] = (uint32_t)tc_row0(map, tile * BS + hf * HB) + (uint32_t)(side * NH + w2 * CPL) * SSTR;
+    const uint32_t ystep = SSTR * ldY;               // dY floats between consecutive sequences
+    float dbacc[4] = {0.f, 0.f, 0.f, 0.f};
+    float dcn[2][CPL], ct[2][CPL], cpv[LSN][CPL], dyv[LSN][CPL];
+    uint2 gv[LSN][CPL];                              // four gates of a cell as IEEE half
+    auto issue_loads = [&](int hf, int t) {          // everything of (half hf, step t) that does not depend on the recurrence
+      const int ls = (LSN == 1) ? 0 : hf;
+      const uint32_t r0 = row00[hf] + (uint32_t)t * TSTR;
+      const uint32_t rp = (t > 0) ? r0 - TSTR : r0;  // row of c_{t-1} (clamped; ignored at t == 0)
+      const uint2* gp = G16 + (size_t)r0 * U + col;
+      const float* cp = Cst + (size_t)rp * U + col;
+      const float* yp = dY + (size_t)r0 * ldY + col;
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) {
+        gv[ls][j] = __ldg(gp + (size_t)j * (SSTR * U));
+        cpv[ls][j] = __ldg(cp + (size_t)j * (SSTR * U));
+        dyv[ls][j] = __ldg(yp + (size_t)j * ystep);
+      }
+    };
+    // pull the lines issue_loads(hf, t) will read into L2: a warp reads 256 B of gates and 128 B each of c and dY per cell
+    auto prefetch_l2 = [&](int hf, int t) {
+      const uint32_t r0 = row00[hf] + (uint32_t)t * TSTR;
+      const uint32_t rp = (t > 0) ? r0 - TSTR : r0;
+      const uint2* gp = G16 + (size_t)r0 * U + col;
+      const float* cp = Cst + (size_t)rp * U + col;
+      const float* yp = dY + (size_t)r0 * ldY + col;
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) {
+        if ((lane & 15) == 0) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(gp + (size_t)j * (SSTR * U)));
+        if (lane == 0) {
+          asm volatile("prefetch.global.L2 [%0];\n" ::"l"(cp + (size_t)j * (SSTR * U)));
+          asm volatile("prefetch.global.L2 [%0];\n" ::"l"(yp + (size_t)j * ystep));
+        }
+      }
+    };
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      const float* cp = Cst + (size_t)(row00[hf] + (uint32_t)(steps - 1) * TSTR) * U + col;
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) {
+        dcn[hf][j] = 0.f;
+        ct[hf][j] = cp[(size_t)j * (SSTR * U)];
+      }
+    }
+#pragma unroll
+    for (int ls = 0; ls < LSN; ++ls) issue_loads(ls, steps - 1);
+    if constexpr (LSN == 1) prefetch_l2(1, steps - 1);
+    uint32_t par = 0;
+    const bool tr = (warp == 1 && lane == 0);
+    for (int t = steps - 1; t >= 0; --t) {
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        float dh[CPL];
+        if (t != steps - 1) {
+          mbar_wait(sbase + BAR_ACC + 8 * hf, par ^ 1u);   // produced by issuer round t+1
+          tc_fence_after();
+          if (tr) DJ_TR(t, 8 + 3 * hf);
+          uint32_t acc[CPL];
+#pragma unroll
+          for (int p4 = 0; p4 < CPL / 4; ++p4)
+            tmem_ld4(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(hf * NH + w2 * CPL + p4 * 4), acc + p4 * 4);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < CPL; ++j) dh[j] = __uint_as_float(acc[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < CPL; ++j) dh[j] = 0.f;
+        }
+        const int ls = (LSN == 1) ? 0 : hf;
+        const uint32_t r0 = row00[hf] + (uint32_t)t * TSTR;
+        const uint32_t e0 = r0 * U + col;               // dropout element index of the first cell (32-bit by contract)
+        __nv_bfloat16* const zp = dZ + (size_t)r0 * (4 * U) + 4 * col;
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) {
+          const float4 g4 = unpack_gates16(gv[ls][j]);
+          const float cprev = (t > 0) ? cpv[ls][j] : 0.f;
+          const float dht = fmaf(dyv[ls][j], dj_dropmul(d_y, e0 + (uint32_t)j * (SSTR * U)), dh[j]);
+          const float tc = fast_tanh(ct[hf][j]);
+          const float d_o = dht * tc;
+          const float dc = fmaf(dht * g4.w, 1.f - tc * tc, dcn[hf][j]);
+          dcn[hf][j] = dc * g4.y;
+          const float dz0 = dc * g4.z * dj_gate_dact(g4.x, hard);
+          const float dz1 = dc * cprev * dj_gate_dact(g4.y, hard);
+          const float dz2 = dc * g4.x * (1.f - g4.z * g4.z);
+          const float dz3 = d_o * dj_gate_dact(g4.w, hard);
+          __nv_bfloat162 lo = __floats2bfloat162_rn(dz0, dz1), hi = __floats2bfloat162_rn(dz2, dz3);
+          uint2 pk;
+          pk.x = *reinterpret_cast<uint32_t*>(&lo);
+          pk.y = *reinterpret_cast<uint32_t*>(&hi);
+          *reinterpret_cast<uint2*>(zp + (size_t)j * (SSTR * 4 * U)) = pk;
+          dbacc[0] += dz0; dbacc[1] += dz1; dbacc[2] += dz2; dbacc[3] += dz3;
+          ct[hf][j] = cprev;                // c_{t-1} is the cell state of the next (earlier) step
+        }
+        if (tr) DJ_TR(t, 9 + 3 * hf);
+        if (t > 0) {
+          tc_fence_before();
+          fence_proxy_async_all();          // dz_t (generic-proxy global stores) -> later TMA (async proxy) reads
+          __syncwarp();
+          if (lane == 0) mbar_arrive(sbase + BAR_DONE + 8 * hf);   // release.cta: hands this warp's stores to the issuer
+          if constexpr (LSN == 2) issue_loads(hf, t - 1);   // land during this half's publish / TMA / MMA chain
+        }
+        if (tr) DJ_TR(t, 10 + 3 * hf);
+        if constexpr (LSN == 1) {
+          // one operand set in registers: load what the NEXT epilogue in program order needs (its lines were
+          // prefetched into L2 one epilogue ago), and prefetch for the one after it
+          if (hf == 0) { issue_loads(1, t); if (t > 0) prefetch_l2(0, t - 1); }
+          else if (t > 0) { issue_loads(0, t - 1); prefetch_l2(1, t - 1); }
+        }
+      }
+      par ^= 1u;
+    }
+    if (db_part != nullptr) {
+      // deterministic mode: one partial per (tile, sequence group of the CTA), added later in index order; the four
+      // sequence groups (side, w2) of a CTA and the CTAs of a cluster together cover every column exactly once
+      float* dst = db_part + ((size_t)(tile * 4 + side * 2 + w2) * (4 * U)) + 4 * col;
+      *reinterpret_cast<float4*>(dst) = make_float4(dbacc[0], dbacc[1], dbacc[2], dbacc[3]);
+    } else {
+#pragma unroll
+      for (int gq = 0; gq < 4; ++gq) atomicAdd(db + 4 * col + gq, dbacc[gq]);
+    }
+  }
+  tc_fence_before();
+  cluster.sync();
+  if (warp == 0) tmem_dealloc2(tmem_base, TMEM_COLS);
+}
+
+#endif  // DJ_EXPERIMENTS (pair reverse scan)
 
 [[maybe_unused]] inline bool bwd_split_enabled() {   // DJ_BWD_NS=1 forces the unsplit tile (experiments)
   static int env = -1;
@@ -962,6 +1281,69 @@ int launch_tc_bwd_inst(const void* Un_bf, const void* gates, const float* c, con
   if (db_part != nullptr) return dj_ordered_reduce(db_part, tiles * 4, (int64_t)4 * U, 1, 4 * U, 4 * U, db, 4 * U, (void*)st);
   return 0;
 }
+
+#ifdef DJ_EXPERIMENTS
+inline bool bwd_pair_enabled() {   // DJ_BWD_PAIR=1: the note-axis reverse scan on CTA pairs
+  static int env = -1;
+  if (env < 0) {
+    const char* e = getenv("DJ_BWD_PAIR");
+    env = (e && atoi(e) == 1) ? 1 : 0;
+  }
+  return env != 0;
+}
+
+template <int U, int BS, bool AXIS_TIME, int LSN, bool DIRECT>
+int launch_tc_bwd_pair(const void* Un_bf, const void* gates, const float* c, const float* dY, int64_t ldY, dj_dropout d_y,
+                       void* dZ, float* db, int S, int steps, const TcMap& map_in, int hard, cudaStream_t st) {
+  constexpr int C = U / 64, KA = 4 * U / 64, KPC = KA / C, NH = BS / 4;
+  using SM = TcBwdPairSmem<U, BS>;
+  DJ_CHECK_ARG(S % BS == 0, "dj_lstm_scan_tc_bwd: the number of sequences (%d) must be a multiple of %d", S, BS);
+  static_assert(!AXIS_TIME || BS == 96, "time-axis pair tiles are two batch elements");
+  TcMap map = map_in;
+  CUtensorMap tmU, tmZ;
+  int rc;
+  if ((rc = make_map_2d(&tmU, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Un_bf, (uint64_t)4 * U, (uint64_t)U, (uint64_t)4 * U, 64, 64)))
+    return rc;
+  if (AXIS_TIME) {   // dZ viewed as [b][t*48+n][atom][64]; a half-tile is one batch element
+    const uint64_t rows_per_b = (uint64_t)map.outer_stride, B = (uint64_t)(S / 48);
+    const uint64_t dims[4] = {64, rows_per_b, (uint64_t)KA, B}, str[3] = {(uint64_t)4 * U, 64, rows_per_b * 4 * U};
+    const uint32_t box[4] = {64, (uint32_t)NH, (uint32_t)KPC, 1};
+    if ((rc = make_map(&tmZ, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dZ, 4, dims, str, box))) return rc;
+    map.seq_stride = map.inner_stride;
+  } else {           // dZ viewed as [n][atom][seq][64] (strides: seq 48*4U, atom 64, n 4U)
+    const uint64_t dims[4] = {64, (uint64_t)S, (uint64_t)KA, 48}, str[3] = {(uint64_t)48 * 4 * U, 64, (uint64_t)4 * U};
+    const uint32_t box[4] = {64, (uint32_t)NH, (uint32_t)KPC, 1};
+    if ((rc = make_map(&tmZ, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dZ, 4, dims, str, box))) return rc;
+    map.seq_stride = map.outer_stride;
+  }
+  auto kernel = scan_tc_bwd_pair_kernel<U, BS, AXIS_TIME, LSN, DIRECT>;
+  DJ_CUDA(cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((S / BS) * C);   // one cluster per tile
+  cfg.blockDim = dim3(TCB_THREADS);
+  cfg.dynamicSmemBytes = SM::TOTAL;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  if (getenv("DJ_DEBUG_OCC")) {
+    int n = 0;
+    cudaOccupancyMaxActiveClusters(&n, (const void*)kernel, &cfg);
+    fprintf(stderr, "scan_tc_bwd_pair<%d,%d>: %d clusters of %d launched, %d can be resident\n", U, BS, S / BS, C, n);
+  }
+  __nv_bfloat16* dzp = (__nv_bfloat16*)dZ;
+  const uint32_t ldy32 = (uint32_t)ldY;
+  const uint2* g16 = (const uint2*)gates;
+  const int tiles = S / BS;
+  float* db_part = nullptr;
+  if (dj_reduce_workspace((void*)st, (int64_t)tiles * 4 * 4 * U, &db_part)) return -1;
+  DJ_CUDA(cudaLaunchKernelEx(&cfg, kernel, tmU, tmZ, g16, c, dY, ldy32, d_y, dzp, db, steps, map, hard, db_part));
+  if (db_part != nullptr) return dj_ordered_reduce(db_part, tiles * 4, (int64_t)4 * U, 1, 4 * U, 4 * U, db, 4 * U, (void*)st);
+  return 0;
+}
+
+#endif  // DJ_EXPERIMENTS
 
 template <int U, int BS, int UPC, bool AXIS_TIME>
 int launch_tc_bwd(const void* Un_bf, const void* gates, const float* c, const float* dY, int64_t ldY, dj_dropout d_y,
@@ -1054,12 +1436,26 @@ extern "C" int dj_lstm_scan_tc_bwd(const void* gates, const float* c, const floa
     if (one_wave && S % 96 == 0 && S / 48 > 33)
       return launch_tc_bwd_inst<256, 96, 64, true, 2, true>(Un_bf16, gates, c, dY, ldY, d_y, dZ_bf16, db, S, steps, map, hard, st);
 #endif
+#ifdef DJ_EXPERIMENTS
+    // CTA pairs (96 sequences per cluster at the staging and ingest cost of 48, one wave): correct, and measured
+    // SLOWER than two waves at 64 sequences per GPU (0.85 against 0.71 ms).  DJ_BWD_PAIR_TIME=1.
+    static int pair_time = -1;
+    if (pair_time < 0) { const char* e = getenv("DJ_BWD_PAIR_TIME"); pair_time = (e && atoi(e) == 1) ? 1 : 0; }
+    if (pair_time && S % 96 == 0)
+      return launch_tc_bwd_pair<256, 96, true, 1, true>(Un_bf16, gates, c, dY, ldY, d_y, dZ_bf16, db, S, steps, map, hard, st);
+#endif
     return launch_tc_bwd<256, 48, 64, true>(Un_bf16, gates, c, dY, ldY, d_y, dZ_bf16, db, S, steps, map, hard, st);
   }
   if (time_map && units == 512)   // scaled model: 32 units per CTA, 16-CTA clusters, a third of a batch element per tile
     return launch_tc_bwd<512, 16, 32, true>(Un_bf16, gates, c, dY, ldY, d_y, dZ_bf16, db, S, steps, map, hard, st);
-  if (note_map && units == 128)
+  if (note_map && units == 128) {
+#ifdef DJ_EXPERIMENTS
+    // one pair per cluster, 64 sequences: 0.30 against 0.33 ms alone, no difference inside the step (DJ_BWD_PAIR=1)
+    if (bwd_pair_enabled() && S % 64 == 0)
+      return launch_tc_bwd_pair<128, 64, false, 1, false>(Un_bf16, gates, c, dY, ldY, d_y, dZ_bf16, db, S, steps, map, hard, st);
+#endif
     return launch_tc_bwd<128, 32, 64, false>(Un_bf16, gates, c, dY, ldY, d_y, dZ_bf16, db, S, steps, map, hard, st);
+  }
   if (note_map && units == 256)   // scaled model, note axis
     return launch_tc_bwd<256, 32, 64, false>(Un_bf16, gates, c, dY, ldY, d_y, dZ_bf16, db, S, steps, map, hard, st);
   DJ_CHECK_ARG(false, "dj_lstm_scan_tc_bwd: units=%d unsupported on this axis (time: 256/512, note: 128/256)", units);

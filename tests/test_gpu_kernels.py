@@ -352,7 +352,8 @@ def test_lstm_scan_tcgen05_matches_fp32_scan(lib, axis, B, T, mode):
 
 @pytest.mark.parametrize("axis,B,T", [("time", 3, 8), ("note", 2, 32), ("note", 40, 128), ("note256", 2, 32),
                                       ("time", 40, 6), ("time", 64, 5),   # > 33 tiles: 96-sequence tiles, shared staging
-                                      ("time", 35, 4)])                    # odd batch: two waves of 48-sequence tiles
+                                      ("time", 35, 4),                     # odd batch: two waves of 48-sequence tiles
+                                      ("time", 2, 8), ("time", 68, 3)])    # one tile pair; more clusters than are resident
 def test_lstm_scan_bwd_tcgen05_matches_fp32_scan(lib, axis, B, T):
     """Reverse scan on tcgen05 (bf16 dz.U^T) against the fp32 CUDA-core reverse scan."""
     from music_generator_b200 import _lib

@@ -7,6 +7,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import music_generator_b200  # noqa
 from music_generator_b200 import _lib
 
+if os.environ.get("DJ_PROBE_LIB"):
+    _lib.LIB_PATH = os.path.join(os.path.dirname(_lib.LIB_PATH), os.environ["DJ_PROBE_LIB"])
 lib = _lib.load()
 P = lambda t: C.c_void_p(t.data_ptr())
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
