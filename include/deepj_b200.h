@@ -203,6 +203,22 @@ int dj_lstm_scan_tc_infer(const float* Z, float* h_out, void* h_hi, void* h_lo, 
                           const void* Ut_lo, float acc_scale, int S, int steps, int units, int seq_inner,
                           int64_t seq_outer_stride, int64_t seq_inner_stride, int64_t step_stride, int hard,
                           void* stream);
+/* Generation with one or two sequences: BOTH time-axis layers (model.py:75-85 at inference, generate.py:106-109) in
+ * one launch, layer 1 running one step behind layer 0 (129 sequential step latencies per window instead of 256).
+ * Layer 1's input projection is part of its recurrent product: with no dropout its input is h0_t + sp (sp = the style
+ * projection, constant over the window), so z1_t = h0_t.W1 + c1 + h1_{t-1}.U1 with c1[b, 4U] = sp[b].W1 + b1
+ * computed by the caller (fp32, gate-interleaved columns like Z).  Z0 [S*steps, 4U] = layer 0's x.W + b.
+ * h0_hi/h0_lo/h1_hi/h1_lo: the layers' exchange buffers, IEEE half, [S*steps + 48, U] rows (one spare timestep).
+ * Weights as for dj_lstm_scan_tc_infer (half hi + lo, pre-scaled by 1/acc_scale); Wt1 = layer 1's W^T [4U, 256].
+ * One sequence (S = 48) runs as THREE sets of clusters -- layer 0, the input projection of layer 1 (which writes
+ * z1in_t = h0_t.W1 + c1 into Z1 [S*steps, 4U], scratch) and layer 1 --, two sequences as two (projection fused into
+ * layer 1's MMA; Z1 unused).  flags: 2*S/16 scratch words.  h1_out [S*steps, U]: only the rows of the LAST step are
+ * written (time_out[:, -1]).
+ * Time-axis map (seq = (b, n), rows (b*steps + t)*48 + n), 256 units, S <= 96. */
+int dj_lstm_scan_tc_gen2(const float* Z0, float* Z1, const float* c1, float* h1_out, void* h0_hi, void* h0_lo, void* h1_hi,
+                         void* h1_lo, const void* Ut0_hi, const void* Ut0_lo, const void* Ut1_hi, const void* Ut1_lo,
+                         const void* Wt1_hi, const void* Wt1_lo, float acc_scale, uint32_t* flags, int S, int steps,
+                         int hard, void* stream);
 /* Tensor-core variant of the reverse scan (dz.U^T on tcgen05): U is passed as
  * Un_bf16 [units, 4*units] (bf16, natural, gate-interleaved columns); dZ is bf16
  * (gradients need its exponent range) and doubles as the inter-CTA exchange buffer;

@@ -51,6 +51,7 @@ SIGNATURES = {
     "dj_cast16_multi": (_i, [_i, C.POINTER(_p), C.POINTER(_i), C.POINTER(_i), C.POINTER(_p), C.POINTER(_p),
                              C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_f), _p]),
     "dj_lstm_scan_tc_infer": (_i, [_p, _p, _p, _p, _p, _p, _f, _i, _i, _i, _i, _i64, _i64, _i64, _i, _p]),
+    "dj_lstm_scan_tc_gen2": (_i, [_p] * 14 + [_f, _p, _i, _i, _i, _p]),
     "dj_lstm_scan_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i64, _i64, _i64, _i, _p]),
     "dj_lstm_scan_tc_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i64, _i64, _i64, _i, _p]),
     "dj_lstm_scan_tc_bwd": (_i, [_p, _p, _p, _i64, Dropout, _p, _p, _p, _i, _i, _i, _i, _i64, _i64, _i64, _i, _p]),

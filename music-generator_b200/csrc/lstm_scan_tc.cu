@@ -1345,6 +1345,347 @@ int launch_tc_bwd_pair(const void* Un_bf, const void* gates, const float* c, con
 
 #endif  // DJ_EXPERIMENTS
 
+// ---------------------------------------------------------------------------
+// Generation, a handful of sequences: BOTH time-axis layers in one launch, as a wavefront.
+// The window recompute of generate.py:106-109 is 2 layers x 128 sequential steps; for one to a few sequences every
+// step is a pure latency chain (publish -> multicast -> MMA -> epilogue, ~2.2 us), so the layers are overlapped instead
+// of run back to back: clusters [0, NT) run layer 0 exactly as the inference scan does and, after every step, bump a
+// per-tile counter in global memory (gpu-scope release); clusters [NT, 2 NT) run layer 1 one step behind.  Layer 1's
+// input projection is folded into its recurrent MMA: with no dropout at inference its input is h0_t + sp (sp = the
+// style projection, constant over the window), so
+//     z1_t = h0_t.W1 + (sp.W1 + b1) + h1_{t-1}.U1
+// -- the bracket is a per-sequence constant computed once (c1), and h0_t.W1 is three more MMA passes on the SAME
+// accumulator (W1^T hi in tensor memory next to U1^T hi, W1^T lo in shared memory next to U1^T lo) whose B operand is
+// layer 0's own exchange buffer (h0_t as half hi + lo, TMA-loaded once the counter says all eight CTAs of the layer-0
+// tile have published step t).  The W pass of step t does not depend on h1_{t-1}: it is issued while the epilogue of
+// step t-1 is still running, into the other of two accumulator column sets, so the sequential chain stays one
+// recurrent step per timestep and the window costs 129 step latencies instead of 256.
+// 16-sequence tiles, 8 CTAs per cluster (32 hidden units = 128 gate rows each), one CTA per SM.
+// ---------------------------------------------------------------------------
+struct TcGen2Smem {
+  static constexpr int A_BYTES = 128 * 256 * 2;                 // U^T lo slice: [4 atoms][128 rows][128 B]
+  static constexpr int T_BYTES = 16 * 256 * 2;                  // one [16 x 256] half tile
+  static constexpr int A_OFF = 0, W_OFF = A_BYTES, H_OFF = 2 * A_BYTES, HLO_OFF = H_OFF + T_BYTES,
+                       X_OFF = HLO_OFF + T_BYTES;               // X: [2 buffers][hi | lo]
+  static constexpr int BAR_OFF = X_OFF + 4 * T_BYTES;
+  static constexpr int TOTAL = BAR_OFF + 128;
+};
+
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(uint32_t* p, uint32_t v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+
+// ROLES = 2: layer 0 | layer 1 with the fused input pass (above).  ROLES = 3 (one sequence: 9 clusters): the input
+// pass doubles layer 1's tensor-pipe time per step (96 small MMAs, ~2 us), which then bounds the step, so it moves to
+// a THIRD set of clusters: "P" multiplies h0_t by W1 as soon as layer 0 publishes it and writes z1in_t = h0_t.W1 + c1
+// (fp32 rows of Z1) behind a second counter; layer 1 is then the plain inference scan that waits for its Z rows.
+template <bool HARD, int ROLES>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+scan_tc_gen2_kernel(const __grid_constant__ CUtensorMap tmU0lo, const __grid_constant__ CUtensorMap tmU1lo,
+                    const __grid_constant__ CUtensorMap tmW1lo, const __grid_constant__ CUtensorMap tmH0,
+                    const __grid_constant__ CUtensorMap tmH0lo, const __grid_constant__ CUtensorMap tmH1,
+                    const __grid_constant__ CUtensorMap tmH1lo, const __grid_constant__ CUtensorMap tmX,
+                    const __grid_constant__ CUtensorMap tmXlo, const float* __restrict__ Z0, float* __restrict__ Z1,
+                    const float* __restrict__ C1, float* __restrict__ H1out, uint16_t* __restrict__ H0hi,
+                    uint16_t* __restrict__ H0lo, uint16_t* __restrict__ H1hi, uint16_t* __restrict__ H1lo,
+                    const uint32_t* __restrict__ Ut0_words, const uint32_t* __restrict__ Ut1_words,
+                    const uint32_t* __restrict__ Wt1_words, uint32_t* __restrict__ flags, int ntiles, int steps,
+                    float acc_scale) {
+  constexpr int U = 256, C = 8, KA = 4, BS = 16, RH = 8;
+  constexpr uint32_t AU_COL0 = 32, AW_COL0 = 32 + U / 2, TMEM_COLS = 512;
+  using SM = TcGen2Smem;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  // barriers: a | w | acc[2] | h | x[2] | done | pub | tmem slot
+  const uint32_t bar_a = sbase + SM::BAR_OFF, bar_w = bar_a + 8, bar_acc0 = bar_a + 16, bar_h = bar_a + 32,
+                 bar_x0 = bar_a + 40, bar_done = bar_a + 56, bar_pub = bar_a + 64;
+  volatile uint32_t* tmem_slot_p = (volatile uint32_t*)(smem + SM::BAR_OFF + 72);
+
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int cl = blockIdx.x / C;
+  const bool isL0 = cl < ntiles;
+  const bool isP = (ROLES == 3) && !isL0 && cl < 2 * ntiles;     // input projection of layer 1 (ROLES = 3)
+  const bool isL1 = !isL0 && !isP;
+  const bool fusedL1 = isL1 && ROLES == 2;      // layer 1 multiplies h0_t by W1 itself
+  const bool plainL1 = isL1 && ROLES == 3;      // layer 1 reads z1in_t from Z1
+  const int tile = cl % ntiles;                 // 16 sequences: pitches [16*(tile%3), +16) of batch element tile/3
+  const int tile_b = tile / 3, tile_r = (tile % 3) * BS;
+  const int warp = uniform_warp_id(), lane = threadIdx.x & 31;
+  uint32_t* const flags0 = flags + tile;            // steps of layer 0 published, x8 CTAs
+  uint32_t* const flags1 = flags + ntiles + tile;   // rows of Z1 published by P, x8 CTAs
+  uint16_t* Hhi = isL1 ? H1hi : H0hi;
+  uint16_t* Hlo = isL1 ? H1lo : H0lo;
+  const CUtensorMap* tmH = isL1 ? &tmH1 : &tmH0;
+  const CUtensorMap* tmHl = isL1 ? &tmH1lo : &tmH0lo;
+  // the "recurrent" operand slots (tensor-memory columns AU, shared-memory slot A) hold U^T of the layer -- or, in
+  // a P cluster, W1^T; the second pair (AW, slot W) holds W1^T in a fused layer-1 cluster
+  const uint32_t* a_words = isP ? Wt1_words : isL1 ? Ut1_words : Ut0_words;
+  const CUtensorMap* tmAlo = isP ? &tmW1lo : isL1 ? &tmU1lo : &tmU0lo;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      if (sbase & 1023u) { printf("deepj scan_tc_gen2: dynamic smem not 1024-aligned\n"); __trap(); }
+      prefetch_tmap(tmAlo); prefetch_tmap(&tmW1lo); prefetch_tmap(tmH); prefetch_tmap(tmHl);
+      prefetch_tmap(&tmX); prefetch_tmap(&tmXlo);
+      mbar_init(bar_a, 1); mbar_init(bar_w, 1);
+      mbar_init(bar_acc0, 1); mbar_init(bar_acc0 + 8, 1);
+      mbar_init(bar_h, 1); mbar_init(bar_x0, 1); mbar_init(bar_x0 + 8, 1);
+      mbar_init(bar_done, TC_EPI_WARPS); mbar_init(bar_pub, C);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(sbase + SM::BAR_OFF + 72, TMEM_COLS);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_p;
+  if (warp >= 1 && warp <= 4) {
+    // resident A operands in tensor memory: lane = one row of this CTA's 128-row slice
+    const uint32_t row = (uint32_t)(128 * rank + 32 * (warp & 3) + lane);
+    const uint32_t* srcs[2] = {a_words + (size_t)row * (U / 2), Wt1_words + (size_t)row * (U / 2)};
+    const uint32_t col0[2] = {AU_COL0, AW_COL0};
+    for (int m = 0; m < (fusedL1 ? 2 : 1); ++m) {
+#pragma unroll 1
+      for (int c = 0; c < U / 2; c += 16) {
+        uint32_t w[16];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint4 q4 = *reinterpret_cast<const uint4*>(srcs[m] + c + 4 * j);
+          w[4 * j] = q4.x; w[4 * j + 1] = q4.y; w[4 * j + 2] = q4.z; w[4 * j + 3] = q4.w;
+        }
+        tmem_st16(tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + col0[m] + (uint32_t)c, w);
+      }
+    }
+    tmem_st_wait();
+    tc_fence_before();
+  }
+  cluster.sync();   // peers' barriers are initialised before any multicast / remote arrive can target them (and A is in TMEM)
+  tc_fence_after();
+
+  if (warp == 0) {
+    // ================= issuer =================
+    if (elect_one()) {   // shared-memory A operands: the half-precision residuals of the tensor-memory ones, rows [128*rank, +128)
+      mbar_expect_tx(bar_a, SM::A_BYTES);
+#pragma unroll
+      for (int ka = 0; ka < KA; ++ka)
+        tma_load_2d(sbase + SM::A_OFF + ka * 16384, tmAlo, bar_a, ka * 64, 128 * rank);
+      if (fusedL1) {
+        mbar_expect_tx(bar_w, SM::A_BYTES);
+#pragma unroll
+        for (int ka = 0; ka < KA; ++ka)
+          tma_load_2d(sbase + SM::W_OFF + ka * 16384, &tmW1lo, bar_w, ka * 64, 128 * rank);
+      }
+    }
+    __syncwarp();
+    const int my_ka = rank >> 1, my_hh = rank & 1;       // the slice of h_t this CTA multicasts
+    // kind::f16 with IEEE-half operands (format bits 7 / 10 of the instruction descriptor: 0 = f16)
+    const uint32_t idesc = make_idesc(128, BS, 0, 0) & ~((1u << 7) | (1u << 10));
+    // three passes of one 256-deep product A.b on accumulator `d`: A_hi.b_hi + A_lo.b_hi + A_hi.b_lo
+    auto three_pass = [&](uint32_t d, uint32_t a_tmem, uint32_t a_smem, uint32_t b_hi, uint32_t b_lo, bool first_zero) {
+      const uint64_t adesc0 = make_smem_desc(a_smem, 16, 1024);
+      const uint64_t bh0 = make_smem_desc(b_hi, 16, 1024), bl0 = make_smem_desc(b_lo, 16, 1024);
+#pragma unroll
+      for (int ka = 0; ka < KA; ++ka)
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16_ts(d, a_tmem + (uint32_t)(ka * 32 + k * 8), bh0 + (uint64_t)((ka * (BS * 128) + k * 32) >> 4), idesc,
+                       (first_zero && (ka | k) == 0) ? 0u : 1u);
+#pragma unroll
+      for (int ka = 0; ka < KA; ++ka)
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(d, adesc0 + (uint64_t)((ka * 16384 + k * 32) >> 4), bh0 + (uint64_t)((ka * (BS * 128) + k * 32) >> 4),
+                    idesc, 1);
+#pragma unroll
+      for (int ka = 0; ka < KA; ++ka)
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16_ts(d, a_tmem + (uint32_t)(ka * 32 + k * 8), bl0 + (uint64_t)((ka * (BS * 128) + k * 32) >> 4), idesc, 1);
+    };
+    auto wait_counter = [&](const uint32_t* ctr, uint32_t want, int t) {
+      if (lane == 0) {
+        const long long t0 = clock64();
+        while (ld_acquire_gpu(ctr) < want) {
+          if (clock64() - t0 > 4000000000LL) { printf("deepj scan_tc_gen2: cluster %d waited in vain for step %d\n", cl, t); __trap(); }
+        }
+      }
+      __syncwarp();
+    };
+    // Round t produces the accumulator of step t: [fused layer 1 / P: h0_t.W1] + [layers: h_{t-1}.U].  (Layer 0,
+    // t = 0: nothing to multiply; the empty commit keeps the phases of the accumulator barriers the same for all roles.)
+    for (int t = 0; t < steps; ++t) {
+      const uint32_t d = tmem_base + (uint32_t)((t & 1) * BS);
+      if (fusedL1 || isP) {
+        // ---- input pass: wait until all eight CTAs of the layer-0 tile have published h0_t, fetch it, multiply
+        wait_counter(flags0, (uint32_t)(C * (t + 1)), t);
+        const uint32_t xb = sbase + SM::X_OFF + (uint32_t)((t & 1) * 2 * SM::T_BYTES), bar_x = bar_x0 + 8 * (t & 1);
+        if (elect_one()) {
+          mbar_expect_tx(bar_x, 2 * SM::T_BYTES);
+#pragma unroll
+          for (int ka = 0; ka < KA; ++ka) {
+            tma_load_3d(xb + ka * (BS * 128), &tmX, bar_x, ka * 64, (t + 1) * 48 + tile_r, tile_b);
+            tma_load_3d(xb + SM::T_BYTES + ka * (BS * 128), &tmXlo, bar_x, ka * 64, (t + 1) * 48 + tile_r, tile_b);
+          }
+        }
+        __syncwarp();
+        if (t == 0) mbar_wait(isP ? bar_a : bar_w, 0);
+        mbar_wait(bar_x, (uint32_t)(t >> 1) & 1u);
+        tc_fence_after();
+        if (elect_one())
+          three_pass(d, tmem_base + (isP ? AU_COL0 : AW_COL0), sbase + (isP ? SM::A_OFF : SM::W_OFF), xb, xb + SM::T_BYTES, true);
+        __syncwarp();
+      }
+      if (isP) {
+        // rows t-1 of Z1 are stored (the epilogue cannot be further: it needs the commit below): publish them
+        if (t > 0) {
+          mbar_wait(bar_done, (uint32_t)(t - 1) & 1u);
+          if (elect_one()) red_release_gpu_add(flags1, 1u);
+          __syncwarp();
+        }
+      } else if (t > 0) {
+        // ---- recurrent pass: h_{t-1} published by every CTA of this cluster, all-gathered by multicast
+        const uint32_t par = (uint32_t)(t - 1) & 1u;
+        mbar_wait(bar_done, par);                         // this CTA's epilogue warps stored their part of h_{t-1}
+        if (lane < C) mbar_arrive_remote(bar_pub, (uint32_t)lane);  // release.cluster, cumulative
+        // layer 0: tell P / layer 1 as well (cumulative gpu-scope release).  Issued by a lane that does no remote
+        // arrive, AFTER the arrives, so its fence overlaps the wait for the other CTAs instead of preceding it
+        if (isL0 && lane == C) red_release_gpu_add(flags0, 1u);
+        __syncwarp();
+        mbar_wait(bar_pub, par);
+        if (elect_one()) {
+          mbar_expect_tx(bar_h, 2 * SM::T_BYTES);
+          tma_load_3d_mc(sbase + SM::H_OFF + my_ka * (BS * 128) + my_hh * (RH * 128), tmH, bar_h, my_ka * 64,
+                         t * 48 + tile_r + my_hh * RH, tile_b, (uint16_t)((1u << C) - 1u));
+          tma_load_3d_mc(sbase + SM::HLO_OFF + my_ka * (BS * 128) + my_hh * (RH * 128), tmHl, bar_h, my_ka * 64,
+                         t * 48 + tile_r + my_hh * RH, tile_b, (uint16_t)((1u << C) - 1u));
+        }
+        __syncwarp();
+        if (t == 1) mbar_wait(bar_a, 0);
+        mbar_wait(bar_h, par);
+        tc_fence_after();
+        if (elect_one()) three_pass(d, tmem_base + AU_COL0, sbase + SM::A_OFF, sbase + SM::H_OFF, sbase + SM::HLO_OFF, !fusedL1);
+        __syncwarp();
+      }
+      if (elect_one()) umma_commit(bar_acc0 + 8 * (t & 1));
+      __syncwarp();
+    }
+    if (isL0 || isP) {   // the last step feeds no recurrence here, but its consumer still waits for it
+      mbar_wait(bar_done, (uint32_t)(steps - 1) & 1u);
+      if (elect_one()) red_release_gpu_add(isL0 ? flags0 : flags1, 1u);
+      __syncwarp();
+    }
+  } else if (warp <= TC_EPI_WARPS) {
+    // ================= epilogue warps (as the inference scan: one 16-sequence chunk) =================
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int w2 = (warp - 1) >> 2;         // which 8 of the 16 sequences
+    const int up = lane >> 2;               // unit inside the warp (0..7)
+    const int g = lane & 3;                 // gate held before the transpose / sequence slot after it
+    const uint32_t col = 32 * rank + 8 * q + up;          // global hidden unit
+    const uint32_t zc = 128 * rank + 32 * q + lane;       // gate-interleaved column this lane reads
+    const uint32_t rowb = (uint32_t)(tile_b * steps * 48 + tile_r + 8 * w2);   // row of this warp's first sequence, step 0
+    const float c1 = (isL0 || plainL1) ? 0.f : C1[(size_t)tile_b * (4 * U) + zc];
+    if (isP) {
+      // ---- P: z1in_t = h0_t.W1 + c1 -> rows t of Z1 (lane = gate column, 8 sequences: eight 128-byte row segments per warp)
+      for (int t = 0; t < steps; ++t) {
+        mbar_wait(bar_acc0 + 8 * (t & 1), (uint32_t)(t >> 1) & 1u);
+        tc_fence_after();
+        uint32_t acc[8];
+        tmem_ld8(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)((t & 1) * BS + 8 * w2), acc);
+        tmem_ld_wait();
+        float* zp = Z1 + (size_t)(rowb + (uint32_t)t * 48u) * (4 * U) + zc;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) __stcg(zp + (size_t)j * (4 * U), fmaf(__uint_as_float(acc[j]), acc_scale, c1));
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_done);   // release.cta: the issuer's gpu-scope release publishes these stores
+      }
+    } else {
+      float cst[2] = {0.f, 0.f};
+      float zreg[8];
+      auto load_z = [&](int t) {      // pre-activations of step t that do not depend on this layer's recurrence
+        if (isL0) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) zreg[j] = Z0[(size_t)(rowb + j + (uint32_t)t * 48u) * (4 * U) + zc];
+        } else if (plainL1) {
+          if (lane == 0) {
+            const long long t0 = clock64();
+            while (ld_acquire_gpu(flags1) < (uint32_t)(C * (t + 1))) {
+              if (clock64() - t0 > 4000000000LL) { printf("deepj scan_tc_gen2: layer 1 waited in vain for Z1 rows of step %d\n", t); __trap(); }
+            }
+          }
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) zreg[j] = __ldcg(Z1 + (size_t)(rowb + j + (uint32_t)t * 48u) * (4 * U) + zc);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) zreg[j] = c1;
+        }
+      };
+      load_z(0);
+      for (int t = 0; t < steps; ++t) {
+        const bool not_last = (t + 1 < steps);
+        float v[8];
+        if (fusedL1 || t > 0) {
+          mbar_wait(bar_acc0 + 8 * (t & 1), (uint32_t)(t >> 1) & 1u);
+          tc_fence_after();
+          uint32_t acc[8];
+          tmem_ld8(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)((t & 1) * BS + 8 * w2), acc);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = fmaf(__uint_as_float(acc[j]), acc_scale, zreg[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = zreg[j];
+        }
+        // this lane's cell after the transpose: sequence 8*w2 + 4*blk + g, unit `col`
+        const size_t o1 = (size_t)(rowb + (uint32_t)g + (uint32_t)t * 48u) * U + col;
+#pragma unroll
+        for (int blk = 0; blk < 2; ++blk) {
+          // 4x4 transpose across the 4 lanes of a unit: lane g ends with i,f,g,o of sequence 4*blk+g
+          const float a0 = v[4 * blk], a1 = v[4 * blk + 1], a2 = v[4 * blk + 2], a3 = v[4 * blk + 3];
+          const bool odd = g & 1, hi = g & 2;
+          const float x1 = __shfl_xor_sync(0xffffffffu, odd ? a0 : a1, 1);
+          const float x2 = __shfl_xor_sync(0xffffffffu, odd ? a2 : a3, 1);
+          const float b0 = odd ? x1 : a0, b1 = odd ? a1 : x1, b2 = odd ? x2 : a2, b3 = odd ? a3 : x2;
+          const float y0 = __shfl_xor_sync(0xffffffffu, hi ? b0 : b2, 2);
+          const float y1 = __shfl_xor_sync(0xffffffffu, hi ? b1 : b3, 2);
+          const float zi = hi ? y0 : b0, zf = hi ? y1 : b1, zg_ = hi ? b2 : y0, zo = hi ? b3 : y1;
+          const float gi = gate_act_fast<HARD>(zi), gf = gate_act_fast<HARD>(zf);
+          const float gg = fast_tanh(zg_), go = gate_act_fast<HARD>(zo);
+          const float cn = fmaf(gf, cst[blk], gi * gg);
+          const float hn = go * fast_tanh(cn);
+          cst[blk] = cn;
+          // h_t as half hi + lo at the NEXT step's row of this layer's exchange buffer (layer 0: also after its last
+          // step, for its consumer; the buffers have one spare timestep of rows)
+          if (isL0 || not_last) {
+            const __half hh = __float2half_rn(hn);
+            Hhi[o1 + (size_t)(blk * 4 + 48) * U] = __half_as_ushort(hh);
+            Hlo[o1 + (size_t)(blk * 4 + 48) * U] = __half_as_ushort(__float2half_rn(hn - __half2float(hh)));
+          }
+          if (isL1 && !not_last) H1out[o1 + (size_t)(blk * 4) * U] = hn;     // time_out of the window's last step
+        }
+        if (isL0 || not_last) {
+          tc_fence_before();
+          fence_proxy_async_all();   // generic-proxy global stores of h_t -> later async-proxy (TMA) reads
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_done);   // release.cta: hands this warp's stores to the issuer
+        }
+        if (not_last) load_z(t + 1);              // lands during this step's publish / all-gather / MMA chain
+      }
+    }
+  }
+  tc_fence_before();
+  cluster.sync();
+  if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
 template <int U, int BS, int UPC, bool AXIS_TIME>
 int launch_tc_bwd(const void* Un_bf, const void* gates, const float* c, const float* dY, int64_t ldY, dj_dropout d_y,
                   void* dZ, float* db, int S, int steps, const TcMap& map, int hard, cudaStream_t st) {
@@ -1411,6 +1752,63 @@ extern "C" int dj_lstm_scan_tc_infer(const float* Z, float* h_out, void* h_hi, v
   }
   if (hard) return launch_tc_fwd_inst<256, 48, true, true, 1, 1, true>(Ut_hi, Ut_lo, 1, Z, nullptr, h_out, nullptr, h_hi, S, steps, map, st, h_lo, acc_scale);
   return launch_tc_fwd_inst<256, 48, true, false, 1, 1, true>(Ut_hi, Ut_lo, 1, Z, nullptr, h_out, nullptr, h_hi, S, steps, map, st, h_lo, acc_scale);
+}
+
+extern "C" int dj_lstm_scan_tc_gen2(const float* Z0, float* Z1, const float* c1, float* h1_out, void* h0_hi, void* h0_lo, void* h1_hi,
+                                    void* h1_lo, const void* Ut0_hi, const void* Ut0_lo, const void* Ut1_hi,
+                                    const void* Ut1_lo, const void* Wt1_hi, const void* Wt1_lo, float acc_scale,
+                                    uint32_t* flags, int S, int steps, int hard, void* stream) {
+  DJ_CHECK_ARG(Z0 && Z1 && c1 && h1_out && h0_hi && h0_lo && h1_hi && h1_lo && Ut0_hi && Ut0_lo && Ut1_hi && Ut1_lo && Wt1_hi &&
+                   Wt1_lo && flags, "dj_lstm_scan_tc_gen2: NULL pointer");
+  DJ_CHECK_ARG(S > 0 && S % 48 == 0 && steps > 0 && acc_scale > 0.f, "dj_lstm_scan_tc_gen2: bad sizes");
+  constexpr int U = 256, C = 8;
+  const int ntiles = S / 16;
+  // every cluster of both layers must be resident at once (layer 1 spins on layer 0's counters): B200 keeps 15
+  // clusters of 8 one-CTA-per-SM blocks resident
+  DJ_CHECK_ARG(2 * ntiles <= 14, "dj_lstm_scan_tc_gen2: at most 2 sequences x 48 pitches (got %d rows); use dj_lstm_scan_tc_infer", S);
+  cudaStream_t st = (cudaStream_t)stream;
+  CUtensorMap tmU0lo, tmU1lo, tmW1lo, tmH0, tmH0lo, tmH1, tmH1lo, tmX, tmXlo;
+  int rc;
+  const CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;   // any 16-bit type: TMA only moves the bytes
+  if ((rc = make_map_2d(&tmU0lo, dt, 2, Ut0_lo, U, 4 * U, U, 64, 128))) return rc;
+  if ((rc = make_map_2d(&tmU1lo, dt, 2, Ut1_lo, U, 4 * U, U, 64, 128))) return rc;
+  if ((rc = make_map_2d(&tmW1lo, dt, 2, Wt1_lo, U, 4 * U, U, 64, 128))) return rc;
+  const uint64_t rows_per_b = (uint64_t)steps * 48, B = (uint64_t)(S / 48);
+  {   // own-layer exchange buffers viewed as [b][t*48+n][U]: 8-row slices
+    const uint64_t dims[3] = {(uint64_t)U, rows_per_b, B}, str[2] = {(uint64_t)U, rows_per_b * U};
+    const uint32_t box[3] = {64, 8, 1};
+    if ((rc = make_map(&tmH0, dt, 2, h0_hi, 3, dims, str, box))) return rc;
+    if ((rc = make_map(&tmH0lo, dt, 2, h0_lo, 3, dims, str, box))) return rc;
+    if ((rc = make_map(&tmH1, dt, 2, h1_hi, 3, dims, str, box))) return rc;
+    if ((rc = make_map(&tmH1lo, dt, 2, h1_lo, 3, dims, str, box))) return rc;
+  }
+  {   // layer 0's buffers as layer 1 reads them: whole 16-row tiles, one extra timestep of rows per batch element (h0 of
+      // the last step sits at row T; the views of consecutive batch elements overlap by that timestep)
+    const uint64_t dims[3] = {(uint64_t)U, rows_per_b + 48, B}, str[2] = {(uint64_t)U, rows_per_b * U};
+    const uint32_t box[3] = {64, 16, 1};
+    if ((rc = make_map(&tmX, dt, 2, h0_hi, 3, dims, str, box))) return rc;
+    if ((rc = make_map(&tmXlo, dt, 2, h0_lo, 3, dims, str, box))) return rc;
+  }
+  DJ_CUDA(cudaMemsetAsync(flags, 0, sizeof(uint32_t) * 2 * (size_t)ntiles, st));
+  // one sequence: three roles (layer 0 | input projection of layer 1 | layer 1) on 9 clusters; two: two roles on 12
+  const int roles = (3 * ntiles <= 14 && !getenv("DJ_GEN2_ROLES2")) ? 3 : 2;
+  auto kernel = roles == 3 ? (hard ? scan_tc_gen2_kernel<true, 3> : scan_tc_gen2_kernel<false, 3>)
+                           : (hard ? scan_tc_gen2_kernel<true, 2> : scan_tc_gen2_kernel<false, 2>);
+  DJ_CUDA(cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGen2Smem::TOTAL));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(roles * ntiles * C);   // clusters [0, ntiles): layer 0; then (3 roles) P; the last ntiles: layer 1
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = TcGen2Smem::TOTAL;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  DJ_CUDA(cudaLaunchKernelEx(&cfg, kernel, tmU0lo, tmU1lo, tmW1lo, tmH0, tmH0lo, tmH1, tmH1lo, tmX, tmXlo, Z0, Z1, c1, h1_out,
+                             (uint16_t*)h0_hi, (uint16_t*)h0_lo, (uint16_t*)h1_hi, (uint16_t*)h1_lo,
+                             (const uint32_t*)Ut0_hi, (const uint32_t*)Ut1_hi, (const uint32_t*)Wt1_hi, flags, ntiles, steps,
+                             acc_scale));
+  return 0;
 }
 
 extern "C" int dj_lstm_scan_tc_bwd(const void* gates, const float* c, const float* dY, int64_t ldY, dj_dropout d_y,

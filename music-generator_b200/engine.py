@@ -54,8 +54,9 @@ class Workspace:
             self.A.append(torch.empty(M, ld, dtype=adt, device=dev))
             self.A_lo.append(torch.empty(M, ld, dtype=adt, device=dev) if (mixed or gen) else None)
             tl = gen and L["axis"] == "time"
-            self.h_hi.append(torch.empty(M, L["U"], dtype=torch.float16, device=dev) if tl else None)
-            self.h_lo.append(torch.empty(M, L["U"], dtype=torch.float16, device=dev) if tl else None)
+            # + one spare timestep of rows: the fused two-layer scan keeps h of the LAST step at row T for layer 1
+            self.h_hi.append(torch.empty(M + N, L["U"], dtype=torch.float16, device=dev) if tl else None)
+            self.h_lo.append(torch.empty(M + N, L["U"], dtype=torch.float16, device=dev) if tl else None)
             self.Z.append(torch.empty(M, 4 * L["U"], **f32))
             self.h.append(torch.empty(M, L["U"], **f32))
             self.c.append(torch.empty(M, L["U"], **f32) if train else None)
@@ -68,6 +69,12 @@ class Workspace:
         self.G16 = [torch.empty(M, 4 * L["U"], dtype=torch.float16, device=dev) if (train and bf16) else None
                     for L in cfg.layers()]
         self.probs = torch.empty(M, 3, **f32)
+        if gen:
+            # fused two-layer generation scan (dj_lstm_scan_tc_gen2): per-sequence constant part of layer 1's
+            # pre-activations (style projection through W1, + bias) and the per-tile step counters
+            self.c1 = torch.empty(B, 4 * cfg.time_axis_units, **f32)
+            self.c1_version = -1
+            self.flags = torch.zeros(2 * (B * N // 16), dtype=torch.int32, device=dev)
         if train:
             un = cfg.note_axis_units
             self.dXtop = torch.empty(M, un, **f32)
@@ -190,6 +197,9 @@ class Engine:
         # generation window on the tensor cores at fp32 grade (half hi+lo operands, 3 MMA passes); DJ_GEN_TC=0 = the
         # CUDA-core fp32 kernels
         self.gen_tc = os.environ.get("DJ_GEN_TC", "1") != "0"
+        # one or two sequences: both time-axis layers of the window in ONE launch, as a wavefront (DJ_GEN_FUSED=0: one
+        # inference scan per layer)
+        self.gen_fused = os.environ.get("DJ_GEN_FUSED", "1") != "0"
         # Deterministic gradients (DJ_DETERMINISTIC=1): every sum over CTAs in the backward pass (split weight-gradient
         # GEMMs, bias / conv / style gradients) goes through per-CTA partials added in index order instead of fp32
         # atomics, so two runs -- and 1 GPU vs N GPUs on the same shards -- give the same bits.  One workspace per
@@ -490,12 +500,33 @@ class Engine:
                    _ptr(ws.A_lo[0]), ws.ld[0], adt, _stream())
         M = B * T * N
         self._gate_gemm(0, ws, bf16, M)
+        if (ws.gen and self.gen_fused and style_done and B <= 2 and self.layers[0]["U"] == 256
+                and self.layers[1]["U"] == 256):      # style_done: the generation loop, style constant over the window
+            return self._scan_gen2(ws, B, T)
         self._scan_fwd(0, ws, B, T, train)
         L1 = self.layers[1]
         self._call("dj_layer_input", _ptr(ws.h[0]), self.layers[0]["U"], 0, T * N, d[6], _ptr(ws.sp[1]), L1["F"],
                    d[7], None, 0, NO_DROPOUT, B, T, _ptr(ws.A[1]), _ptr(ws.A_lo[1]), ws.ld[1], adt, _stream())
         self._gate_gemm(1, ws, bf16, M)
         self._scan_fwd(1, ws, B, T, train)
+
+    def _scan_gen2(self, ws: Workspace, B: int, T: int):
+        """Both time-axis layers of a generation window in one launch (layer 1 one step behind layer 0; its input
+        projection folded into its recurrent MMA): model.py:75-85 at inference.  ws.h[1] gets the last step only."""
+        L0, L1 = self.layers[0], self.layers[1]
+        P, n0, n1 = self.params, L0["name"], L1["name"]
+        if ws.c1_version != self._version:
+            # c1[b] = sp1[b].W1 + b1: the style term of layer 1's input (constant over the window) through its kernel
+            self._call("dj_gemm_simt", _ptr(ws.sp[1]), DJ_F32, T * L1["F"], 1, _ptr(P[f"{n1}.lstm.W"]), DJ_F32,
+                       4 * L1["U"], 1, _ptr(ws.c1), 4 * L1["U"], _ptr(P[f"{n1}.lstm.b"]), B, 4 * L1["U"], L1["F"],
+                       0, 0, 0, _stream())
+            ws.c1_version = self._version
+        self._tag = ":time01"
+        self._call("dj_lstm_scan_tc_gen2", _ptr(ws.Z[0]), _ptr(ws.Z[1]), _ptr(ws.c1), _ptr(ws.h[1]), _ptr(ws.h_hi[0]), _ptr(ws.h_lo[0]),
+                   _ptr(ws.h_hi[1]), _ptr(ws.h_lo[1]), _ptr(self._wbf[f"{n0}.gUt"]), _ptr(self._wbf[f"{n0}.gUt_lo"]),
+                   _ptr(self._wbf[f"{n1}.gUt"]), _ptr(self._wbf[f"{n1}.gUt_lo"]), _ptr(self._wbf[f"{n1}.gWt"]),
+                   _ptr(self._wbf[f"{n1}.gWt_lo"]), 1.0 / self.GEN_SCALE, _ptr(ws.flags), B * N, T, self.hard, _stream())
+        self._tag = ""
 
     def forward_note(self, ws: Workspace, h_time, h_row0, h_b_rows, chosen, chosen_bstride, B, T, d, bf16,
                      train, target=None):

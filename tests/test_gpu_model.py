@@ -24,6 +24,11 @@ def make_engine(precision="fp32", seed=0, **cfg_kw):
     return e
 
 
+def generate_events_(*a, **k):
+    from music_generator_b200.sampler import generate_events
+    return generate_events(*a, **k)
+
+
 def batch_dev(B, T, seed=1234):
     b = O.synthetic_batch(CFG, B, T, seed, torch.float32)
     return b, [t.cuda().contiguous() for t in b]
@@ -466,6 +471,28 @@ def _lockstep(e, styles, steps, u, default_temp=1.0):
     assert np.array_equal(info["temperature"], oinfo["temperature"])
     assert np.array_equal(info["silent_time"], oinfo["silent_time"])
     return ev, info, oinfo, err
+
+
+def test_generation_fused_two_layer_scan_equals_layer_by_layer():
+    """One or two sequences: both time-axis layers of the window run in ONE launch as a wavefront
+    (dj_lstm_scan_tc_gen2: layer 1 one step behind layer 0, its input projection folded into its recurrent MMA).
+    Same arithmetic regrouped, so the probabilities agree with the layer-by-layer path to fp32 rounding and the
+    sampled events are identical."""
+    for G in (1, 2):
+        stys = [np.eye(23)[(3 * i + 1) % 23] for i in range(G)]
+        u = np.random.RandomState(5 + G).random_sample(12 * G * 48 * 2)
+        out = {}
+        for fused in (True, False):
+            e = make_engine("fp32", seed=2)
+            e.gen_fused = fused
+            ev, info = generate_events_(e, stys, 12, u)
+            out[fused] = (ev, info["probs"], e)
+        assert np.array_equal(out[True][0][..., :2], out[False][0][..., :2])       # play / replay decisions
+        assert np.abs(out[True][0][..., 2] - out[False][0][..., 2]).max() < 2e-6    # volume: a float output
+        assert np.abs(out[True][1] - out[False][1]).max() < 2e-6, np.abs(out[True][1] - out[False][1]).max()
+        p32 = {k: torch.tensor(v) for k, v in out[True][2].get_params().items()}
+        oev, oinfo = O.generate(p32, CFG, stys, 12, u, mode="incremental", forced_events=out[True][0])
+        assert np.array_equal(oinfo["decisions"][..., :2], out[True][0][..., :2])
 
 
 def test_generation_silence_raises_temperature_on_device():

@@ -1,0 +1,13 @@
+#!/bin/bash
+# round 2, call L: fused two-layer generation scan
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_model.py -m gpu -q -x -k "generation or smoke" --timeout 600 -rP > gpurun_out/r02l_pytest_gen.log 2>&1
+echo "pytest gen exit $?"; grep -E "passed|failed|error|lock-step|Error|timed out" gpurun_out/r02l_pytest_gen.log | tail -12
+timeout 200 python tools/gen_probe.py 1 > gpurun_out/r02l_probe_fused1.log 2>&1
+echo "probe fused exit $?"; head -n 4 gpurun_out/r02l_probe_fused1.log
+timeout 300 python bench.py --workload gen1 --no-cpu-baseline > gpurun_out/r02l_bench_gen1.json 2> gpurun_out/r02l_bench_gen1.err; echo "bench gen1 exit $?"
+python - <<'PY'
+import json
+d = json.loads(open("gpurun_out/r02l_bench_gen1.json").read().strip().splitlines()[-1])
+print({k: d.get(k) for k in ("metric", "value", "unit", "ms_per_step")}, d.get("e2e"), json.dumps(d.get("generation") or d.get("config"))[:500])
+PY
