@@ -257,26 +257,29 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NTHR, 1) gen_sample
 
 // ---------------------------------------------------------------------------
 // One sequence per cluster (the indexed stream mode, and reference order with a single sequence): the same
-// arithmetic without a single barrier.cluster or __syncthreads inside the note loop.  The kernel above spends 60 % of
-// a note in barriers (ncu: stall_barrier + stall_membar; three barrier.cluster round trips with their membar and L1
-// flush, six block barriers).  Here
-//   * warps 0..3 of every CTA own the CTA's 128 gate columns (lane = column, the whole K = 128 per lane: no k-split,
-//     hence no block-level reduction); the four gates of a unit sit in four adjacent lanes and are exchanged by shuffle;
-//   * h0 / h1 / the sampled event travel as st.async stores that complete on the DESTINATION's mbarrier (lane `gate`
-//     of a unit pushes to CTA `gate`), double-buffered by note parity; a consumer waits on a local mbarrier;
-//   * the two mat-vecs that do not depend on the current note's sample (U0.h0 and U1.h1 of the NEXT note) are computed
-//     while CTA 0's head warp evaluates the heads and samples, so the per-note critical path is
-//     cell 0 -> push -> W1.h0 -> cell 1 -> push -> heads -> sample -> push.
+// arithmetic with the weights in REGISTERS and no barrier inside the note loop.  The kernel above spends 60 % of a
+// note in barriers (ncu: stall_barrier + stall_membar; three barrier.cluster round trips with their membar and L1
+// flush, six block barriers), and a first barrier-free version was bound by the shared-memory port instead (three
+// 128 x 128 mat-vecs per note = 1 500 warp-wide LDS per CTA and note).  Here
+//   * the CTA's 3 x 128 x 128 weight slice lives in the register file: 16 warps, lane = (column c8 of the warp's 8
+//     gate columns, k-quarter kq), 32 weights of each of U0, W1, U1 per lane; a mat-vec is 32 FMAs on x read as 8
+//     conflict-free LDS.128 plus two shuffles over the four k-quarters;
+//   * the four gates of a unit sit in four lane groups of the same warp and are exchanged by shuffle;
+//   * h0 and h1 travel as st.async stores that complete on the DESTINATION's mbarrier, double-buffered by note parity;
+//     a consumer waits on a local mbarrier: two exchanges per note and nothing else;
+//   * the heads and the sampling decision are evaluated REDUNDANTLY by every warp of the cluster from the same
+//     all-gathered h1 (same instructions on the same bits: the same decision everywhere), so the sampled event -- the
+//     next note's `chosen` input -- never has to be sent anywhere; one lane of the cluster writes the outputs;
+//   * U1.h1 and the next note's U0.h0 are computed while the exchanges are in flight: the per-note critical path is
+//     cell 0 -> push -> W1.h0 -> cell 1 -> push -> heads + sample.
 // W1.(h0 + sp) is evaluated as W1.h0 + (W1.sp + b1) with the bracket precomputed per launch.
 // ---------------------------------------------------------------------------
 struct Gen1Smem {
-  float U0[UN * CW], W1[UN * CW], U1[UN * CW];   // [k][local column]
   float h0[2][UN], h1[2][UN];                    // all-gathered hidden states, by note parity
-  float prev[2][4];                              // chosen_{n-1} (play, replay, volume), by note parity
   float wh[3][UN];
   float bh[4];
   float sp[UN];
-  unsigned long long bar_h0[2], bar_h1[2], bar_prev[2];
+  unsigned long long bar_h0[2], bar_h1[2];
 };
 
 __device__ __forceinline__ uint32_t g_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -288,11 +291,6 @@ __device__ __forceinline__ uint32_t g_mapa(uint32_t addr, uint32_t cta) {
 __device__ __forceinline__ void g_st_async_f32(uint32_t raddr, float v, uint32_t rbar) {
   asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];\n" ::"r"(raddr),
                "r"(__float_as_uint(v)), "r"(rbar)
-               : "memory");
-}
-__device__ __forceinline__ void g_st_async_f4(uint32_t raddr, float a, float b, float c, float d, uint32_t rbar) {
-  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];\n" ::"r"(raddr),
-               "f"(a), "f"(b), "f"(c), "f"(d), "r"(rbar)
                : "memory");
 }
 __device__ __forceinline__ void g_bar_init(uint32_t bar, uint32_t count) {
@@ -320,9 +318,12 @@ __device__ __forceinline__ void g_bar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
-constexpr int NTHR1 = 256;    // warps 0..3: the CTA's 128 gate columns; warp 4 of CTA 0: heads + sampling
+constexpr int NTHR1 = 512;    // 16 warps x (8 or 4) gate columns
 
-__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NTHR1, 1) gen_sample1_kernel(
+// CLS = cluster size: 4 (32 units per CTA, 96 weight registers per lane: the register file is full and ~35 of them
+// spill to local memory) or 8 (16 units per CTA, 48 weight registers; used when all clusters still fit the GPU at once)
+template <int CLS>
+__global__ void __launch_bounds__(NTHR1, 1) gen_sample1_kernel(
     const float* __restrict__ zpre, const float* __restrict__ W0c, const float* __restrict__ U0,
     const float* __restrict__ W1, const float* __restrict__ U1, const float* __restrict__ b1,
     const float* __restrict__ sp1, const float* __restrict__ Wn, const float* __restrict__ bn,
@@ -334,182 +335,164 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NTHR1, 1) gen_sampl
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int g = blockIdx.x / CL;                       // the sequence of this cluster
+  constexpr int CWc = G4 / CLS;                        // gate columns per CTA (128 / 64)
+  constexpr int UPCc = CWc / 4;                        // hidden units per CTA (32 / 16)
+  constexpr int CPW = CWc / 16;                        // columns per warp (8 / 4)
+  constexpr int KQN = 32 / CPW;                        // lanes sharing a column = k-slices (4 / 8) = CLS
+  constexpr int KPL = UN / KQN;                        // weights of one matrix per lane (32 / 16)
+  constexpr int NJ = KPL / 4;                          // float4 chunks of x per lane (8 / 4)
+  static_assert(KQN == CLS, "one pushing lane per destination CTA");
+  const int g = blockIdx.x / CLS;                      // the sequence of this cluster
+  const int kq = lane % KQN, cw = lane / KQN;          // k-slice; column inside the warp's CPW
+  const int col = CPW * warp + cw;                     // local gate column (= 4*unit + gate)
+  const int gate = cw & 3, ub16 = (cw >> 2) * 4 * KQN; // first lane of this lane's unit
 
-  for (int i = tid; i < UN * CW; i += NTHR1) {          // resident weight slices
-    const int k = i / CW, cc = i % CW;
-    S.U0[i] = U0[k * G4 + rank * CW + cc];
-    S.W1[i] = W1[k * G4 + rank * CW + cc];
-    S.U1[i] = U1[k * G4 + rank * CW + cc];
+  // the lane's KPL weights of each matrix: k = 4*KQN*j + 4*kq + i  (j < NJ, i < 4), column `col`
+  float wU0[KPL], wW1[KPL], wU1[KPL];
+  {
+    const size_t cg_ = (size_t)rank * CWc + col;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const size_t src = (size_t)(4 * KQN * j + 4 * kq + i) * G4 + cg_;
+        wU0[4 * j + i] = U0[src]; wW1[4 * j + i] = W1[src]; wU1[4 * j + i] = U1[src];
+      }
   }
   for (int i = tid; i < 2 * UN; i += NTHR1) { (&S.h0[0][0])[i] = 0.f; (&S.h1[0][0])[i] = 0.f; }
   for (int i = tid; i < UN; i += NTHR1) {
     S.wh[0][i] = Wn[i * 2]; S.wh[1][i] = Wn[i * 2 + 1]; S.wh[2][i] = Wv[i];
     S.sp[i] = sp1[(int64_t)g * UN + i];
   }
-  if (tid < 8) (&S.prev[0][0])[tid] = 0.f;
   if (tid == 0) {
     S.bh[0] = bn[0]; S.bh[1] = bn[1]; S.bh[2] = bv[0];
 #pragma unroll
-    for (int b = 0; b < 2; ++b) {
-      g_bar_init(g_smem_u32(&S.bar_h0[b]), 1); g_bar_init(g_smem_u32(&S.bar_h1[b]), 1); g_bar_init(g_smem_u32(&S.bar_prev[b]), 1);
-    }
+    for (int b = 0; b < 2; ++b) { g_bar_init(g_smem_u32(&S.bar_h0[b]), 1); g_bar_init(g_smem_u32(&S.bar_h1[b]), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   __syncthreads();
-  const bool main_warp = warp < 4;
-  const int col = 32 * warp + lane;                    // main warps: local gate column (= 4*unit + gate)
-  const int gate = lane & 3, ubase = lane & ~3;
-  // per-column constants of the main warps
-  float w0c0 = 0.f, w0c1 = 0.f, w0c2 = 0.f, c1const = 0.f;
-  if (main_warp) {
-    const int gc = rank * CW + col;
-    w0c0 = W0c[gc]; w0c1 = W0c[G4 + gc]; w0c2 = W0c[2 * G4 + gc];
-    float a = b1[gc];                                  // W1.(h0 + sp) + b1 = W1.h0 + (W1.sp + b1)
-    for (int k = 0; k < UN; ++k) a = fmaf(S.sp[k], S.W1[k * CW + col], a);
-    c1const = a;
-  }
-  const uint32_t sbase = g_smem_u32(&S);
-  uint32_t rbase[CL];
-#pragma unroll
-  for (int r = 0; r < CL; ++r) rbase[r] = g_mapa(sbase, (uint32_t)r);
-  const uint32_t off_h0 = (uint32_t)((const uint8_t*)&S.h0[0][0] - (const uint8_t*)&S),
-                 off_h1 = (uint32_t)((const uint8_t*)&S.h1[0][0] - (const uint8_t*)&S),
-                 off_prev = (uint32_t)((const uint8_t*)&S.prev[0][0] - (const uint8_t*)&S),
-                 off_bh0 = (uint32_t)((const uint8_t*)&S.bar_h0[0] - (const uint8_t*)&S),
-                 off_bh1 = (uint32_t)((const uint8_t*)&S.bar_h1[0] - (const uint8_t*)&S),
-                 off_bprev = (uint32_t)((const uint8_t*)&S.bar_prev[0] - (const uint8_t*)&S);
-  cluster.sync();   // every CTA's barriers and buffers are initialised before anybody pushes into them
-
-  auto matvec = [&](const float* __restrict__ Wm, const float* __restrict__ x) {
+  // one column of W.x: KPL FMAs per lane, then the k-slices are added by shuffle (every lane gets the sum)
+  auto matvec = [&](const float (&w)[KPL], const float* __restrict__ x) {
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 8
-    for (int k = 0; k < UN; k += 4) {
-      const float4 x4 = *reinterpret_cast<const float4*>(x + k);
-      a0 = fmaf(x4.x, Wm[k * CW + col], a0);
-      a1 = fmaf(x4.y, Wm[(k + 1) * CW + col], a1);
-      a2 = fmaf(x4.z, Wm[(k + 2) * CW + col], a2);
-      a3 = fmaf(x4.w, Wm[(k + 3) * CW + col], a3);
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const float4 x4 = *reinterpret_cast<const float4*>(x + 4 * KQN * j + 4 * kq);
+      a0 = fmaf(x4.x, w[4 * j], a0); a1 = fmaf(x4.y, w[4 * j + 1], a1);
+      a2 = fmaf(x4.z, w[4 * j + 2], a2); a3 = fmaf(x4.w, w[4 * j + 3], a3);
     }
-    return (a0 + a1) + (a2 + a3);
+    float s = (a0 + a1) + (a2 + a3);
+#pragma unroll
+    for (int o = 1; o < KQN; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    return s;
   };
-  // one LSTM cell from the four gate pre-activations held by the four lanes of a unit (every lane computes it)
+  // one LSTM cell from the four gate pre-activations of a unit (lanes ub16 + KQN*gate; every lane of the unit computes it)
   auto cell = [&](float z, float& c) {
-    const float zi = __shfl_sync(0xffffffffu, z, ubase), zf = __shfl_sync(0xffffffffu, z, ubase + 1);
-    const float zg = __shfl_sync(0xffffffffu, z, ubase + 2), zo = __shfl_sync(0xffffffffu, z, ubase + 3);
+    const float zi = __shfl_sync(0xffffffffu, z, ub16), zf = __shfl_sync(0xffffffffu, z, ub16 + KQN);
+    const float zg = __shfl_sync(0xffffffffu, z, ub16 + 2 * KQN), zo = __shfl_sync(0xffffffffu, z, ub16 + 3 * KQN);
     const float gi = dj_gate_act(zi, hard), gf = dj_gate_act(zf, hard);
     const float gg = tanhf(zg), go = dj_gate_act(zo, hard);
     c = fmaf(gf, c, gi * gg);
     return go * tanhf(c);
   };
+  const int gc = rank * CWc + col;
+  const float w0c0 = W0c[gc], w0c1 = W0c[G4 + gc], w0c2 = W0c[2 * G4 + gc];
+  const float c1const = b1[gc] + matvec(wW1, S.sp);    // W1.(h0 + sp) + b1 = W1.h0 + (W1.sp + b1)
+  const uint32_t sbase = g_smem_u32(&S);
+  const uint32_t rdst = g_mapa(sbase, (uint32_t)kq);   // lane kq of a unit's gate-0 group pushes the unit's h to CTA kq
+  const bool pusher = (gate == 0);
+  const uint32_t off_h0 = (uint32_t)((const uint8_t*)&S.h0[0][0] - (const uint8_t*)&S),
+                 off_h1 = (uint32_t)((const uint8_t*)&S.h1[0][0] - (const uint8_t*)&S),
+                 off_bh0 = (uint32_t)((const uint8_t*)&S.bar_h0[0] - (const uint8_t*)&S),
+                 off_bh1 = (uint32_t)((const uint8_t*)&S.bar_h1[0] - (const uint8_t*)&S);
+  cluster.sync();   // every CTA's barriers and buffers are initialised before anybody pushes into them
 
-  if (main_warp) {
-    // ================= the CTA's 32 cells of both note-axis layers =================
-    float c0 = 0.f, c1 = 0.f, a0 = 0.f, a1 = 0.f;      // cell states; U0.h0 and U1.h1 of the coming note (h = 0 at n = 0)
-    const float* zrow = zpre + (int64_t)g * N_ * G4 + rank * CW + col;
-    float zp = zrow[0];
-    const uint32_t hslot = (uint32_t)((rank * 32 + (col >> 2)) * 4);     // this unit inside an all-gathered h vector
-    for (int n = 0; n < N_; ++n) {
-      const int cur = n & 1, nxt = cur ^ 1;
-      const uint32_t par = (uint32_t)(n >> 1) & 1u;
-      if (tid == 0) {   // arm this note's three exchanges (their previous phases were consumed two notes ago)
-        g_bar_expect_tx(sbase + off_bh0 + 8 * nxt, CL * 32 * 4);
-        g_bar_expect_tx(sbase + off_bh1 + 8 * nxt, CL * 32 * 4);
-        g_bar_expect_tx(sbase + off_bprev + 8 * nxt, 16);
-      }
-      const float zp_next = (n + 1 < N_) ? zrow[(int64_t)(n + 1) * G4] : 0.f;
-      // ---- layer 0: z = zpre + chosen_{n-1}.W0[Ut:Ut+3] + U0.h0
-      if (n > 0) g_bar_wait(sbase + off_bprev + 8 * cur, (uint32_t)((n - 1) >> 1) & 1u);
-      float z = zp;
-      z = fmaf(S.prev[cur][0], w0c0, z);
-      z = fmaf(S.prev[cur][1], w0c1, z);
-      z = fmaf(S.prev[cur][2], w0c2, z);
-      z += a0;
-      const float h0n = cell(z, c0);
-      g_st_async_f32(rbase[gate] + off_h0 + (uint32_t)(nxt * UN * 4) + hslot, h0n, rbase[gate] + off_bh0 + 8 * nxt);
-      zp = zp_next;
-      // ---- layer 1: z = (W1.sp + b1) + W1.h0 + U1.h1
-      g_bar_wait(sbase + off_bh0 + 8 * nxt, par);
-      const float z1 = c1const + matvec(S.W1, S.h0[nxt]) + a1;
-      const float h1n = cell(z1, c1);
-      g_st_async_f32(rbase[gate] + off_h1 + (uint32_t)(nxt * UN * 4) + hslot, h1n, rbase[gate] + off_bh1 + 8 * nxt);
-      // ---- off the critical path (CTA 0's head warp is sampling now): the recurrent terms of the next note
-      a0 = matvec(S.U0, S.h0[nxt]);
-      g_bar_wait(sbase + off_bh1 + 8 * nxt, par);
-      a1 = matvec(S.U1, S.h1[nxt]);
+  const bool writer = (rank == 0 && tid == 0);         // the one lane of the cluster that owns the outputs
+  float c0 = 0.f, c1 = 0.f, a0 = 0.f, a1 = 0.f;        // cell states; U0.h0 and U1.h1 of the coming note (h = 0 at n = 0)
+  float e0 = 0.f, e1 = 0.f, e2 = 0.f;                  // chosen_{n-1}: the event sampled for the previous note
+  int64_t cursor = (stream_mode == 0 && ucursor != nullptr) ? *ucursor : 0;
+  const double temp = temperature[g];
+  int played_any = 0;
+  double margin = 1e300;
+  const float* zrow = zpre + (int64_t)g * N_ * G4 + gc;
+  float zp = zrow[0];
+  const uint32_t hslot = (uint32_t)((rank * UPCc + (col >> 2)) * 4);   // this unit inside an all-gathered h vector
+  for (int n = 0; n < N_; ++n) {
+    const int cur = n & 1, nxt = cur ^ 1;
+    const uint32_t par = (uint32_t)(n >> 1) & 1u;
+    if (tid == 0) {   // arm this note's two exchanges (their previous phases were consumed two notes ago)
+      g_bar_expect_tx(sbase + off_bh0 + 8 * nxt, UN * 4);
+      g_bar_expect_tx(sbase + off_bh1 + 8 * nxt, UN * 4);
     }
-  } else if (warp == 4 && rank == 0) {
-    // ================= heads + sampling (model.py:94-95, generate.py:47-58) =================
-    int64_t cursor = (stream_mode == 0 && ucursor != nullptr) ? *ucursor : 0;
-    const double temp = temperature[g];
-    int played_any = 0;
-    double margin = 1e300;
-    for (int n = 0; n < N_; ++n) {
-      const int nxt = (n & 1) ^ 1;
-      const uint32_t par = (uint32_t)(n >> 1) & 1u;
-      // the first uniform this note is certain to consume
-      double upre0 = 0.0;
-      if (lane == 0) upre0 = (stream_mode == 0) ? uniforms[cursor] : uniforms[((int64_t)g * N_ + n) * 2];
-      g_bar_wait(sbase + off_bh1 + 8 * nxt, par);
-      float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    const float zp_next = (n + 1 < N_) ? zrow[(int64_t)(n + 1) * G4] : 0.f;
+    // the first uniform this note is certain to consume
+    const double u1 = (stream_mode == 0) ? uniforms[cursor] : uniforms[((int64_t)g * N_ + n) * 2];
+    // ---- layer 0: z = zpre + chosen_{n-1}.W0[Ut:Ut+3] + U0.h0
+    float z = zp;
+    z = fmaf(e0, w0c0, z);
+    z = fmaf(e1, w0c1, z);
+    z = fmaf(e2, w0c2, z);
+    z += a0;
+    const float h0n = cell(z, c0);
+    if (pusher) g_st_async_f32(rdst + off_h0 + (uint32_t)(nxt * UN * 4) + hslot, h0n, rdst + off_bh0 + 8 * nxt);
+    zp = zp_next;
+    if (n > 0) a1 = matvec(wU1, S.h1[cur]);            // recurrent term of layer 1, while h0 is in flight
+    // ---- layer 1: z = (W1.sp + b1) + W1.h0 + U1.h1
+    g_bar_wait(sbase + off_bh0 + 8 * nxt, par);
+    const float z1 = c1const + matvec(wW1, S.h0[nxt]) + a1;
+    const float h1n = cell(z1, c1);
+    if (pusher) g_st_async_f32(rdst + off_h1 + (uint32_t)(nxt * UN * 4) + hslot, h1n, rdst + off_bh1 + 8 * nxt);
+    a0 = matvec(wU0, S.h0[nxt]);                       // recurrent term of layer 0 of the NEXT note, while h1 is in flight
+    // ---- heads + sampling (model.py:94-95, generate.py:47-58), by every warp alike
+    g_bar_wait(sbase + off_bh1 + 8 * nxt, par);
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
 #pragma unroll
-      for (int k = lane; k < UN; k += 32) {
-        const float hv = S.h1[nxt][k];
-        s0 = fmaf(hv, S.wh[0][k], s0); s1 = fmaf(hv, S.wh[1][k], s1); s2 = fmaf(hv, S.wh[2][k], s2);
-      }
-      s0 = dj_warp_sum(s0); s1 = dj_warp_sum(s1); s2 = dj_warp_sum(s2);
-      float e0 = 0.f, e1 = 0.f, e2 = 0.f;
-      if (lane == 0) {
-        float p0 = dj_sigmoid(s0 + S.bh[0]), p1 = dj_sigmoid(s1 + S.bh[1]);
-        const float vol = s2 + S.bh[2];
-        if (probs_out != nullptr) {
-          float* po = probs_out + ((int64_t)g * N_ + n) * 3;
-          po[0] = p0; po[1] = p1; po[2] = vol;
-        }
-        if (temp != 1.0) {   // generate.py:81-91, float32 arithmetic like NumPy on a float32 array
-          const float tf = (float)temp;
-          const float xa = -logf(1.0f / p0 - 1.0f), xb = -logf(1.0f / p1 - 1.0f);
-          p0 = 1.0f / (1.0f + expf(-xa / tf));
-          p1 = 1.0f / (1.0f + expf(-xb / tf));
-        }
-        double u2;
-        const double* ui = uniforms + ((int64_t)g * N_ + n) * 2;
-        const double u1 = upre0;
-        if (stream_mode == 0) cursor++;
-        double mg = fabs(u1 - (double)p0);
-        if (u1 <= (double)p0) {   // generate.py:52
-          e0 = 1.f; e2 = vol;
-          if (stream_mode == 0) u2 = uniforms[cursor++]; else u2 = ui[1];
-          mg = fmin(mg, fabs(u2 - (double)p1));
-          if (u2 <= (double)p1) e1 = 1.f;   // generate.py:57
-          played_any = 1;
-        }
-        margin = fmin(margin, mg);
-        float* ev = events + ((int64_t)g * N_ + n) * 3;
-        ev[0] = e0; ev[1] = e1; ev[2] = e2;
-      }
-      e0 = __shfl_sync(0xffffffffu, e0, 0); e1 = __shfl_sync(0xffffffffu, e1, 0); e2 = __shfl_sync(0xffffffffu, e2, 0);
-      // the event row is the next note's `chosen` input: lane r pushes it to CTA r
-      if (lane < CL)
-        g_st_async_f4(rbase[lane] + off_prev + (uint32_t)(nxt * 16), e0, e1, e2, 0.f, rbase[lane] + off_bprev + 8 * nxt);
+    for (int k = lane; k < UN; k += 32) {
+      const float hv = S.h1[nxt][k];
+      s0 = fmaf(hv, S.wh[0][k], s0); s1 = fmaf(hv, S.wh[1][k], s1); s2 = fmaf(hv, S.wh[2][k], s2);
     }
-    // ---- end_time (generate.py:60-79): silence raises the temperature
-    if (lane == 0) {
-      if (!played_any) {   // np.count_nonzero(next_note) == 0  <=>  nothing played
-        const int st = silent_time[g] + 1;
-        silent_time[g] = st;
-        if (st >= DJ_BEAT) temperature[g] = temperature[g] + 0.1;
-      } else {
-        silent_time[g] = 0;
-        temperature[g] = default_temp;
-      }
-      if (margin_out != nullptr) margin_out[g] = fmin(margin_out[g], margin);
-      if (stream_mode == 0 && ucursor != nullptr) *ucursor = cursor;
+    s0 = dj_warp_sum(s0); s1 = dj_warp_sum(s1); s2 = dj_warp_sum(s2);
+    float p0 = dj_sigmoid(s0 + S.bh[0]), p1 = dj_sigmoid(s1 + S.bh[1]);
+    const float vol = s2 + S.bh[2];
+    if (writer && probs_out != nullptr) {
+      float* po = probs_out + ((int64_t)g * N_ + n) * 3;
+      po[0] = p0; po[1] = p1; po[2] = vol;
+    }
+    if (temp != 1.0) {   // generate.py:81-91, float32 arithmetic like NumPy on a float32 array
+      const float tf = (float)temp;
+      const float xa = -logf(1.0f / p0 - 1.0f), xb = -logf(1.0f / p1 - 1.0f);
+      p0 = 1.0f / (1.0f + expf(-xa / tf));
+      p1 = 1.0f / (1.0f + expf(-xb / tf));
+    }
+    if (stream_mode == 0) cursor++;
+    e0 = 0.f; e1 = 0.f; e2 = 0.f;
+    double mg = fabs(u1 - (double)p0);
+    if (u1 <= (double)p0) {   // generate.py:52 (warp-uniform: every lane holds the same values)
+      e0 = 1.f; e2 = vol;
+      const double u2 = (stream_mode == 0) ? uniforms[cursor++] : uniforms[((int64_t)g * N_ + n) * 2 + 1];
+      mg = fmin(mg, fabs(u2 - (double)p1));
+      if (u2 <= (double)p1) e1 = 1.f;   // generate.py:57
+      played_any = 1;
+    }
+    margin = fmin(margin, mg);
+    if (writer) {
+      float* ev = events + ((int64_t)g * N_ + n) * 3;
+      ev[0] = e0; ev[1] = e1; ev[2] = e2;
     }
   }
-  // the last note's event row is still in flight to every CTA: its barrier must complete before anyone exits
-  if (tid == 32) g_bar_wait(sbase + off_bprev + 8 * ((N_ - 1) & 1 ^ 1), (uint32_t)((N_ - 1) >> 1) & 1u);
-  cluster.sync();
+  // ---- end_time (generate.py:60-79): silence raises the temperature
+  if (writer) {
+    if (!played_any) {   // np.count_nonzero(next_note) == 0  <=>  nothing played
+      const int st = silent_time[g] + 1;
+      silent_time[g] = st;
+      if (st >= DJ_BEAT) temperature[g] = temperature[g] + 0.1;
+    } else {
+      silent_time[g] = 0;
+      temperature[g] = default_temp;
+    }
+    if (margin_out != nullptr) margin_out[g] = fmin(margin_out[g], margin);
+    if (stream_mode == 0 && ucursor != nullptr) *ucursor = cursor;
+  }
+  cluster.sync();   // nobody exits while a peer may still push into it (every push of the last note has been waited for)
 }
 
 }  // namespace
@@ -534,12 +517,21 @@ extern "C" int dj_gen_sample(const float* zpre, const float* W0c, const float* U
   static int fast1 = -1;      // DJ_GEN_SAMPLE1=0: the barrier-synchronised kernel also for one sequence per cluster
   if (fast1 < 0) { const char* e = getenv("DJ_GEN_SAMPLE1"); fast1 = (e && atoi(e) == 0) ? 0 : 1; }
   if (gcount == 1 && fast1) {
-    DJ_CUDA(cudaFuncSetAttribute((const void*)gen_sample1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)sizeof(Gen1Smem)));
-    gen_sample1_kernel<<<nclusters * CL, NTHR1, sizeof(Gen1Smem), (cudaStream_t)stream>>>(
-        zpre, W0c, U0, W1, U1, b1, sp1, Wn, bn, Wv, bv, uniforms, ucursor, stream_mode, temperature, silent_time,
-        default_temp, hard, events, probs_out, margin_out);
-    DJ_LAUNCH_CHECK();
+    // clusters of 8 halve the weights per lane (no register spills) as long as every cluster is resident at once
+    const int cls = (nclusters * 8 <= 120) ? 8 : 4;
+    auto kernel = cls == 8 ? gen_sample1_kernel<8> : gen_sample1_kernel<4>;
+    DJ_CUDA(cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Gen1Smem)));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(nclusters * cls);
+    cfg.blockDim = dim3(NTHR1);
+    cfg.dynamicSmemBytes = sizeof(Gen1Smem);
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cls; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    DJ_CUDA(cudaLaunchKernelEx(&cfg, kernel, zpre, W0c, U0, W1, U1, b1, sp1, Wn, bn, Wv, bv, uniforms, ucursor, stream_mode,
+                               temperature, silent_time, default_temp, hard, events, probs_out, margin_out));
     return 0;
   }
   DJ_CUDA(cudaFuncSetAttribute((const void*)gen_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
