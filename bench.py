@@ -626,8 +626,10 @@ def _run_generation(args):
             "e2e": {"value": e2e, "unit": "timesteps/s", "h2d_bytes_per_step": int(u.nbytes // max(K + W, 1)) if mode == 1 else 16 * N_NOTES,
                     "d2h_bytes_per_step": G * N_NOTES * 3 * 4, "ms_per_step": ms_e2e / K},
             "gpu_launches": launches, "clocks": clocks,
-            "roofline": dict({"kernel": "time-axis window recompute (2 LSTM layers x 128 steps per generated timestep): "
-                                        "dj_gate_gemm_16s + dj_lstm_scan_tc_infer" if eng.gen_tc else
+            "roofline": dict({"kernel": ("time-axis window recompute (2 LSTM layers x 128 steps per generated timestep): "
+                                         + ("dj_gate_gemm_16s + dj_lstm_scan_tc_gen2 (both layers in one launch, layer 1 one "
+                                            "step behind layer 0: ~130 sequential steps)" if (single and eng.gen_fused) else
+                                            "dj_gate_gemm_16s + dj_lstm_scan_tc_infer")) if eng.gen_tc else
                                         "time-axis window recompute: dj_gemm_simt + dj_lstm_scan_fwd",
                               "achieved": flops / 1e12, "unit": "TFLOP/s", "frac": flops / 1e12 / roof["peak"],
                               "traffic": None}, **roof),
