@@ -68,6 +68,32 @@ def test_peer_exchange_rejects_bad_arguments_before_any_launch(lib):
     assert lib.dj_peer_open(None, None) < 0 and lib.dj_peer_close(None) < 0 and lib.dj_peer_free(None) < 0
 
 
+def test_round2_entry_points_validate_arguments_on_the_host(lib):
+    """The entry points added in round 2 reject bad arguments before any CUDA call (so this runs without a GPU)."""
+    import ctypes as C
+    one = C.c_void_p(16)
+    # fused two-layer generation scan: NULL pointers, ragged sequence counts, more clusters than can be co-resident
+    P13 = [one] * 13
+    assert lib.dj_lstm_scan_tc_gen2(None, *P13, 1.0 / 1024, one, 48, 128, 1, None) < 0
+    assert b"NULL" in lib.dj_last_error()
+    assert lib.dj_lstm_scan_tc_gen2(one, *P13, 1.0 / 1024, one, 50, 128, 1, None) < 0
+    assert lib.dj_lstm_scan_tc_gen2(one, *P13, 1.0 / 1024, one, 48 * 3, 128, 1, None) < 0
+    assert b"at most 2 sequences" in lib.dj_last_error()
+    assert lib.dj_lstm_scan_tc_gen2(one, *P13, 0.0, one, 48, 128, 1, None) < 0
+    # deterministic-reduction workspace: registering, replacing and unregistering is host-side bookkeeping
+    st = C.c_void_p(0x1000)
+    assert lib.dj_set_reduce_workspace(st, None, 64) < 0            # a size without a buffer
+    assert lib.dj_set_reduce_workspace(st, one, -1) < 0
+    assert lib.dj_set_reduce_workspace(st, one, 1 << 20) == 0
+    assert lib.dj_set_reduce_workspace(st, one, 1 << 21) == 0       # same stream: replaced, not a second slot
+    assert lib.dj_set_reduce_workspace(st, None, 0) == 0
+    for i in range(8):                                              # eight streams fit, the ninth is refused
+        assert lib.dj_set_reduce_workspace(C.c_void_p(0x2000 + i), one, 16) == 0
+    assert lib.dj_set_reduce_workspace(C.c_void_p(0x3000), one, 16) < 0
+    for i in range(8):
+        assert lib.dj_set_reduce_workspace(C.c_void_p(0x2000 + i), None, 0) == 0
+
+
 def test_dropout_key_matches_numpy_twin(lib):
     from music_generator_b200 import _lib
     import helpers
