@@ -185,6 +185,8 @@ class Engine:
         # reverse scan) on a high-priority stream, the weight / style / conv gradients behind it on the caller's
         self.overlap = os.environ.get("DJ_NO_OVERLAP", "") == ""
         self._hi = None
+        self._light = None
+        self.bwd_streams = int(os.environ.get("DJ_BWD_STREAMS", "3"))
         self._tag = ""
         self.peer = None      # parallel.PeerNadam: fused gradient exchange + Nadam over peer memory
         # The training step as ONE CUDA graph launch (DJ_GRAPH=0: ~56 launches from Python).  Per-step values live in
@@ -601,12 +603,23 @@ class Engine:
         if two and self._hi is None:
             self._hi = torch.cuda.Stream(device=self.dev, priority=-1)
         chain = self._hi if two else main
+        # third stream (DJ_BWD_STREAMS=2 turns it off): the style / conv gradients (HBM- and FMA-bound, small) no longer
+        # queue behind the weight-gradient GEMMs, which run in the shadow of the chain's scans and are stretched by
+        # them; both side streams then have less left to do when the chain ends
+        three = two and self.bwd_streams >= 3
+        if three and self._light is None:
+            self._light = torch.cuda.Stream(device=self.dev)
+        light = self._light if three else main
         if self.deterministic:
             self._register_reduce_ws(main)
             if two:
                 self._register_reduce_ws(chain)
+            if three:
+                self._register_reduce_ws(light)
         if two:
             chain.wait_stream(main)           # forward, zeroed gradients
+        if three:
+            light.wait_stream(main)
         dY, ldY = ws.dXtop, cfg.note_axis_units
         first_style = True
         if bf16 and ws.hprev[0].dtype == torch.float16:
@@ -661,26 +674,30 @@ class Engine:
                            _ptr(G[f"{name}.lstm.U"]), U4, None, U, U4, M, 1, shift, period, _stream())
             # style projection backward (model.py:77-82 / 113-117) needs dA of this layer
             if two:
-                main.wait_event(ev_dgrad)
-            self._call("dj_style_bwd_reduce", _ptr(ws.dA[li]), ld, F, _ptr(ws.sp[li]), d[L["site_sp"]], BT,
-                       _ptr(ws.ds[li]), _stream())
-            self._call("dj_gemm_simt", _ptr(ws.emb), DJ_F32, 1, cfg.style_units, _ptr(ws.ds[li]), DJ_F32, F, 1,
-                       _ptr(G[f"{name}.sd.W"]), F, None, cfg.style_units, F, BT, 1, 0, 0, _stream())
-            self._call("dj_colsum", _ptr(ws.ds[li]), F, BT, F, _ptr(G[f"{name}.sd.b"]), 1, _stream())
-            self._call("dj_gemm_simt", _ptr(ws.ds[li]), DJ_F32, F, 1, _ptr(P[f"{name}.sd.W"]), DJ_F32, 1, F,
-                       _ptr(ws.demb), cfg.style_units, None, BT, cfg.style_units, F, 0 if first_style else 1, 0, 0,
-                       _stream())
+                light.wait_event(ev_dgrad)
+            with torch.cuda.stream(light):
+                self._call("dj_style_bwd_reduce", _ptr(ws.dA[li]), ld, F, _ptr(ws.sp[li]), d[L["site_sp"]], BT,
+                           _ptr(ws.ds[li]), _stream())
+                self._call("dj_gemm_simt", _ptr(ws.emb), DJ_F32, 1, cfg.style_units, _ptr(ws.ds[li]), DJ_F32, F, 1,
+                           _ptr(G[f"{name}.sd.W"]), F, None, cfg.style_units, F, BT, 1, 0, 0, _stream())
+                self._call("dj_colsum", _ptr(ws.ds[li]), F, BT, F, _ptr(G[f"{name}.sd.b"]), 1, _stream())
+                self._call("dj_gemm_simt", _ptr(ws.ds[li]), DJ_F32, F, 1, _ptr(P[f"{name}.sd.W"]), DJ_F32, 1, F,
+                           _ptr(ws.demb), cfg.style_units, None, BT, cfg.style_units, F, 0 if first_style else 1, 0, 0,
+                           _stream())
             first_style = False
             dY, ldY = ws.dA[li], ld
         self._tag = ""
-        self._call("dj_conv_bwd", _ptr(st["notes"]), T * N * 3, B, T, _ptr(P["conv.W"]), _ptr(P["conv.b"]), d[1],
-                   d[4], _ptr(ws.dA[0]), ws.ld[0], _ptr(G["conv.W"]), _ptr(G["conv.b"]), _stream())
-        ns = cfg.num_styles
-        self._call("dj_gemm_simt", _ptr(st["style"]), DJ_F32, 1, ns, _ptr(ws.demb), DJ_F32, cfg.style_units, 1,
-                   _ptr(G["style.W"]), cfg.style_units, None, ns, cfg.style_units, BT, 1, 0, 0, _stream())
-        self._call("dj_colsum", _ptr(ws.demb), cfg.style_units, BT, cfg.style_units, _ptr(G["style.b"]), 1, _stream())
+        with torch.cuda.stream(light):
+            self._call("dj_conv_bwd", _ptr(st["notes"]), T * N * 3, B, T, _ptr(P["conv.W"]), _ptr(P["conv.b"]), d[1],
+                       d[4], _ptr(ws.dA[0]), ws.ld[0], _ptr(G["conv.W"]), _ptr(G["conv.b"]), _stream())
+            ns = cfg.num_styles
+            self._call("dj_gemm_simt", _ptr(st["style"]), DJ_F32, 1, ns, _ptr(ws.demb), DJ_F32, cfg.style_units, 1,
+                       _ptr(G["style.W"]), cfg.style_units, None, ns, cfg.style_units, BT, 1, 0, 0, _stream())
+            self._call("dj_colsum", _ptr(ws.demb), cfg.style_units, BT, cfg.style_units, _ptr(G["style.b"]), 1, _stream())
         if two:
             main.wait_stream(chain)
+        if three:
+            main.wait_stream(light)
         if self.deterministic:
             self._unregister_reduce_ws()      # the registration is per calling thread and stream: leave none behind
         return ws.loss
