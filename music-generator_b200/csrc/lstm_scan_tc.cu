@@ -1543,20 +1543,14 @@ scan_tc_gen2_kernel(const __grid_constant__ CUtensorMap tmU0lo, const __grid_con
         __syncwarp();
       }
       if (isP) {
-        // rows t-1 of Z1 are stored (the epilogue cannot be further: it needs the commit below): publish them
-        if (t > 0) {
-          mbar_wait(bar_done, (uint32_t)(t - 1) & 1u);
-          if (elect_one()) red_release_gpu_add(flags1, 1u);
-          __syncwarp();
-        }
+        // the epilogue of step t-1 must have read its accumulator set before round t+1 reuses it, and it cannot be
+        // further than t-1 (it needs the commit below): waiting here keeps the parity waits one phase apart
+        if (t > 0) mbar_wait(bar_done, (uint32_t)(t - 1) & 1u);
       } else if (t > 0) {
         // ---- recurrent pass: h_{t-1} published by every CTA of this cluster, all-gathered by multicast
         const uint32_t par = (uint32_t)(t - 1) & 1u;
         mbar_wait(bar_done, par);                         // this CTA's epilogue warps stored their part of h_{t-1}
         if (lane < C) mbar_arrive_remote(bar_pub, (uint32_t)lane);  // release.cluster, cumulative
-        // layer 0: tell P / layer 1 as well (cumulative gpu-scope release).  Issued by a lane that does no remote
-        // arrive, AFTER the arrives, so its fence overlaps the wait for the other CTAs instead of preceding it
-        if (isL0 && lane == C) red_release_gpu_add(flags0, 1u);
         __syncwarp();
         mbar_wait(bar_pub, par);
         if (elect_one()) {
@@ -1576,10 +1570,17 @@ scan_tc_gen2_kernel(const __grid_constant__ CUtensorMap tmU0lo, const __grid_con
       if (elect_one()) umma_commit(bar_acc0 + 8 * (t & 1));
       __syncwarp();
     }
-    if (isL0 || isP) {   // the last step feeds no recurrence here, but its consumer still waits for it
-      mbar_wait(bar_done, (uint32_t)(steps - 1) & 1u);
-      if (elect_one()) red_release_gpu_add(isL0 ? flags0 : flags1, 1u);
-      __syncwarp();
+  } else if (warp == 1 + TC_EPI_WARPS) {
+    // ================= publisher (layer 0 and P): one counter bump per step for the next stage =================
+    // A gpu-scope release costs ~1 000 cycles; in the issuer warp it would sit on the step's chain, so this otherwise
+    // idle warp watches the same `done` barrier (the epilogue's stores of step t are complete and CTA-visible) and
+    // publishes them: the release is cumulative over what the acquire of the barrier wait made visible to this thread.
+    if (isL0 || isP) {
+      for (int t = 0; t < steps; ++t) {
+        mbar_wait(bar_done, (uint32_t)t & 1u);
+        if (lane == 0) red_release_gpu_add(isL0 ? flags0 : flags1, 1u);
+        __syncwarp();
+      }
     }
   } else if (warp <= TC_EPI_WARPS) {
     // ================= epilogue warps (as the inference scan: one 16-sequence chunk) =================
