@@ -142,3 +142,45 @@ def test_not_hdf5_and_new_style_files_are_clear_errors(tmp_path):
     p.write_bytes(b"\x89HDF\r\n\x1a\n\x02" + b"\0" * 600)        # superblock version 2 (libver='latest')
     with pytest.raises(h5lite.H5Error, match="superblock version 2"):
         h5lite.File(str(p))
+
+
+def test_reader_handles_chunked_deflate_shuffle_datasets(tmp_path):
+    """Keras never writes chunked weights, other producers do (h5py with compression=...): data layout class 2 through
+    the version-1 raw-data B-tree, with the shuffle and deflate filters.  The file is assembled here from the
+    specification's structures (the writer only emits contiguous datasets)."""
+    import zlib
+    w = h5lite._Writer()
+    a = (np.arange(7 * 10, dtype=np.float32).reshape(7, 10) * 0.5 - 3).astype("<f4")
+    chunk = (4, 8)
+    keys = []
+    for r0 in range(0, 7, chunk[0]):
+        for c0 in range(0, 10, chunk[1]):
+            tile = np.zeros(chunk, "<f4")
+            blk = a[r0:r0 + chunk[0], c0:c0 + chunk[1]]
+            tile[:blk.shape[0], :blk.shape[1]] = blk
+            raw = np.frombuffer(tile.tobytes(), np.uint8).reshape(-1, 4).T.tobytes()      # shuffle (filter 2)
+            raw = zlib.compress(raw)                                                       # deflate (filter 1)
+            keys.append((len(raw), (r0, c0, 0), w.alloc(raw)))
+    node = bytearray(b"TREE" + struct.pack("<BBHQQ", 1, 0, len(keys), h5lite.UNDEF, h5lite.UNDEF))
+    for size, offs, addr in keys:
+        node += struct.pack("<II", size, 0) + struct.pack("<QQQ", *offs) + struct.pack("<Q", addr)
+    node += struct.pack("<II", 0, 0) + struct.pack("<QQQ", 8, 0, 0)                        # the closing key
+    btree = w.alloc(bytes(node))
+    filt = struct.pack("<BB6x", 1, 2)                                                      # pipeline v1, two filters
+    filt += struct.pack("<HHHH", 2, 0, 0, 1) + struct.pack("<II", 4, 0)                    # shuffle, 1 client value (+pad)
+    filt += struct.pack("<HHHH", 1, 0, 0, 1) + struct.pack("<II", 6, 0)                    # deflate level 6 (+pad)
+    msgs = [(0x0001, h5lite._space_msg(a.shape)), (0x0003, h5lite._dtype_msg(a.dtype)),
+            (0x0005, struct.pack("<BBBBI", 2, 2, 2, 1, 0)), (0x000B, filt),
+            (0x0008, struct.pack("<BBBQIII", 3, 2, 3, btree, chunk[0], chunk[1], 4))]
+    dset = w.alloc(h5lite._header(msgs))
+    # a root group holding that one dataset: reuse the writer's group builder with a placeholder, then patch the link
+    root = w.group({"x": np.zeros(1, np.float32)})
+    data = bytearray(w.finish(root))
+    snod = data.index(b"SNOD")
+    struct.pack_into("<Q", data, snod + 8 + 8, dset)                                        # entry 0: object header address
+    p = tmp_path / "chunked.h5"
+    p.write_bytes(bytes(data))
+    with h5lite.File(str(p)) as f:
+        d = f["x"]
+        assert d.shape == (7, 10) and d._filters() == [(2, (4,)), (1, (6,))]
+        assert np.array_equal(d.read(), a)
