@@ -350,6 +350,74 @@ def test_lstm_scan_tcgen05_matches_fp32_scan(lib, axis, B, T, mode):
     assert torch.equal(p4, want.to(hdt).float())
 
 
+def _keras_lstm_f64(Z0, Uw, rows, S, steps, U):
+    """float64 restatement of the Keras LSTM step (gate-interleaved columns i,f,c,o, hard_sigmoid, zero
+    initial state) over rows[seq, step]."""
+    Z64, U64 = Z0.double(), Uw.double()
+    hs, cs = torch.zeros(S, U, dtype=torch.float64), torch.zeros(S, U, dtype=torch.float64)
+    href = torch.zeros(Z0.shape[0], U, dtype=torch.float64)
+    for t in range(steps):
+        z = (Z64[rows[:, t]] + hs @ U64).view(S, U, 4)
+        i, f, o = [(0.2 * z[..., k] + 0.5).clamp(0, 1) for k in (0, 1, 3)]
+        cs = f * cs + i * torch.tanh(z[..., 2])
+        hs = o * torch.tanh(cs)
+        href[rows[:, t]] = hs
+    return href
+
+
+@pytest.mark.parametrize("axis,B,T", [("time", 2, 24), ("note", 2, 32), ("time", 34, 6)])
+def test_lstm_scan_tcgen05_matches_float64_recurrence(lib, axis, B, T):
+    """The training recurrence on the tensor cores (h in IEEE half, U as half hi + lo) DIRECTLY against the float64
+    restatement of the Keras step, not through the fp32 kernel: the error is the half rounding of h, 1e-4 class."""
+    from music_generator_b200 import _lib
+    g = torch.Generator().manual_seed(21)
+    U = 256 if axis == "time" else 128
+    M = B * T * 48
+    Z0 = torch.randn(M, 4 * U, generator=g)
+    Uw = torch.randn(U, 4 * U, generator=g) * 0.06
+    if axis == "time":
+        S, steps, m = B * 48, T, (48, T * 48, 1, 48)
+        rows = torch.arange(M).view(B, T, 48).permute(0, 2, 1).reshape(S, steps)
+    else:
+        S, steps, m = B * T, 48, (1, 48, 0, 1)
+        rows = torch.arange(M).view(S, steps)
+    Ut, Ut_lo = _split16(Uw.t().contiguous(), torch.float16)
+    Zt, Ut, Ut_lo = Z0.cuda(), Ut.cuda(), Ut_lo.cuda()
+    ht, ct = torch.zeros(M, U, device="cuda"), torch.zeros(M, U, device="cuda")
+    hp = torch.zeros(M, U, device="cuda", dtype=torch.float16)
+    G16 = torch.zeros(M, 4 * U, device="cuda", dtype=torch.float16)
+    _lib.check(lib.dj_lstm_scan_tc_fwd(P(Zt), P(G16), P(ht), P(ct), P(hp), P(Ut), P(Ut_lo), 2, S, steps, U, *m, 1, None))
+    torch.cuda.synchronize()
+    href = _keras_lstm_f64(Z0, Uw, rows, S, steps, U)
+    err = (ht.cpu().double() - href).abs()
+    print(f"scan_tc_fwd vs float64 [{axis},{B},{T}]: max {float(err.max()):.2e} mean {float(err.mean()):.2e}")
+    assert float(err.max()) < 1e-3 and float(err.mean()) < 3e-5
+
+
+def test_lstm_scan_tcgen05_inference_matches_float64_recurrence(lib):
+    """The generation window's recurrence (h and U as half hi + lo, three MMA passes) directly against float64."""
+    from music_generator_b200 import _lib
+    g = torch.Generator().manual_seed(22)
+    B, T, U = 1, 128, 256
+    M = B * T * 48
+    Z0 = torch.randn(M, 4 * U, generator=g)
+    Uw = torch.randn(U, 4 * U, generator=g) * 0.06
+    S, steps, m = B * 48, T, (48, T * 48, 1, 48)
+    rows = torch.arange(M).view(B, T, 48).permute(0, 2, 1).reshape(S, steps)
+    scale = 1024.0
+    Ut, Ut_lo = _split16((Uw.t().contiguous() * scale), torch.float16)
+    Zt, Ut, Ut_lo = Z0.cuda(), Ut.cuda(), Ut_lo.cuda()
+    ht = torch.zeros(M, U, device="cuda")
+    hhi = torch.zeros(M + 48, U, device="cuda", dtype=torch.float16)
+    hlo = torch.zeros(M + 48, U, device="cuda", dtype=torch.float16)
+    _lib.check(lib.dj_lstm_scan_tc_infer(P(Zt), P(ht), P(hhi), P(hlo), P(Ut), P(Ut_lo), 1.0 / scale, S, steps, U, *m, 1, None))
+    torch.cuda.synchronize()
+    href = _keras_lstm_f64(Z0, Uw, rows, S, steps, U)
+    err = (ht.cpu().double() - href).abs()
+    print(f"scan_tc_infer vs float64: max {float(err.max()):.2e} mean {float(err.mean()):.2e}")
+    assert float(err.max()) < 5e-6
+
+
 @pytest.mark.parametrize("axis,B,T", [("time", 3, 8), ("note", 2, 32), ("note", 40, 128), ("note256", 2, 32),
                                       ("time", 40, 6), ("time", 64, 5),   # > 33 tiles: 96-sequence tiles, shared staging
                                       ("time", 35, 4),                     # odd batch: two waves of 48-sequence tiles
