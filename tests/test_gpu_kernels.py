@@ -456,6 +456,60 @@ def test_lstm_scan_bwd_tcgen05_matches_fp32_scan(lib, axis, B, T):
     assert helpers.rel_err(dbt.cpu().numpy(), dbr.cpu().numpy()) < 0.02
 
 
+@pytest.mark.parametrize("axis,B,T", [("time", 2, 12), ("note", 2, 32)])
+def test_lstm_scan_bwd_tcgen05_matches_float64_autograd(lib, axis, B, T):
+    """The reverse scan on the tensor cores against AUTOGRAD through the float64 restatement of the Keras step (not
+    through the repo's fp32 reverse scan): dZ = d(sum dY*mask*h)/dZ and its column sum db, with the dropout mask of
+    the layer output replayed by the NumPy twin.  Operands of the recurrent product are bf16: 1 % class."""
+    from music_generator_b200 import _lib
+    g = torch.Generator().manual_seed(31)
+    U = 256 if axis == "time" else 128
+    M = B * T * 48
+    Z0 = torch.randn(M, 4 * U, generator=g)
+    Uw = (torch.randn(U, 4 * U, generator=g) * 0.06).bfloat16().float()       # bf16-representable recurrent weights
+    if axis == "time":
+        S, steps, m = B * 48, T, (48, T * 48, 1, 48)
+        rows = torch.arange(M).view(B, T, 48).permute(0, 2, 1).reshape(S, steps)
+    else:
+        S, steps, m = B * T, 48, (1, 48, 0, 1)
+        rows = torch.arange(M).view(S, steps)
+    ld = U + 32
+    dY = torch.randn(M, ld, generator=g) * 0.1
+    seed, site = 11, 6
+    d = _lib.make_dropout(seed, site, 0.5)
+    mask = torch.tensor(helpers.keep_mask(seed, site, 0.5, M, U)).double() * 2.0
+    # ---- float64 reference with autograd
+    Z64 = Z0.double().requires_grad_(True)
+    U64 = Uw.double()
+    hs, cs = torch.zeros(S, U, dtype=torch.float64), torch.zeros(S, U, dtype=torch.float64)
+    loss = 0.0
+    for t in range(steps):
+        z = (Z64[rows[:, t]] + hs @ U64).view(S, U, 4)
+        i, f, o = [(0.2 * z[..., k] + 0.5).clamp(0, 1) for k in (0, 1, 3)]
+        cs = f * cs + i * torch.tanh(z[..., 2])
+        hs = o * torch.tanh(cs)
+        loss = loss + (hs * mask[rows[:, t]] * dY[rows[:, t], :U].double()).sum()
+    loss.backward()
+    dZref = Z64.grad
+    # ---- device: fp32 forward scan for the saved gates / cell states, tensor-core reverse scan
+    Z, Ud = Z0.cuda(), Uw.cuda()
+    h, c = torch.empty(M, U, device="cuda"), torch.empty(M, U, device="cuda")
+    _lib.check(lib.dj_lstm_scan_fwd(P(Z), P(h), P(c), None, P(Ud), S, steps, U, *m, 1, None))
+    G16 = _gates16(Z)
+    dZt = torch.zeros(M, 4 * U, device="cuda").bfloat16()
+    dbt = torch.zeros(4 * U, device="cuda")
+    dYd = dY.cuda()
+    _lib.check(lib.dj_lstm_scan_tc_bwd(P(G16), P(c), P(dYd), ld, d, P(Uw.bfloat16().cuda()), P(dZt), P(dbt), S, steps, U,
+                                       *m, 1, None))
+    torch.cuda.synchronize()
+    a, b = dZt.float().cpu().double(), dZref
+    scale = float(b.abs().max())
+    print(f"scan_tc_bwd vs float64 autograd [{axis}]: max |d| / max {float((a - b).abs().max()) / scale:.2e}, "
+          f"mean |d| / mean {float((a - b).abs().mean() / b.abs().mean()):.2e}")
+    assert float((a - b).abs().max()) / scale < 0.02 and float((a - b).abs().mean() / b.abs().mean()) < 0.01
+    assert helpers.rel_err(dbt.cpu().numpy(), b.sum(0).numpy()) < 0.01
+
+
 @pytest.mark.parametrize("Uprev,chosen", [(256, False), (256, True), (128, False), (512, True)])
 @pytest.mark.parametrize("dtype", ["bf16", "f16"])
 @pytest.mark.parametrize("drop", [True, False])
