@@ -456,6 +456,55 @@ def test_lstm_scan_bwd_tcgen05_matches_fp32_scan(lib, axis, B, T):
     assert helpers.rel_err(dbt.cpu().numpy(), dbr.cpu().numpy()) < 0.02
 
 
+@pytest.mark.parametrize("G", [1, 2])
+def test_generation_two_layer_scan_matches_float64_and_stays_in_bounds(lib, G):
+    """dj_lstm_scan_tc_gen2 (both time-axis layers of a generation window in one launch; G = 1: three roles, G = 2:
+    two) against the float64 two-layer recurrence  z1_t = h0_t.W1 + c1 + h1_{t-1}.U1  on random weights, and a bounds
+    check: every buffer carries a guard region of sentinels behind its documented size that must come back intact."""
+    from music_generator_b200 import _lib
+    g = torch.Generator().manual_seed(40 + G)
+    U, T = 256, 24
+    S, M = G * 48, G * T * 48
+    Z0 = torch.randn(M, 4 * U, generator=g)
+    U0 = torch.randn(U, 4 * U, generator=g) * 0.06
+    U1 = torch.randn(U, 4 * U, generator=g) * 0.06
+    W1 = torch.randn(U, 4 * U, generator=g) * 0.06
+    c1 = torch.randn(G, 4 * U, generator=g) * 0.5
+    rows = torch.arange(M).view(G, T, 48).permute(0, 2, 1).reshape(S, T)
+    # float64 reference
+    h0 = _keras_lstm_f64(Z0, U0, rows, S, T, U)
+    Z1 = h0 @ W1.double() + c1.double().repeat_interleave(T * 48, dim=0)
+    h1 = _keras_lstm_f64(Z1, U1, rows, S, T, U)
+    # device
+    scale, GUARD, SENT = 1024.0, 64, 12345.0
+    def split_t(Wm):
+        hi, lo = _split16(Wm.t().contiguous() * scale, torch.float16)
+        return hi.cuda(), lo.cuda()
+    Ut0, Ut0lo = split_t(U0); Ut1, Ut1lo = split_t(U1); Wt1, Wt1lo = split_t(W1)
+    def guarded(n_rows, cols, dtype):
+        t = torch.full((n_rows + GUARD, cols), SENT, dtype=dtype, device="cuda")
+        return t
+    hbuf = [guarded(M + 48, U, torch.float16) for _ in range(4)]          # h0_hi, h0_lo, h1_hi, h1_lo
+    h1out = guarded(M, U, torch.float32)
+    Z1d = guarded(M, 4 * U, torch.float32)
+    flags = torch.full((2 * (S // 16) + 16,), 77, dtype=torch.int32, device="cuda")
+    Zd, c1d = Z0.cuda(), c1.cuda()
+    _lib.check(lib.dj_lstm_scan_tc_gen2(P(Zd), P(Z1d), P(c1d), P(h1out), P(hbuf[0]), P(hbuf[1]), P(hbuf[2]), P(hbuf[3]),
+                                        P(Ut0), P(Ut0lo), P(Ut1), P(Ut1lo), P(Wt1), P(Wt1lo), 1.0 / scale, P(flags),
+                                        S, T, 1, None))
+    torch.cuda.synchronize()
+    last = rows[:, T - 1]
+    err = (h1out[:M].cpu().double()[last] - h1[last]).abs()
+    print(f"scan_tc_gen2 G={G}: max |h1 - float64| at the last step {float(err.max()):.2e}")
+    assert float(err.max()) < 1e-5
+    for t in hbuf:
+        assert bool((t[M + 48:] == SENT).all())                            # nothing behind the spare timestep
+    assert bool((hbuf[2][M:] == SENT).all()) and bool((hbuf[3][M:] == SENT).all())   # layer 1 never uses its spare rows
+    assert bool((h1out[M:] == SENT).all()) and bool((Z1d[M:] == SENT).all())
+    assert bool((flags[2 * (S // 16):] == 77).all())
+    assert torch.equal(Zd.cpu(), Z0)                                       # the pre-activations are read only
+
+
 @pytest.mark.parametrize("axis,B,T", [("time", 2, 12), ("note", 2, 32)])
 def test_lstm_scan_bwd_tcgen05_matches_float64_autograd(lib, axis, B, T):
     """The reverse scan on the tensor cores against AUTOGRAD through the float64 restatement of the Keras step (not
