@@ -371,6 +371,10 @@ __global__ void __launch_bounds__(256) layer_input_fast_kernel(
         const float4 s0 = __ldg(reinterpret_cast<const float4*>(sp + (size_t)bt * F + f8));
         const float4 s1 = __ldg(reinterpret_cast<const float4*>(sp + (size_t)bt * F + f8 + 4));
         s[0] = s0.x; s[1] = s0.y; s[2] = s0.z; s[3] = s0.w; s[4] = s1.x; s[5] = s1.y; s[6] = s1.z; s[7] = s1.w;
+      } else if (f8 + 8 <= F) {   // F = Uprev + 3: the rows of sp are not 16-byte aligned, but 32 of the 36 chunks are whole
+        const float* sr = sp + (size_t)bt * F + f8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s[j] = __ldg(sr + j);
       } else {
 #pragma unroll
         for (int j = 0; j < 8; ++j) s[j] = (f8 + j < F) ? __ldg(sp + (size_t)bt * F + f8 + j) : 0.f;
@@ -384,8 +388,7 @@ __global__ void __launch_bounds__(256) layer_input_fast_kernel(
         for (int j = 0; j < 8; ++j) m[j] = 1.f;
       }
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (!CHOSEN || f8 + j < F) v[j] = fmaf(s[j], m[j], v[j]);
+      for (int j = 0; j < 8; ++j) v[j] = fmaf(s[j], m[j], v[j]);      // s is zero beyond F
     }
     const uint4 hi = pack8(v, TA());
     *reinterpret_cast<uint4*>(A + (size_t)row * (ld8 * 8) + f8) = hi;
