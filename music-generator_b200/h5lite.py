@@ -44,7 +44,6 @@ class _Reader:
             base = 512 if base == 0 else base * 2
         if base >= len(buf):
             raise H5Error("not an HDF5 file (no superblock signature at 0, 512, 1024, ...)")
-        self.base0 = base
         ver = buf[base + 8]
         if ver not in (0, 1):
             raise H5Error(f"superblock version {ver} (new-style file, libver='latest') is not supported; "

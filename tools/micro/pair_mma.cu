@@ -5,7 +5,7 @@
 //   and commits to the accumulator barrier of its pair and to a count-2 "free" barrier of all four CTAs.
 // Prints where every accumulator element landed (lane, column) against the expected layout
 //   unit = 128*pair + 64*(c & 1) + (lane & 63),  sequence = (lane >> 6) * NH + column.
-// Build + run:  nvcc -gencode arch=compute_100a,code=sm_100a -O2 -std=c++17 -o /tmp/pair_mma tools/micro/pair_mma.cu -lcuda && /tmp/pair_mma
+// Build + run:  nvcc -gencode arch=compute_100a,code=sm_100a -O2 -std=c++17 -o tools/micro/pair_mma.bin tools/micro/pair_mma.cu && tools/micro/pair_mma.bin
 #include <cooperative_groups.h>
 #include <cstdarg>
 #include <cstdlib>
